@@ -1,0 +1,77 @@
+/* cfhd_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain C, scalar) of the CineForm transform hot path used as
+ * the parity checker for the CUDA kernels.  It is NOT product code: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load liboracle.so.  The product library
+ * (cineform-sdk_b200/csrc) never links or calls it and has no CPU fallback.
+ *
+ * Parity status: PINNED -- every function below is validated bit-for-bit
+ * against the unmodified reference compiled in place (oracle/_ref, see
+ * Makefile and tests/test_oracle_vs_ref.py), on Qbist frames and on
+ * adversarial inputs that exercise the reference's saturating-SIMD /
+ * int32-scalar column split.
+ *
+ * Each function cites the reference file:line it restates (paths relative to
+ * the reference tree, commit 11574d02).
+ */
+#ifndef CFHD_ORACLE_H
+#define CFHD_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* variants of the fused forward level (differences only matter on int16 overflow) */
+#define ORC_FWD_PLAIN 0  /* FilterSpatialQuant16s      Codec/spatial.c:10026 (prescale 0)        */
+#define ORC_FWD_V210  1  /* FilterSpatialV210Quant16s  Codec/spatial.c:12942 (prescale 2)        */
+#define ORC_FWD_YUV   2  /* FilterSpatialYUVQuant16s   Codec/spatial.c:14726 (packed 4:2:2 rows) */
+
+#define ORC_FMT_YUYV 0
+#define ORC_FMT_UYVY 1
+
+/* Codec/spatial.c:253 FilterHorizontalRow16s (prescale==0) and
+ * Codec/spatial.c:3669 FilterHorizontalRow10bit16s (prescale==2). width even, >= 18. */
+void orc_fwd_row(const int16_t *in, int16_t *low, int16_t *high, int width, int prescale);
+
+/* Codec/quantize.c:1395 QuantizeRow16sTo16s. midpoint_prequant is the value of the
+ * reference's global g_midpoint_prequant (2 for the default pre-emphasis). */
+void orc_quantize_row(const int16_t *in, int16_t *out, int length, int divisor, int midpoint_prequant);
+
+/* One fused forward level on an int16 plane: horizontal 2-6, vertical 2-6, quantise.
+ * Pitches are in BYTES (as in the reference). quant[0..3] = LL,LH,HL,HH divisors. */
+void orc_fwd_level(const int16_t *in, int in_pitch, int width, int height, int variant,
+                   const int quant[4], int midpoint_prequant,
+                   int16_t *ll, int16_t *lh, int16_t *hl, int16_t *hh, int out_pitch);
+
+/* Codec/convert.c:4667 UnpackRowYUV16s default branch (value << shift), one channel
+ * (0 = Y, 1 = V, 2 = U as the encoder numbers them) of one packed row. */
+void orc_unpack_row_422(const uint8_t *in, int16_t *out, int width, int channel, int format, int shift);
+
+/* Level 1 of a packed 8-bit 4:2:2 frame for one channel (Codec/wavelet.c:2823 +
+ * Codec/spatial.c:14726).  width/height are the CHANNEL's input dimensions. */
+void orc_fwd_level_422(const uint8_t *frame, int frame_pitch, int width, int height, int channel,
+                       int format, int precision, const int quant[4], int midpoint_prequant,
+                       int16_t *ll, int16_t *lh, int16_t *hl, int16_t *hh, int out_pitch);
+
+/* Codec/decoder.c:20551 DeQuantFSM semantics applied to a dense band: c = (int16)(v*quant). */
+void orc_dequantize_band(const int16_t *in, int16_t *out, int width, int height, int pitch, int quant);
+
+/* Inverse level (bands already dequantised): Codec/spatial.c:21877 InvertSpatialQuant16s +
+ * Codec/InvertHorizontalStrip16s.c:459 (descale==0) or Codec/spatial.c:22414
+ * InvertSpatialQuantDescale16s + InvertHorizontalStrip16s.c:1700 (descale==2).
+ * width/height = band dimensions; output is 2*width x 2*height. Pitches in bytes. */
+void orc_inv_level(const int16_t *ll, const int16_t *lh, const int16_t *hl, const int16_t *hh,
+                   int band_pitch, int width, int height, int descale,
+                   int16_t *out, int out_pitch);
+
+/* 3-level pyramid helpers are composed in Python (tests/) from the calls above. */
+
+int orc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

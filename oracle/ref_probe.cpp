@@ -1,0 +1,165 @@
+// ref_probe.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Our own shim, compiled together with the UNMODIFIED reference sources (in
+// place, from /root/reference) into oracle/_ref/libcfhd_ref.so.  It exposes the
+// reference's coefficient-level functions of the transform path through a flat
+// C ABI so that tests can (1) pin oracle/cfhd_oracle.c against the real thing and
+// (2) use the real thing as the CPU baseline.  It contains no codec logic: each
+// entry point only marshals buffers (16-byte aligned copies, as the SSE2 loads
+// in the reference require) and calls the cited reference function.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+extern "C" {
+#include "config.h"
+#include "encoder.h"
+#include "wavelet.h"
+#include "spatial.h"
+#include "quantize.h"
+#include "convert.h"
+#include "frame.h"
+#include "image.h"
+}
+#include "qbist.h"
+#include "CFHDTypes.h"
+
+extern "C" int g_midpoint_prequant;   // Codec/quantize.c:183
+extern "C" void FilterHorizontalRow10bit16s(PIXEL *input, PIXEL *lowpass, PIXEL *highpass, int width, PIXEL *buffer);
+
+namespace {
+struct Aligned {
+    void *p = nullptr;
+    explicit Aligned(size_t n) { if (posix_memalign(&p, 64, n ? n : 64)) p = nullptr; else memset(p, 0, n ? n : 64); }
+    ~Aligned() { free(p); }
+    template <class T> T *as() { return (T *)p; }
+};
+inline int align16(int x) { return (x + 15) & ~15; }
+inline size_t align64(size_t x) { return (x + 63) & ~(size_t)63; }
+
+// copy a (pitch-strided) 2-D array into / out of an aligned, 16-byte-pitched scratch
+void copy_in(uint8_t *dst, int dpitch, const uint8_t *src, int spitch, int rowbytes, int rows) {
+    for (int r = 0; r < rows; r++) memcpy(dst + (size_t)r * dpitch, src + (size_t)r * spitch, rowbytes);
+}
+}  // namespace
+
+extern "C" {
+
+int ref_probe_version(void) { return 2; }
+
+// Codec/spatial.c:253 / :3669
+void ref_fwd_row(const int16_t *in, int16_t *low, int16_t *high, int width, int prescale)
+{
+    Aligned a((size_t)width * 2 + 64), l((size_t)width + 64), h((size_t)width + 64), b((size_t)width * 2 + 64);
+    memcpy(a.p, in, (size_t)width * 2);
+    if (prescale) FilterHorizontalRow10bit16s(a.as<PIXEL>(), l.as<PIXEL>(), h.as<PIXEL>(), width, b.as<PIXEL>());
+    else FilterHorizontalRow16s(a.as<PIXEL>(), l.as<PIXEL>(), h.as<PIXEL>(), width);
+    memcpy(low, l.p, (size_t)width);
+    memcpy(high, h.p, (size_t)width);
+}
+
+// Codec/quantize.c:1395
+void ref_quantize_row(const int16_t *in, int16_t *out, int length, int divisor, int midpoint_prequant)
+{
+    Aligned a((size_t)length * 2 + 64), o((size_t)length * 2 + 64);
+    memcpy(a.p, in, (size_t)length * 2);
+    g_midpoint_prequant = midpoint_prequant;
+    QuantizeRow16sTo16s(a.as<PIXEL>(), o.as<PIXEL>(), length, divisor);
+    memcpy(out, o.p, (size_t)length * 2);
+}
+
+// variant 0: FilterSpatialQuant16s (spatial.c:10026); 1: FilterSpatialV210Quant16s (:12942)
+void ref_fwd_level(const int16_t *in, int in_pitch, int width, int height, int variant,
+                   const int quant[4], int midpoint_prequant,
+                   int16_t *ll, int16_t *lh, int16_t *hl, int16_t *hh, int out_pitch)
+{
+    const int ow = width / 2, oh = height / 2;
+    const int ip = align16(width * 2), op = align16(ow * 2);
+    Aligned ain((size_t)ip * height), b0((size_t)op * oh), b1((size_t)op * oh), b2((size_t)op * oh), b3((size_t)op * oh);
+    const size_t bufsize = 32 * align64((size_t)width * 2) + 4096;
+    Aligned scratch(bufsize);
+    copy_in(ain.as<uint8_t>(), ip, (const uint8_t *)in, in_pitch, width * 2, height);
+    int q[4] = {quant[0], quant[1], quant[2], quant[3]};
+    ROI roi = {width, height};
+    g_midpoint_prequant = midpoint_prequant;
+    if (variant == 1)
+        FilterSpatialV210Quant16s(ain.as<PIXEL>(), ip, b0.as<PIXEL>(), op, b1.as<PIXEL>(), op, b2.as<PIXEL>(), op,
+                                  b3.as<PIXEL>(), op, scratch.as<PIXEL>(), bufsize, roi, q);
+    else
+        FilterSpatialQuant16s(ain.as<PIXEL>(), ip, b0.as<PIXEL>(), op, b1.as<PIXEL>(), op, b2.as<PIXEL>(), op,
+                              b3.as<PIXEL>(), op, scratch.as<PIXEL>(), bufsize, roi, q);
+    copy_in((uint8_t *)ll, out_pitch, b0.as<uint8_t>(), op, ow * 2, oh);
+    copy_in((uint8_t *)lh, out_pitch, b1.as<uint8_t>(), op, ow * 2, oh);
+    copy_in((uint8_t *)hl, out_pitch, b2.as<uint8_t>(), op, ow * 2, oh);
+    copy_in((uint8_t *)hh, out_pitch, b3.as<uint8_t>(), op, ow * 2, oh);
+}
+
+// Codec/spatial.c:14726 FilterSpatialYUVQuant16s for one channel of a packed 4:2:2 frame.
+// width = channel input width (luma: frame width; chroma: frame width / 2). format: 0 YUYV, 1 UYVY.
+void ref_fwd_level_422(const uint8_t *frame, int frame_pitch, int width, int height, int channel,
+                       int format, int precision, const int quant[4], int midpoint_prequant,
+                       int16_t *ll, int16_t *lh, int16_t *hl, int16_t *hh, int out_pitch)
+{
+    const int ow = width / 2, oh = height / 2;
+    const int frame_width = (channel == 0) ? width : 2 * width;
+    const int ip = align16(frame_width * 2), op = align16(ow * 2);
+    Aligned ain((size_t)ip * height + 64), b0((size_t)op * oh), b1((size_t)op * oh), b2((size_t)op * oh), b3((size_t)op * oh);
+    const size_t bufsize = 40 * align64((size_t)frame_width * 2) + 4096;
+    Aligned scratch(bufsize);
+    copy_in(ain.as<uint8_t>(), ip, frame, frame_pitch, frame_width * 2, height);
+    int q[4] = {quant[0], quant[1], quant[2], quant[3]};
+    ROI roi = {width, height};
+    FRAME_INFO info;
+    memset(&info, 0, sizeof(info));
+    info.width = frame_width; info.height = height;
+    info.format = format ? COLOR_FORMAT_UYVY : COLOR_FORMAT_YUYV;
+    g_midpoint_prequant = midpoint_prequant;
+    FilterSpatialYUVQuant16s(ain.as<uint8_t>(), ip, b0.as<PIXEL>(), op, b1.as<PIXEL>(), op, b2.as<PIXEL>(), op,
+                             b3.as<PIXEL>(), op, scratch.as<PIXEL>(), bufsize, roi, channel, q, &info,
+                             precision, 0, 0);
+    copy_in((uint8_t *)ll, out_pitch, b0.as<uint8_t>(), op, ow * 2, oh);
+    copy_in((uint8_t *)lh, out_pitch, b1.as<uint8_t>(), op, ow * 2, oh);
+    copy_in((uint8_t *)hl, out_pitch, b2.as<uint8_t>(), op, ow * 2, oh);
+    copy_in((uint8_t *)hh, out_pitch, b3.as<uint8_t>(), op, ow * 2, oh);
+}
+
+// descale 0: InvertSpatialQuant16s (spatial.c:21877); descale 2: InvertSpatialQuantDescale16s (:22414)
+void ref_inv_level(const int16_t *ll, const int16_t *lh, const int16_t *hl, const int16_t *hh,
+                   int band_pitch, int width, int height, int descale, int16_t *out, int out_pitch)
+{
+    const int bp = align16(width * 2), op = align16(width * 4);
+    // the SIMD loops read up to 8 coefficients past the row end and 2 rows below: pad generously
+    const size_t bsz = (size_t)bp * (height + 4) + 256;
+    Aligned b0(bsz), b1(bsz), b2(bsz), b3(bsz), o((size_t)op * height * 2 + 256);
+    const size_t bufsize = 16 * (size_t)align16(width * 2) + 4096;
+    Aligned scratch(bufsize);
+    copy_in(b0.as<uint8_t>(), bp, (const uint8_t *)ll, band_pitch, width * 2, height);
+    copy_in(b1.as<uint8_t>(), bp, (const uint8_t *)lh, band_pitch, width * 2, height);
+    copy_in(b2.as<uint8_t>(), bp, (const uint8_t *)hl, band_pitch, width * 2, height);
+    copy_in(b3.as<uint8_t>(), bp, (const uint8_t *)hh, band_pitch, width * 2, height);
+    ROI roi = {width, height};
+    int q[4] = {1, 1, 1, 1};
+    if (descale)
+        InvertSpatialQuantDescale16s(b0.as<PIXEL>(), bp, b1.as<PIXEL>(), bp, b2.as<PIXEL>(), bp, b3.as<PIXEL>(), bp,
+                                     o.as<PIXEL>(), op, roi, scratch.as<PIXEL>(), bufsize, descale, q);
+    else
+        InvertSpatialQuant16s(b0.as<PIXEL>(), bp, b1.as<PIXEL>(), bp, b2.as<PIXEL>(), bp, b3.as<PIXEL>(), bp,
+                              o.as<PIXEL>(), op, roi, scratch.as<PIXEL>(), bufsize, q);
+    copy_in((uint8_t *)out, out_pitch, o.as<uint8_t>(), op, width * 4, height * 2);
+}
+
+// Example/qbist.cpp:252 RunQBist driven exactly like Example/TestCFHD.cpp:1149-1219:
+// GetRand(seed); initBaseTransform(); then one RunQBist() per frame; returns frame number `nframes` (1-based).
+void ref_qbist_frames(unsigned seed, int width, int height, int pitch, unsigned pixel_format, int nframes, uint8_t *out)
+{
+    Aligned buf((size_t)width * height * 8 + 64);
+    GetRand(seed);
+    initBaseTransform();
+    // frame 1 = first RunQBist call, frame k = k-th call (RunQBist mutates its genes at the end of each call)
+    for (int i = 0; i < nframes; i++)
+        RunQBist(width, height, pitch, (CFHD_PixelFormat)pixel_format, 0, buf.as<unsigned char>());
+    memcpy(out, buf.p, (size_t)pitch * height);
+}
+
+}  // extern "C"
