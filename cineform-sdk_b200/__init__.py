@@ -1,0 +1,253 @@
+"""cineform-sdk_b200 -- host-side mirror (ctypes) of the C ABI in include/cfhd_b200.h.
+
+The product is the native library ``libcfhd_b200.so`` (CUDA kernels for sm_100a +
+C-ABI); this module only marshals numpy buffers into it for tests and bench.py.
+There is no Python or CPU implementation of the transform here: if the native
+library is missing or no B200 is present, calls fail loudly.
+
+Import with ``importlib.import_module("cineform-sdk_b200")`` (the directory name
+follows the reference repo's name and is not a Python identifier).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcfhd_b200.so")
+
+PIXEL_YUYV, PIXEL_UYVY, PIXEL_RG48, PIXEL_BYR4, PIXEL_PLANAR16 = 0, 1, 2, 3, 4
+MAX_CHANNELS, NUM_LEVELS, NUM_BANDS, MAX_BATCH = 4, 3, 4, 16
+BAND_NAMES = ("LL", "LH", "HL", "HH")
+
+OK = 0
+ERROR_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "OUTOFMEMORY", 3: "BADFORMAT", 10: "UNEXPECTED", 13: "NOT_FINISHED",
+               100: "NO_DEVICE", 101: "CUDA", 102: "UNSUPPORTED"}
+
+
+class CfbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cfb error {code} ({ERROR_NAMES.get(code, '?')}): {msg}")
+        self.code = code
+
+
+class FrameDesc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("pixel_format", C.c_int32), ("reserved", C.c_int32)]
+
+    def __init__(self, width=0, height=0, pixel_format=0):
+        super().__init__(width, height, pixel_format, 0)
+
+
+class BandLayout(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("width", C.c_int32), ("height", C.c_int32), ("pitch", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class Layout(C.Structure):
+    _fields_ = [("num_channels", C.c_int32), ("precision", C.c_int32), ("coded_bytes", C.c_int64),
+                ("total_bytes", C.c_int64), ("frame_bytes", C.c_int64), ("frame_pitch", C.c_int32),
+                ("reserved", C.c_int32), ("band", BandLayout * NUM_BANDS * NUM_LEVELS * MAX_CHANNELS)]
+
+
+class Quant(C.Structure):
+    _fields_ = [("prescale", C.c_int32 * NUM_LEVELS), ("midpoint_prequant", C.c_int32),
+                ("divisor", C.c_int32 * NUM_BANDS * NUM_LEVELS * MAX_CHANNELS)]
+
+    def table(self, nchan=3):
+        return [[[self.divisor[c][k][b] for b in range(4)] for k in range(3)] for c in range(nchan)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("frames_forward", C.c_uint64), ("frames_inverse", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the native library (built in-tree by __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python __graft_entry__.py` (nvcc, sm_100a) first; "
+                          "there is no Python/CPU fallback for the transform path")
+    L = C.CDLL(LIB_PATH)
+    vp, i = C.c_void_p, C.c_int
+    L.cfb_version.restype = i
+    L.cfb_last_error_string.restype = C.c_char_p
+    L.cfb_device_count.restype = i
+    L.cfb_context_create.argtypes = [i, C.POINTER(vp)]
+    L.cfb_context_destroy.argtypes = [vp]
+    L.cfb_context_destroy.restype = None
+    L.cfb_context_synchronize.argtypes = [vp]
+    L.cfb_context_stream.argtypes = [vp]
+    L.cfb_context_stream.restype = vp
+    L.cfb_context_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.cfb_layout_compute.argtypes = [C.POINTER(FrameDesc), C.POINTER(Layout)]
+    L.cfb_quant_for_quality.argtypes = [C.POINTER(FrameDesc), i, C.POINTER(Quant)]
+    L.cfb_codec_create.argtypes = [vp, C.POINTER(FrameDesc), i, C.POINTER(vp)]
+    L.cfb_codec_destroy.argtypes = [vp]
+    L.cfb_codec_destroy.restype = None
+    L.cfb_codec_layout.argtypes = [vp, C.POINTER(Layout)]
+    L.cfb_codec_device_frame.argtypes = [vp, i]
+    L.cfb_codec_device_frame.restype = vp
+    L.cfb_codec_device_pyramid.argtypes = [vp, i]
+    L.cfb_codec_device_pyramid.restype = vp
+    L.cfb_forward_device.argtypes = [vp, i, C.POINTER(vp), i, C.POINTER(Quant), C.POINTER(vp)]
+    L.cfb_forward_host.argtypes = [vp, i, C.POINTER(vp), i, C.POINTER(Quant), C.POINTER(vp)]
+    L.cfb_inverse_device.argtypes = [vp, i, C.POINTER(vp), C.POINTER(Quant), i, C.POINTER(vp), i]
+    L.cfb_inverse_host.argtypes = [vp, i, C.POINTER(vp), C.POINTER(Quant), i, C.POINTER(vp), i]
+    _lib = L
+    return L
+
+
+def _check(code):
+    if code != OK:
+        raise CfbError(code, lib().cfb_last_error_string().decode("utf-8", "replace"))
+
+
+def device_count():
+    return lib().cfb_device_count()
+
+
+def layout_for(desc):
+    out = Layout()
+    _check(lib().cfb_layout_compute(C.byref(desc), C.byref(out)))
+    return out
+
+
+def quant_for_quality(desc, quality):
+    out = Quant()
+    _check(lib().cfb_quant_for_quality(C.byref(desc), quality, C.byref(out)))
+    return out
+
+
+def make_quant(divisors, prescale, midpoint_prequant=2):
+    """divisors[c][k][b] (k = 0 is level 1)."""
+    q = Quant()
+    for k in range(NUM_LEVELS):
+        q.prescale[k] = prescale[k]
+    q.midpoint_prequant = midpoint_prequant
+    for c, per_c in enumerate(divisors):
+        for k, per_k in enumerate(per_c):
+            for b, d in enumerate(per_k):
+                q.divisor[c][k][b] = d
+    return q
+
+
+def _ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))()
+    for n, p in enumerate(ptrs):
+        arr[n] = p
+    return arr
+
+
+class Context:
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(lib().cfb_context_create(device, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().cfb_context_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def synchronize(self):
+        _check(lib().cfb_context_synchronize(self.h))
+
+    @property
+    def stream(self):
+        return lib().cfb_context_stream(self.h)
+
+    def stats(self):
+        s = Stats()
+        _check(lib().cfb_context_stats(self.h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+
+
+class Codec:
+    def __init__(self, ctx, desc, max_batch=1):
+        self.ctx, self.desc, self.max_batch = ctx, desc, max_batch
+        self.h = C.c_void_p()
+        _check(lib().cfb_codec_create(ctx.h, C.byref(desc), max_batch, C.byref(self.h)))
+        self.layout = Layout()
+        _check(lib().cfb_codec_layout(self.h, C.byref(self.layout)))
+
+    def close(self):
+        if self.h:
+            lib().cfb_codec_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def device_frame(self, slot):
+        return lib().cfb_codec_device_frame(self.h, slot)
+
+    def device_pyramid(self, slot):
+        return lib().cfb_codec_device_pyramid(self.h, slot)
+
+    # -- forward -----------------------------------------------------------
+    def forward_device(self, d_frames, frame_pitch, quant, d_pyramids):
+        n = len(d_frames)
+        _check(lib().cfb_forward_device(self.h, n, _ptr_array(d_frames), frame_pitch, C.byref(quant),
+                                        _ptr_array(d_pyramids)))
+
+    def forward_host(self, frames, quant, out=None):
+        """frames: list of 2-D uint8/uint16 arrays (rows x pitch-bytes/itemsize). Returns coded buffers (uint8)."""
+        n = len(frames)
+        frames = [np.ascontiguousarray(f) for f in frames]
+        pitch = frames[0].strides[0]
+        if out is None:
+            out = [np.empty(self.layout.coded_bytes, np.uint8) for _ in range(n)]
+        _check(lib().cfb_forward_host(self.h, n, _ptr_array([f.ctypes.data for f in frames]), pitch, C.byref(quant),
+                                      _ptr_array([o.ctypes.data for o in out])))
+        return out
+
+    # -- inverse -----------------------------------------------------------
+    def inverse_device(self, d_pyramids, quant, out_format, d_frames, frame_pitch):
+        n = len(d_pyramids)
+        _check(lib().cfb_inverse_device(self.h, n, _ptr_array(d_pyramids), C.byref(quant), out_format,
+                                        _ptr_array(d_frames), frame_pitch))
+
+    def inverse_host(self, coded, quant, out_format, out_frames):
+        n = len(coded)
+        pitch = out_frames[0].strides[0]
+        _check(lib().cfb_inverse_host(self.h, n, _ptr_array([c.ctypes.data for c in coded]), C.byref(quant),
+                                      out_format, _ptr_array([o.ctypes.data for o in out_frames]), pitch))
+        return out_frames
+
+    # -- helpers -----------------------------------------------------------
+    def band_view(self, buf, c, k, b):
+        """View of band (channel c, level index k, band b) inside a coefficient buffer (uint8 array)."""
+        bl = self.layout.band[c][k][b]
+        flat = buf[bl.offset: bl.offset + bl.pitch * bl.height].view(np.int16)
+        return flat.reshape(bl.height, bl.pitch // 2)[:, :bl.width]
+
+    def unpack_coded(self, buf):
+        """dict {(c, level(1..3), band_name): array} of every band in the coded region."""
+        out = {}
+        for c in range(self.layout.num_channels):
+            for k in range(NUM_LEVELS):
+                for b in range(NUM_BANDS):
+                    if b == 0 and k != NUM_LEVELS - 1:
+                        continue
+                    out[(c, k + 1, BAND_NAMES[b])] = self.band_view(buf, c, k, b).copy()
+        return out
+
+    def pack_coded(self, bands):
+        buf = np.zeros(self.layout.coded_bytes, np.uint8)
+        for (c, lvl, name), arr in bands.items():
+            self.band_view(buf, c, lvl - 1, BAND_NAMES.index(name))[:] = arr
+        return buf

@@ -1,0 +1,460 @@
+// cfb_api.cu -- C-ABI implementation (see include/cfhd_b200.h).
+//
+// Host side of the transform path: pyramid layout, quantisation schedule, CUDA
+// context / staging management and the kernel launch sequences.  No transform
+// arithmetic is ever done on the host: if no sm_100 device is usable every
+// transform entry point fails with CFB_ERROR_NO_DEVICE.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "cfb_host.h"
+
+namespace cfb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+cfb_error cuda_fail(cudaError_t e, const char *what)
+{
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return CFB_ERROR_NO_DEVICE;
+    if (e == cudaErrorMemoryAllocation) return CFB_ERROR_OUTOFMEMORY;
+    return CFB_ERROR_CUDA;
+}
+
+// Codec/quantize.c:1395-1427: multiplier = 65536/d, midpoint = d/g (g in [2,9)), minus one when g == 2.
+QuantParam make_quant_param(int divisor, int g)
+{
+    QuantParam q;
+    if (divisor <= 1) { q.m = 65536; q.cpos = 0; q.cneg = 65535; q.pad = 0; return q; }
+    int mid = 0;
+    if (g >= 2 && g < 9) { mid = divisor / g; if (g == 2 && mid) mid--; }
+    q.m = 65536 / divisor;
+    q.cpos = mid * q.m;
+    q.cneg = 65535 - mid * q.m;
+    q.pad = 0;
+    return q;
+}
+
+static inline int align16(int x) { return (x + 15) & ~15; }
+static inline int64_t align64(int64_t x) { return (x + 63) & ~(int64_t)63; }
+
+static int channels_of(int fmt) { return fmt == CFB_PIXEL_BYR4 ? 4 : 3; }
+
+// choose the number of output rows per warp so that the launch has enough warps to fill the GPU
+static int pick_th(int strips, int oh, int planes, int sm_count)
+{
+    static const int cand[] = {64, 48, 32, 24, 16, 12, 8, 6, 4};
+    const long long want = (long long)sm_count * 24;
+    for (int th : cand) {
+        long long warps = (long long)strips * ((oh + th - 1) / th) * planes;
+        if (warps >= want) return th;
+    }
+    return 4;
+}
+
+}  // namespace cfb
+
+using namespace cfb;
+
+extern "C" {
+
+int cfb_version(void) { return 100; }
+
+const char *cfb_last_error_string(void) { return g_err; }
+
+int cfb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---------------------------------------------------------------------------
+// Layout: Codec/wavelet.c:1208-1283 (AllocTransform), :427 (AllocWaveletStack), :302 (InitWaveletStack)
+cfb_error cfb_layout_compute(const cfb_frame_desc *desc, cfb_layout *out)
+{
+    if (!desc || !out) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    const int W = desc->width, H = desc->height, fmt = desc->pixel_format;
+    if (W <= 0 || H <= 0) { set_error("bad dimensions %dx%d", W, H); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (fmt < CFB_PIXEL_YUYV || fmt > CFB_PIXEL_PLANAR16) { set_error("bad pixel format %d", fmt); return CFB_ERROR_BADFORMAT; }
+    memset(out, 0, sizeof(*out));
+    int cw[CFB_MAX_CHANNELS], ch[CFB_MAX_CHANNELS];
+    const int nc = channels_of(fmt);
+    out->num_channels = nc;
+    switch (fmt) {
+    case CFB_PIXEL_YUYV: case CFB_PIXEL_UYVY:
+        out->precision = 10;
+        cw[0] = W; cw[1] = cw[2] = W / 2; ch[0] = ch[1] = ch[2] = H;
+        out->frame_pitch = W * 2;
+        if (W % 64) { set_error("4:2:2 width %d must be a multiple of 64", W); return CFB_ERROR_UNSUPPORTED; }
+        break;
+    case CFB_PIXEL_RG48: case CFB_PIXEL_PLANAR16:
+        out->precision = 12;
+        for (int c = 0; c < 3; c++) { cw[c] = W; ch[c] = H; }
+        out->frame_pitch = (fmt == CFB_PIXEL_RG48) ? W * 6 : W * 2;
+        if (W % 32) { set_error("4:4:4 width %d must be a multiple of 32", W); return CFB_ERROR_UNSUPPORTED; }
+        break;
+    case CFB_PIXEL_BYR4:
+        out->precision = 12;
+        for (int c = 0; c < 4; c++) { cw[c] = W / 2; ch[c] = H / 2; }
+        out->frame_pitch = W * 2;
+        if (W % 64 || H % 2) { set_error("Bayer width %d must be a multiple of 64", W); return CFB_ERROR_UNSUPPORTED; }
+        break;
+    }
+    for (int c = 0; c < nc; c++)
+        if (ch[c] % 8 || ch[c] < 48) { set_error("channel height %d must be a multiple of 8 and >= 48", ch[c]); return CFB_ERROR_UNSUPPORTED; }
+    out->frame_bytes = (int64_t)out->frame_pitch * H * (fmt == CFB_PIXEL_PLANAR16 ? 3 : 1);
+
+    // coded region: per channel LL3, then highpass of level 3, 2, 1
+    int64_t off = 0;
+    for (int c = 0; c < nc; c++) {
+        for (int k = CFB_NUM_LEVELS - 1; k >= 0; k--) {
+            const int w = cw[c] >> (k + 1), h = ch[c] >> (k + 1);
+            const int pitch = align16(w * 2);
+            const int64_t bsz = align64((int64_t)pitch * h);
+            for (int b = (k == CFB_NUM_LEVELS - 1 ? 0 : 1); b < CFB_NUM_BANDS; b++) {
+                cfb_band_layout &bl = out->band[c][k][b];
+                bl.offset = off; bl.width = w; bl.height = h; bl.pitch = pitch;
+                off += bsz;
+            }
+        }
+    }
+    out->coded_bytes = off;
+    // scratch region: LL1, LL2
+    for (int c = 0; c < nc; c++) {
+        for (int k = 0; k < CFB_NUM_LEVELS - 1; k++) {
+            const int w = cw[c] >> (k + 1), h = ch[c] >> (k + 1);
+            const int pitch = align16(w * 2);
+            cfb_band_layout &bl = out->band[c][k][0];
+            bl.offset = off; bl.width = w; bl.height = h; bl.pitch = pitch;
+            off += align64((int64_t)pitch * h);
+        }
+    }
+    out->total_bytes = off;
+    return CFB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Quantisation schedule for a fixed quality, GOP 1, progressive, rate control idle:
+// Codec/quantize.c:186-584 (QuantizationSetQuality), :2865-3356 (SetTransformQuantization, spatial
+// case with vbrscale 256 => VSCALE(q,m,256) = 256 q), Codec/wavelet.c:7022 (SetTransformScale:
+// band scales {4,2,2,1}, {16,8,8,4}, {64,32,32,16}), Codec/wavelet.c:1710 (SetTransformPrescale).
+cfb_error cfb_quant_for_quality(const cfb_frame_desc *desc, int quality, cfb_quant *out)
+{
+    if (!desc || !out) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_layout lay;
+    cfb_error err = cfb_layout_compute(desc, &lay);
+    if (err) return err;
+    static const int luma_tab[4][17] = {
+        {4, 4, 5, 5, 4, 5, 5, 9, 8, 8, 8, 4, 4, 4, 4, 4, 4},            // default
+        {4, 8, 8, 12, 8, 8, 12, 9, 12, 12, 16, 32, 32, 48, 32, 32, 48},   // low
+        {4, 6, 6, 8, 6, 6, 8, 5, 8, 8, 12, 16, 16, 24, 16, 16, 24},       // medium
+        {4, 4, 4, 6, 4, 4, 6, 5, 8, 8, 8, 8, 8, 12, 8, 8, 12}};           // high
+    static const int chroma_tab[4][17] = {
+        {4, 4, 5, 5, 4, 5, 5, 9, 8, 8, 8, 8, 8, 8, 8, 8, 8},
+        {4, 8, 8, 12, 8, 8, 12, 9, 12, 12, 16, 32, 32, 48, 32, 32, 48},
+        {4, 6, 6, 8, 6, 6, 8, 5, 8, 8, 12, 16, 16, 32, 16, 16, 32},
+        {4, 6, 6, 8, 6, 6, 8, 5, 8, 8, 8, 8, 8, 16, 8, 8, 16}};
+    memset(out, 0, sizeof(*out));
+    const int precision = lay.precision;
+    const bool chroma_full = (desc->pixel_format == CFB_PIXEL_BYR4);   // format >= COLOR_FORMAT_BAYER (encoder.c:1139)
+    int factor = quality & 0xff;
+    const int detail = (quality & 0x0e0000) >> 17;
+    int rgb_quality = (quality & 0x06000000) >> 25;
+    if (rgb_quality > 2) rgb_quality = 2;
+    int g = detail + 2;
+    if (g > 8) g = 0;
+    if (quality & 0x1f00) factor = 5;
+    const int new_quality = factor;
+    int limiter = 0;                                    // FSratelimiter on the first frame
+    if (new_quality == 5) limiter = 8; else if (new_quality == 6) limiter = 4;
+    if (factor < 1 || factor > 10) factor = 0;
+    if (factor > 3) factor = 3;
+    int ql[17], qc[17];
+    memcpy(ql, luma_tab[factor], sizeof(ql));
+    memcpy(qc, chroma_full ? luma_tab[factor] : chroma_tab[factor], sizeof(qc));
+    int lowfreq = 4;
+    if (precision >= 10) {
+        int scale = 4 * 16;
+        if (limiter > 16) limiter = 16;
+        if (new_quality == 4) { lowfreq = 3; scale = 3 * 16; }
+        else if (new_quality >= 5 && new_quality <= 10) { lowfreq = 2; scale = 16 + limiter * 2; }
+        if (new_quality >= 5 && scale >= 4) scale >>= 1;
+        if (new_quality == 10 && scale >= 6) { scale *= 2; scale /= 3; }
+        if (new_quality >= 4) for (int i = 1; i < 7; i++) ql[i] = qc[i] = lowfreq;
+        for (int i = 8; i < 17; i++) {
+            ql[i] = (ql[i] * scale) >> 4; if (ql[i] < 2) ql[i] = 2;
+            qc[i] = (qc[i] * scale) >> 4; if (qc[i] < 2) qc[i] = 2;
+        }
+        ql[7] = qc[7] = 4;
+    }
+    if (precision == 12) {
+        if (new_quality >= 4) for (int i = 1; i < 7; i++) ql[i] = qc[i] = lowfreq;
+        for (int i = 4; i < 7; i++) { ql[i] *= 4; qc[i] *= 4; }
+        static const int gains[4] = {8, 6, 4, 4};
+        const int chromagain = gains[rgb_quality];
+        for (int i = 11; i < 17; i++) { ql[i] *= 4; qc[i] *= chromagain; }
+    }
+    // GOP length 1 (quantize.c:552-567)
+    for (int i = 0; i < 3; i++) { ql[7 + i] = ql[11 + i]; qc[7 + i] = qc[11 + i]; }
+
+    static const int scale[3][4] = {{4, 2, 2, 1}, {16, 8, 8, 4}, {64, 32, 32, 16}};
+    out->midpoint_prequant = g;
+    out->prescale[0] = 0; out->prescale[1] = 2; out->prescale[2] = (precision == 12) ? 2 : 0;
+    for (int c = 0; c < lay.num_channels; c++) {
+        const int *q = (c > 0) ? qc : ql;
+        int subband = 1;
+        for (int k = 2; k >= 0; k--) {
+            out->divisor[c][k][0] = 1;
+            for (int b = 1; b < 4; b++) {
+                int d = (k == 0) ? q[subband] : ((q[subband] * scale[k][b]) >> 2);
+                if (g) { d *= g; d /= (g - 1) * 2; } else d /= 2;
+                out->divisor[c][k][b] = d;
+                subband++;
+            }
+        }
+    }
+    return CFB_OK;
+}
+
+// ---------------------------------------------------------------------------
+cfb_error cfb_context_create(int device, cfb_context **out)
+{
+    if (!out) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s): the transform path has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return CFB_ERROR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) { set_error("device %d out of range [0,%d)", device, n); return CFB_ERROR_INVALID_ARGUMENT; }
+    cudaDeviceProp prop;
+    CFB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+        return CFB_ERROR_NO_DEVICE;
+    }
+    CFB_CUDA(cudaSetDevice(device));
+    cfb_context *ctx = new (std::nothrow) cfb_context();
+    if (!ctx) return CFB_ERROR_OUTOFMEMORY;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return cuda_fail(e, "cudaStreamCreate"); }
+    *out = ctx;
+    return CFB_OK;
+}
+
+void cfb_context_destroy(cfb_context *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+cfb_error cfb_context_synchronize(cfb_context *ctx)
+{
+    if (!ctx) return CFB_ERROR_INVALID_ARGUMENT;
+    CFB_CUDA(cudaSetDevice(ctx->device));
+    CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CFB_OK;
+}
+
+void *cfb_context_stream(cfb_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+cfb_error cfb_context_stats(cfb_context *ctx, cfb_stats *out)
+{
+    if (!ctx || !out) return CFB_ERROR_INVALID_ARGUMENT;
+    out->kernel_launches = ctx->kernel_launches.load();
+    out->frames_forward = ctx->frames_forward.load();
+    out->frames_inverse = ctx->frames_inverse.load();
+    out->h2d_bytes = ctx->h2d_bytes.load();
+    out->d2h_bytes = ctx->d2h_bytes.load();
+    return CFB_OK;
+}
+
+// ---------------------------------------------------------------------------
+cfb_error cfb_codec_create(cfb_context *ctx, const cfb_frame_desc *desc, int max_batch, cfb_codec **out)
+{
+    if (!ctx || !desc || !out) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    *out = nullptr;
+    if (max_batch < 1 || max_batch > CFB_MAX_BATCH) { set_error("max_batch %d out of range", max_batch); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_layout lay;
+    cfb_error err = cfb_layout_compute(desc, &lay);
+    if (err) return err;
+    CFB_CUDA(cudaSetDevice(ctx->device));
+    cfb_codec *cd = new (std::nothrow) cfb_codec();
+    if (!cd) return CFB_ERROR_OUTOFMEMORY;
+    cd->ctx = ctx; cd->desc = *desc; cd->layout = lay; cd->max_batch = max_batch;
+    cd->frame_stride = (size_t)((lay.frame_bytes + 255) & ~(int64_t)255);
+    cd->pyramid_stride = (size_t)((lay.total_bytes + 255) & ~(int64_t)255);
+    cudaError_t e = cudaMalloc((void **)&cd->d_frames, cd->frame_stride * max_batch);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&cd->d_pyramids, cd->pyramid_stride * max_batch);
+    if (e != cudaSuccess) { cfb_codec_destroy(cd); return cuda_fail(e, "cudaMalloc(codec staging)"); }
+    // deterministic contents for the pitch padding (the reference's entropy coder walks it, encoder.c:5811)
+    e = cudaMemsetAsync(cd->d_pyramids, 0, cd->pyramid_stride * max_batch, ctx->stream);
+    if (e != cudaSuccess) { cfb_codec_destroy(cd); return cuda_fail(e, "cudaMemsetAsync"); }
+    *out = cd;
+    return CFB_OK;
+}
+
+void cfb_codec_destroy(cfb_codec *cd)
+{
+    if (!cd) return;
+    if (cd->ctx) cudaSetDevice(cd->ctx->device);
+    if (cd->d_frames) cudaFree(cd->d_frames);
+    if (cd->d_pyramids) cudaFree(cd->d_pyramids);
+    delete cd;
+}
+
+cfb_error cfb_codec_layout(const cfb_codec *cd, cfb_layout *out)
+{
+    if (!cd || !out) return CFB_ERROR_INVALID_ARGUMENT;
+    *out = cd->layout;
+    return CFB_OK;
+}
+
+void *cfb_codec_device_frame(cfb_codec *cd, int slot)
+{
+    return (cd && slot >= 0 && slot < cd->max_batch) ? cd->d_frames + cd->frame_stride * slot : nullptr;
+}
+void *cfb_codec_device_pyramid(cfb_codec *cd, int slot)
+{
+    return (cd && slot >= 0 && slot < cd->max_batch) ? cd->d_pyramids + cd->pyramid_stride * slot : nullptr;
+}
+
+// ---------------------------------------------------------------------------
+// forward
+static void fill_level_geom(const cfb_codec *cd, const cfb_quant *q, int c, int k, PlaneGeom &g)
+{
+    const cfb_layout &L = cd->layout;
+    const cfb_band_layout &ll = L.band[c][k][0];
+    g.width = ll.width * 2; g.height = ll.height * 2;
+    g.out_pitch = ll.pitch;
+    for (int b = 0; b < 4; b++) {
+        g.band_off[b] = L.band[c][k][b].offset;
+        g.q[b] = make_quant_param(q->divisor[c][k][b], q->midpoint_prequant);
+    }
+    // only the unprescaled planar filter ever quantises LL (spatial.c:10480; compiled out at :12942, absent at :14726)
+    g.quant_ll = 0;
+    if (k > 0) { g.in_off = L.band[c][k - 1][0].offset; g.in_pitch = L.band[c][k - 1][0].pitch; }
+    g.pad = 0;
+}
+
+cfb_error cfb_forward_device(cfb_codec *cd, int n, const void *const *d_frames, int frame_pitch,
+                             const cfb_quant *quant, void *const *d_pyramids)
+{
+    if (!cd || !d_frames || !quant || !d_pyramids) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (n < 1 || n > kMaxBatch) { set_error("batch %d out of range [1,%d]", n, kMaxBatch); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (frame_pitch < cd->layout.frame_pitch || (frame_pitch & 15)) { set_error("frame pitch %d must be >= %d and 16-byte aligned", frame_pitch, cd->layout.frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_context *ctx = cd->ctx;
+    const cfb_layout &L = cd->layout;
+    const int fmt = cd->desc.pixel_format;
+    CFB_CUDA(cudaSetDevice(ctx->device));
+    for (int i = 0; i < n; i++)
+        if (!d_frames[i] || !d_pyramids[i] || ((uintptr_t)d_frames[i] & 15) || ((uintptr_t)d_pyramids[i] & 15)) {
+            set_error("frame/pyramid %d null or not 16-byte aligned", i);
+            return CFB_ERROR_INVALID_ARGUMENT;
+        }
+    for (int lvl = 0; lvl < CFB_NUM_LEVELS; lvl++)
+        if (quant->prescale[lvl] != 0 && quant->prescale[lvl] != 2) { set_error("prescale %d unsupported", quant->prescale[lvl]); return CFB_ERROR_UNSUPPORTED; }
+
+    FwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.nchan = L.num_channels; p.nframes = n;
+    // ---- level 1 ----
+    if (fmt == CFB_PIXEL_YUYV || fmt == CFB_PIXEL_UYVY) {
+        for (int c = 0; c < 3; c++) { fill_level_geom(cd, quant, c, 0, p.ch[c]); p.ch[c].in_off = 0; p.ch[c].in_pitch = frame_pitch; }
+        for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_frames[i]; p.out_base[i] = (unsigned char *)d_pyramids[i]; }
+        p.shift = L.precision - 8; p.uyvy = (fmt == CFB_PIXEL_UYVY);
+        p.th = pick_th((p.ch[0].width + kStripIn - 1) / kStripIn, p.ch[0].height / 2, n, ctx->sm_count);
+        CFB_CUDA(launch_fwd_422(p, ctx->stream));
+        ctx->kernel_launches++;
+    } else if (fmt == CFB_PIXEL_PLANAR16) {
+        for (int c = 0; c < 3; c++) {
+            fill_level_geom(cd, quant, c, 0, p.ch[c]);
+            p.ch[c].in_pitch = frame_pitch; p.ch[c].in_off = (long long)c * frame_pitch * cd->desc.height;
+            p.ch[c].quant_ll = quant->divisor[c][0][0] > 1;
+        }
+        for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_frames[i]; p.out_base[i] = (unsigned char *)d_pyramids[i]; }
+        p.th = pick_th((p.ch[0].width + kStripIn - 1) / kStripIn, p.ch[0].height / 2, n * 3, ctx->sm_count);
+        CFB_CUDA(launch_fwd_plane(p, quant->prescale[0], ctx->stream));
+        ctx->kernel_launches++;
+    } else {
+        set_error("forward level 1 for pixel format %d not implemented yet", fmt);
+        return CFB_ERROR_UNSUPPORTED;
+    }
+    // ---- levels 2, 3: input = LL of the previous level inside the pyramid ----
+    for (int k = 1; k < CFB_NUM_LEVELS; k++) {
+        for (int c = 0; c < L.num_channels; c++) {
+            fill_level_geom(cd, quant, c, k, p.ch[c]);
+            p.ch[c].quant_ll = (quant->prescale[k] == 0) && quant->divisor[c][k][0] > 1;
+        }
+        for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_pyramids[i]; p.out_base[i] = (unsigned char *)d_pyramids[i]; }
+        int maxw = 0, maxoh = 0;
+        for (int c = 0; c < L.num_channels; c++) { if (p.ch[c].width > maxw) maxw = p.ch[c].width; if (p.ch[c].height / 2 > maxoh) maxoh = p.ch[c].height / 2; }
+        p.th = pick_th((maxw + kStripIn - 1) / kStripIn, maxoh, n * L.num_channels, ctx->sm_count);
+        CFB_CUDA(launch_fwd_plane(p, quant->prescale[k], ctx->stream));
+        ctx->kernel_launches++;
+    }
+    ctx->frames_forward += n;
+    return CFB_OK;
+}
+
+cfb_error cfb_forward_host(cfb_codec *cd, int n, const void *const *h_frames, int frame_pitch,
+                           const cfb_quant *quant, void *const *h_coded)
+{
+    if (!cd || !h_frames || !quant || !h_coded) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (n < 1 || n > cd->max_batch) { set_error("batch %d exceeds codec max_batch %d", n, cd->max_batch); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_context *ctx = cd->ctx;
+    const cfb_layout &L = cd->layout;
+    CFB_CUDA(cudaSetDevice(ctx->device));
+    const int rows = (int)(L.frame_bytes / L.frame_pitch);
+    const void *dfr[kMaxBatch];
+    void *dpy[kMaxBatch];
+    for (int i = 0; i < n; i++) {
+        if (!h_frames[i] || !h_coded[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
+        dfr[i] = cfb_codec_device_frame(cd, i);
+        dpy[i] = cfb_codec_device_pyramid(cd, i);
+        CFB_CUDA(cudaMemcpy2DAsync((void *)dfr[i], L.frame_pitch, h_frames[i], frame_pitch, L.frame_pitch, rows,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_bytes += (uint64_t)L.frame_bytes;
+    }
+    cfb_error err = cfb_forward_device(cd, n, dfr, L.frame_pitch, quant, dpy);
+    if (err) return err;
+    for (int i = 0; i < n; i++) {
+        CFB_CUDA(cudaMemcpyAsync(h_coded[i], dpy[i], (size_t)L.coded_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h_bytes += (uint64_t)L.coded_bytes;
+    }
+    CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CFB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// inverse (kernels in cfb_inverse.cu) -- wired in a later milestone
+cfb_error cfb_inverse_device(cfb_codec *, int, void *const *, const cfb_quant *, int, void *const *, int)
+{
+    set_error("inverse transform not built into this revision");
+    return CFB_ERROR_UNSUPPORTED;
+}
+cfb_error cfb_inverse_host(cfb_codec *, int, const void *const *, const cfb_quant *, int, void *const *, int)
+{
+    set_error("inverse transform not built into this revision");
+    return CFB_ERROR_UNSUPPORTED;
+}
+
+}  // extern "C"

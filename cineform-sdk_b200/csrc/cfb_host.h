@@ -1,0 +1,45 @@
+// cfb_host.h -- host-side internals shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/cfhd_b200.h"
+#include "cfb_common.cuh"
+
+namespace cfb {
+
+void set_error(const char *fmt, ...);
+cfb_error cuda_fail(cudaError_t e, const char *what);
+
+#define CFB_CUDA(call)                                                  \
+    do {                                                                \
+        cudaError_t e_ = (call);                                        \
+        if (e_ != cudaSuccess) return ::cfb::cuda_fail(e_, #call);      \
+    } while (0)
+
+QuantParam make_quant_param(int divisor, int midpoint_prequant);
+
+// kernel launchers (cfb_forward.cu / cfb_inverse.cu)
+cudaError_t launch_fwd_plane(const FwdParams &p, int prescale, cudaStream_t stream);
+cudaError_t launch_fwd_422(const FwdParams &p, cudaStream_t stream);
+
+}  // namespace cfb
+
+struct cfb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    std::atomic<uint64_t> kernel_launches{0}, frames_forward{0}, frames_inverse{0}, h2d_bytes{0}, d2h_bytes{0};
+};
+
+struct cfb_codec {
+    cfb_context *ctx = nullptr;
+    cfb_frame_desc desc{};
+    cfb_layout layout{};
+    int max_batch = 0;
+    unsigned char *d_frames = nullptr;      // max_batch packed frames
+    unsigned char *d_pyramids = nullptr;    // max_batch pyramids
+    size_t frame_stride = 0;                // bytes between device frame slots
+    size_t pyramid_stride = 0;
+};

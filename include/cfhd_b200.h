@@ -1,0 +1,179 @@
+/* cfhd_b200.h -- C ABI of the B200-native CineForm transform path.
+ *
+ * Drop-in boundary for the one hot path of gopro/cineform-sdk that this library
+ * replaces: the 3-level 2-6 wavelet pyramid + per-subband quantise/dequantise.
+ * Plain C, plain pointers and sizes; no torch / C++ types cross this boundary.
+ *
+ * What each entry point replaces in the reference (paths relative to the
+ * reference tree):
+ *
+ *   cfb_forward_*      Codec/encoder.c:3121  TransformForwardSpatialYUV (level 1, packed 4:2:2)
+ *                      Codec/encoder.c:3193  TransformForwardSpatial    (level 1, planar channels)
+ *                      Codec/encoder.c:3254  ComputeGroupTransformQuant (levels 2,3)
+ *                      i.e. Codec/wavelet.c:2823/:2420 -> Codec/spatial.c:14726/:10026/:12942
+ *                      + Codec/quantize.c:1395 QuantizeRow16sTo16s, for every channel of a frame.
+ *   cfb_inverse_*      Codec/decoder.c:11756/:11765 ReconstructWaveletBand (levels 3->2, 2->1)
+ *                      i.e. Codec/wavelet.c:5685 TransformInverseSpatialQuantLowpass ->
+ *                      Codec/spatial.c:21877/:22414 + Codec/InvertHorizontalStrip16s.c:459/:1700,
+ *                      and Codec/decoder.c:11836 ReconstructSampleFrameToBuffer (level 1 -> pixels),
+ *                      with the dequantisation of Codec/decoder.c:20551 DeQuantFSM fused into the load.
+ *   cfb_layout_*       Codec/wavelet.c:427 AllocWaveletStack / :302 InitWaveletStack / :1173 AllocTransform
+ *                      (band pitch = ALIGN16(2*width), bands 64-byte aligned).
+ *   cfb_quant_*        Codec/quantize.c:186 QuantizationSetQuality + :2865 SetTransformQuantization +
+ *                      Codec/wavelet.c:1710 SetTransformPrescale (host-side table derivation).
+ *   cfb_pool_*         EncoderSDK/EncoderPool.cpp:239 CEncoderPool::EncodeSample / EncoderQueue.h:311-352
+ *                      (bounded, in-order frame queue) re-hosted on GPU streams, frames sharded over GPUs.
+ *
+ * There is NO CPU fallback: every transform call runs CUDA kernels on an sm_100a
+ * device and fails with CFB_ERROR_NO_DEVICE / CFB_ERROR_CUDA otherwise.
+ */
+#ifndef CFHD_B200_H
+#define CFHD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define CFB_API __declspec(dllexport)
+#else
+#define CFB_API __attribute__((visibility("default")))
+#endif
+
+/* Error codes: 0,1,2,10 carry the meaning of the same values in Common/CFHDError.h:25-84. */
+typedef enum cfb_error {
+    CFB_OK = 0,
+    CFB_ERROR_INVALID_ARGUMENT = 1,
+    CFB_ERROR_OUTOFMEMORY = 2,
+    CFB_ERROR_BADFORMAT = 3,
+    CFB_ERROR_UNEXPECTED = 10,
+    CFB_ERROR_NOT_FINISHED = 13,
+    CFB_ERROR_NO_DEVICE = 100,      /* no CUDA device / not sm_100 */
+    CFB_ERROR_CUDA = 101,           /* a CUDA call failed; see cfb_last_error_string() */
+    CFB_ERROR_UNSUPPORTED = 102     /* geometry the kernels do not cover (see cfb_frame_desc) */
+} cfb_error;
+
+/* Input / output pixel layouts of level 1 (the reference's COLOR_FORMAT_* subset used by the
+ * BASELINE configs; Codec/encoder.c:2336-2865). */
+typedef enum cfb_pixel_format {
+    CFB_PIXEL_YUYV = 0,     /* 8-bit packed 4:2:2  Y0 U Y1 V  (CFHD_PIXEL_FORMAT_YUY2)          */
+    CFB_PIXEL_UYVY = 1,     /* 8-bit packed 4:2:2  U Y0 V Y1  (CFHD_PIXEL_FORMAT_2VUY)          */
+    CFB_PIXEL_RG48 = 2,     /* 16-bit packed R,G,B -> 3 planes G,R,B at 12 bits (frame.c:5968)  */
+    CFB_PIXEL_BYR4 = 3,     /* 16-bit Bayer -> 4 half-size planes at 12 bits   (frame.c:4993)  */
+    CFB_PIXEL_PLANAR16 = 4  /* channels already unpacked to int16 planes (testing / chaining)   */
+} cfb_pixel_format;
+
+enum { CFB_MAX_CHANNELS = 4, CFB_NUM_LEVELS = 3, CFB_NUM_BANDS = 4 };
+
+/* Geometry of one frame. width/height are the FRAME dimensions in pixels.
+ * Requirements (else CFB_ERROR_UNSUPPORTED): height % 8 == 0 (the reference rounds
+ * up to 8, encoder.c:2236); every channel's level-3 input width % 8 == 0
+ * (4:2:2: width % 64 == 0; 4:4:4: width % 32 == 0; Bayer: width % 64 == 0). */
+typedef struct cfb_frame_desc {
+    int32_t width;
+    int32_t height;
+    int32_t pixel_format;       /* cfb_pixel_format */
+    int32_t reserved;
+} cfb_frame_desc;
+
+/* One band of the pyramid inside a coefficient buffer. */
+typedef struct cfb_band_layout {
+    int64_t offset;     /* bytes from the start of the frame's coefficient buffer */
+    int32_t width;      /* coefficients per row */
+    int32_t height;     /* rows */
+    int32_t pitch;      /* bytes per row = ALIGN16(2*width) (wavelet.c:439-442) */
+    int32_t reserved;
+} cfb_band_layout;
+
+/* Per-frame coefficient buffer ("pyramid"). All int16, little endian.
+ *   [0, coded_bytes)            what the entropy coder consumes / produces:
+ *                               per channel: LL3, then LH,HL,HH of levels 3,2,1
+ *   [coded_bytes, total_bytes)  device-side scratch: LL1, LL2 of every channel
+ * band[c][k][b]: channel c, level k (0 = level 1 ... 2 = level 3), band b
+ * (0 = LL, 1 = LH "lowhigh", 2 = HL "highlow", 3 = HH, numbering of Codec/image.h:237). */
+typedef struct cfb_layout {
+    int32_t num_channels;
+    int32_t precision;          /* 10 (4:2:2 sources) or 12 (RGB / Bayer), encoder.c:2480 */
+    int64_t coded_bytes;
+    int64_t total_bytes;
+    int64_t frame_bytes;        /* bytes of one packed input/output frame at the natural pitch */
+    int32_t frame_pitch;        /* natural pitch of the packed frame in bytes */
+    int32_t reserved;
+    cfb_band_layout band[CFB_MAX_CHANNELS][CFB_NUM_LEVELS][CFB_NUM_BANDS];
+} cfb_layout;
+
+/* Quantisation schedule of one frame: divisors per channel/level/band (band 0 = LL, normally 1),
+ * the level prescale shifts ({0,2,0} for 10-bit, {0,2,2} for 12-bit, wavelet.c:1710-1782) and the
+ * quantiser midpoint rule (quantize.c:1415-1427: g = 2 + pre-emphasis bits). */
+typedef struct cfb_quant {
+    int32_t prescale[CFB_NUM_LEVELS];
+    int32_t midpoint_prequant;
+    int32_t divisor[CFB_MAX_CHANNELS][CFB_NUM_LEVELS][CFB_NUM_BANDS];
+} cfb_quant;
+
+typedef struct cfb_context cfb_context;     /* one CUDA device + stream pool      */
+typedef struct cfb_codec cfb_codec;         /* plan for one frame geometry        */
+typedef struct cfb_pool cfb_pool;           /* async, in-order, multi-GPU frame queue */
+
+/* ---- library / device ---------------------------------------------------- */
+CFB_API int cfb_version(void);
+CFB_API const char *cfb_last_error_string(void);              /* thread-local */
+CFB_API int cfb_device_count(void);                           /* 0 when no usable GPU */
+
+CFB_API cfb_error cfb_context_create(int device, cfb_context **out);
+CFB_API void cfb_context_destroy(cfb_context *ctx);
+CFB_API cfb_error cfb_context_synchronize(cfb_context *ctx);
+CFB_API void *cfb_context_stream(cfb_context *ctx);           /* the cudaStream_t kernels are launched on */
+
+/* ---- geometry + quantisation tables (host only; usable without a GPU) ---- */
+CFB_API cfb_error cfb_layout_compute(const cfb_frame_desc *desc, cfb_layout *out);
+/* FILMSCAN-style fixed quality (CFHD_EncodingQuality low byte 1..6, Common/CFHDTypes.h:200-223). */
+CFB_API cfb_error cfb_quant_for_quality(const cfb_frame_desc *desc, int quality, cfb_quant *out);
+
+/* ---- codec plan ---------------------------------------------------------- */
+/* max_batch = frames processed per launch (1..CFB_MAX_BATCH). Allocates device staging for
+ * max_batch packed frames and max_batch pyramids plus pinned host staging. */
+enum { CFB_MAX_BATCH = 16 };
+CFB_API cfb_error cfb_codec_create(cfb_context *ctx, const cfb_frame_desc *desc, int max_batch, cfb_codec **out);
+CFB_API void cfb_codec_destroy(cfb_codec *codec);
+CFB_API cfb_error cfb_codec_layout(const cfb_codec *codec, cfb_layout *out);
+/* device staging owned by the codec: slot i in [0, max_batch) */
+CFB_API void *cfb_codec_device_frame(cfb_codec *codec, int slot);
+CFB_API void *cfb_codec_device_pyramid(cfb_codec *codec, int slot);
+
+/* ---- forward: packed frames -> quantised pyramids ------------------------- */
+/* Device-resident: frames and pyramids are DEVICE pointers (n of each); kernels only, asynchronous
+ * on cfb_context_stream(). frame_pitch in bytes (16-byte aligned, positive). */
+CFB_API cfb_error cfb_forward_device(cfb_codec *codec, int n, const void *const *d_frames, int frame_pitch,
+                                     const cfb_quant *quant, void *const *d_pyramids);
+/* Host buffers: copies each frame H2D, transforms, copies the coded region [0, coded_bytes)
+ * of each pyramid D2H into h_coded[i]; returns when the data is in host memory. */
+CFB_API cfb_error cfb_forward_host(cfb_codec *codec, int n, const void *const *h_frames, int frame_pitch,
+                                   const cfb_quant *quant, void *const *h_coded);
+
+/* ---- inverse: quantised pyramids -> packed frames -------------------------- */
+/* The coded region holds QUANTISED values (as entropy-decoded with quant 1); dequantisation by
+ * quant->divisor is fused into the kernels' loads. out_format: CFB_PIXEL_YUYV/UYVY (8-bit, see
+ * DESIGN.md for the rounding rule), CFB_PIXEL_PLANAR16 (int16 planes at codec precision). */
+CFB_API cfb_error cfb_inverse_device(cfb_codec *codec, int n, void *const *d_pyramids, const cfb_quant *quant,
+                                     int out_format, void *const *d_frames, int frame_pitch);
+CFB_API cfb_error cfb_inverse_host(cfb_codec *codec, int n, const void *const *h_coded, const cfb_quant *quant,
+                                   int out_format, void *const *h_frames, int frame_pitch);
+
+/* ---- statistics ------------------------------------------------------------ */
+typedef struct cfb_stats {
+    uint64_t kernel_launches;   /* kernels launched by this library on this context */
+    uint64_t frames_forward;
+    uint64_t frames_inverse;
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+} cfb_stats;
+CFB_API cfb_error cfb_context_stats(cfb_context *ctx, cfb_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFHD_B200_H */

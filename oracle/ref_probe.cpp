@@ -21,6 +21,8 @@ extern "C" {
 #include "convert.h"
 #include "frame.h"
 #include "image.h"
+#include "bitstream.h"
+#include "codec.h"
 }
 #include "qbist.h"
 #include "CFHDTypes.h"
@@ -160,6 +162,61 @@ void ref_qbist_frames(unsigned seed, int width, int height, int pitch, unsigned 
     for (int i = 0; i < nframes; i++)
         RunQBist(width, height, pitch, (CFHD_PixelFormat)pixel_format, 0, buf.as<unsigned char>());
     memcpy(out, buf.p, (size_t)pitch * height);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Whole-frame probe: run the reference's own Codec/encoder.c:1897 EncodeSample on one frame and copy
+// out every wavelet band plus the quantisation / prescale tables it used.
+//   color_format : COLOR_FORMAT_* (Codec/color.h), e.g. 1 = YUYV, 2 = UYVY, 120 = RG48 ...
+//   sampling_444 : 0 -> FRAME_SAMPLING_422, 1 -> FRAME_SAMPLING_444
+// Outputs (caller-allocated):
+//   dims[c*3+k][3] = {width, height, pitch_bytes};  quant[c*12 + k*4 + b];  prescale[c*3 + k]
+//   bands: for c, for k (level 1..3), for b (LL,LH,HL,HH): height*width int16, dense, concatenated.
+// Returns the encoded sample size in bytes (0 on failure).
+
+int ref_encode_frame_bands(const uint8_t *frame, int width, int height, int pitch, int color_format,
+                           int sampling_444, int num_channels, int quality,
+                           int32_t *dims, int32_t *quant, int32_t *prescale, int16_t *bands, int64_t bands_capacity,
+                           uint8_t *sample_out, int64_t sample_capacity)
+{
+    ENCODER *enc = (ENCODER *)calloc(1, sizeof(ENCODER));
+    TRANSFORM *tr[FRAME_MAX_CHANNELS];
+    for (int c = 0; c < FRAME_MAX_CHANNELS; c++) { tr[c] = (TRANSFORM *)calloc(1, sizeof(TRANSFORM)); InitTransform(tr[c]); }
+    ENCODING_PARAMETERS p;
+    memset(&p, 0, sizeof(p));
+    p.version = 1; p.gop_length = 1; p.encoded_width = width; p.encoded_height = height;
+    p.fixed_quality = quality; p.progressive = 1; p.format = color_format;
+    p.frame_sampling = sampling_444 ? FRAME_SAMPLING_444 : FRAME_SAMPLING_422;
+    p.colorspace_yuv = 2; p.colorspace_rgb = 1;
+    if (!InitializeEncoderWithParameters(NULL, enc, tr, num_channels, &p)) return 0;
+    size_t scratch_size = 0;
+    PIXEL *scratch = CreateEncodingBuffer(NULL, width, height, pitch, color_format, 1, true, &scratch_size);
+    const size_t outcap = (size_t)width * height * 8 + 65536;
+    Aligned out(outcap), fr((size_t)pitch * (height + 16) + 64);
+    memcpy(fr.p, frame, (size_t)pitch * height);
+    BITSTREAM bs;
+    InitBitstreamBuffer(&bs, out.as<uint8_t>(), outcap, BITSTREAM_ACCESS_WRITE);
+    bool ok = EncodeSample(enc, fr.as<uint8_t>(), width, height, pitch, color_format, tr, num_channels, &bs,
+                           scratch, scratch_size, quality, 0, NULL, 0.0f, NULL);
+    if (!ok) return 0;
+    int64_t pos = 0;
+    for (int c = 0; c < num_channels; c++) {
+        for (int k = 0; k < 3; k++) {
+            IMAGE *w = tr[c]->wavelet[k];
+            dims[(c * 3 + k) * 3 + 0] = w->width; dims[(c * 3 + k) * 3 + 1] = w->height; dims[(c * 3 + k) * 3 + 2] = w->pitch;
+            prescale[c * 3 + k] = tr[c]->prescale[k];
+            for (int b = 0; b < 4; b++) {
+                quant[c * 12 + k * 4 + b] = w->quant[b];
+                if (pos + (int64_t)w->width * w->height > bands_capacity) return 0;
+                for (int r = 0; r < w->height; r++)
+                    memcpy(bands + pos + (int64_t)r * w->width, (uint8_t *)w->band[b] + (size_t)r * w->pitch, (size_t)w->width * 2);
+                pos += (int64_t)w->width * w->height;
+            }
+        }
+    }
+    int size = (int)BitstreamSize(&bs);
+    if (sample_out && size > 0 && size <= sample_capacity) memcpy(sample_out, out.p, size);
+    return size;
 }
 
 }  // extern "C"

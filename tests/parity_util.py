@@ -1,0 +1,100 @@
+"""Shared helpers for the parity tests (test infrastructure)."""
+import ctypes as C
+
+import numpy as np
+
+import oracle_lib as ol
+
+COLOR_FORMAT_UYVY, COLOR_FORMAT_YUYV, COLOR_FORMAT_RG48, COLOR_FORMAT_BYR4 = 1, 2, 120, 104  # Codec/color.h:64-131
+BAND_NAMES = ("LL", "LH", "HL", "HH")
+
+
+# ---------------------------------------------------------------- synthetic frames
+def synthetic_yuyv(rng, width, height, kind="natural"):
+    """Packed 8-bit 4:2:2 frame (height x 2*width bytes)."""
+    if kind == "random":
+        return rng.integers(0, 256, (height, width * 2)).astype(np.uint8)
+    if kind == "extreme":
+        return np.where(rng.integers(0, 2, (height, width * 2)) == 0, 0, 255).astype(np.uint8)
+    if kind == "constant":
+        return np.full((height, width * 2), 128, np.uint8)
+    # smooth gradients + texture + mild noise: natural-image-like statistics
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
+    luma = 110 + 70 * np.sin(xx / 37.0) * np.cos(yy / 23.0) + 30 * np.sin((xx + 2 * yy) / 5.0) * (xx > width / 2)
+    luma += rng.normal(0, 2.0, luma.shape)
+    cb = 128 + 40 * np.sin(xx[:, ::2] / 91.0 + yy[:, ::2] / 57.0)
+    cr = 128 + 40 * np.cos(xx[:, ::2] / 71.0 - yy[:, ::2] / 43.0)
+    f = np.empty((height, width * 2), np.uint8)
+    f[:, 0::2] = np.clip(luma, 0, 255).astype(np.uint8)
+    f[:, 1::4] = np.clip(cb, 0, 255).astype(np.uint8)
+    f[:, 3::4] = np.clip(cr, 0, 255).astype(np.uint8)
+    return f
+
+
+def yuyv_to_uyvy(frame):
+    out = np.empty_like(frame)
+    out[:, 0::2] = frame[:, 1::2]
+    out[:, 1::2] = frame[:, 0::2]
+    return out
+
+
+def qbist_yuy2(ref_lib, width, height, frame_number=1, seed=50):
+    """Frame `frame_number` (1-based) of the TestCFHD Qbist sequence (Example/TestCFHD.cpp:1149-1219)."""
+    pitch = width * 2
+    out = np.zeros((height, pitch), np.uint8)
+    ref_lib.ref_qbist_frames(seed, width, height, pitch, ol.CFHD_PIXEL_FORMAT_YUY2, frame_number, out.reshape(-1))
+    return out
+
+
+# ---------------------------------------------------------------- oracle pyramids
+def quant_table(quant, nchan=3):
+    return [[[quant.divisor[c][k][b] for b in range(4)] for k in range(3)] for c in range(nchan)]
+
+
+def forward_pyramid_422(impl, frame, divisors, prescale=(0, 2, 0), fmt=0, midpoint=2):
+    """3-level pyramid of a packed 4:2:2 frame with `impl` (oracle or reference building blocks).
+    Returns {(c, level, band_name): array}, LL only for level 3 plus ('LL', level) intermediates under key
+    (c, level, 'LL')."""
+    out = {}
+    for c in range(3):
+        ll, lh, hl, hh = impl.fwd_level_422(frame, c, fmt, divisors[c][0], precision=10, midpoint=midpoint)
+        out[(c, 1, "LL")], out[(c, 1, "LH")], out[(c, 1, "HL")], out[(c, 1, "HH")] = ll, lh, hl, hh
+        for k in (1, 2):
+            variant = 1 if prescale[k] == 2 else 0
+            ll, lh, hl, hh = impl.fwd_level(ll, variant, divisors[c][k], midpoint)
+            out[(c, k + 1, "LL")], out[(c, k + 1, "LH")], out[(c, k + 1, "HL")], out[(c, k + 1, "HH")] = ll, lh, hl, hh
+    return out
+
+
+def oracle_forward_422(orc, frame, quant, fmt=0):
+    """Coded-region bands (LL3 + all highpass) the CUDA path must reproduce."""
+    pyr = forward_pyramid_422(orc, frame, quant_table(quant), tuple(quant.prescale), fmt, quant.midpoint_prequant)
+    return {k: v for k, v in pyr.items() if not (k[2] == "LL" and k[1] != 3)}
+
+
+# ---------------------------------------------------------------- whole-frame reference probe
+def ref_encode_frame(ref_lib, frame, width, height, color_format, sampling_444, num_channels, quality):
+    """Run the reference's real EncodeSample; returns (bands dict, divisors[c][k][b], prescale[c][k], sample bytes)."""
+    fn = ref_lib.ref_encode_frame_bands
+    fn.restype = C.c_int
+    frame = np.ascontiguousarray(frame)
+    pitch = frame.strides[0]
+    dims = np.zeros(num_channels * 9, np.int32)
+    quant = np.zeros(num_channels * 12, np.int32)
+    prescale = np.zeros(num_channels * 3, np.int32)
+    cap = width * height * 4 * num_channels
+    bands = np.zeros(cap, np.int16)
+    sample = np.zeros(width * height * 4 + 65536, np.uint8)
+    size = fn(frame.ctypes.data_as(C.c_void_p), width, height, pitch, color_format, sampling_444, num_channels, quality,
+              dims.ctypes.data_as(C.c_void_p), quant.ctypes.data_as(C.c_void_p), prescale.ctypes.data_as(C.c_void_p),
+              bands.ctypes.data_as(C.c_void_p), C.c_int64(cap), sample.ctypes.data_as(C.c_void_p), C.c_int64(sample.size))
+    assert size > 0, "reference EncodeSample failed"
+    out, pos = {}, 0
+    for c in range(num_channels):
+        for k in range(3):
+            w, h = int(dims[(c * 3 + k) * 3]), int(dims[(c * 3 + k) * 3 + 1])
+            for b in range(4):
+                out[(c, k + 1, BAND_NAMES[b])] = bands[pos:pos + w * h].reshape(h, w).copy()
+                pos += w * h
+    div = quant.reshape(num_channels, 3, 4).tolist()
+    return out, div, prescale.reshape(num_channels, 3).tolist(), sample[:size].copy()

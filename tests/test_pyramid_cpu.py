@@ -1,0 +1,100 @@
+"""CPU-side gates: (1) the oracle composed into a 3-level pyramid reproduces what the reference's real
+EncodeSample leaves in transform[c]->wavelet[k]->band[b] for Qbist frames (the known-answer this repo
+pins parity on); (2) the product library's host-side tables (layout, quantisation schedule)
+match the reference; (3) the C-ABI library loads and exports every declared symbol."""
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import parity_util as pu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+needs_ref = pytest.mark.skipif(not ol.ref_available(), reason="oracle/_ref not built (reference absent)")
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return importlib.import_module("cineform-sdk_b200")
+
+
+@needs_ref
+@pytest.mark.parametrize("size,frame_no", [((256, 64), 1), ((512, 128), 3), ((1920, 1080), 1)])
+def test_oracle_pyramid_matches_reference_encoder(size, frame_no):
+    w, h = size
+    ref_lib = ol.load_ref()
+    frame = pu.qbist_yuy2(ref_lib, w, h, frame_no)
+    bands_ref, div, prescale, sample = pu.ref_encode_frame(ref_lib, frame, w, h, pu.COLOR_FORMAT_YUYV, 0, 3, 4)
+    assert prescale[0] == [0, 2, 0]
+    assert div[0] == [[1, 24, 24, 36], [1, 6, 6, 3], [1, 24, 24, 12]]          # BASELINE.md, FS1 luma
+    assert div[1] == [[1, 24, 24, 48], [1, 6, 6, 3], [1, 24, 24, 12]]
+    pyr = pu.forward_pyramid_422(ol.oracle(), frame, div, tuple(prescale[0]), fmt=0)
+    for key, want in bands_ref.items():
+        assert np.array_equal(pyr[key], want), f"band {key}"
+
+
+@needs_ref
+def test_known_answer_sample_size():
+    """TestCFHD -D, 1920x1080 YUY2 FS1 frame 1 encodes to ~592 268 bytes (metadata varies by ~100 B)."""
+    ref_lib = ol.load_ref()
+    frame = pu.qbist_yuy2(ref_lib, 1920, 1080, 1)
+    _, _, _, sample = pu.ref_encode_frame(ref_lib, frame, 1920, 1080, pu.COLOR_FORMAT_YUYV, 0, 3, 4)
+    assert abs(sample.size - 592268) < 2048
+
+
+@needs_ref
+@pytest.mark.parametrize("quality", [1, 2, 3, 4, 5, 6, 4 | (1 << 17), 4 | (3 << 17)])
+def test_quant_schedule_matches_reference(pkg, quality):
+    w, h = 256, 64
+    ref_lib = ol.load_ref()
+    frame = pu.qbist_yuy2(ref_lib, w, h, 1)
+    _, div, prescale, _ = pu.ref_encode_frame(ref_lib, frame, w, h, pu.COLOR_FORMAT_YUYV, 0, 3, quality)
+    q = pkg.quant_for_quality(pkg.FrameDesc(w, h, pkg.PIXEL_YUYV), quality)
+    assert q.table(3) == div
+    assert list(q.prescale) == prescale[0]
+
+
+def test_layout_rules(pkg):
+    lay = pkg.layout_for(pkg.FrameDesc(3840, 2160, pkg.PIXEL_YUYV))
+    assert lay.num_channels == 3 and lay.precision == 10
+    y1 = lay.band[0][0][1]
+    assert (y1.width, y1.height, y1.pitch) == (1920, 1080, 3840)
+    c3 = lay.band[1][2][0]
+    assert (c3.width, c3.height, c3.pitch) == (240, 270, 480)
+    # coded region = exactly one int16 per plane pixel for these (pitch == 2*width) sizes, 64-byte aligned bands
+    assert lay.coded_bytes >= 2 * 3840 * 2160 * 2 and lay.coded_bytes < 2 * 3840 * 2160 * 2 + 64 * 30
+    offs = []
+    for c in range(3):
+        for k in range(3):
+            for b in range(4):
+                bl = lay.band[c][k][b]
+                assert bl.offset % 64 == 0 and bl.pitch % 16 == 0 and bl.pitch >= 2 * bl.width
+                offs.append((bl.offset, bl.offset + bl.pitch * bl.height))
+    offs.sort()
+    for (a0, a1), (b0, b1) in zip(offs, offs[1:]):
+        assert a1 <= b0, "bands overlap"
+    assert offs[-1][1] <= lay.total_bytes
+    with pytest.raises(pkg.CfbError):
+        pkg.layout_for(pkg.FrameDesc(100, 64, pkg.PIXEL_YUYV))
+
+
+def test_abi_exports_every_declared_symbol(pkg):
+    hdr = open(os.path.join(ROOT, "include", "cfhd_b200.h")).read()
+    names = set(re.findall(r"CFB_API\s+[\w\s\*]+?\b(cfb_\w+)\s*\(", hdr))
+    assert len(names) >= 15
+    lib = pkg.lib()
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in include/cfhd_b200.h but not exported"
+    assert lib.cfb_version() >= 100
+
+
+def test_no_cpu_fallback_without_device(pkg):
+    """On a box without a GPU the transform entry points must fail loudly (never compute on the host)."""
+    if pkg.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.CfbError) as ei:
+        pkg.Context(0)
+    assert ei.value.code == 100
