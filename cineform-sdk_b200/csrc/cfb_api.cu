@@ -300,7 +300,12 @@ cfb_error cfb_codec_create(cfb_context *ctx, const cfb_frame_desc *desc, int max
     cfb_codec *cd = new (std::nothrow) cfb_codec();
     if (!cd) return CFB_ERROR_OUTOFMEMORY;
     cd->ctx = ctx; cd->desc = *desc; cd->layout = lay; cd->max_batch = max_batch;
-    cd->frame_stride = (size_t)((lay.frame_bytes + 255) & ~(int64_t)255);
+    // frame staging must also hold the PLANAR16 rendition (channel planes stacked at the frame's luma pitch)
+    int64_t planar_rows = 0;
+    for (int c = 0; c < lay.num_channels; c++) planar_rows += lay.band[c][0][0].height * 2;
+    int64_t fbytes = lay.frame_bytes;
+    if (planar_rows * desc->width * 2 > fbytes) fbytes = planar_rows * desc->width * 2;
+    cd->frame_stride = (size_t)((fbytes + 255) & ~(int64_t)255);
     cd->pyramid_stride = (size_t)((lay.total_bytes + 255) & ~(int64_t)255);
     cudaError_t e = cudaMalloc((void **)&cd->d_frames, cd->frame_stride * max_batch);
     if (e == cudaSuccess) e = cudaMalloc((void **)&cd->d_pyramids, cd->pyramid_stride * max_batch);
@@ -445,16 +450,118 @@ cfb_error cfb_forward_host(cfb_codec *cd, int n, const void *const *h_frames, in
 }
 
 // ---------------------------------------------------------------------------
-// inverse (kernels in cfb_inverse.cu) -- wired in a later milestone
-cfb_error cfb_inverse_device(cfb_codec *, int, void *const *, const cfb_quant *, int, void *const *, int)
+// inverse
+static void fill_inv_geom(const cfb_codec *cd, const cfb_quant *q, int c, int k, InvGeom &g)
 {
-    set_error("inverse transform not built into this revision");
-    return CFB_ERROR_UNSUPPORTED;
+    const cfb_layout &L = cd->layout;
+    const cfb_band_layout &ll = L.band[c][k][0];
+    g.width = ll.width; g.height = ll.height; g.pitch = ll.pitch;
+    for (int b = 0; b < 4; b++) {
+        g.band_off[b] = L.band[c][k][b].offset;
+        const int d = q->divisor[c][k][b];
+        g.dq[b] = d > 1 ? d : 1;
+    }
+    g.dq[0] = 1;        // LL is carried unquantised through the pyramid (only LL3 is coded, raw)
+    if (k > 0) { g.out_off = L.band[c][k - 1][0].offset; g.out_pitch = L.band[c][k - 1][0].pitch; }
 }
-cfb_error cfb_inverse_host(cfb_codec *, int, const void *const *, const cfb_quant *, int, void *const *, int)
+
+cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, const cfb_quant *quant,
+                             int out_format, void *const *d_frames, int frame_pitch)
 {
-    set_error("inverse transform not built into this revision");
-    return CFB_ERROR_UNSUPPORTED;
+    if (!cd || !d_pyramids || !quant || !d_frames) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (n < 1 || n > kMaxBatch) { set_error("batch %d out of range [1,%d]", n, kMaxBatch); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_context *ctx = cd->ctx;
+    const cfb_layout &L = cd->layout;
+    const int fmt = cd->desc.pixel_format;
+    const bool is422 = (fmt == CFB_PIXEL_YUYV || fmt == CFB_PIXEL_UYVY);
+    if (out_format == CFB_PIXEL_YUYV || out_format == CFB_PIXEL_UYVY) {
+        if (!is422) { set_error("8-bit 4:2:2 output needs a 4:2:2 codec"); return CFB_ERROR_BADFORMAT; }
+        if (frame_pitch < cd->desc.width * 2 || (frame_pitch & 15)) { set_error("bad output pitch %d", frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
+    } else if (out_format == CFB_PIXEL_PLANAR16) {
+        if (frame_pitch < cd->desc.width * 2 || (frame_pitch & 15)) { set_error("bad output pitch %d", frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
+    } else { set_error("output format %d not implemented", out_format); return CFB_ERROR_UNSUPPORTED; }
+    for (int i = 0; i < n; i++)
+        if (!d_frames[i] || !d_pyramids[i] || ((uintptr_t)d_frames[i] & 15) || ((uintptr_t)d_pyramids[i] & 15)) {
+            set_error("frame/pyramid %d null or not 16-byte aligned", i);
+            return CFB_ERROR_INVALID_ARGUMENT;
+        }
+    CFB_CUDA(cudaSetDevice(ctx->device));
+
+    InvParams p;
+    memset(&p, 0, sizeof(p));
+    p.nchan = L.num_channels; p.nframes = n;
+    // levels 3 -> 2 -> 1: output = LL of the level below, inside the pyramid
+    for (int k = CFB_NUM_LEVELS - 1; k >= 1; k--) {
+        int maxw = 0, maxh = 0;
+        for (int c = 0; c < L.num_channels; c++) {
+            fill_inv_geom(cd, quant, c, k, p.ch[c]);
+            if (p.ch[c].width > maxw) maxw = p.ch[c].width;
+            if (p.ch[c].height > maxh) maxh = p.ch[c].height;
+        }
+        for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_pyramids[i]; p.out_base[i] = (unsigned char *)d_pyramids[i]; }
+        p.th = pick_th((maxw + kInvStrip - 1) / kInvStrip, maxh, n * L.num_channels, ctx->sm_count);
+        CFB_CUDA(launch_inv_plane(p, quant->prescale[k], ctx->stream));
+        ctx->kernel_launches++;
+    }
+    // level 1 -> pixels
+    for (int c = 0; c < L.num_channels; c++) fill_inv_geom(cd, quant, c, 0, p.ch[c]);
+    for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_pyramids[i]; p.out_base[i] = (unsigned char *)d_frames[i]; }
+    if (out_format == CFB_PIXEL_PLANAR16) {
+        // planes stacked channel after channel, each channel at its own width, pitch = frame_pitch
+        long long off = 0;
+        int maxw = 0, maxh = 0;
+        for (int c = 0; c < L.num_channels; c++) {
+            p.ch[c].out_off = off; p.ch[c].out_pitch = frame_pitch;
+            off += (long long)frame_pitch * p.ch[c].height * 2;
+            if (p.ch[c].width > maxw) maxw = p.ch[c].width;
+            if (p.ch[c].height > maxh) maxh = p.ch[c].height;
+        }
+        p.th = pick_th((maxw + kInvStrip - 1) / kInvStrip, maxh, n * L.num_channels, ctx->sm_count);
+        CFB_CUDA(launch_inv_plane(p, quant->prescale[0], ctx->stream));
+    } else {
+        for (int c = 0; c < 3; c++) { p.ch[c].out_off = 0; p.ch[c].out_pitch = frame_pitch; }
+        p.shift = L.precision - 8; p.uyvy = (out_format == CFB_PIXEL_UYVY);
+        p.th = pick_th((p.ch[0].width + kInvStrip - 1) / kInvStrip, p.ch[0].height, n, ctx->sm_count);
+        CFB_CUDA(launch_inv_422(p, ctx->stream));
+    }
+    ctx->kernel_launches++;
+    ctx->frames_inverse += n;
+    return CFB_OK;
+}
+
+cfb_error cfb_inverse_host(cfb_codec *cd, int n, const void *const *h_coded, const cfb_quant *quant,
+                           int out_format, void *const *h_frames, int frame_pitch)
+{
+    if (!cd || !h_coded || !quant || !h_frames) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (n < 1 || n > cd->max_batch) { set_error("batch %d exceeds codec max_batch %d", n, cd->max_batch); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_context *ctx = cd->ctx;
+    const cfb_layout &L = cd->layout;
+    CFB_CUDA(cudaSetDevice(ctx->device));
+    int rows, rowbytes, dpitch;
+    if (out_format == CFB_PIXEL_PLANAR16) {
+        rows = 0;
+        for (int c = 0; c < L.num_channels; c++) rows += L.band[c][0][0].height * 2;
+        rowbytes = cd->desc.width * 2; dpitch = cd->desc.width * 2;
+        if ((size_t)dpitch * rows > cd->frame_stride) { set_error("planar16 output does not fit the codec's frame staging"); return CFB_ERROR_UNSUPPORTED; }
+    } else {
+        rows = cd->desc.height; rowbytes = cd->desc.width * 2; dpitch = cd->desc.width * 2;
+    }
+    void *dpy[kMaxBatch], *dfr[kMaxBatch];
+    for (int i = 0; i < n; i++) {
+        if (!h_coded[i] || !h_frames[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
+        dpy[i] = cfb_codec_device_pyramid(cd, i);
+        dfr[i] = cfb_codec_device_frame(cd, i);
+        CFB_CUDA(cudaMemcpyAsync(dpy[i], h_coded[i], (size_t)L.coded_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_bytes += (uint64_t)L.coded_bytes;
+    }
+    cfb_error err = cfb_inverse_device(cd, n, dpy, quant, out_format, dfr, dpitch);
+    if (err) return err;
+    for (int i = 0; i < n; i++) {
+        CFB_CUDA(cudaMemcpy2DAsync(h_frames[i], frame_pitch, dfr[i], dpitch, rowbytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h_bytes += (uint64_t)rowbytes * rows;
+    }
+    CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CFB_OK;
 }
 
 }  // extern "C"

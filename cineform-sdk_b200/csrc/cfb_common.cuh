@@ -52,6 +52,30 @@ struct FwdParams {
     unsigned char *out_base[kMaxBatch];
 };
 
+constexpr int kInvStrip = 120;    // band columns written per warp-row by the inverse kernels (30 lanes x 4)
+
+struct InvGeom {
+    int width;          // band width (coefficients)
+    int height;         // band rows
+    int pitch;          // band pitch in bytes
+    int out_pitch;      // bytes
+    long long band_off[4];
+    long long out_off;
+    int dq[4];          // dequantisation factors (divisors); LL normally 1
+};
+
+struct InvParams {
+    int nchan;
+    int nframes;
+    int th;             // band rows per warp
+    int shift;          // 4:2:2 output: precision - 8
+    int uyvy;
+    int pad;
+    InvGeom ch[kMaxChannels];
+    const unsigned char *in_base[kMaxBatch];
+    unsigned char *out_base[kMaxBatch];
+};
+
 __device__ __forceinline__ int clamp16(int v) { return max(-32768, min(32767, v)); }
 
 __device__ __forceinline__ int quant1(int x, const QuantParam &q) {

@@ -23,6 +23,8 @@ QuantParam make_quant_param(int divisor, int midpoint_prequant);
 // kernel launchers (cfb_forward.cu / cfb_inverse.cu)
 cudaError_t launch_fwd_plane(const FwdParams &p, int prescale, cudaStream_t stream);
 cudaError_t launch_fwd_422(const FwdParams &p, cudaStream_t stream);
+cudaError_t launch_inv_plane(const InvParams &p, int descale, cudaStream_t stream);
+cudaError_t launch_inv_422(const InvParams &p, cudaStream_t stream);
 
 }  // namespace cfb
 

@@ -23,9 +23,11 @@ extern "C" {
 #include "image.h"
 #include "bitstream.h"
 #include "codec.h"
+#include "decoder.h"
 }
 #include "qbist.h"
 #include "CFHDTypes.h"
+#include "CFHDDecoder.h"
 
 extern "C" int g_midpoint_prequant;   // Codec/quantize.c:183
 extern "C" void FilterHorizontalRow10bit16s(PIXEL *input, PIXEL *lowpass, PIXEL *highpass, int width, PIXEL *buffer);
@@ -217,6 +219,64 @@ int ref_encode_frame_bands(const uint8_t *frame, int width, int height, int pitc
     int size = (int)BitstreamSize(&bs);
     if (sample_out && size > 0 && size <= sample_capacity) memcpy(sample_out, out.p, size);
     return size;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decode a sample with the reference's public API (DecoderSDK/CFHDDecoder.cpp:716 CFHD_DecodeSample)
+// at full resolution into `pixel_format` (FOURCC). Returns 0 on success, else the CFHD_Error.
+int ref_decode_sample(const uint8_t *sample, int64_t size, int width, int height, unsigned pixel_format,
+                      uint8_t *out, int out_pitch)
+{
+    CFHD_DecoderRef dec = NULL;
+    CFHD_Error err = CFHD_OpenDecoder(&dec, NULL);
+    if (err) return (int)err;
+    Aligned smp((size_t)size + 64), o((size_t)out_pitch * height + 64);
+    memcpy(smp.p, sample, (size_t)size);
+    int aw = 0, ah = 0;
+    CFHD_PixelFormat af = (CFHD_PixelFormat)0;
+    err = CFHD_PrepareToDecode(dec, width, height, (CFHD_PixelFormat)pixel_format, CFHD_DECODED_RESOLUTION_FULL,
+                               CFHD_DECODING_FLAGS_NONE, smp.p, (size_t)size, &aw, &ah, &af);
+    if (!err) err = CFHD_DecodeSample(dec, smp.p, (size_t)size, o.p, out_pitch);
+    if (!err) memcpy(out, o.p, (size_t)out_pitch * height);
+    CFHD_CloseDecoder(dec);
+    return (int)err;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Codec-level decode (Codec/decoder.c:1497 DecodeInit + :10078 DecodeSample) that also copies out the
+// DECODER's wavelet bands as they stand after the decode: highpass bands hold the DEQUANTISED
+// coefficients produced by the FSM entropy decoder (decoder.c:20551), band[0] of level 3 the raw LL3
+// and band[0] of levels 2,1 the reconstructed lowpass images.  Same output conventions as
+// ref_encode_frame_bands.  decoded_format: DECODED_FORMAT_* (== COLOR_FORMAT_*).  Returns 0 on success.
+int ref_decode_sample_bands(const uint8_t *sample, int64_t size, int width, int height, int decoded_format,
+                            int num_channels, uint8_t *out, int out_pitch,
+                            int32_t *dims, int32_t *quant, int16_t *bands, int64_t bands_capacity)
+{
+    DECODER *dec = (DECODER *)calloc(1, DecoderSize());
+    if (!DecodeInit(NULL, dec, width, height, decoded_format, DECODED_RESOLUTION_FULL, NULL)) return 1;
+    SetDecoderColorFlags(dec, COLOR_SPACE_CG_709);
+    Aligned smp((size_t)size + 64), o((size_t)out_pitch * (height + 16) + 64);
+    memcpy(smp.p, sample, (size_t)size);
+    BITSTREAM bs;
+    InitBitstreamBuffer(&bs, smp.as<uint8_t>(), (size_t)size, BITSTREAM_ACCESS_READ);
+    if (!DecodeSample(dec, &bs, o.as<uint8_t>(), out_pitch, NULL, NULL)) return 2;
+    memcpy(out, o.p, (size_t)out_pitch * height);
+    int64_t pos = 0;
+    for (int c = 0; c < num_channels; c++) {
+        for (int k = 0; k < 3; k++) {
+            IMAGE *w = dec->transform[c]->wavelet[k];
+            if (!w) return 3;
+            dims[(c * 3 + k) * 3 + 0] = w->width; dims[(c * 3 + k) * 3 + 1] = w->height; dims[(c * 3 + k) * 3 + 2] = w->pitch;
+            for (int b = 0; b < 4; b++) {
+                quant[c * 12 + k * 4 + b] = w->quantization[b];
+                if (pos + (int64_t)w->width * w->height > bands_capacity) return 4;
+                for (int r = 0; r < w->height; r++)
+                    memcpy(bands + pos + (int64_t)r * w->width, (uint8_t *)w->band[b] + (size_t)r * w->pitch, (size_t)w->width * 2);
+                pos += (int64_t)w->width * w->height;
+            }
+        }
+    }
+    return 0;
 }
 
 }  // extern "C"

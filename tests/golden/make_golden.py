@@ -4,8 +4,9 @@ the unmodified reference compiled in place).  Run in the build container (needs 
     python tests/golden/make_golden.py
 
 Each .npz holds a Qbist input frame (TestCFHD's generator, seed 50) and every wavelet band the
-reference's own EncodeSample produced for it (transform[c]->wavelet[k]->band[b]), plus the
-quantisation tables it used.  tests/test_golden.py (CPU, oracle) and tests/test_forward_gpu.py
+reference's own EncodeSample produced for it (transform[c]->wavelet[k]->band[b]), the quantisation
+tables it used, the DEQUANTISED bands the reference's decoder holds after entropy-decoding that sample
+(d_*) and the 8-bit YUY2 frame its DecodeSample reconstructs from them.  tests/test_golden.py (CPU, oracle) and tests/test_forward_gpu.py
 (GPU, CUDA path) compare against these files, so the GPU box needs neither the reference tree
 nor oracle/_ref."""
 import os
@@ -24,10 +25,19 @@ def main():
     for (w, h, frame_no, quality) in [(256, 64, 1, 4), (512, 128, 2, 4), (704, 96, 1, 3)]:
         frame = pu.qbist_yuy2(ref_lib, w, h, frame_no)
         bands, div, prescale, sample = pu.ref_encode_frame(ref_lib, frame, w, h, pu.COLOR_FORMAT_YUYV, 0, 3, quality)
-        arrays = {"frame": frame, "divisors": np.array(div, np.int32), "prescale": np.array(prescale[0], np.int32),
+        import ctypes as C
+        _, dec_bands = pu.ref_decode_sample_bands(ref_lib, sample, w, h)      # Codec-level: band dump
+        decoded = np.zeros_like(frame)                                      # public API: the decoded picture
+        rc = ref_lib.ref_decode_sample(sample.ctypes.data_as(C.c_void_p), C.c_int64(sample.size), w, h,
+                                       ol.CFHD_PIXEL_FORMAT_YUY2, decoded.ctypes.data_as(C.c_void_p), w * 2)
+        assert rc == 0
+        arrays = {"frame": frame, "decoded_yuy2": decoded, "divisors": np.array(div, np.int32), "prescale": np.array(prescale[0], np.int32),
                   "quality": np.array(quality), "sample_size": np.array(sample.size)}
         for (c, lvl, name), a in bands.items():
             arrays[f"b_{c}_{lvl}_{name}"] = a
+        for (c, lvl, name), a in dec_bands.items():      # decoder side: dequantised, as the FSM decoder leaves them
+            if name != "LL" or lvl == 3:
+                arrays[f"d_{c}_{lvl}_{name}"] = a
         path = os.path.join(HERE, f"qbist_yuy2_{w}x{h}_f{frame_no}_q{quality}.npz")
         np.savez_compressed(path, **arrays)
         print(path, os.path.getsize(path))

@@ -98,3 +98,73 @@ def ref_encode_frame(ref_lib, frame, width, height, color_format, sampling_444, 
                 pos += w * h
     div = quant.reshape(num_channels, 3, 4).tolist()
     return out, div, prescale.reshape(num_channels, 3).tolist(), sample[:size].copy()
+
+
+# ---------------------------------------------------------------- inverse composition
+def dequantize(band, divisor):
+    """Codec/decoder.c:20551 DeQuantFSM semantics on a dense band: (int16)(v * quant)."""
+    if divisor <= 1:
+        return band.copy()
+    return (band.astype(np.int32) * divisor).astype(np.int16)
+
+
+def inverse_pyramid(impl, bands, divisors, prescale, nchan=3):
+    """bands: {(c, level, name)} QUANTISED coded-region bands (LL3 + highpass of levels 1..3).
+    Returns the reconstructed int16 plane of every channel at codec precision (list)."""
+    planes = []
+    for c in range(nchan):
+        ll = bands[(c, 3, "LL")]
+        for k in (2, 1, 0):
+            lh = dequantize(bands[(c, k + 1, "LH")], divisors[c][k][1])
+            hl = dequantize(bands[(c, k + 1, "HL")], divisors[c][k][2])
+            hh = dequantize(bands[(c, k + 1, "HH")], divisors[c][k][3])
+            ll = impl.inv_level(ll, lh, hl, hh, 2 if prescale[k] == 2 else 0)
+        planes.append(ll)
+    return planes
+
+
+def yuyv_envelope(planes, shift=2, uyvy=False):
+    """The two 8-bit values the reference's dithered reduction can produce at every byte of the packed frame:
+    out = sat_u8((max(v,0) + d) >> shift), d in {0,1}  (InvertHorizontalStrip16s.c:3807-3892)."""
+    y, v, u = planes
+    h, w = y.shape
+    lo = np.zeros((h, w * 2), np.int32)
+    yo, co = (1, 0) if uyvy else (0, 1)
+    lo[:, yo::2] = y
+    lo[:, co::4] = u
+    lo[:, co + 2::4] = v
+    lo = np.maximum(lo, 0)
+    a = np.clip(lo >> shift, 0, 255).astype(np.uint8)
+    b = np.clip((lo + 1) >> shift, 0, 255).astype(np.uint8)
+    return a, b
+
+
+def psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+def ref_decode_sample_bands(ref_lib, sample, width, height, decoded_format=COLOR_FORMAT_YUYV, num_channels=3):
+    """Reference Codec-level decode; returns (decoded packed frame, {(c, level, name): DEQUANTISED band})."""
+    out = np.zeros((height, width * 2), np.uint8)
+    dims = np.zeros(num_channels * 9, np.int32)
+    quant = np.zeros(num_channels * 12, np.int32)
+    cap = width * height * 4 * num_channels
+    b = np.zeros(cap, np.int16)
+    sample = np.ascontiguousarray(sample)
+    rc = ref_lib.ref_decode_sample_bands(sample.ctypes.data_as(C.c_void_p), C.c_int64(sample.size), width, height,
+                                         decoded_format, num_channels, out.ctypes.data_as(C.c_void_p), width * 2,
+                                         dims.ctypes.data_as(C.c_void_p), quant.ctypes.data_as(C.c_void_p),
+                                         b.ctypes.data_as(C.c_void_p), C.c_int64(cap))
+    assert rc == 0, f"reference decode failed ({rc})"
+    bands, pos = {}, 0
+    for c in range(num_channels):
+        for k in range(3):
+            w, h = int(dims[(c * 3 + k) * 3]), int(dims[(c * 3 + k) * 3 + 1])
+            for bi in range(4):
+                bands[(c, k + 1, BAND_NAMES[bi])] = b[pos:pos + w * h].reshape(h, w).copy()
+                pos += w * h
+    return out, bands
+
+
+UNIT_DIVISORS = [[[1, 1, 1, 1]] * 3] * 3

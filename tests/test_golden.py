@@ -32,3 +32,27 @@ def test_oracle_reproduces_golden(path):
     pyr = pu.forward_pyramid_422(ol.oracle(), frame, div, prescale, fmt=0)
     for key, want in bands.items():
         assert np.array_equal(pyr[key], want), f"band {key}"
+
+
+def load_golden_decoder_side(path):
+    z = np.load(path)
+    bands = {}
+    for k in z.files:
+        if k.startswith("d_"):
+            _, c, lvl, name = k.split("_")
+            bands[(int(c), int(lvl), name)] = z[k]
+    return bands, z["decoded_yuy2"]
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_oracle_inverse_inside_reference_decoder_envelope(path):
+    """Oracle inverse pyramid applied to the bands the reference's decoder held, against the frame the
+    reference's DecodeSample produced.  The reference's 8-bit reduction is dithered with rand(), so every
+    byte must be one of the two values the oracle's 10-bit reconstruction allows."""
+    frame, div, prescale, quality, _ = load_golden(path)
+    bands, dec = load_golden_decoder_side(path)
+    planes = pu.inverse_pyramid(ol.oracle(), bands, pu.UNIT_DIVISORS, prescale)
+    a, b = pu.yuyv_envelope(planes)
+    ok = (dec == a) | (dec == b)
+    assert ok.all(), f"{(~ok).sum()} bytes outside the dither envelope"
+    assert pu.psnr(dec[:, 0::2], frame[:, 0::2]) > 45.0
