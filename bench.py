@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: 4K YUY2 encode+decode fps per B200, wavelet HBM GB/s vs roofline.
+
+A "step" = one pass of the hot path (forward 3-level 2-6 wavelet + quantise, then dequantise + inverse
+3-level wavelet) over one batch of synthetic 3840x2160 YUY2 frames.
+
+  value   : whole-job throughput, frames (encode+decode pairs) per second, inputs resident in HBM,
+            kernels only, CUDA events on the launching stream, max over ranks.
+  e2e     : the same metric through the C ABI with HOST buffers (cfb_forward_host + cfb_inverse_host):
+            every step copies the frames H2D, the coded coefficients D2H, then H2D again and the decoded
+            frames D2H, from/to pinned host memory.
+  roofline: the dominant kernel (level-1 forward, k_fwd_422) timed alone, live, with CUDA events.
+  cpu_baseline / --impl reference: the reference's own calls for this path (oracle/_ref, the unmodified
+            reference compiled in place) on the box's host cores.
+
+Multi-GPU: frames are independent (GOP 1) -> each rank owns its own frames, no data-path collective;
+torch.distributed (NCCL) is used only for the barrier and the max-over-ranks of the timing.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WIDTH, HEIGHT, QUALITY = 3840, 2160, 4          # BASELINE.json configs[2]: TestCFHD -E/-D 3840x2160 YUY2 4:2:2, FILMSCAN1
+METRIC = "4K YUY2 encode+decode fps"
+WORKLOAD = "TestCFHD -E/-D 3840x2160 YUY2 4:2:2 (BASELINE.json configs[2]), FILMSCAN1, GOP 1, progressive"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [l.strip().split(", ") for l in open(self.path) if l.strip()]
+            sm = sorted(int(r[0]) for r in rows if r[0].isdigit())
+            if sm:
+                out["sm_mhz"] = sm[len(sm) // 2]
+                out["sm_max_mhz"] = int(rows[0][1])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for k, n in enumerate(names):
+                if any(len(r) > 2 + k and r[2 + k].strip().lower() == "active" for r in rows):
+                    out["reasons"].append(n)
+            out["samples"] = len(sm)
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except Exception:
+                pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def synthetic_frames(n, width, height, seed=0):
+    """n distinct natural-statistics 4:2:2 frames (gradients + texture + mild noise), deterministic."""
+    import parity_util as pu
+    rng = np.random.default_rng(seed)
+    base = pu.synthetic_yuyv(rng, width, height, "natural")
+    return [np.ascontiguousarray(np.roll(base, (17 * i) % height, axis=0)) for i in range(n)]
+
+
+def cpu_reference_run(width, height, quality, threads, iters):
+    """Times the reference's own transform calls (oracle/_ref) on `threads` host threads, `iters` frames each.
+    Returns (frames_per_second, kind, sample_description)."""
+    import oracle_lib as ol
+    import parity_util as pu
+    rng = np.random.default_rng(1)
+    frame = pu.synthetic_yuyv(rng, width, height, "natural")
+    if ol.ref_available():
+        ref = ol.load_ref()
+        results = [None] * threads
+
+        def work(t):
+            f, i = C.c_double(), C.c_double()
+            rc = ref.ref_time_transform_422(frame.ctypes.data_as(C.c_void_p), width, height, width * 2, quality,
+                                            iters, 1, C.byref(f), C.byref(i), None)
+            results[t] = (rc, f.value, i.value)
+
+        t0 = time.perf_counter()
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        wall = time.perf_counter() - t0
+        assert all(r and r[0] == 0 for r in results), "reference timing probe failed"
+        # the probe's setup (one full encode + decode per thread) is outside its own timed loops:
+        busy = max(r[1] + r[2] for r in results)
+        fps = threads * iters / busy
+        desc = (f"{threads} threads x {iters} frames, each: TransformForwardSpatialYUV + ComputeGroupTransformQuant, then "
+                f"ReconstructWaveletBand x2/channel + ReconstructSampleFrameToBuffer (8-bit YUYV); unmodified reference, "
+                f"gcc -O2 -msse2; wall {wall:.1f}s incl. setup")
+        return fps, "reference", desc
+    # port: the scalar C restatement (single thread)
+    orc = ol.oracle()
+    pkg = importlib.import_module("cineform-sdk_b200")
+    q = pkg.quant_for_quality(pkg.FrameDesc(width, height, pkg.PIXEL_YUYV), quality)
+    t0 = time.perf_counter()
+    bands = pu.oracle_forward_422(orc, frame, q, 0)
+    pu.inverse_pyramid(orc, bands, q.table(3), tuple(q.prescale))
+    dt = time.perf_counter() - t0
+    return 1.0 / dt, "port", "1 frame forward+inverse with oracle/liboracle.so (scalar C restatement), 1 thread"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    iters = max(1, args.ref_iters)
+    steps_ms = []
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        fps, kind, desc = cpu_reference_run(WIDTH, HEIGHT, QUALITY, threads, iters)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            steps_ms.append((fps, dt))
+    fps = float(np.mean([f for f, _ in steps_ms]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "fps", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * threads * iters / fps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": threads * iters, "stage": "wavelet+quant transform path only "
+                   "(entropy coding excluded on both arms)"},
+        "cpu_baseline": {"value": fps, "unit": "fps", "cores": threads, "kind": kind, "sample": desc},
+        "e2e": {"value": fps, "unit": "fps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("cineform-sdk_b200")        # raises if libcfhd_b200.so is missing
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the transform path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    B = args.batch
+    ctx = pkg.Context(local_rank)
+    desc = pkg.FrameDesc(WIDTH, HEIGHT, pkg.PIXEL_YUYV)
+    quant = pkg.quant_for_quality(desc, QUALITY)
+    codec = pkg.Codec(ctx, desc, B)
+    lay = codec.layout
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    frames = synthetic_frames(B, WIDTH, HEIGHT, seed=rank)
+
+    # ---- device-resident working set: B frames in, B pyramids, B frames out (>> 126 MB L2) ----
+    with torch.cuda.stream(stream):
+        d_in = [torch.from_numpy(f).cuda(non_blocking=False) for f in frames]
+        d_pyr = [torch.zeros(lay.total_bytes, dtype=torch.uint8, device="cuda") for _ in range(B)]
+        d_out = [torch.zeros(lay.frame_bytes, dtype=torch.uint8, device="cuda") for _ in range(B)]
+    ip, pp, op = [t.data_ptr() for t in d_in], [t.data_ptr() for t in d_pyr], [t.data_ptr() for t in d_out]
+    ctx.synchronize()
+
+    def step_device():
+        codec.forward_device(ip, lay.frame_pitch, quant, pp)
+        codec.inverse_device(pp, quant, pkg.PIXEL_YUYV, op, lay.frame_pitch)
+
+    def timed(fn, warmup, steps):
+        for _ in range(warmup):
+            fn()
+        ctx.synchronize(); torch.cuda.synchronize(); barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        ctx.synchronize(); torch.cuda.synchronize(); barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.stats()["kernel_launches"]
+    total_ms = timed(step_device, args.warmup, args.steps)
+    launches = ctx.stats()["kernel_launches"] - launches0 - 6 * args.warmup
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = world * B * args.steps / (total_ms / 1000.0)
+
+    # ---- parity spot check of what was just timed (decoded frame vs input, PSNR) ----
+    with torch.cuda.stream(stream):
+        back = d_out[0].cpu().numpy().reshape(HEIGHT, -1)
+    import parity_util as pu
+    psnr = pu.psnr(back[:, 0::2], frames[0][:, 0::2])
+
+    # ---- roofline: dominant kernel (level-1 forward) alone ----
+    codec.set_level_mask(1, 0)
+    k_ms = timed(lambda: codec.forward_device(ip, lay.frame_pitch, quant, pp), 3, max(10, args.steps)) / max(10, args.steps)
+    codec.set_level_mask(0, 1)
+    ki_ms = timed(lambda: codec.inverse_device(pp, quant, pkg.PIXEL_YUYV, op, lay.frame_pitch), 3, max(10, args.steps)) / max(10, args.steps)
+    codec.set_level_mask(7, 7)
+    plane_px = WIDTH * HEIGHT * 2                       # P: Y + U + V samples of a 4:2:2 frame
+    l1_bytes = (lay.frame_bytes + 2 * plane_px) * B     # K-L1 = input bytes + 2P, per frame
+    peak, peak_src = peaks()
+    achieved = l1_bytes / (k_ms * 1e-3) / 1e9
+    achieved_inv = l1_bytes / (ki_ms * 1e-3) / 1e9
+
+    # ---- e2e through the C ABI with pinned host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        h_in = [torch.from_numpy(f).pin_memory() for f in frames]
+        h_coded = [torch.empty(lay.coded_bytes, dtype=torch.uint8).pin_memory() for _ in range(B)]
+        h_out = [torch.empty((HEIGHT, lay.frame_pitch), dtype=torch.uint8).pin_memory() for _ in range(B)]
+        n_in, n_cd, n_out = [t.numpy() for t in h_in], [t.numpy() for t in h_coded], [t.numpy() for t in h_out]
+
+        def step_host():
+            codec.forward_host(n_in, quant, out=n_cd)
+            codec.inverse_host(n_cd, quant, pkg.PIXEL_YUYV, n_out)
+
+        for _ in range(max(1, args.warmup // 2)):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            step_host()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert pu.psnr(n_out[0][:, 0::2], frames[0][:, 0::2]) > 40.0
+        e2e = {"value": world * B * args.e2e_steps / dt, "unit": "fps",
+               "h2d_bytes_per_step": int(B * (lay.frame_bytes + lay.coded_bytes)),
+               "d2h_bytes_per_step": int(B * (lay.coded_bytes + lay.frame_bytes)),
+               "api": "cfb_forward_host + cfb_inverse_host, pinned host buffers, synchronous"}
+
+    # ---- CPU baseline (rank 0, N == 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        fps, kind, descr = cpu_reference_run(WIDTH, HEIGHT, QUALITY, threads, args.ref_iters)
+        cpu = {"value": fps, "unit": "fps", "cores": threads, "kind": kind, "sample": descr}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "fps", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "global_frames_per_step": B * world,
+                       "parallelism": f"frame-parallel x{world} (no collective)",
+                       "l2_hygiene": f"inputs larger than L2: {B} distinct frames + pyramids + outputs = "
+                                     f"{B * (2 * lay.frame_bytes + lay.total_bytes) / 1e6:.0f} MB per step",
+                       "stage": "wavelet+quant transform path only (entropy coding stays on the host and is not timed)",
+                       "roundtrip_luma_psnr_db": round(float(psnr), 2)},
+            "roofline": {"bound": "hbm", "kernel": "k_fwd_422 (level-1 forward, packed 4:2:2 -> 12 bands, fused quant)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": l1_bytes,
+                         "kernel_ms": k_ms,
+                         "inverse_l1": {"kernel": "k_inv_422", "achieved": achieved_inv, "frac": achieved_inv / peak,
+                                        "kernel_ms": ki_ms}},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="frames per step per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--ref-iters", type=int, default=3, help="frames per host thread in the CPU baseline")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

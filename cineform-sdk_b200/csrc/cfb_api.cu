@@ -333,6 +333,13 @@ cfb_error cfb_codec_layout(const cfb_codec *cd, cfb_layout *out)
     return CFB_OK;
 }
 
+cfb_error cfb_codec_set_level_mask(cfb_codec *cd, int forward_mask, int inverse_mask)
+{
+    if (!cd) return CFB_ERROR_INVALID_ARGUMENT;
+    cd->fwd_mask = forward_mask & 7; cd->inv_mask = inverse_mask & 7;
+    return CFB_OK;
+}
+
 void *cfb_codec_device_frame(cfb_codec *cd, int slot)
 {
     return (cd && slot >= 0 && slot < cd->max_batch) ? cd->d_frames + cd->frame_stride * slot : nullptr;
@@ -382,7 +389,8 @@ cfb_error cfb_forward_device(cfb_codec *cd, int n, const void *const *d_frames, 
     memset(&p, 0, sizeof(p));
     p.nchan = L.num_channels; p.nframes = n;
     // ---- level 1 ----
-    if (fmt == CFB_PIXEL_YUYV || fmt == CFB_PIXEL_UYVY) {
+    if (!(cd->fwd_mask & 1)) {
+    } else if (fmt == CFB_PIXEL_YUYV || fmt == CFB_PIXEL_UYVY) {
         for (int c = 0; c < 3; c++) { fill_level_geom(cd, quant, c, 0, p.ch[c]); p.ch[c].in_off = 0; p.ch[c].in_pitch = frame_pitch; }
         for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_frames[i]; p.out_base[i] = (unsigned char *)d_pyramids[i]; }
         p.shift = L.precision - 8; p.uyvy = (fmt == CFB_PIXEL_UYVY);
@@ -405,6 +413,7 @@ cfb_error cfb_forward_device(cfb_codec *cd, int n, const void *const *d_frames, 
     }
     // ---- levels 2, 3: input = LL of the previous level inside the pyramid ----
     for (int k = 1; k < CFB_NUM_LEVELS; k++) {
+        if (!(cd->fwd_mask & (1 << k))) continue;
         for (int c = 0; c < L.num_channels; c++) {
             fill_level_geom(cd, quant, c, k, p.ch[c]);
             p.ch[c].quant_ll = (quant->prescale[k] == 0) && quant->divisor[c][k][0] > 1;
@@ -492,6 +501,7 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
     p.nchan = L.num_channels; p.nframes = n;
     // levels 3 -> 2 -> 1: output = LL of the level below, inside the pyramid
     for (int k = CFB_NUM_LEVELS - 1; k >= 1; k--) {
+        if (!(cd->inv_mask & (1 << k))) continue;
         int maxw = 0, maxh = 0;
         for (int c = 0; c < L.num_channels; c++) {
             fill_inv_geom(cd, quant, c, k, p.ch[c]);
@@ -504,6 +514,7 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
         ctx->kernel_launches++;
     }
     // level 1 -> pixels
+    if (!(cd->inv_mask & 1)) { ctx->frames_inverse += n; return CFB_OK; }
     for (int c = 0; c < L.num_channels; c++) fill_inv_geom(cd, quant, c, 0, p.ch[c]);
     for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_pyramids[i]; p.out_base[i] = (unsigned char *)d_frames[i]; }
     if (out_format == CFB_PIXEL_PLANAR16) {

@@ -44,4 +44,5 @@ struct cfb_codec {
     unsigned char *d_pyramids = nullptr;    // max_batch pyramids
     size_t frame_stride = 0;                // bytes between device frame slots
     size_t pyramid_stride = 0;
+    int fwd_mask = 7, inv_mask = 7;         // profiling aid: levels to run
 };

@@ -144,6 +144,10 @@ CFB_API cfb_error cfb_codec_layout(const cfb_codec *codec, cfb_layout *out);
 CFB_API void *cfb_codec_device_frame(cfb_codec *codec, int slot);
 CFB_API void *cfb_codec_device_pyramid(cfb_codec *codec, int slot);
 
+/* Profiling aid: restrict the following forward/inverse calls to a subset of pyramid levels
+ * (bit k = level k+1; default 7 = all).  Used by bench.py to time one kernel in isolation. */
+CFB_API cfb_error cfb_codec_set_level_mask(cfb_codec *codec, int forward_mask, int inverse_mask);
+
 /* ---- forward: packed frames -> quantised pyramids ------------------------- */
 /* Device-resident: frames and pyramids are DEVICE pointers (n of each); kernels only, asynchronous
  * on cfb_context_stream(). frame_pitch in bytes (16-byte aligned, positive). */

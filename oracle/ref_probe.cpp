@@ -255,6 +255,7 @@ int ref_decode_sample_bands(const uint8_t *sample, int64_t size, int width, int 
     DECODER *dec = (DECODER *)calloc(1, DecoderSize());
     if (!DecodeInit(NULL, dec, width, height, decoded_format, DECODED_RESOLUTION_FULL, NULL)) return 1;
     SetDecoderColorFlags(dec, COLOR_SPACE_CG_709);
+    SetDecoderFlags(dec, DECODER_FLAGS_RENDER);      // as CSampleDecoder::DecodeSample does (SampleDecoder.cpp:1507)
     Aligned smp((size_t)size + 64), o((size_t)out_pitch * (height + 16) + 64);
     memcpy(smp.p, sample, (size_t)size);
     BITSTREAM bs;
@@ -276,6 +277,76 @@ int ref_decode_sample_bands(const uint8_t *sample, int64_t size, int width, int 
             }
         }
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CPU baseline: time exactly the reference calls that the CUDA path replaces, on one thread,
+// for one packed 4:2:2 frame (call from several threads with separate buffers for a pool run).
+//   forward  = Codec/encoder.c:3121 TransformForwardSpatialYUV + :3254 ComputeGroupTransformQuant
+//   inverse  = Codec/decoder.c:11756/:11765 ReconstructWaveletBand (levels 3->2, 2->1, every channel)
+//              + Codec/decoder.c:11836 ReconstructSampleFrameToBuffer (level 1 -> 8-bit YUYV)
+// The entropy coder/decoder run once outside the timed loops (to build a valid DECODER state).
+// Returns 0 on success; *fwd_seconds / *inv_seconds = total time of `iters` iterations.
+#include <time.h>
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+extern "C" void ReconstructWaveletBand(DECODER *decoder, TRANSFORM *transform, int channel, IMAGE *wavelet, int index,
+                                       int precision, const SCRATCH *scratch, int allocations_only);
+extern "C" void ReconstructSampleFrameToBuffer(DECODER *decoder, int frame, uint8_t *output, int pitch);
+
+int ref_time_transform_422(const uint8_t *frame, int width, int height, int pitch, int quality, int iters, int cpu_limit,
+                           double *fwd_seconds, double *inv_seconds, uint8_t *decoded_out)
+{
+    const int color_format = COLOR_FORMAT_YUYV, num_channels = 3;
+    ENCODER *enc = (ENCODER *)calloc(1, sizeof(ENCODER));
+    TRANSFORM *tr[FRAME_MAX_CHANNELS];
+    for (int c = 0; c < FRAME_MAX_CHANNELS; c++) { tr[c] = (TRANSFORM *)calloc(1, sizeof(TRANSFORM)); InitTransform(tr[c]); }
+    ENCODING_PARAMETERS p;
+    memset(&p, 0, sizeof(p));
+    p.version = 1; p.gop_length = 1; p.encoded_width = width; p.encoded_height = height;
+    p.fixed_quality = quality; p.progressive = 1; p.format = color_format;
+    p.frame_sampling = FRAME_SAMPLING_422; p.colorspace_yuv = 2; p.colorspace_rgb = 1;
+    if (!InitializeEncoderWithParameters(NULL, enc, tr, num_channels, &p)) return 1;
+    size_t scratch_size = 0;
+    PIXEL *scratch = CreateEncodingBuffer(NULL, width, height, pitch, color_format, 1, true, &scratch_size);
+    const size_t outcap = (size_t)width * height * 8 + 65536;
+    Aligned out(outcap), fr((size_t)pitch * (height + 16) + 64), dec_out((size_t)pitch * (height + 16) + 64);
+    memcpy(fr.p, frame, (size_t)pitch * height);
+    BITSTREAM bs;
+    InitBitstreamBuffer(&bs, out.as<uint8_t>(), outcap, BITSTREAM_ACCESS_WRITE);
+    if (!EncodeSample(enc, fr.as<uint8_t>(), width, height, pitch, color_format, tr, num_channels, &bs,
+                      scratch, scratch_size, quality, 0, NULL, 0.0f, NULL)) return 2;
+    const int sample_size = (int)BitstreamSize(&bs);
+    FRAME_INFO info;
+    InitFrameInfo(&info, width, height, color_format);
+    double t0 = now_s();
+    for (int i = 0; i < iters; i++) {
+        TransformForwardSpatialYUV(fr.as<uint8_t>(), pitch, &info, tr, 0, num_channels, scratch, scratch_size,
+                                   enc->codec.chroma_offset, 0, enc->codec.precision, 0, 0);
+        ComputeGroupTransformQuant(enc, tr, num_channels);
+    }
+    *fwd_seconds = now_s() - t0;
+
+    DECODER *dec = (DECODER *)calloc(1, DecoderSize());
+    if (!DecodeInit(NULL, dec, width, height, DECODED_FORMAT_YUYV, DECODED_RESOLUTION_FULL, NULL)) return 3;
+    SetDecoderColorFlags(dec, COLOR_SPACE_CG_709);
+    SetDecoderFlags(dec, DECODER_FLAGS_RENDER);
+    if (cpu_limit > 0) { dec->cfhddata.cpu_limit = cpu_limit; }
+    BITSTREAM in;
+    InitBitstreamBuffer(&in, out.as<uint8_t>(), (size_t)sample_size, BITSTREAM_ACCESS_READ);
+    if (!DecodeSample(dec, &in, dec_out.as<uint8_t>(), pitch, NULL, NULL)) return 4;
+    const int precision = dec->codec.precision;
+    t0 = now_s();
+    for (int i = 0; i < iters; i++) {
+        for (int c = 0; c < num_channels; c++) {
+            TRANSFORM *t = dec->transform[c];
+            ReconstructWaveletBand(dec, t, c, t->wavelet[2], 2, precision, &dec->scratch, 0);
+            ReconstructWaveletBand(dec, t, c, t->wavelet[1], 1, precision, &dec->scratch, 0);
+        }
+        ReconstructSampleFrameToBuffer(dec, 0, dec_out.as<uint8_t>(), pitch);
+    }
+    *inv_seconds = now_s() - t0;
+    if (decoded_out) memcpy(decoded_out, dec_out.p, (size_t)pitch * height);
     return 0;
 }
 
