@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 
 #include "cfb_host.h"
@@ -50,11 +51,15 @@ static inline int64_t align64(int64_t x) { return (x + 63) & ~(int64_t)63; }
 
 static int channels_of(int fmt) { return fmt == CFB_PIXEL_BYR4 ? 4 : 3; }
 
-// choose the number of output rows per warp so that the launch has enough warps to fill the GPU
+// Rows per warp.  Measured on B200 (tools/microbench.py, 16 x 4K frames): 8..16 rows per warp is the sweet
+// spot -- enough warps (>= ~60 per SM over the launch) that wave quantisation and the tail vanish, while the
+// one-pair halo each warp re-reads stays <= 6-12 % (and is served by L2).  Larger blocks only pay off when
+// the launch is too small to fill the machine anyway.
 static int pick_th(int strips, int oh, int planes, int sm_count)
 {
-    static const int cand[] = {64, 48, 32, 24, 16, 12, 8, 6, 4};
-    const long long want = (long long)sm_count * 24;
+    static const int cand[] = {16, 12, 8, 6, 4};
+    if (const char *e = getenv("CFB_TH")) { int v = atoi(e); if (v >= 2) return v; }     // tuning knob (development)
+    const long long want = (long long)sm_count * 48;
     for (int th : cand) {
         long long warps = (long long)strips * ((oh + th - 1) / th) * planes;
         if (warps >= want) return th;

@@ -15,22 +15,30 @@
 // the vertical 2-6 filter is   low_j = S_j,  high_j = ((S_{j+1} - S_{j-1} + 4) >> 3) + D_j,
 // the top/bottom 6-tap border filters are (-3 S0 + 8 D0 + 4 S1 - S2 + 4) >> 3 and
 // (3 S_n + 8 D_n - 4 S_{n-1} + S_{n-2} + 4) >> 3 (same identities horizontally).
-// Every input sample is read from global memory once (+ 2 halo row pairs per strip
+// Every input sample is read from global memory once (+ 1 halo row pair per strip
 // block, served by L2) and every coefficient is written once with 64-bit stores.
+//
+// Work split inside one launch: "main" warps run a compact loop that emits every
+// LL/LH row and the interior HL/HH rows; the two border rows of HL/HH (first and
+// last output row, which use the 6-tap border filters) are produced by dedicated
+// border warps in an extra CTA row, so the hot loop carries no border code.
 #include "cfb_common.cuh"
 
 namespace cfb {
 
-constexpr unsigned kFull = 0xffffffffu;
-
 // ----------------------------------------------------------------------------
-// vertical state of NC low + NC high columns held by one lane
-template <int NC>
-struct VState {
+struct LaneInfo {
+    unsigned amask;         // lanes of this warp that hold image columns
+    bool left_border;       // lane owns output column 0
+    bool right_border;      // lane owns the last output column
+    bool has_border;        // warp-uniform: this strip touches the left or right image border
+    bool use_lh, use_rh;    // lane 0 / last lane need a halo word from the neighbouring strip
+};
+
+template <int NC> struct VState {
     int llp[2 * NC];    // S_{j-2}
     int llc[2 * NC];    // S_{j-1}
     int dc[2 * NC];     // D_{j-1}
-    int d0[2 * NC];     // D_0 (top border only)
 };
 
 template <int NC> struct VecStore;
@@ -44,7 +52,6 @@ template <> struct VecStore<2> {
         *reinterpret_cast<unsigned *>(p) = a;
     }
 };
-
 template <int NC>
 __device__ __forceinline__ void store_raw(unsigned char *p, const int *v) {
     if (NC == 4) VecStore<4>::st(p, pack_lo(v[0], v[1]), pack_lo(v[2], v[3]));
@@ -58,75 +65,63 @@ __device__ __forceinline__ void store_quant(unsigned char *p, const int *v, cons
         VecStore<2>::st(p, pack_hi(quant1(v[0], q), quant1(v[1], q)), 0u);
 }
 
-// One vertical step: rows 2j (a) and 2j+1 (b) of the horizontal outputs, [0,NC) = low, [NC,2NC) = high.
+// One vertical step on the horizontal outputs of rows 2j (a) and 2j+1 (b); [0,NC) = low, [NC,2NC) = high.
+// emit_low : store LL/LH of output row j        at byte offset off
+// emit_high: store HL/HH of output row j-1      at byte offset off - pitch   (interior formula)
+// Both flags are warp-uniform.
 template <int NC>
-__device__ __forceinline__ void vstep(VState<NC> &s, int j, const int *a, const int *b, int y0, int y1, int oh,
-                                      const PlaneGeom &g, unsigned char *out, int colbyte, bool active)
+__device__ __forceinline__ void vstep(VState<NC> &s, const int *a, const int *b, const PlaneGeom &g, unsigned char *out,
+                                      unsigned off, bool emit_low, bool emit_high)
 {
     int v[2 * NC], dn[2 * NC];
 #pragma unroll
     for (int i = 0; i < 2 * NC; i++) { v[i] = a[i] + b[i]; dn[i] = a[i] - b[i]; }
-
-    if (active && j >= y0 && j < y1) {
-        unsigned char *pll = out + g.band_off[0] + (long long)j * g.out_pitch + colbyte;
-        unsigned char *plh = out + g.band_off[1] + (long long)j * g.out_pitch + colbyte;
-        if (g.quant_ll) store_quant<NC>(pll, v, g.q[0]); else store_raw<NC>(pll, v);
-        store_quant<NC>(plh, v + NC, g.q[1]);
+    if (emit_low) {
+        if (g.quant_ll) store_quant<NC>(out + (g.band_off[0] + off), v, g.q[0]);
+        else store_raw<NC>(out + (g.band_off[0] + off), v);
+        store_quant<NC>(out + (g.band_off[1] + off), v + NC, g.q[1]);
     }
-    const int r = j - 1;
-    if (active && r >= y0 && r < y1 && r >= 1) {
+    if (emit_high) {
         int h[2 * NC];
 #pragma unroll
         for (int i = 0; i < 2 * NC; i++) h[i] = ((v[i] - s.llp[i] + 4) >> 3) + s.dc[i];
-        store_quant<NC>(out + g.band_off[2] + (long long)r * g.out_pitch + colbyte, h, g.q[2]);
-        store_quant<NC>(out + g.band_off[3] + (long long)r * g.out_pitch + colbyte, h + NC, g.q[3]);
-    }
-    if (j == 2 && y0 == 0 && active) {          // top border row (spatial.c:10166-10208)
-        int h[2 * NC];
-#pragma unroll
-        for (int i = 0; i < 2 * NC; i++)
-            h[i] = clamp16((-3 * s.llp[i] + 8 * s.d0[i] + 4 * s.llc[i] - v[i] + 4) >> 3);
-        store_quant<NC>(out + g.band_off[2] + colbyte, h, g.q[2]);
-        store_quant<NC>(out + g.band_off[3] + colbyte, h + NC, g.q[3]);
-    }
-    if (j == oh - 1 && y1 == oh && active) {    // bottom border row (spatial.c:10516-10558)
-        int h[2 * NC];
-#pragma unroll
-        for (int i = 0; i < 2 * NC; i++)
-            h[i] = clamp16((3 * v[i] + 8 * dn[i] - 4 * s.llc[i] + s.llp[i] + 4) >> 3);
-        store_quant<NC>(out + g.band_off[2] + (long long)(oh - 1) * g.out_pitch + colbyte, h, g.q[2]);
-        store_quant<NC>(out + g.band_off[3] + (long long)(oh - 1) * g.out_pitch + colbyte, h + NC, g.q[3]);
+        const unsigned offh = off - (unsigned)g.out_pitch;
+        store_quant<NC>(out + (g.band_off[2] + offh), h, g.q[2]);
+        store_quant<NC>(out + (g.band_off[3] + offh), h + NC, g.q[3]);
     }
 #pragma unroll
-    for (int i = 0; i < 2 * NC; i++) {
-        s.llp[i] = s.llc[i]; s.llc[i] = v[i]; s.dc[i] = dn[i];
-        if (j == 0) s.d0[i] = dn[i];
-    }
+    for (int i = 0; i < 2 * NC; i++) { s.llp[i] = s.llc[i]; s.llc[i] = v[i]; s.dc[i] = dn[i]; }
 }
 
-// rows of pairs [jb, je] are needed to emit output rows [y0, y1)
-__device__ __forceinline__ void pair_range(int y0, int y1, int oh, int &jb, int &je) {
-    jb = max(y0 - 1, 0);
-    je = min(y1, oh - 1);
-    if (y1 == oh) jb = min(jb, max(oh - 3, 0));
-    if (y0 == 0) je = max(je, min(2, oh - 1));
+// Border rows of HL/HH from three consecutive pairs (S,D of each): spatial.c:10166-10208 / :10516-10558.
+//   top   : pairs 0,1,2      -> row 0     = clamp((-3 S0 + 8 D0 + 4 S1 - S2 + 4) >> 3)
+//   bottom: pairs n-2,n-1,n  -> row n     = clamp(( 3 Sn + 8 Dn - 4 S(n-1) + S(n-2) + 4) >> 3)
+template <int NC>
+__device__ __forceinline__ void border_emit(const int *s0, const int *s1, const int *s2, const int *dsel, bool bottom,
+                                            const PlaneGeom &g, unsigned char *out, unsigned off)
+{
+    int h[2 * NC];
+#pragma unroll
+    for (int i = 0; i < 2 * NC; i++)
+        h[i] = bottom ? clamp16((3 * s2[i] + 8 * dsel[i] - 4 * s1[i] + s0[i] + 4) >> 3)
+                      : clamp16((-3 * s0[i] + 8 * dsel[i] + 4 * s1[i] - s2[i] + 4) >> 3);
+    store_quant<NC>(out + (g.band_off[2] + off), h, g.q[2]);
+    store_quant<NC>(out + (g.band_off[3] + off), h + NC, g.q[3]);
 }
 
 // ----------------------------------------------------------------------------
 // int16 plane input
 struct RawPlaneRow {
-    uint4 v;        // 8 samples of this lane
-    unsigned lh;    // samples [-2,-1] of the strip (lane 0 only)
-    unsigned rh;    // samples [256,257] of the strip (lane 31 only)
+    uint4 v;            // 8 samples of this lane
+    unsigned halo;      // lane 0: samples [-2,-1] of the strip; last lane: samples [+256,+257]
 };
 
-__device__ __forceinline__ void load_plane_row(const unsigned char *in, int pitch, int row, int col0, bool active,
-                                               bool use_lh, bool use_rh, RawPlaneRow &r)
+__device__ __forceinline__ void load_plane_row(const unsigned char *p, const LaneInfo &L, RawPlaneRow &r)
 {
-    const unsigned char *p = in + (long long)row * pitch + (long long)col0 * 2;
-    r.v = active ? __ldg(reinterpret_cast<const uint4 *>(p)) : make_uint4(0, 0, 0, 0);
-    r.lh = use_lh ? __ldg(reinterpret_cast<const unsigned *>(p - 4)) : 0u;
-    r.rh = use_rh ? __ldg(reinterpret_cast<const unsigned *>(p + 16)) : 0u;
+    r.v = __ldg(reinterpret_cast<const uint4 *>(p));
+    r.halo = 0u;
+    if (L.use_lh) r.halo = __ldg(reinterpret_cast<const unsigned *>(p - 4));
+    if (L.use_rh) r.halo = __ldg(reinterpret_cast<const unsigned *>(p + 16));
 }
 
 template <int PRESCALE>
@@ -135,8 +130,7 @@ __device__ __forceinline__ int tap(int x) { return PRESCALE ? ((x + 3) >> 2) : x
 // horizontal 2-6 for the lane's 4 output columns: o[0..3] = low, o[4..7] = high
 // (Codec/spatial.c:253 FilterHorizontalRow16s / :3669 FilterHorizontalRow10bit16s)
 template <int PRESCALE>
-__device__ __forceinline__ void hfilter_plane(const RawPlaneRow &r, bool left_border, bool right_border,
-                                              bool use_lh, bool use_rh, int *o)
+__device__ __forceinline__ void hfilter_plane(const RawPlaneRow &r, const LaneInfo &L, int *o)
 {
     const unsigned w[4] = {r.v.x, r.v.y, r.v.z, r.v.w};
     int S[4], d[4];
@@ -148,16 +142,33 @@ __device__ __forceinline__ void hfilter_plane(const RawPlaneRow &r, bool left_bo
         d[k] = t0 - t1;
         o[k] = PRESCALE ? ((x0 + x1 + 3) >> 2) : S[k];
     }
-    int Sp = __shfl_up_sync(kFull, S[3], 1);
-    int Sn = __shfl_down_sync(kFull, S[0], 1);
-    if (use_lh) Sp = tap<PRESCALE>(lo16(r.lh)) + tap<PRESCALE>(hi16(r.lh));
-    if (use_rh) Sn = tap<PRESCALE>(lo16(r.rh)) + tap<PRESCALE>(hi16(r.rh));
+    int Sp = __shfl_up_sync(L.amask, S[3], 1);
+    int Sn = __shfl_down_sync(L.amask, S[0], 1);
+    const int hs = tap<PRESCALE>(lo16(r.halo)) + tap<PRESCALE>(hi16(r.halo));
+    Sp = L.use_lh ? hs : Sp;
+    Sn = L.use_rh ? hs : Sn;
     o[4] = ((S[1] - Sp + 4) >> 3) + d[0];
     o[5] = ((S[2] - S[0] + 4) >> 3) + d[1];
     o[6] = ((S[3] - S[1] + 4) >> 3) + d[2];
     o[7] = ((Sn - S[2] + 4) >> 3) + d[3];
-    if (left_border) o[4] = clamp16((-3 * S[0] + 8 * d[0] + 4 * S[1] - S[2] + 4) >> 3);
-    if (right_border) o[7] = clamp16((3 * S[3] + 8 * d[3] - 4 * S[2] + S[1] + 4) >> 3);
+    if (L.has_border) {     // warp-uniform: only the first and last strip of a row carry a border lane
+        if (L.left_border) o[4] = clamp16((-3 * S[0] + 8 * d[0] + 4 * S[1] - S[2] + 4) >> 3);
+        if (L.right_border) o[7] = clamp16((3 * S[3] + 8 * d[3] - 4 * S[2] + S[1] + 4) >> 3);
+    }
+}
+
+__device__ __forceinline__ bool lane_setup(int strip, int width, int lane, LaneInfo &L)
+{
+    const int col0 = strip * kStripIn + lane * 8;
+    const bool active = col0 < width;
+    L.amask = __ballot_sync(0xffffffffu, active);
+    if (!active) return false;
+    L.left_border = (col0 == 0);
+    L.right_border = (col0 + 8 == width);
+    L.has_border = (strip == 0) || ((strip + 1) * kStripIn >= width);
+    L.use_lh = (lane == 0) && (strip > 0);
+    L.use_rh = (lane == 31) && (col0 + 8 < width);
+    return true;
 }
 
 template <int PRESCALE>
@@ -169,39 +180,63 @@ __global__ void __launch_bounds__(128) k_fwd_plane(const __grid_constant__ FwdPa
     const int strip = blockIdx.x;
     if (strip * kStripIn >= g.width) return;
     const int oh = g.height >> 1;
+    LaneInfo L;
+    if (!lane_setup(strip, g.width, lane, L)) return;
+    const unsigned colbyte = (unsigned)((strip * kStripOut + lane * 4) * 2);
+    const unsigned char *in = p.in_base[f] + g.in_off + (strip * kStripIn + lane * 8) * 2;
+    unsigned char *out = p.out_base[f];
+
+    if (blockIdx.y == gridDim.y - 1) {
+        // ---- border warps: warp 0 -> first HL/HH row, warp 1 -> last HL/HH row ----
+        if (threadIdx.y > 1) return;
+        const bool bottom = (threadIdx.y == 1);
+        const int j0 = bottom ? oh - 3 : 0;
+        int s[3][8], dsel[8];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            RawPlaneRow r0, r1;
+            int a[8], b[8];
+            load_plane_row(in + (long long)(2 * (j0 + k)) * g.in_pitch, L, r0);
+            load_plane_row(in + (long long)(2 * (j0 + k) + 1) * g.in_pitch, L, r1);
+            hfilter_plane<PRESCALE>(r0, L, a);
+            hfilter_plane<PRESCALE>(r1, L, b);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                s[k][i] = a[i] + b[i];
+                if (k == (bottom ? 2 : 0)) dsel[i] = a[i] - b[i];
+            }
+        }
+        border_emit<4>(s[0], s[1], s[2], dsel, bottom, g, out, (unsigned)((bottom ? oh - 1 : 0) * g.out_pitch) + colbyte);
+        return;
+    }
+
     const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * p.th;
     if (y0 >= oh) return;
     const int y1 = min(y0 + p.th, oh);
-
-    const int col0 = strip * kStripIn + lane * 8;
-    const bool active = col0 < g.width;
-    const bool left_border = (col0 == 0);
-    const bool right_border = (col0 + 8 == g.width);
-    const bool use_lh = (lane == 0) && (strip > 0);
-    const bool use_rh = (lane == 31) && (col0 + 8 < g.width);
-    const unsigned char *in = p.in_base[f] + g.in_off;
-    unsigned char *out = p.out_base[f];
-    const int colbyte = (strip * kStripOut + lane * 4) * 2;
-
-    int jb, je;
-    pair_range(y0, y1, oh, jb, je);
+    const int jfirst = max(y0 - 1, 0), jlast = min(y1, oh - 1);
+    const int hlo = max(y0, 1);     // first HL/HH row this warp emits (row 0 belongs to the border warp)
 
     VState<4> st;
 #pragma unroll
-    for (int i = 0; i < 8; i++) { st.llp[i] = st.llc[i] = st.dc[i] = st.d0[i] = 0; }
+    for (int i = 0; i < 8; i++) { st.llp[i] = st.llc[i] = st.dc[i] = 0; }
 
+    const unsigned char *rp = in + (long long)(2 * jfirst) * g.in_pitch;
     RawPlaneRow c0, c1, n0, n1;
-    load_plane_row(in, g.in_pitch, 2 * jb, col0, active, use_lh, use_rh, c0);
-    load_plane_row(in, g.in_pitch, 2 * jb + 1, col0, active, use_lh, use_rh, c1);
-    for (int j = jb; j <= je; j++) {
-        if (j < je) {
-            load_plane_row(in, g.in_pitch, 2 * j + 2, col0, active, use_lh, use_rh, n0);
-            load_plane_row(in, g.in_pitch, 2 * j + 3, col0, active, use_lh, use_rh, n1);
+    load_plane_row(rp, L, c0);
+    load_plane_row(rp + g.in_pitch, L, c1);
+    n0 = c0; n1 = c1;
+    unsigned off = (unsigned)(jfirst * g.out_pitch) + colbyte;
+    for (int j = jfirst; j <= jlast; j++) {
+        rp += 2 * g.in_pitch;
+        if (j < jlast) {
+            load_plane_row(rp, L, n0);
+            load_plane_row(rp + g.in_pitch, L, n1);
         }
         int a[8], b[8];
-        hfilter_plane<PRESCALE>(c0, left_border, right_border, use_lh, use_rh, a);
-        hfilter_plane<PRESCALE>(c1, left_border, right_border, use_lh, use_rh, b);
-        vstep<4>(st, j, a, b, y0, y1, oh, g, out, colbyte, active);
+        hfilter_plane<PRESCALE>(c0, L, a);
+        hfilter_plane<PRESCALE>(c1, L, b);
+        vstep<4>(st, a, b, g, out, off, j >= y0 && j < y1, j - 1 >= hlo);
+        off += (unsigned)g.out_pitch;
         c0 = n0; c1 = n1;
     }
 }
@@ -211,17 +246,15 @@ __global__ void __launch_bounds__(128) k_fwd_plane(const __grid_constant__ FwdPa
 // U and V strips (64 columns each) from a single read of the packed rows.
 struct Raw422Row {
     uint4 v;        // 8 luma + 4 U + 4 V of this lane
-    uint2 lh;       // previous 8 bytes (lane 0 only)
-    uint2 rh;       // next 8 bytes (lane 31 only)
+    uint2 halo;     // lane 0: previous 8 bytes; last lane: next 8 bytes
 };
 
-__device__ __forceinline__ void load_422_row(const unsigned char *in, int pitch, int row, int byte0, bool active,
-                                             bool use_lh, bool use_rh, Raw422Row &r)
+__device__ __forceinline__ void load_422_row(const unsigned char *p, const LaneInfo &L, Raw422Row &r)
 {
-    const unsigned char *p = in + (long long)row * pitch + byte0;
-    r.v = active ? __ldg(reinterpret_cast<const uint4 *>(p)) : make_uint4(0, 0, 0, 0);
-    r.lh = use_lh ? __ldg(reinterpret_cast<const uint2 *>(p - 8)) : make_uint2(0, 0);
-    r.rh = use_rh ? __ldg(reinterpret_cast<const uint2 *>(p + 16)) : make_uint2(0, 0);
+    r.v = __ldg(reinterpret_cast<const uint4 *>(p));
+    r.halo = make_uint2(0u, 0u);
+    if (L.use_lh) r.halo = __ldg(reinterpret_cast<const uint2 *>(p - 8));
+    if (L.use_rh) r.halo = __ldg(reinterpret_cast<const uint2 *>(p + 16));
 }
 
 struct Sel422 {     // dp4a coefficient words (already scaled by 1 << shift)
@@ -229,8 +262,7 @@ struct Sel422 {     // dp4a coefficient words (already scaled by 1 << shift)
 };
 
 // Y: oy[0..3] low, oy[4..7] high.  U/V: o[0..1] low, o[2..3] high.
-__device__ __forceinline__ void hfilter_422(const Raw422Row &r, const Sel422 &sel, bool left_border, bool right_border,
-                                            bool use_lh, bool use_rh, int *oy, int *ou, int *ov)
+__device__ __forceinline__ void hfilter_422(const Raw422Row &r, const Sel422 &sel, const LaneInfo &L, int *oy, int *ou, int *ov)
 {
     const unsigned w[4] = {r.v.x, r.v.y, r.v.z, r.v.w};
     int S[4], d[4], cu[4], cv[4];
@@ -242,20 +274,17 @@ __device__ __forceinline__ void hfilter_422(const Raw422Row &r, const Sel422 &se
         cv[k] = dp4a_us(w[k], sel.v, 0);
         oy[k] = S[k];
     }
-    int Su[2] = {cu[0] + cu[1], cu[2] + cu[3]}, du[2] = {cu[0] - cu[1], cu[2] - cu[3]};
-    int Sv[2] = {cv[0] + cv[1], cv[2] + cv[3]}, dv[2] = {cv[0] - cv[1], cv[2] - cv[3]};
-    int Sp = __shfl_up_sync(kFull, S[3], 1), Sn = __shfl_down_sync(kFull, S[0], 1);
-    int Sup = __shfl_up_sync(kFull, Su[1], 1), Sun = __shfl_down_sync(kFull, Su[0], 1);
-    int Svp = __shfl_up_sync(kFull, Sv[1], 1), Svn = __shfl_down_sync(kFull, Sv[0], 1);
-    if (use_lh) {
-        Sp = dp4a_us(r.lh.y, sel.ysum, 0);
-        Sup = dp4a_us(r.lh.y, sel.u, dp4a_us(r.lh.x, sel.u, 0));
-        Svp = dp4a_us(r.lh.y, sel.v, dp4a_us(r.lh.x, sel.v, 0));
-    }
-    if (use_rh) {
-        Sn = dp4a_us(r.rh.x, sel.ysum, 0);
-        Sun = dp4a_us(r.rh.y, sel.u, dp4a_us(r.rh.x, sel.u, 0));
-        Svn = dp4a_us(r.rh.y, sel.v, dp4a_us(r.rh.x, sel.v, 0));
+    const int Su[2] = {cu[0] + cu[1], cu[2] + cu[3]}, du[2] = {cu[0] - cu[1], cu[2] - cu[3]};
+    const int Sv[2] = {cv[0] + cv[1], cv[2] + cv[3]}, dv[2] = {cv[0] - cv[1], cv[2] - cv[3]};
+    int Sp = __shfl_up_sync(L.amask, S[3], 1), Sn = __shfl_down_sync(L.amask, S[0], 1);
+    int Sup = __shfl_up_sync(L.amask, Su[1], 1), Sun = __shfl_down_sync(L.amask, Su[0], 1);
+    int Svp = __shfl_up_sync(L.amask, Sv[1], 1), Svn = __shfl_down_sync(L.amask, Sv[0], 1);
+    if (L.use_lh | L.use_rh) {      // lane 0 / 31 of strips with a neighbour strip (divergent but tiny)
+        // left halo: luma pair of the later word (.y), chroma pair = both words; right halo: luma pair of word .x
+        const int hy = dp4a_us(L.use_lh ? r.halo.y : r.halo.x, sel.ysum, 0);
+        const int hu = dp4a_us(r.halo.y, sel.u, dp4a_us(r.halo.x, sel.u, 0));
+        const int hv = dp4a_us(r.halo.y, sel.v, dp4a_us(r.halo.x, sel.v, 0));
+        if (L.use_lh) { Sp = hy; Sup = hu; Svp = hv; } else { Sn = hy; Sun = hu; Svn = hv; }
     }
     oy[4] = ((S[1] - Sp + 4) >> 3) + d[0];
     oy[5] = ((S[2] - S[0] + 4) >> 3) + d[1];
@@ -267,15 +296,17 @@ __device__ __forceinline__ void hfilter_422(const Raw422Row &r, const Sel422 &se
     ov[0] = Sv[0]; ov[1] = Sv[1];
     ov[2] = ((Sv[1] - Svp + 4) >> 3) + dv[0];
     ov[3] = ((Svn - Sv[0] + 4) >> 3) + dv[1];
-    if (left_border) {
-        oy[4] = clamp16((-3 * S[0] + 8 * d[0] + 4 * S[1] - S[2] + 4) >> 3);
-        ou[2] = clamp16((-3 * Su[0] + 8 * du[0] + 4 * Su[1] - Sun + 4) >> 3);
-        ov[2] = clamp16((-3 * Sv[0] + 8 * dv[0] + 4 * Sv[1] - Svn + 4) >> 3);
-    }
-    if (right_border) {
-        oy[7] = clamp16((3 * S[3] + 8 * d[3] - 4 * S[2] + S[1] + 4) >> 3);
-        ou[3] = clamp16((3 * Su[1] + 8 * du[1] - 4 * Su[0] + Sup + 4) >> 3);
-        ov[3] = clamp16((3 * Sv[1] + 8 * dv[1] - 4 * Sv[0] + Svp + 4) >> 3);
+    if (L.has_border) {
+        if (L.left_border) {
+            oy[4] = clamp16((-3 * S[0] + 8 * d[0] + 4 * S[1] - S[2] + 4) >> 3);
+            ou[2] = clamp16((-3 * Su[0] + 8 * du[0] + 4 * Su[1] - Sun + 4) >> 3);
+            ov[2] = clamp16((-3 * Sv[0] + 8 * dv[0] + 4 * Sv[1] - Svn + 4) >> 3);
+        }
+        if (L.right_border) {
+            oy[7] = clamp16((3 * S[3] + 8 * d[3] - 4 * S[2] + S[1] + 4) >> 3);
+            ou[3] = clamp16((3 * Su[1] + 8 * du[1] - 4 * Su[0] + Sup + 4) >> 3);
+            ov[3] = clamp16((3 * Sv[1] + 8 * dv[1] - 4 * Sv[0] + Svp + 4) >> 3);
+        }
     }
 }
 
@@ -290,21 +321,12 @@ __global__ void __launch_bounds__(128) k_fwd_422(const __grid_constant__ FwdPara
     const int strip = blockIdx.x;
     if (strip * kStripIn >= gy.width) return;
     const int oh = gy.height >> 1;
-    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * p.th;
-    if (y0 >= oh) return;
-    const int y1 = min(y0 + p.th, oh);
-
-    const int col0 = strip * kStripIn + lane * 8;       // luma sample index
-    const bool active = col0 < gy.width;
-    const bool left_border = (col0 == 0);
-    const bool right_border = (col0 + 8 == gy.width);
-    const bool use_lh = (lane == 0) && (strip > 0);
-    const bool use_rh = (lane == 31) && (col0 + 8 < gy.width);
-    const unsigned char *in = p.in_base[f] + gy.in_off;
+    LaneInfo L;
+    if (!lane_setup(strip, gy.width, lane, L)) return;
+    const unsigned colbyte_y = (unsigned)((strip * kStripOut + lane * 4) * 2);
+    const unsigned colbyte_c = (unsigned)((strip * (kStripOut / 2) + lane * 2) * 2);
+    const unsigned char *in = p.in_base[f] + gy.in_off + (strip * kStripIn + lane * 8) * 2;
     unsigned char *out = p.out_base[f];
-    const int colbyte_y = (strip * kStripOut + lane * 4) * 2;
-    const int colbyte_c = (strip * (kStripOut / 2) + lane * 2) * 2;
-    const int byte0 = col0 * 2;
 
     Sel422 sel;
     {
@@ -317,36 +339,77 @@ __global__ void __launch_bounds__(128) k_fwd_422(const __grid_constant__ FwdPara
         }
     }
 
-    int jb, je;
-    pair_range(y0, y1, oh, jb, je);
+    if (blockIdx.y == gridDim.y - 1) {
+        // ---- border warps: warp 0 -> first HL/HH row, warp 1 -> last HL/HH row (all three channels) ----
+        if (threadIdx.y > 1) return;
+        const bool bottom = (threadIdx.y == 1);
+        const int j0 = bottom ? oh - 3 : 0;
+        int sy[3][8], su[3][4], sv[3][4], dy[8], du[4], dv[4];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            Raw422Row r0, r1;
+            int ay[8], by[8], au[4], bu[4], av[4], bv[4];
+            load_422_row(in + (long long)(2 * (j0 + k)) * gy.in_pitch, L, r0);
+            load_422_row(in + (long long)(2 * (j0 + k) + 1) * gy.in_pitch, L, r1);
+            hfilter_422(r0, sel, L, ay, au, av);
+            hfilter_422(r1, sel, L, by, bu, bv);
+            const bool keep = (k == (bottom ? 2 : 0));
+#pragma unroll
+            for (int i = 0; i < 8; i++) { sy[k][i] = ay[i] + by[i]; if (keep) dy[i] = ay[i] - by[i]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                su[k][i] = au[i] + bu[i]; sv[k][i] = av[i] + bv[i];
+                if (keep) { du[i] = au[i] - bu[i]; dv[i] = av[i] - bv[i]; }
+            }
+        }
+        const int row = bottom ? oh - 1 : 0;
+        border_emit<4>(sy[0], sy[1], sy[2], dy, bottom, gy, out, (unsigned)(row * gy.out_pitch) + colbyte_y);
+        border_emit<2>(su[0], su[1], su[2], du, bottom, gu, out, (unsigned)(row * gu.out_pitch) + colbyte_c);
+        border_emit<2>(sv[0], sv[1], sv[2], dv, bottom, gv, out, (unsigned)(row * gv.out_pitch) + colbyte_c);
+        return;
+    }
+
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * p.th;
+    if (y0 >= oh) return;
+    const int y1 = min(y0 + p.th, oh);
+    const int jfirst = max(y0 - 1, 0), jlast = min(y1, oh - 1);
+    const int hlo = max(y0, 1);
 
     VState<4> sy;
     VState<2> su, sv;
 #pragma unroll
-    for (int i = 0; i < 8; i++) { sy.llp[i] = sy.llc[i] = sy.dc[i] = sy.d0[i] = 0; }
+    for (int i = 0; i < 8; i++) { sy.llp[i] = sy.llc[i] = sy.dc[i] = 0; }
 #pragma unroll
-    for (int i = 0; i < 4; i++) { su.llp[i] = su.llc[i] = su.dc[i] = su.d0[i] = 0; sv.llp[i] = sv.llc[i] = sv.dc[i] = sv.d0[i] = 0; }
+    for (int i = 0; i < 4; i++) { su.llp[i] = su.llc[i] = su.dc[i] = 0; sv.llp[i] = sv.llc[i] = sv.dc[i] = 0; }
 
+    const unsigned char *rp = in + (long long)(2 * jfirst) * gy.in_pitch;
     Raw422Row c0, c1, n0, n1;
-    load_422_row(in, gy.in_pitch, 2 * jb, byte0, active, use_lh, use_rh, c0);
-    load_422_row(in, gy.in_pitch, 2 * jb + 1, byte0, active, use_lh, use_rh, c1);
-    for (int j = jb; j <= je; j++) {
-        if (j < je) {
-            load_422_row(in, gy.in_pitch, 2 * j + 2, byte0, active, use_lh, use_rh, n0);
-            load_422_row(in, gy.in_pitch, 2 * j + 3, byte0, active, use_lh, use_rh, n1);
+    load_422_row(rp, L, c0);
+    load_422_row(rp + gy.in_pitch, L, c1);
+    n0 = c0; n1 = c1;
+    unsigned offy = (unsigned)(jfirst * gy.out_pitch) + colbyte_y;
+    unsigned offc = (unsigned)(jfirst * gu.out_pitch) + colbyte_c;
+    for (int j = jfirst; j <= jlast; j++) {
+        rp += 2 * gy.in_pitch;
+        if (j < jlast) {
+            load_422_row(rp, L, n0);
+            load_422_row(rp + gy.in_pitch, L, n1);
         }
         int ay[8], by[8], au[4], bu[4], av[4], bv[4];
-        hfilter_422(c0, sel, left_border, right_border, use_lh, use_rh, ay, au, av);
-        hfilter_422(c1, sel, left_border, right_border, use_lh, use_rh, by, bu, bv);
-        vstep<4>(sy, j, ay, by, y0, y1, oh, gy, out, colbyte_y, active);
-        vstep<2>(su, j, au, bu, y0, y1, oh, gu, out, colbyte_c, active);
-        vstep<2>(sv, j, av, bv, y0, y1, oh, gv, out, colbyte_c, active);
+        hfilter_422(c0, sel, L, ay, au, av);
+        hfilter_422(c1, sel, L, by, bu, bv);
+        const bool emit_low = (j >= y0) && (j < y1), emit_high = (j - 1 >= hlo);
+        vstep<4>(sy, ay, by, gy, out, offy, emit_low, emit_high);
+        vstep<2>(su, au, bu, gu, out, offc, emit_low, emit_high);
+        vstep<2>(sv, av, bv, gv, out, offc, emit_low, emit_high);
+        offy += (unsigned)gy.out_pitch;
+        offc += (unsigned)gu.out_pitch;
         c0 = n0; c1 = n1;
     }
 }
 
 // ----------------------------------------------------------------------------
-// host-side launchers (called from cfb_api.cu)
+// host-side launchers (called from cfb_api.cu).  gridDim.y = row blocks + 1 border CTA row.
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 cudaError_t launch_fwd_plane(const FwdParams &p, int prescale, cudaStream_t stream)
@@ -354,7 +417,7 @@ cudaError_t launch_fwd_plane(const FwdParams &p, int prescale, cudaStream_t stre
     int maxw = 0, maxoh = 0;
     for (int c = 0; c < p.nchan; c++) { maxw = max(maxw, p.ch[c].width); maxoh = max(maxoh, p.ch[c].height / 2); }
     dim3 block(32, 4);
-    dim3 grid(ceil_div(maxw, kStripIn), ceil_div(ceil_div(maxoh, p.th), (int)block.y), p.nframes * p.nchan);
+    dim3 grid(ceil_div(maxw, kStripIn), ceil_div(ceil_div(maxoh, p.th), (int)block.y) + 1, p.nframes * p.nchan);
     if (prescale) k_fwd_plane<2><<<grid, block, 0, stream>>>(p);
     else k_fwd_plane<0><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
@@ -363,7 +426,7 @@ cudaError_t launch_fwd_plane(const FwdParams &p, int prescale, cudaStream_t stre
 cudaError_t launch_fwd_422(const FwdParams &p, cudaStream_t stream)
 {
     dim3 block(32, 4);
-    dim3 grid(ceil_div(p.ch[0].width, kStripIn), ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y), p.nframes);
+    dim3 grid(ceil_div(p.ch[0].width, kStripIn), ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y) + 1, p.nframes);
     k_fwd_422<<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }

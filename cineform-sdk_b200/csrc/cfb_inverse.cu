@@ -19,6 +19,58 @@ namespace cfb {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 
+// raw (still packed, still quantised) coefficients of NC columns of one band row
+template <int NC> struct RawCols;
+template <> struct RawCols<4> { uint2 w; };
+template <> struct RawCols<2> { unsigned w; };
+
+template <int NC>
+__device__ __forceinline__ void load_raw(const unsigned char *in, long long band_off, unsigned off, bool active, RawCols<NC> &r);
+template <>
+__device__ __forceinline__ void load_raw<4>(const unsigned char *in, long long band_off, unsigned off, bool active, RawCols<4> &r) {
+    r.w = active ? __ldg(reinterpret_cast<const uint2 *>(in + band_off + off)) : make_uint2(0, 0);
+}
+template <>
+__device__ __forceinline__ void load_raw<2>(const unsigned char *in, long long band_off, unsigned off, bool active, RawCols<2> &r) {
+    r.w = active ? __ldg(reinterpret_cast<const unsigned *>(in + band_off + off)) : 0u;
+}
+
+// dp2a with signed 16-bit halves (a) and unsigned byte coefficients (b): lo16(a)*b0 + hi16(a)*b1 (+ c)
+__device__ __forceinline__ int dp2a_lo_su(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// unpack + dequantise one packed pair.  SMALLDQ: divisor <= 255 -> one dp2a per coefficient.
+template <bool SMALLDQ>
+__device__ __forceinline__ void deq_pair(unsigned w, int dq, int &lo, int &hi) {
+    if (SMALLDQ) {
+        lo = dp2a_lo_su(w, (unsigned)dq, 0);
+        hi = dp2a_lo_su(w, (unsigned)dq << 8, 0);
+    } else {
+        lo = lo16(w) * dq;
+        hi = hi16(w) * dq;
+    }
+}
+__device__ __forceinline__ void unpack_pair(unsigned w, int &lo, int &hi) { lo = lo16(w); hi = hi16(w); }
+
+template <bool SMALLDQ, int NC>
+struct Expand;
+template <bool SMALLDQ>
+struct Expand<SMALLDQ, 4> {
+    static __device__ __forceinline__ void ll(const RawCols<4> &r, int *v) { unpack_pair(r.w.x, v[0], v[1]); unpack_pair(r.w.y, v[2], v[3]); }
+    static __device__ __forceinline__ void hp(const RawCols<4> &r, int dq, int *v) {
+        deq_pair<SMALLDQ>(r.w.x, dq, v[0], v[1]); deq_pair<SMALLDQ>(r.w.y, dq, v[2], v[3]);
+    }
+};
+template <bool SMALLDQ>
+struct Expand<SMALLDQ, 2> {
+    static __device__ __forceinline__ void ll(const RawCols<2> &r, int *v) { unpack_pair(r.w, v[0], v[1]); }
+    static __device__ __forceinline__ void hp(const RawCols<2> &r, int dq, int *v) { deq_pair<SMALLDQ>(r.w, dq, v[0], v[1]); }
+};
+
+// legacy helper used only on the border rows
 template <int NC>
 __device__ __forceinline__ void load_cols(const unsigned char *band, int pitch, int row, int colbyte, int dq, bool active, int *v)
 {
@@ -41,7 +93,7 @@ __device__ __forceinline__ void vinv_mid(const int *p, const int *c, const int *
         o[i] = (((n[i] - p[i] + 4) >> 3) + c[i] - h[i]) >> 1;
     }
 }
-// top border: a0,a1,a2 = rows 0,1,2 ; bottom border: call with a0,a1,a2 = rows H-1,H-2,H-3 and swap=true
+// top border: a0,a1,a2 = rows 0,1,2 ; bottom border: call with a0,a1,a2 = rows H-1,H-2,H-3 and bottom=true
 template <int NC>
 __device__ __forceinline__ void vinv_border(const int *a0, const int *a1, const int *a2, const int *h, bool bottom, int *e, int *o)
 {
@@ -57,7 +109,7 @@ __device__ __forceinline__ void vinv_border(const int *a0, const int *a1, const 
 // horizontal inverse for NC columns -> 2*NC samples t (BEFORE the final >>1 / <<1):
 //   t[2i] = ((l[i-1] - l[i+1] + 4) >> 3) + l[i] + h[i],  t[2i+1] = ((l[i+1] - l[i-1] + 4) >> 3) + l[i] - h[i]
 template <int NC>
-__device__ __forceinline__ void hinv(const int *l, const int *h, bool left_border, bool right_border, int *t)
+__device__ __forceinline__ void hinv(const int *l, const int *h, bool has_border, bool left_border, bool right_border, int *t)
 {
     const int lp = __shfl_up_sync(kFullMask, l[NC - 1], 1);
     const int ln = __shfl_down_sync(kFullMask, l[0], 1);
@@ -68,6 +120,7 @@ __device__ __forceinline__ void hinv(const int *l, const int *h, bool left_borde
         t[2 * i] = ((a - b + 4) >> 3) + l[i] + h[i];
         t[2 * i + 1] = ((b - a + 4) >> 3) + l[i] - h[i];
     }
+    if (has_border) {
     if (left_border) {
         const int l2 = (NC > 2) ? l[2] : ln;
         t[0] = ((11 * l[0] - 4 * l[1] + l2 + 4) >> 3) + h[0];
@@ -79,6 +132,7 @@ __device__ __forceinline__ void hinv(const int *l, const int *h, bool left_borde
         t[2 * k] = ((5 * l[k] + 4 * l[k - 1] - l2 + 4) >> 3) + h[k];
         t[2 * k + 1] = ((11 * l[k] - 4 * l[k - 1] + l2 + 4) >> 3) - h[k];
     }
+    }
 }
 
 __device__ __forceinline__ unsigned pack_sat16(int lo, int hi) {
@@ -88,8 +142,85 @@ __device__ __forceinline__ unsigned pack_sat16(int lo, int hi) {
 }
 
 // ----------------------------------------------------------------------------
+// Per-channel inverse engine: a three-row window of LL and LH (already expanded to int32) plus a
+// one-iteration-ahead prefetch of the raw band rows.
+template <int NC>
+struct InvChan {
+    int lp[NC], lc[NC], hp[NC], hc[NC];                 // LL / LH rows r-1, r
+    RawCols<NC> nll, nlh, nhl, nhh;                     // prefetched: LL,LH row r+1 ; HL,HH row r
+};
+
+template <int NC, bool SMALLDQ>
+__device__ __forceinline__ void inv_prologue(InvChan<NC> &s, const InvGeom &g, const unsigned char *in, int y0, int H,
+                                             unsigned colbyte, bool active)
+{
+    RawCols<NC> a, b;
+    const unsigned rp = (unsigned)max(y0 - 1, 0) * g.pitch + colbyte, rc = (unsigned)y0 * g.pitch + colbyte;
+    load_raw<NC>(in, g.band_off[0], rp, active, a); Expand<SMALLDQ, NC>::ll(a, s.lp);
+    load_raw<NC>(in, g.band_off[1], rp, active, b); Expand<SMALLDQ, NC>::hp(b, g.dq[1], s.hp);
+    load_raw<NC>(in, g.band_off[0], rc, active, a); Expand<SMALLDQ, NC>::ll(a, s.lc);
+    load_raw<NC>(in, g.band_off[1], rc, active, b); Expand<SMALLDQ, NC>::hp(b, g.dq[1], s.hc);
+    const unsigned rn = (unsigned)min(y0 + 1, H - 1) * g.pitch + colbyte;
+    load_raw<NC>(in, g.band_off[0], rn, active, s.nll);
+    load_raw<NC>(in, g.band_off[1], rn, active, s.nlh);
+    load_raw<NC>(in, g.band_off[2], rc, active, s.nhl);
+    load_raw<NC>(in, g.band_off[3], rc, active, s.nhh);
+}
+
+// One band row r -> the 2*NC "t" values (before the final shift) of output rows 2r (te) and 2r+1 (to).
+template <int NC, bool SMALLDQ>
+__device__ __forceinline__ void inv_step(InvChan<NC> &s, const InvGeom &g, const unsigned char *in, int r, int y1, int H,
+                                         unsigned colbyte, bool active, bool has_border, bool left_border, bool right_border,
+                                         int *te, int *to)
+{
+    int ln[NC], hn[NC], vhl[NC], vhh[NC];
+    Expand<SMALLDQ, NC>::ll(s.nll, ln);
+    Expand<SMALLDQ, NC>::hp(s.nlh, g.dq[1], hn);
+    Expand<SMALLDQ, NC>::hp(s.nhl, g.dq[2], vhl);
+    Expand<SMALLDQ, NC>::hp(s.nhh, g.dq[3], vhh);
+    if (r + 1 < y1) {       // prefetch the next iteration's rows
+        const unsigned rn = (unsigned)min(r + 2, H - 1) * g.pitch + colbyte, rc = (unsigned)(r + 1) * g.pitch + colbyte;
+        load_raw<NC>(in, g.band_off[0], rn, active, s.nll);
+        load_raw<NC>(in, g.band_off[1], rn, active, s.nlh);
+        load_raw<NC>(in, g.band_off[2], rc, active, s.nhl);
+        load_raw<NC>(in, g.band_off[3], rc, active, s.nhh);
+    }
+    int el[NC], ol[NC], eh[NC], oh[NC];
+    vinv_mid<NC>(s.lp, s.lc, ln, vhl, el, ol);
+    vinv_mid<NC>(s.hp, s.hc, hn, vhh, eh, oh);
+    hinv<NC>(el, eh, has_border, left_border, right_border, te);
+    hinv<NC>(ol, oh, has_border, left_border, right_border, to);
+#pragma unroll
+    for (int i = 0; i < NC; i++) { s.lp[i] = s.lc[i]; s.lc[i] = ln[i]; s.hp[i] = s.hc[i]; s.hc[i] = hn[i]; }
+}
+
+// Border band rows (r = 0 or r = H-1), computed from scratch by the border warps
+// (spatial.c:21980-22060 top, :22320-22400 bottom).
+template <int NC>
+__device__ __forceinline__ void inv_border_row(const InvGeom &g, const unsigned char *in, bool bottom, int H, unsigned colbyte,
+                                               bool active, bool has_border, bool left_border, bool right_border,
+                                               int *te, int *to)
+{
+    const int r0 = bottom ? H - 1 : 0, r1 = bottom ? H - 2 : 1, r2 = bottom ? H - 3 : 2;
+    int a0[NC], a1[NC], a2[NC], b0[NC], b1[NC], b2[NC], vhl[NC], vhh[NC];
+    load_cols<NC>(in + g.band_off[0], g.pitch, r0, colbyte, 1, active, a0);
+    load_cols<NC>(in + g.band_off[0], g.pitch, r1, colbyte, 1, active, a1);
+    load_cols<NC>(in + g.band_off[0], g.pitch, r2, colbyte, 1, active, a2);
+    load_cols<NC>(in + g.band_off[1], g.pitch, r0, colbyte, g.dq[1], active, b0);
+    load_cols<NC>(in + g.band_off[1], g.pitch, r1, colbyte, g.dq[1], active, b1);
+    load_cols<NC>(in + g.band_off[1], g.pitch, r2, colbyte, g.dq[1], active, b2);
+    load_cols<NC>(in + g.band_off[2], g.pitch, r0, colbyte, g.dq[2], active, vhl);
+    load_cols<NC>(in + g.band_off[3], g.pitch, r0, colbyte, g.dq[3], active, vhh);
+    int el[NC], ol[NC], eh[NC], oh[NC];
+    vinv_border<NC>(a0, a1, a2, vhl, bottom, el, ol);
+    vinv_border<NC>(b0, b1, b2, vhh, bottom, eh, oh);
+    hinv<NC>(el, eh, has_border, left_border, right_border, te);
+    hinv<NC>(ol, oh, has_border, left_border, right_border, to);
+}
+
+// ----------------------------------------------------------------------------
 // generic level: 4 bands -> int16 plane (2W x 2H)
-template <int DESCALE>
+template <int DESCALE, bool SMALLDQ>
 __global__ void __launch_bounds__(128) k_inv_plane(const __grid_constant__ InvParams p)
 {
     const int lane = threadIdx.x;
@@ -98,72 +229,53 @@ __global__ void __launch_bounds__(128) k_inv_plane(const __grid_constant__ InvPa
     const int strip = blockIdx.x;
     if (strip * kInvStrip >= g.width) return;
     const int H = g.height;
-    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * p.th;
-    if (y0 >= H) return;
-    const int y1 = min(y0 + p.th, H);
 
     const int col0 = strip * kInvStrip - 4 + lane * 4;          // first band column of this lane
     const bool active = (col0 >= 0) && (col0 < g.width);
     const bool writer = active && lane >= 1 && lane <= 30;
     const bool left_border = (col0 == 0);
     const bool right_border = (col0 + 4 == g.width);
-    const int colbyte = col0 * 2;
+    const bool has_border = (strip == 0) || ((strip + 1) * kInvStrip + 4 >= g.width);
+    const unsigned colbyte = (unsigned)(col0 * 2);
     const unsigned char *in = p.in_base[f];
-    const unsigned char *bll = in + g.band_off[0], *blh = in + g.band_off[1];
-    const unsigned char *bhl = in + g.band_off[2], *bhh = in + g.band_off[3];
     unsigned char *out = p.out_base[f] + g.out_off + (long long)col0 * 4;
 
-    int lp[4], lc[4], ln[4], hp[4], hc[4], hn[4];      // LL and LH rows r-1, r, r+1
-    int r = y0;
-    load_cols<4>(bll, g.pitch, max(r - 1, 0), colbyte, g.dq[0], active, lp);
-    load_cols<4>(blh, g.pitch, max(r - 1, 0), colbyte, g.dq[1], active, hp);
-    load_cols<4>(bll, g.pitch, r, colbyte, g.dq[0], active, lc);
-    load_cols<4>(blh, g.pitch, r, colbyte, g.dq[1], active, hc);
-    for (; r < y1; r++) {
-        int vhl[4], vhh[4];
-        const int rn = min(r + 1, H - 1);
-        load_cols<4>(bll, g.pitch, rn, colbyte, g.dq[0], active, ln);
-        load_cols<4>(blh, g.pitch, rn, colbyte, g.dq[1], active, hn);
-        load_cols<4>(bhl, g.pitch, r, colbyte, g.dq[2], active, vhl);
-        load_cols<4>(bhh, g.pitch, r, colbyte, g.dq[3], active, vhh);
-        int el[4], ol[4], eh[4], oh[4];
-        if (r == 0) {
-            int l2[4], h2[4];
-            load_cols<4>(bll, g.pitch, 2, colbyte, g.dq[0], active, l2);
-            load_cols<4>(blh, g.pitch, 2, colbyte, g.dq[1], active, h2);
-            vinv_border<4>(lc, ln, l2, vhl, false, el, ol);
-            vinv_border<4>(hc, hn, h2, vhh, false, eh, oh);
-        } else if (r == H - 1) {
-            int l2[4], h2[4];
-            load_cols<4>(bll, g.pitch, H - 3, colbyte, g.dq[0], active, l2);
-            load_cols<4>(blh, g.pitch, H - 3, colbyte, g.dq[1], active, h2);
-            vinv_border<4>(lc, lp, l2, vhl, true, el, ol);
-            vinv_border<4>(hc, hp, h2, vhh, true, eh, oh);
+    auto emit = [&](int r, const int *te, const int *to) {
+        uint4 a, b;
+        if (DESCALE) {
+            a = make_uint4(pack_sat16(te[0] << 1, te[1] << 1), pack_sat16(te[2] << 1, te[3] << 1),
+                           pack_sat16(te[4] << 1, te[5] << 1), pack_sat16(te[6] << 1, te[7] << 1));
+            b = make_uint4(pack_sat16(to[0] << 1, to[1] << 1), pack_sat16(to[2] << 1, to[3] << 1),
+                           pack_sat16(to[4] << 1, to[5] << 1), pack_sat16(to[6] << 1, to[7] << 1));
         } else {
-            vinv_mid<4>(lp, lc, ln, vhl, el, ol);
-            vinv_mid<4>(hp, hc, hn, vhh, eh, oh);
+            a = make_uint4(pack_sat16(te[0] >> 1, te[1] >> 1), pack_sat16(te[2] >> 1, te[3] >> 1),
+                           pack_sat16(te[4] >> 1, te[5] >> 1), pack_sat16(te[6] >> 1, te[7] >> 1));
+            b = make_uint4(pack_sat16(to[0] >> 1, to[1] >> 1), pack_sat16(to[2] >> 1, to[3] >> 1),
+                           pack_sat16(to[4] >> 1, to[5] >> 1), pack_sat16(to[6] >> 1, to[7] >> 1));
         }
+        unsigned char *o = out + (long long)(2 * r) * g.out_pitch;
+        *reinterpret_cast<uint4 *>(o) = a;
+        *reinterpret_cast<uint4 *>(o + g.out_pitch) = b;
+    };
+
+    if (blockIdx.y == gridDim.y - 1) {          // border warps: band rows 0 and H-1
+        if (threadIdx.y > 1) return;
+        const bool bottom = (threadIdx.y == 1);
         int te[8], to[8];
-        hinv<4>(el, eh, left_border, right_border, te);
-        hinv<4>(ol, oh, left_border, right_border, to);
-        if (writer) {
-            uint4 a, b;
-            if (DESCALE) {
-                a = make_uint4(pack_sat16(te[0] << 1, te[1] << 1), pack_sat16(te[2] << 1, te[3] << 1),
-                               pack_sat16(te[4] << 1, te[5] << 1), pack_sat16(te[6] << 1, te[7] << 1));
-                b = make_uint4(pack_sat16(to[0] << 1, to[1] << 1), pack_sat16(to[2] << 1, to[3] << 1),
-                               pack_sat16(to[4] << 1, to[5] << 1), pack_sat16(to[6] << 1, to[7] << 1));
-            } else {
-                a = make_uint4(pack_sat16(te[0] >> 1, te[1] >> 1), pack_sat16(te[2] >> 1, te[3] >> 1),
-                               pack_sat16(te[4] >> 1, te[5] >> 1), pack_sat16(te[6] >> 1, te[7] >> 1));
-                b = make_uint4(pack_sat16(to[0] >> 1, to[1] >> 1), pack_sat16(to[2] >> 1, to[3] >> 1),
-                               pack_sat16(to[4] >> 1, to[5] >> 1), pack_sat16(to[6] >> 1, to[7] >> 1));
-            }
-            *reinterpret_cast<uint4 *>(out + (long long)(2 * r) * g.out_pitch) = a;
-            *reinterpret_cast<uint4 *>(out + (long long)(2 * r + 1) * g.out_pitch) = b;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) { lp[i] = lc[i]; lc[i] = ln[i]; hp[i] = hc[i]; hc[i] = hn[i]; }
+        inv_border_row<4>(g, in, bottom, H, colbyte, active, has_border, left_border, right_border, te, to);
+        if (writer) emit(bottom ? H - 1 : 0, te, to);
+        return;
+    }
+    const int y0 = max((int)(blockIdx.y * blockDim.y + threadIdx.y) * p.th, 1);
+    const int y1 = min((int)(blockIdx.y * blockDim.y + threadIdx.y + 1) * p.th, H - 1);
+    if (y0 >= y1) return;
+
+    InvChan<4> st;
+    inv_prologue<4, SMALLDQ>(st, g, in, y0, H, colbyte, active);
+    for (int r = y0; r < y1; r++) {
+        int te[8], to[8];
+        inv_step<4, SMALLDQ>(st, g, in, r, y1, H, colbyte, active, has_border, left_border, right_border, te, to);
+        if (writer) emit(r, te, to);
     }
 }
 
@@ -173,8 +285,6 @@ __global__ void __launch_bounds__(128) k_inv_plane(const __grid_constant__ InvPa
 // d = rand() & 1 per position (InvertHorizontalStrip16s.c:3807-3892) - not reproducible.  We use the
 // deterministic ordered dither d = (x ^ y) & 1, i.e. out = sat_u8((t + 2d) >> 3), which stays inside the
 // reference's envelope {(v) >> 2, (v + 1) >> 2} at every pixel.
-struct Col3 { int p[4], c[4], n[4]; };
-
 __device__ __forceinline__ unsigned pack_u8x4(int a, int b, int c, int d) {
     // bytes (LSB first): a, b, c, d, each saturated to [0,255].
     // cvt.pack.sat.u8.s32.b32 r, x, y, z  ->  r = (z << 16) | (sat(x) << 8) | sat(y)
@@ -184,42 +294,7 @@ __device__ __forceinline__ unsigned pack_u8x4(int a, int b, int c, int d) {
     return r;
 }
 
-template <int NC>
-__device__ __forceinline__ void inv_rows(const InvGeom &g, const unsigned char *in, int r, int H, int colbyte, bool active,
-                                         int *lp, int *lc, int *ln, int *hp, int *hc, int *hn,
-                                         bool left_border, bool right_border, int *te, int *to)
-{
-    const unsigned char *bll = in + g.band_off[0], *blh = in + g.band_off[1];
-    const unsigned char *bhl = in + g.band_off[2], *bhh = in + g.band_off[3];
-    int vhl[NC], vhh[NC];
-    const int rn = min(r + 1, H - 1);
-    load_cols<NC>(bll, g.pitch, rn, colbyte, g.dq[0], active, ln);
-    load_cols<NC>(blh, g.pitch, rn, colbyte, g.dq[1], active, hn);
-    load_cols<NC>(bhl, g.pitch, r, colbyte, g.dq[2], active, vhl);
-    load_cols<NC>(bhh, g.pitch, r, colbyte, g.dq[3], active, vhh);
-    int el[NC], ol[NC], eh[NC], oh[NC];
-    if (r == 0) {
-        int l2[NC], h2[NC];
-        load_cols<NC>(bll, g.pitch, 2, colbyte, g.dq[0], active, l2);
-        load_cols<NC>(blh, g.pitch, 2, colbyte, g.dq[1], active, h2);
-        vinv_border<NC>(lc, ln, l2, vhl, false, el, ol);
-        vinv_border<NC>(hc, hn, h2, vhh, false, eh, oh);
-    } else if (r == H - 1) {
-        int l2[NC], h2[NC];
-        load_cols<NC>(bll, g.pitch, H - 3, colbyte, g.dq[0], active, l2);
-        load_cols<NC>(blh, g.pitch, H - 3, colbyte, g.dq[1], active, h2);
-        vinv_border<NC>(lc, lp, l2, vhl, true, el, ol);
-        vinv_border<NC>(hc, hp, h2, vhh, true, eh, oh);
-    } else {
-        vinv_mid<NC>(lp, lc, ln, vhl, el, ol);
-        vinv_mid<NC>(hp, hc, hn, vhh, eh, oh);
-    }
-    hinv<NC>(el, eh, left_border, right_border, te);
-    hinv<NC>(ol, oh, left_border, right_border, to);
-#pragma unroll
-    for (int i = 0; i < NC; i++) { lp[i] = lc[i]; lc[i] = ln[i]; hp[i] = hc[i]; hc[i] = hn[i]; }
-}
-
+template <bool SMALLDQ>
 __global__ void __launch_bounds__(128) k_inv_422(const __grid_constant__ InvParams p)
 {
     const int lane = threadIdx.x;
@@ -230,61 +305,62 @@ __global__ void __launch_bounds__(128) k_inv_422(const __grid_constant__ InvPara
     const int strip = blockIdx.x;
     if (strip * kInvStrip >= gy.width) return;
     const int H = gy.height;
-    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * p.th;
-    if (y0 >= H) return;
-    const int y1 = min(y0 + p.th, H);
 
     const int col0 = strip * kInvStrip - 4 + lane * 4;      // luma band column
-    const int ccol0 = col0 >> 1;                            // chroma band column (2 per lane)
     const bool active = (col0 >= 0) && (col0 < gy.width);
     const bool writer = active && lane >= 1 && lane <= 30;
     const bool left_border = (col0 == 0);
     const bool right_border = (col0 + 4 == gy.width);
+    const bool has_border = (strip == 0) || ((strip + 1) * kInvStrip + 4 >= gy.width);
+    const unsigned ycol = (unsigned)(col0 * 2), ccol = (unsigned)col0;      // byte offsets (chroma: 2 columns of 2 bytes)
     const unsigned char *in = p.in_base[f];
     unsigned char *out = p.out_base[f] + gy.out_off + (long long)col0 * 4;     // 2 bytes per luma sample, 2 samples per column
 
-    int ylp[4], ylc[4], yln[4], yhp[4], yhc[4], yhn[4];
-    int ulp[2], ulc[2], uln[2], uhp[2], uhc[2], uhn[2];
-    int vlp[2], vlc[2], vln[2], vhp[2], vhc[2], vhn[2];
-    int r = y0;
-    {
-        const int rp = max(r - 1, 0);
-        load_cols<4>(in + gy.band_off[0], gy.pitch, rp, col0 * 2, gy.dq[0], active, ylp);
-        load_cols<4>(in + gy.band_off[1], gy.pitch, rp, col0 * 2, gy.dq[1], active, yhp);
-        load_cols<4>(in + gy.band_off[0], gy.pitch, r, col0 * 2, gy.dq[0], active, ylc);
-        load_cols<4>(in + gy.band_off[1], gy.pitch, r, col0 * 2, gy.dq[1], active, yhc);
-        load_cols<2>(in + gu.band_off[0], gu.pitch, rp, ccol0 * 2, gu.dq[0], active, ulp);
-        load_cols<2>(in + gu.band_off[1], gu.pitch, rp, ccol0 * 2, gu.dq[1], active, uhp);
-        load_cols<2>(in + gu.band_off[0], gu.pitch, r, ccol0 * 2, gu.dq[0], active, ulc);
-        load_cols<2>(in + gu.band_off[1], gu.pitch, r, ccol0 * 2, gu.dq[1], active, uhc);
-        load_cols<2>(in + gv.band_off[0], gv.pitch, rp, ccol0 * 2, gv.dq[0], active, vlp);
-        load_cols<2>(in + gv.band_off[1], gv.pitch, rp, ccol0 * 2, gv.dq[1], active, vhp);
-        load_cols<2>(in + gv.band_off[0], gv.pitch, r, ccol0 * 2, gv.dq[0], active, vlc);
-        load_cols<2>(in + gv.band_off[1], gv.pitch, r, ccol0 * 2, gv.dq[1], active, vhc);
-    }
     const int sh = p.shift + 1;     // final >>1 of the filter merged with the >> (precision-8) reduction
-    for (; r < y1; r++) {
-        int ye[8], yo[8], ue[4], uo[4], ve[4], vo[4];
-        inv_rows<4>(gy, in, r, H, col0 * 2, active, ylp, ylc, yln, yhp, yhc, yhn, left_border, right_border, ye, yo);
-        inv_rows<2>(gu, in, r, H, ccol0 * 2, active, ulp, ulc, uln, uhp, uhc, uhn, left_border, right_border, ue, uo);
-        inv_rows<2>(gv, in, r, H, ccol0 * 2, active, vlp, vlc, vln, vhp, vhc, vhn, left_border, right_border, ve, vo);
-        if (writer) {
+    auto emit = [&](int r, const int *ye, const int *yo, const int *ue, const int *uo, const int *ve, const int *vo) {
+        unsigned char *o = out + (long long)(2 * r) * gy.out_pitch;
 #pragma unroll
-            for (int rr = 0; rr < 2; rr++) {
-                const int *yy = rr ? yo : ye, *uu = rr ? uo : ue, *vv = rr ? vo : ve;
-                const int row = 2 * r + rr;
-                // ordered dither: d = (x ^ y) & 1 on the sample's own column index, scaled to the merged shift
-                const int d0 = ((row & 1) ? 1 : 0) << (sh - 2), d1 = ((row & 1) ? 0 : 1) << (sh - 2);
-                unsigned w[4];
+        for (int rr = 0; rr < 2; rr++) {
+            const int *yy = rr ? yo : ye, *uu = rr ? uo : ue, *vv = rr ? vo : ve;
+            // ordered dither d = (x ^ y) & 1 on the sample's own column index, scaled to the merged shift;
+            // band row r -> output rows 2r (even) and 2r+1 (odd)
+            const int d0 = (rr ? 1 : 0) << (sh - 2), d1 = (rr ? 0 : 1) << (sh - 2);
+            unsigned w[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int ya = (yy[2 * k] + d0) >> sh, yb = (yy[2 * k + 1] + d1) >> sh;
-                    const int cu = (uu[k] + ((k & 1) ? d1 : d0)) >> sh, cv = (vv[k] + ((k & 1) ? d1 : d0)) >> sh;
-                    w[k] = p.uyvy ? pack_u8x4(cu, ya, cv, yb) : pack_u8x4(ya, cu, yb, cv);
-                }
-                *reinterpret_cast<uint4 *>(out + (long long)row * gy.out_pitch) = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int k = 0; k < 4; k++) {
+                const int ya = (yy[2 * k] + d0) >> sh, yb = (yy[2 * k + 1] + d1) >> sh;
+                const int cu = (uu[k] + ((k & 1) ? d1 : d0)) >> sh, cv = (vv[k] + ((k & 1) ? d1 : d0)) >> sh;
+                w[k] = p.uyvy ? pack_u8x4(cu, ya, cv, yb) : pack_u8x4(ya, cu, yb, cv);
             }
+            *reinterpret_cast<uint4 *>(o + (rr ? gy.out_pitch : 0)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
+    };
+
+    if (blockIdx.y == gridDim.y - 1) {          // border warps: band rows 0 and H-1
+        if (threadIdx.y > 1) return;
+        const bool bottom = (threadIdx.y == 1);
+        int ye[8], yo[8], ue[4], uo[4], ve[4], vo[4];
+        inv_border_row<4>(gy, in, bottom, H, ycol, active, has_border, left_border, right_border, ye, yo);
+        inv_border_row<2>(gu, in, bottom, H, ccol, active, has_border, left_border, right_border, ue, uo);
+        inv_border_row<2>(gv, in, bottom, H, ccol, active, has_border, left_border, right_border, ve, vo);
+        if (writer) emit(bottom ? H - 1 : 0, ye, yo, ue, uo, ve, vo);
+        return;
+    }
+    const int y0 = max((int)(blockIdx.y * blockDim.y + threadIdx.y) * p.th, 1);
+    const int y1 = min((int)(blockIdx.y * blockDim.y + threadIdx.y + 1) * p.th, H - 1);
+    if (y0 >= y1) return;
+
+    InvChan<4> sy;
+    InvChan<2> su, sv;
+    inv_prologue<4, SMALLDQ>(sy, gy, in, y0, H, ycol, active);
+    inv_prologue<2, SMALLDQ>(su, gu, in, y0, H, ccol, active);
+    inv_prologue<2, SMALLDQ>(sv, gv, in, y0, H, ccol, active);
+    for (int r = y0; r < y1; r++) {
+        int ye[8], yo[8], ue[4], uo[4], ve[4], vo[4];
+        inv_step<4, SMALLDQ>(sy, gy, in, r, y1, H, ycol, active, has_border, left_border, right_border, ye, yo);
+        inv_step<2, SMALLDQ>(su, gu, in, r, y1, H, ccol, active, has_border, left_border, right_border, ue, uo);
+        inv_step<2, SMALLDQ>(sv, gv, in, r, y1, H, ccol, active, has_border, left_border, right_border, ve, vo);
+        if (writer) emit(r, ye, yo, ue, uo, ve, vo);
     }
 }
 
@@ -296,17 +372,21 @@ cudaError_t launch_inv_plane(const InvParams &p, int descale, cudaStream_t strea
     int maxw = 0, maxh = 0;
     for (int c = 0; c < p.nchan; c++) { maxw = max(maxw, p.ch[c].width); maxh = max(maxh, p.ch[c].height); }
     dim3 block(32, 4);
-    dim3 grid(ceil_div_i(maxw, kInvStrip), ceil_div_i(ceil_div_i(maxh, p.th), (int)block.y), p.nframes * p.nchan);
-    if (descale) k_inv_plane<2><<<grid, block, 0, stream>>>(p);
-    else k_inv_plane<0><<<grid, block, 0, stream>>>(p);
+    dim3 grid(ceil_div_i(maxw, kInvStrip), ceil_div_i(ceil_div_i(maxh, p.th), (int)block.y) + 1, p.nframes * p.nchan);
+    bool small = true;
+    for (int c = 0; c < p.nchan; c++) for (int b = 1; b < 4; b++) small = small && (p.ch[c].dq[b] >= 0 && p.ch[c].dq[b] <= 255);
+    if (descale) { if (small) k_inv_plane<2, true><<<grid, block, 0, stream>>>(p); else k_inv_plane<2, false><<<grid, block, 0, stream>>>(p); }
+    else { if (small) k_inv_plane<0, true><<<grid, block, 0, stream>>>(p); else k_inv_plane<0, false><<<grid, block, 0, stream>>>(p); }
     return cudaGetLastError();
 }
 
 cudaError_t launch_inv_422(const InvParams &p, cudaStream_t stream)
 {
     dim3 block(32, 4);
-    dim3 grid(ceil_div_i(p.ch[0].width, kInvStrip), ceil_div_i(ceil_div_i(p.ch[0].height, p.th), (int)block.y), p.nframes);
-    k_inv_422<<<grid, block, 0, stream>>>(p);
+    dim3 grid(ceil_div_i(p.ch[0].width, kInvStrip), ceil_div_i(ceil_div_i(p.ch[0].height, p.th), (int)block.y) + 1, p.nframes);
+    bool small = true;
+    for (int c = 0; c < 3; c++) for (int b = 1; b < 4; b++) small = small && (p.ch[c].dq[b] >= 0 && p.ch[c].dq[b] <= 255);
+    if (small) k_inv_422<true><<<grid, block, 0, stream>>>(p); else k_inv_422<false><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
