@@ -100,6 +100,17 @@ def lib():
     L.cfb_forward_host.argtypes = [vp, i, C.POINTER(vp), i, C.POINTER(Quant), C.POINTER(vp)]
     L.cfb_inverse_device.argtypes = [vp, i, C.POINTER(vp), C.POINTER(Quant), i, C.POINTER(vp), i]
     L.cfb_inverse_host.argtypes = [vp, i, C.POINTER(vp), C.POINTER(Quant), i, C.POINTER(vp), i]
+    L.cfb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.cfb_host_free.argtypes = [vp]
+    L.cfb_host_free.restype = None
+    L.cfb_pool_create.argtypes = [C.POINTER(C.c_int), i, C.POINTER(FrameDesc), i, i, i, C.POINTER(vp)]
+    L.cfb_pool_destroy.argtypes = [vp]
+    L.cfb_pool_destroy.restype = None
+    L.cfb_pool_submit_forward.argtypes = [vp, C.c_uint32, vp, i, C.POINTER(Quant), vp]
+    L.cfb_pool_submit_inverse.argtypes = [vp, C.c_uint32, vp, C.POINTER(Quant), i, vp, i]
+    L.cfb_pool_wait.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(i)]
+    L.cfb_pool_test.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(i)]
+    L.cfb_pool_stats.argtypes = [vp, C.POINTER(Stats)]
     _lib = L
     return L
 
@@ -255,3 +266,81 @@ class Codec:
         for (c, lvl, name), arr in bands.items():
             self.band_view(buf, c, lvl - 1, BAND_NAMES.index(name))[:] = arr
         return buf
+
+
+def pinned_empty(shape, dtype=np.uint8):
+    """numpy array backed by page-locked host memory from cfb_host_alloc (freed when the array dies)."""
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = C.c_void_p()
+    _check(lib().cfb_host_alloc(nbytes, C.byref(ptr)))
+    buf = (C.c_ubyte * nbytes).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    class _Owner:
+        def __init__(self, p):
+            self.p = p
+
+        def __del__(self):
+            try:
+                lib().cfb_host_free(self.p)
+            except Exception:
+                pass
+
+    _PINNED[id(buf)] = (_Owner(ptr), buf)
+    return arr
+
+
+_PINNED = {}
+
+
+class Pool:
+    """Asynchronous, in-order, multi-GPU frame pool (cfb_pool_*)."""
+
+    def __init__(self, devices, desc, slots=3, batch=4, queue_length=24):
+        self.h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        _check(lib().cfb_pool_create(devs, len(devices), C.byref(desc), slots, batch, queue_length, C.byref(self.h)))
+        self.layout = layout_for(desc)
+
+    def close(self):
+        if self.h:
+            lib().cfb_pool_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def submit_forward(self, frame_number, frame, quant, coded):
+        _check(lib().cfb_pool_submit_forward(self.h, frame_number, frame.ctypes.data, frame.strides[0], C.byref(quant),
+                                             coded.ctypes.data))
+
+    def submit_inverse(self, frame_number, coded, quant, out_format, frame):
+        _check(lib().cfb_pool_submit_inverse(self.h, frame_number, coded.ctypes.data, C.byref(quant), out_format,
+                                             frame.ctypes.data, frame.strides[0]))
+
+    def wait(self):
+        n, e = C.c_uint32(), C.c_int()
+        _check(lib().cfb_pool_wait(self.h, C.byref(n), C.byref(e)))
+        if e.value != OK:
+            raise CfbError(e.value, f"job {n.value} failed")
+        return n.value
+
+    def test(self):
+        """Returns the frame number of the oldest job if it has finished, else None."""
+        n, e = C.c_uint32(), C.c_int()
+        code = lib().cfb_pool_test(self.h, C.byref(n), C.byref(e))
+        if code == 13:
+            return None
+        _check(code)
+        if e.value != OK:
+            raise CfbError(e.value, f"job {n.value} failed")
+        return n.value
+
+    def stats(self):
+        s = Stats()
+        _check(lib().cfb_pool_stats(self.h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in Stats._fields_}

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <cstring>
 #include <string>
 
 #include "../../include/cfhd_b200.h"

@@ -167,7 +167,8 @@ CFB_API cfb_error cfb_inverse_device(cfb_codec *codec, int n, void *const *d_pyr
 CFB_API cfb_error cfb_inverse_host(cfb_codec *codec, int n, const void *const *h_coded, const cfb_quant *quant,
                                    int out_format, void *const *h_frames, int frame_pitch);
 
-/* ---- statistics ------------------------------------------------------------ */
+
+/* ---- statistics record -------------------------------------------------------- */
 typedef struct cfb_stats {
     uint64_t kernel_launches;   /* kernels launched by this library on this context */
     uint64_t frames_forward;
@@ -175,6 +176,39 @@ typedef struct cfb_stats {
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
 } cfb_stats;
+
+/* ---- pinned host memory ------------------------------------------------------ */
+/* Page-locked host buffers (cudaHostAlloc, portable) so that the pool's copies run asynchronously at
+ * full PCIe rate.  Pageable buffers are accepted everywhere but serialise the copies. */
+CFB_API cfb_error cfb_host_alloc(size_t bytes, void **out);
+CFB_API void cfb_host_free(void *p);
+
+/* ---- asynchronous, in-order, multi-GPU frame pool ---------------------------- */
+/* GPU re-hosting of the reference's CEncoderPool (EncoderSDK/EncoderPool.cpp:239, EncoderQueue.h:311-352):
+ *   - jobs are independent frames; job i goes to device devices[i % ndevices] (EncoderPool.cpp:284 round-robin);
+ *   - every device runs `slots` worker slots (own stream + staging), each taking up to `batch` queued jobs per
+ *     launch, so H2D copies, kernels and D2H copies of different slots overlap;
+ *   - submit blocks while `queue_length` jobs are outstanding (AddEncoderJob, EncoderQueue.h:311);
+ *   - results are delivered strictly in submission order (WaitForFinishedJob pops front(), EncoderQueue.h:331);
+ *   - host buffers are BORROWED until the job is returned by cfb_pool_wait/cfb_pool_test (EncoderQueue.h:159).
+ * A failed job is returned in order with its error; the pool keeps running. */
+CFB_API cfb_error cfb_pool_create(const int *devices, int ndevices, const cfb_frame_desc *desc,
+                                  int slots, int batch, int queue_length, cfb_pool **out);
+CFB_API void cfb_pool_destroy(cfb_pool *pool);
+/* forward: h_frame (frame_pitch bytes per row) -> h_coded (cfb_layout.coded_bytes) */
+CFB_API cfb_error cfb_pool_submit_forward(cfb_pool *pool, uint32_t frame_number, const void *h_frame, int frame_pitch,
+                                          const cfb_quant *quant, void *h_coded);
+/* inverse: h_coded -> h_frame in out_format */
+CFB_API cfb_error cfb_pool_submit_inverse(cfb_pool *pool, uint32_t frame_number, const void *h_coded,
+                                          const cfb_quant *quant, int out_format, void *h_frame, int frame_pitch);
+/* oldest job: wait blocks until it has finished; test returns CFB_ERROR_NOT_FINISHED if it has not
+ * (CFHD_ERROR_NOT_FINISHED = 13, EncoderPool.cpp:360).  *job_error receives the job's own result. */
+CFB_API cfb_error cfb_pool_wait(cfb_pool *pool, uint32_t *frame_number, cfb_error *job_error);
+CFB_API cfb_error cfb_pool_test(cfb_pool *pool, uint32_t *frame_number, cfb_error *job_error);
+CFB_API cfb_error cfb_pool_stats(cfb_pool *pool, cfb_stats *out);     /* summed over all devices */
+
+/* ---- statistics ------------------------------------------------------------ */
+
 CFB_API cfb_error cfb_context_stats(cfb_context *ctx, cfb_stats *out);
 
 #ifdef __cplusplus
