@@ -100,6 +100,16 @@ def lib():
     L.cfb_forward_host.argtypes = [vp, i, C.POINTER(vp), i, C.POINTER(Quant), C.POINTER(vp)]
     L.cfb_inverse_device.argtypes = [vp, i, C.POINTER(vp), C.POINTER(Quant), i, C.POINTER(vp), i]
     L.cfb_inverse_host.argtypes = [vp, i, C.POINTER(vp), C.POINTER(Quant), i, C.POINTER(vp), i]
+    L.cfb_sparse_max_bytes.argtypes = [C.POINTER(Layout)]
+    L.cfb_sparse_max_bytes.restype = C.c_size_t
+    L.cfb_sparse_bytes.argtypes = [vp]
+    L.cfb_sparse_bytes.restype = C.c_size_t
+    L.cfb_forward_host_sparse.argtypes = [vp, i, C.POINTER(vp), i, C.POINTER(Quant), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.cfb_inverse_host_sparse.argtypes = [vp, i, C.POINTER(vp), C.POINTER(Quant), i, C.POINTER(vp), i]
+    L.cfb_sparse_expand.argtypes = [C.POINTER(Layout), vp, vp]
+    L.cfb_sparse_compact.argtypes = [C.POINTER(Layout), vp, vp, C.POINTER(C.c_size_t)]
+    L.cfb_pool_submit_forward_sparse.argtypes = [vp, C.c_uint32, vp, i, C.POINTER(Quant), vp]
+    L.cfb_pool_submit_inverse_sparse.argtypes = [vp, C.c_uint32, vp, C.POINTER(Quant), i, vp, i]
     L.cfb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.cfb_host_free.argtypes = [vp]
     L.cfb_host_free.restype = None
@@ -134,6 +144,28 @@ def quant_for_quality(desc, quality):
     out = Quant()
     _check(lib().cfb_quant_for_quality(C.byref(desc), quality, C.byref(out)))
     return out
+
+
+def sparse_max_bytes(layout):
+    return int(lib().cfb_sparse_max_bytes(C.byref(layout)))
+
+
+def sparse_bytes(buf):
+    return int(lib().cfb_sparse_bytes(buf.ctypes.data))
+
+
+def sparse_expand(layout, sparse):
+    """Host-side format conversion: sparse buffer -> dense coded region (uint8 array)."""
+    out = np.empty(layout.coded_bytes, np.uint8)
+    _check(lib().cfb_sparse_expand(C.byref(layout), sparse.ctypes.data, out.ctypes.data))
+    return out
+
+
+def sparse_compact(layout, dense):
+    out = np.zeros(sparse_max_bytes(layout), np.uint8)
+    n = C.c_size_t()
+    _check(lib().cfb_sparse_compact(C.byref(layout), dense.ctypes.data, out.ctypes.data, C.byref(n)))
+    return out[:n.value]
 
 
 def make_quant(divisors, prescale, midpoint_prequant=2):
@@ -230,6 +262,23 @@ class Codec:
                                       _ptr_array([o.ctypes.data for o in out])))
         return out
 
+    def forward_host_sparse(self, frames, quant, out=None):
+        n = len(frames)
+        frames = [np.ascontiguousarray(f) for f in frames]
+        if out is None:
+            out = [np.zeros(sparse_max_bytes(self.layout), np.uint8) for _ in range(n)]
+        sizes = (C.c_size_t * n)()
+        _check(lib().cfb_forward_host_sparse(self.h, n, _ptr_array([f.ctypes.data for f in frames]), frames[0].strides[0],
+                                             C.byref(quant), _ptr_array([o.ctypes.data for o in out]), sizes))
+        return out, [int(s) for s in sizes]
+
+    def inverse_host_sparse(self, sparse, quant, out_format, out_frames):
+        n = len(sparse)
+        _check(lib().cfb_inverse_host_sparse(self.h, n, _ptr_array([s.ctypes.data for s in sparse]), C.byref(quant),
+                                             out_format, _ptr_array([o.ctypes.data for o in out_frames]),
+                                             out_frames[0].strides[0]))
+        return out_frames
+
     # -- inverse -----------------------------------------------------------
     def inverse_device(self, d_pyramids, quant, out_format, d_frames, frame_pitch):
         n = len(d_pyramids)
@@ -321,6 +370,14 @@ class Pool:
     def submit_inverse(self, frame_number, coded, quant, out_format, frame):
         _check(lib().cfb_pool_submit_inverse(self.h, frame_number, coded.ctypes.data, C.byref(quant), out_format,
                                              frame.ctypes.data, frame.strides[0]))
+
+    def submit_forward_sparse(self, frame_number, frame, quant, sparse):
+        _check(lib().cfb_pool_submit_forward_sparse(self.h, frame_number, frame.ctypes.data, frame.strides[0],
+                                                    C.byref(quant), sparse.ctypes.data))
+
+    def submit_inverse_sparse(self, frame_number, sparse, quant, out_format, frame):
+        _check(lib().cfb_pool_submit_inverse_sparse(self.h, frame_number, sparse.ctypes.data, C.byref(quant), out_format,
+                                                    frame.ctypes.data, frame.strides[0]))
 
     def wait(self):
         n, e = C.c_uint32(), C.c_int()

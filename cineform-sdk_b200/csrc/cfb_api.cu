@@ -328,6 +328,9 @@ void cfb_codec_destroy(cfb_codec *cd)
     if (cd->ctx) cudaSetDevice(cd->ctx->device);
     if (cd->d_frames) cudaFree(cd->d_frames);
     if (cd->d_pyramids) cudaFree(cd->d_pyramids);
+    if (cd->d_sparse) cudaFree(cd->d_sparse);
+    if (cd->d_counts) cudaFree(cd->d_counts);
+    if (cd->h_headers) cudaFreeHost(cd->h_headers);
     delete cd;
 }
 

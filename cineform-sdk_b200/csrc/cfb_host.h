@@ -46,4 +46,9 @@ struct cfb_codec {
     size_t frame_stride = 0;                // bytes between device frame slots
     size_t pyramid_stride = 0;
     int fwd_mask = 7, inv_mask = 7;         // profiling aid: levels to run
+    // sparse transfer format staging (allocated on first use)
+    unsigned char *d_sparse = nullptr;      // max_batch sparse buffers
+    unsigned *d_counts = nullptr;           // max_batch * (nseg + 1)
+    unsigned *h_headers = nullptr;          // pinned, 4 u32 per slot
+    size_t sparse_stride = 0;
 };

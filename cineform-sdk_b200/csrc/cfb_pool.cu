@@ -21,6 +21,7 @@ namespace {
 struct Job {
     uint32_t frame_number = 0;
     bool inverse = false;
+    bool sparse = false;
     const void *src = nullptr;
     void *dst = nullptr;
     int pitch = 0;
@@ -69,7 +70,7 @@ void cfb_pool::worker(int slot_index, int device_index)
                 // take up to `batch` untaken jobs of this device, all of the same direction and quant table
                 for (auto &j : queue) {
                     if (j->taken || j->device_index != device_index) continue;
-                    if (!mine.empty() && (j->inverse != mine[0]->inverse || j->out_format != mine[0]->out_format ||
+                    if (!mine.empty() && (j->inverse != mine[0]->inverse || j->sparse != mine[0]->sparse || j->out_format != mine[0]->out_format ||
                                           j->pitch != mine[0]->pitch ||
                                           memcmp(&j->quant, &mine[0]->quant, sizeof(cfb_quant)) != 0))
                         break;
@@ -88,9 +89,11 @@ void cfb_pool::worker(int slot_index, int device_index)
         for (int i = 0; i < n; i++) { src[i] = mine[i]->src; dst[i] = mine[i]->dst; }
         cfb_error e;
         if (!mine[0]->inverse)
-            e = cfb_forward_host(s.codec, n, src, mine[0]->pitch, &mine[0]->quant, dst);
+            e = mine[0]->sparse ? cfb_forward_host_sparse(s.codec, n, src, mine[0]->pitch, &mine[0]->quant, dst, nullptr)
+                                : cfb_forward_host(s.codec, n, src, mine[0]->pitch, &mine[0]->quant, dst);
         else
-            e = cfb_inverse_host(s.codec, n, src, &mine[0]->quant, mine[0]->out_format, dst, mine[0]->pitch);
+            e = mine[0]->sparse ? cfb_inverse_host_sparse(s.codec, n, src, &mine[0]->quant, mine[0]->out_format, dst, mine[0]->pitch)
+                                : cfb_inverse_host(s.codec, n, src, &mine[0]->quant, mine[0]->out_format, dst, mine[0]->pitch);
         {
             std::lock_guard<std::mutex> lk(mu);
             for (auto &j : mine) { j->error = e; j->done = true; }
@@ -188,6 +191,25 @@ cfb_error cfb_pool_submit_inverse(cfb_pool *pool, uint32_t frame_number, const v
     if (!pool || !h_frame || !quant || !h_coded) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
     auto j = std::make_shared<Job>();
     j->frame_number = frame_number; j->inverse = true; j->src = h_coded; j->dst = h_frame; j->pitch = frame_pitch;
+    j->out_format = out_format; j->quant = *quant;
+    return pool_submit(pool, std::move(j));
+}
+
+cfb_error cfb_pool_submit_forward_sparse(cfb_pool *pool, uint32_t frame_number, const void *h_frame, int frame_pitch,
+                                         const cfb_quant *quant, void *h_sparse)
+{
+    if (!pool || !h_frame || !quant || !h_sparse) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    auto j = std::make_shared<Job>();
+    j->frame_number = frame_number; j->inverse = false; j->sparse = true; j->src = h_frame; j->dst = h_sparse; j->pitch = frame_pitch; j->quant = *quant;
+    return pool_submit(pool, std::move(j));
+}
+
+cfb_error cfb_pool_submit_inverse_sparse(cfb_pool *pool, uint32_t frame_number, const void *h_sparse,
+                                         const cfb_quant *quant, int out_format, void *h_frame, int frame_pitch)
+{
+    if (!pool || !h_frame || !quant || !h_sparse) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    auto j = std::make_shared<Job>();
+    j->frame_number = frame_number; j->inverse = true; j->sparse = true; j->src = h_sparse; j->dst = h_frame; j->pitch = frame_pitch;
     j->out_format = out_format; j->quant = *quant;
     return pool_submit(pool, std::move(j));
 }

@@ -1,0 +1,347 @@
+// cfb_sparse.cu -- lossless sparse transfer format for the coded region.
+//
+// After quantisation ~90 % of the highpass coefficients are zero, and the dense int16 bands (33 MB per
+// 4K 4:2:2 frame) are what limits the host<->device path (PCIe), not the kernels.  The host entropy coder
+// only ever needs (zero run, value) sequences (Codec/encoder.c:5386-5847 EncodeQuantLongRuns walks the band
+// counting zeros, incl. the pitch gap :5811), so the natural wire format is
+//
+//     header  : u32 magic 'CFSP', u32 nwords, u32 nvalues, u32 reserved
+//     bitmap  : nwords bits, bit i set <=> int16 word i of the coded region is non-zero (LSB-first in u32s)
+//     values  : the nvalues non-zero int16 words in raster (word index) order
+//
+// over the flat coded region [0, coded_bytes) exactly as laid out by cfb_layout (pitch padding included, it is
+// zero).  Compaction and expansion run on the GPU (three small kernels each: per-256-word segment count,
+// per-frame exclusive scan, scatter / gather); the host helpers cfb_sparse_expand / cfb_sparse_compact are
+// pure format conversions for callers that want dense bands.
+#include "cfb_host.h"
+
+namespace cfb {
+
+constexpr int kSeg = 256;           // words per segment (one warp, 8 words per lane)
+
+struct SparseParams {
+    int nframes;
+    unsigned nwords;                // int16 words in the coded region
+    unsigned nseg;
+    unsigned bitmap_off, values_off;            // byte offsets inside a sparse buffer
+    const unsigned char *dense[kMaxBatch];      // pyramids (coded region at offset 0)
+    unsigned char *sparse[kMaxBatch];
+    unsigned *counts[kMaxBatch];                // nseg + 1 entries: counts, then exclusive offsets after the scan
+};
+
+__device__ __forceinline__ unsigned nonzero_mask8(const uint4 &w) {
+    unsigned m = 0;
+    m |= (w.x & 0xffffu) ? 1u : 0u;   m |= (w.x >> 16) ? 2u : 0u;
+    m |= (w.y & 0xffffu) ? 4u : 0u;   m |= (w.y >> 16) ? 8u : 0u;
+    m |= (w.z & 0xffffu) ? 16u : 0u;  m |= (w.z >> 16) ? 32u : 0u;
+    m |= (w.w & 0xffffu) ? 64u : 0u;  m |= (w.w >> 16) ? 128u : 0u;
+    return m;
+}
+
+// A: per segment, bitmap + count
+__global__ void __launch_bounds__(256) k_sparse_count(const __grid_constant__ SparseParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int f = blockIdx.y;
+    if (seg >= p.nseg) return;
+    const unsigned w0 = seg * kSeg + lane * 8;
+    uint4 w = make_uint4(0, 0, 0, 0);
+    if (w0 < p.nwords) w = __ldg(reinterpret_cast<const uint4 *>(p.dense[f] + (size_t)w0 * 2));
+    const unsigned m8 = nonzero_mask8(w);
+    unsigned m = m8 << ((lane & 3) * 8);
+    m |= __shfl_xor_sync(0xffffffffu, m, 1);
+    m |= __shfl_xor_sync(0xffffffffu, m, 2);
+    if ((lane & 3) == 0 && w0 < p.nwords)
+        reinterpret_cast<unsigned *>(p.sparse[f] + p.bitmap_off)[seg * 8 + (lane >> 2)] = m;
+    unsigned c = __popc(m8);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) p.counts[f][seg] = c;
+}
+
+// A': counts from an uploaded bitmap
+__global__ void __launch_bounds__(256) k_sparse_count_bitmap(const __grid_constant__ SparseParams p)
+{
+    const unsigned seg = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (seg >= p.nseg) return;
+    const uint4 *b = reinterpret_cast<const uint4 *>(p.sparse[f] + p.bitmap_off) + seg * 2;
+    const uint4 a = __ldg(b), c = __ldg(b + 1);
+    p.counts[f][seg] = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(c.x) + __popc(c.y) + __popc(c.z) + __popc(c.w);
+}
+
+// B: per-frame exclusive scan of the segment counts (one CTA per frame); writes the total into the header
+__global__ void __launch_bounds__(1024) k_sparse_scan(const __grid_constant__ SparseParams p, int write_header)
+{
+    __shared__ unsigned wsum[32];
+    __shared__ unsigned chunk_total;
+    const int f = blockIdx.x;
+    unsigned *cnt = p.counts[f];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned carry = 0;
+    for (unsigned base = 0; base < p.nseg; base += 1024 * 4) {
+        unsigned v[4], s = 0;
+        const unsigned i0 = base + tid * 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { v[k] = (i0 + k < p.nseg) ? cnt[i0 + k] : 0u; s += v[k]; }
+        unsigned incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned x = wsum[lane];
+            unsigned xi = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
+            wsum[lane] = xi - x;
+            if (lane == 31) chunk_total = xi;
+        }
+        __syncthreads();
+        unsigned excl = carry + wsum[wid] + (incl - s);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { if (i0 + k < p.nseg) cnt[i0 + k] = excl; excl += v[k]; }
+        carry += chunk_total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        cnt[p.nseg] = carry;
+        if (write_header) {
+            unsigned *h = reinterpret_cast<unsigned *>(p.sparse[f]);
+            h[0] = 0x50534643u; h[1] = p.nwords; h[2] = carry; h[3] = 0;
+        }
+    }
+}
+
+// C: scatter the non-zero words in raster order
+__global__ void __launch_bounds__(256) k_sparse_scatter(const __grid_constant__ SparseParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int f = blockIdx.y;
+    if (seg >= p.nseg) return;
+    const unsigned w0 = seg * kSeg + lane * 8;
+    uint4 w = make_uint4(0, 0, 0, 0);
+    if (w0 < p.nwords) w = __ldg(reinterpret_cast<const uint4 *>(p.dense[f] + (size_t)w0 * 2));
+    const unsigned m8 = nonzero_mask8(w);
+    const unsigned c = __popc(m8);
+    unsigned incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    unsigned pos = p.counts[f][seg] + incl - c;
+    unsigned short *vals = reinterpret_cast<unsigned short *>(p.sparse[f] + p.values_off);
+    const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const unsigned short x = (unsigned short)((k & 1) ? (ws[k >> 1] >> 16) : (ws[k >> 1] & 0xffffu));
+        if (x) vals[pos++] = x;
+    }
+}
+
+// C': gather back into the dense coded region
+__global__ void __launch_bounds__(256) k_sparse_gather(const __grid_constant__ SparseParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int f = blockIdx.y;
+    if (seg >= p.nseg) return;
+    const unsigned w0 = seg * kSeg + lane * 8;
+    if (w0 >= p.nwords) return;         // nwords is a multiple of 8 (bands are 64-byte aligned)
+    const unsigned bw = __ldg(reinterpret_cast<const unsigned *>(p.sparse[f] + p.bitmap_off) + seg * 8 + (lane >> 2));
+    const unsigned m8 = (bw >> ((lane & 3) * 8)) & 0xffu;
+    const unsigned c = __popc(m8);
+    unsigned incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    unsigned pos = p.counts[f][seg] + incl - c;
+    const unsigned short *vals = reinterpret_cast<const unsigned short *>(p.sparse[f] + p.values_off);
+    unsigned out[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (m8 & (1u << k)) {
+            const unsigned x = vals[pos++];
+            out[k >> 1] |= (k & 1) ? (x << 16) : x;
+        }
+    }
+    *reinterpret_cast<uint4 *>(const_cast<unsigned char *>(p.dense[f]) + (size_t)w0 * 2) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+cudaError_t launch_sparse_compact(const SparseParams &p, cudaStream_t stream)
+{
+    dim3 grid((p.nseg + 7) / 8, p.nframes);
+    k_sparse_count<<<grid, 256, 0, stream>>>(p);
+    k_sparse_scan<<<p.nframes, 1024, 0, stream>>>(p, 1);
+    k_sparse_scatter<<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sparse_expand(const SparseParams &p, cudaStream_t stream)
+{
+    dim3 g1((p.nseg + 255) / 256, p.nframes), grid((p.nseg + 7) / 8, p.nframes);
+    k_sparse_count_bitmap<<<g1, 256, 0, stream>>>(p);
+    k_sparse_scan<<<p.nframes, 1024, 0, stream>>>(p, 0);
+    k_sparse_gather<<<grid, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace cfb
+
+// ---------------------------------------------------------------------------
+// C ABI
+using namespace cfb;
+
+static inline unsigned sp_bitmap_off() { return 16u; }
+static inline unsigned sp_values_off(unsigned nwords) { return (16u + nwords / 8u + 15u) & ~15u; }
+
+static cfb_error sparse_prepare(cfb_codec *cd, SparseParams &p, int n)
+{
+    const cfb_layout &L = cd->layout;
+    p.nframes = n;
+    p.nwords = (unsigned)(L.coded_bytes / 2);
+    p.nseg = (p.nwords + kSeg - 1) / kSeg;
+    p.bitmap_off = sp_bitmap_off();
+    p.values_off = sp_values_off(p.nwords);
+    if (!cd->d_sparse) {
+        cd->sparse_stride = (cfb_sparse_max_bytes(&L) + 255) & ~(size_t)255;
+        CFB_CUDA(cudaMalloc((void **)&cd->d_sparse, cd->sparse_stride * cd->max_batch));
+        CFB_CUDA(cudaMalloc((void **)&cd->d_counts, sizeof(unsigned) * (size_t)(p.nseg + 1) * cd->max_batch));
+        CFB_CUDA(cudaHostAlloc((void **)&cd->h_headers, 16 * (size_t)cd->max_batch, cudaHostAllocPortable));
+    }
+    for (int i = 0; i < n; i++) {
+        p.dense[i] = cd->d_pyramids + cd->pyramid_stride * i;
+        p.sparse[i] = cd->d_sparse + cd->sparse_stride * i;
+        p.counts[i] = cd->d_counts + (size_t)(p.nseg + 1) * i;
+    }
+    return CFB_OK;
+}
+
+extern "C" {
+
+size_t cfb_sparse_max_bytes(const cfb_layout *L)
+{
+    if (!L) return 0;
+    const unsigned nwords = (unsigned)(L->coded_bytes / 2);
+    return (size_t)sp_values_off(nwords) + (size_t)nwords * 2;
+}
+
+size_t cfb_sparse_bytes(const void *sparse)
+{
+    if (!sparse) return 0;
+    const unsigned *h = (const unsigned *)sparse;
+    if (h[0] != 0x50534643u) return 0;
+    return (size_t)sp_values_off(h[1]) + (size_t)h[2] * 2;
+}
+
+cfb_error cfb_forward_host_sparse(cfb_codec *cd, int n, const void *const *h_frames, int frame_pitch,
+                                  const cfb_quant *quant, void *const *h_sparse, size_t *sparse_bytes)
+{
+    if (!cd || !h_frames || !quant || !h_sparse) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (n < 1 || n > cd->max_batch) { set_error("batch %d exceeds codec max_batch %d", n, cd->max_batch); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_context *ctx = cd->ctx;
+    const cfb_layout &L = cd->layout;
+    CFB_CUDA(cudaSetDevice(ctx->device));
+    SparseParams sp;
+    cfb_error err = sparse_prepare(cd, sp, n);
+    if (err) return err;
+    const int rows = (int)(L.frame_bytes / L.frame_pitch);
+    const void *dfr[kMaxBatch];
+    void *dpy[kMaxBatch];
+    for (int i = 0; i < n; i++) {
+        if (!h_frames[i] || !h_sparse[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
+        dfr[i] = cfb_codec_device_frame(cd, i);
+        dpy[i] = cfb_codec_device_pyramid(cd, i);
+        CFB_CUDA(cudaMemcpy2DAsync((void *)dfr[i], L.frame_pitch, h_frames[i], frame_pitch, L.frame_pitch, rows,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_bytes += (uint64_t)L.frame_bytes;
+    }
+    err = cfb_forward_device(cd, n, dfr, L.frame_pitch, quant, dpy);
+    if (err) return err;
+    CFB_CUDA(launch_sparse_compact(sp, ctx->stream));
+    ctx->kernel_launches += 3;
+    for (int i = 0; i < n; i++)
+        CFB_CUDA(cudaMemcpyAsync(cd->h_headers + 4 * i, sp.sparse[i], 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; i++) {
+        const size_t bytes = (size_t)sp.values_off + (size_t)cd->h_headers[4 * i + 2] * 2;
+        CFB_CUDA(cudaMemcpyAsync(h_sparse[i], sp.sparse[i], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h_bytes += (uint64_t)bytes;
+        if (sparse_bytes) sparse_bytes[i] = bytes;
+    }
+    CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CFB_OK;
+}
+
+cfb_error cfb_inverse_host_sparse(cfb_codec *cd, int n, const void *const *h_sparse, const cfb_quant *quant,
+                                  int out_format, void *const *h_frames, int frame_pitch)
+{
+    if (!cd || !h_sparse || !quant || !h_frames) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (n < 1 || n > cd->max_batch) { set_error("batch %d exceeds codec max_batch %d", n, cd->max_batch); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (out_format != CFB_PIXEL_YUYV && out_format != CFB_PIXEL_UYVY) { set_error("sparse inverse supports packed 4:2:2 output"); return CFB_ERROR_UNSUPPORTED; }
+    cfb_context *ctx = cd->ctx;
+    CFB_CUDA(cudaSetDevice(ctx->device));
+    SparseParams sp;
+    cfb_error err = sparse_prepare(cd, sp, n);
+    if (err) return err;
+    void *dpy[kMaxBatch], *dfr[kMaxBatch];
+    for (int i = 0; i < n; i++) {
+        if (!h_sparse[i] || !h_frames[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
+        const unsigned *h = (const unsigned *)h_sparse[i];
+        if (h[0] != 0x50534643u || h[1] != sp.nwords || h[2] > sp.nwords) { set_error("sparse buffer %d: bad header", i); return CFB_ERROR_BADFORMAT; }
+        const size_t bytes = (size_t)sp.values_off + (size_t)h[2] * 2;
+        dpy[i] = cfb_codec_device_pyramid(cd, i);
+        dfr[i] = cfb_codec_device_frame(cd, i);
+        CFB_CUDA(cudaMemcpyAsync(sp.sparse[i], h_sparse[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_bytes += (uint64_t)bytes;
+    }
+    CFB_CUDA(launch_sparse_expand(sp, ctx->stream));
+    ctx->kernel_launches += 3;
+    const int dpitch = cd->desc.width * 2;
+    err = cfb_inverse_device(cd, n, dpy, quant, out_format, dfr, dpitch);
+    if (err) return err;
+    for (int i = 0; i < n; i++) {
+        CFB_CUDA(cudaMemcpy2DAsync(h_frames[i], frame_pitch, dfr[i], dpitch, dpitch, cd->desc.height, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h_bytes += (uint64_t)dpitch * cd->desc.height;
+    }
+    CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CFB_OK;
+}
+
+cfb_error cfb_sparse_expand(const cfb_layout *L, const void *sparse, void *dense_coded)
+{
+    if (!L || !sparse || !dense_coded) return CFB_ERROR_INVALID_ARGUMENT;
+    const unsigned *h = (const unsigned *)sparse;
+    const unsigned nwords = (unsigned)(L->coded_bytes / 2);
+    if (h[0] != 0x50534643u || h[1] != nwords) { set_error("bad sparse header"); return CFB_ERROR_BADFORMAT; }
+    const unsigned *bm = (const unsigned *)((const unsigned char *)sparse + sp_bitmap_off());
+    const int16_t *vals = (const int16_t *)((const unsigned char *)sparse + sp_values_off(nwords));
+    int16_t *out = (int16_t *)dense_coded;
+    size_t pos = 0;
+    for (unsigned w = 0; w < nwords; w += 32) {
+        unsigned m = bm[w >> 5];
+        for (int k = 0; k < 32 && w + k < nwords; k++) out[w + k] = (m >> k) & 1u ? vals[pos++] : (int16_t)0;
+    }
+    if (pos != h[2]) { set_error("sparse value count mismatch"); return CFB_ERROR_BADFORMAT; }
+    return CFB_OK;
+}
+
+cfb_error cfb_sparse_compact(const cfb_layout *L, const void *dense_coded, void *sparse, size_t *bytes)
+{
+    if (!L || !sparse || !dense_coded) return CFB_ERROR_INVALID_ARGUMENT;
+    const unsigned nwords = (unsigned)(L->coded_bytes / 2);
+    unsigned *h = (unsigned *)sparse;
+    unsigned *bm = (unsigned *)((unsigned char *)sparse + sp_bitmap_off());
+    int16_t *vals = (int16_t *)((unsigned char *)sparse + sp_values_off(nwords));
+    const int16_t *in = (const int16_t *)dense_coded;
+    size_t pos = 0;
+    for (unsigned w = 0; w < nwords; w += 32) {
+        unsigned m = 0;
+        for (int k = 0; k < 32 && w + k < nwords; k++) if (in[w + k]) { m |= 1u << k; vals[pos++] = in[w + k]; }
+        bm[w >> 5] = m;
+    }
+    h[0] = 0x50534643u; h[1] = nwords; h[2] = (unsigned)pos; h[3] = 0;
+    if (bytes) *bytes = (size_t)sp_values_off(nwords) + pos * 2;
+    return CFB_OK;
+}
+
+}  // extern "C"

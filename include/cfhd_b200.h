@@ -168,6 +168,24 @@ CFB_API cfb_error cfb_inverse_host(cfb_codec *codec, int n, const void *const *h
                                    int out_format, void *const *h_frames, int frame_pitch);
 
 
+
+/* ---- sparse transfer format of the coded region (lossless) ---- */
+/* Layout of a sparse buffer:  16-byte header {u32 'CFSP', u32 nwords, u32 nvalues, u32 0};
+ * bitmap (nwords bits, bit i <=> int16 word i of the coded region [0, coded_bytes) is non-zero);
+ * 16-byte aligned array of the nvalues non-zero int16 words in raster order.  Zero runs (incl. the pitch gap
+ * the reference's run-length coder walks, encoder.c:5811) are implicit in the bitmap. */
+CFB_API size_t cfb_sparse_max_bytes(const cfb_layout *layout);          /* worst case (no zero at all) */
+CFB_API size_t cfb_sparse_bytes(const void *sparse);                    /* actual size, from the header */
+/* forward + GPU compaction; sparse_bytes[i] receives the size written to h_sparse[i] */
+CFB_API cfb_error cfb_forward_host_sparse(cfb_codec *codec, int n, const void *const *h_frames, int frame_pitch,
+                                          const cfb_quant *quant, void *const *h_sparse, size_t *sparse_bytes);
+/* GPU expansion + inverse */
+CFB_API cfb_error cfb_inverse_host_sparse(cfb_codec *codec, int n, const void *const *h_sparse, const cfb_quant *quant,
+                                          int out_format, void *const *h_frames, int frame_pitch);
+/* host-side format conversion (no transform arithmetic): sparse <-> dense coded region */
+CFB_API cfb_error cfb_sparse_expand(const cfb_layout *layout, const void *sparse, void *dense_coded);
+CFB_API cfb_error cfb_sparse_compact(const cfb_layout *layout, const void *dense_coded, void *sparse, size_t *bytes);
+
 /* ---- statistics record -------------------------------------------------------- */
 typedef struct cfb_stats {
     uint64_t kernel_launches;   /* kernels launched by this library on this context */
@@ -201,6 +219,11 @@ CFB_API cfb_error cfb_pool_submit_forward(cfb_pool *pool, uint32_t frame_number,
 /* inverse: h_coded -> h_frame in out_format */
 CFB_API cfb_error cfb_pool_submit_inverse(cfb_pool *pool, uint32_t frame_number, const void *h_coded,
                                           const cfb_quant *quant, int out_format, void *h_frame, int frame_pitch);
+/* same, with the coded region in the sparse transfer format (h_sparse: cfb_sparse_max_bytes) */
+CFB_API cfb_error cfb_pool_submit_forward_sparse(cfb_pool *pool, uint32_t frame_number, const void *h_frame, int frame_pitch,
+                                                 const cfb_quant *quant, void *h_sparse);
+CFB_API cfb_error cfb_pool_submit_inverse_sparse(cfb_pool *pool, uint32_t frame_number, const void *h_sparse,
+                                                 const cfb_quant *quant, int out_format, void *h_frame, int frame_pitch);
 /* oldest job: wait blocks until it has finished; test returns CFB_ERROR_NOT_FINISHED if it has not
  * (CFHD_ERROR_NOT_FINISHED = 13, EncoderPool.cpp:360).  *job_error receives the job's own result. */
 CFB_API cfb_error cfb_pool_wait(cfb_pool *pool, uint32_t *frame_number, cfb_error *job_error);

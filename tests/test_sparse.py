@@ -1,0 +1,60 @@
+"""Sparse transfer format of the coded region: host conversion utilities (CPU) and GPU compaction/expansion."""
+import importlib
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return importlib.import_module("cineform-sdk_b200")
+
+
+@pytest.mark.parametrize("density", [0.0, 0.02, 0.3, 1.0])
+def test_host_compact_expand_roundtrip(pkg, density):
+    lay = pkg.layout_for(pkg.FrameDesc(704, 96, pkg.PIXEL_YUYV))
+    rng = np.random.default_rng(int(density * 100))
+    words = lay.coded_bytes // 2
+    dense = np.zeros(words, np.int16)
+    nz = rng.random(words) < density
+    dense[nz] = rng.integers(-3000, 3000, int(nz.sum())).astype(np.int16)
+    dense[nz & (dense == 0)] = 7
+    dense_u8 = dense.view(np.uint8)
+    sp = pkg.sparse_compact(lay, dense_u8)
+    assert pkg.sparse_bytes(sp) == sp.size
+    hdr = sp[:16].view(np.uint32)
+    assert hdr[0] == 0x50534643 and hdr[1] == words and hdr[2] == int((dense != 0).sum())
+    back = pkg.sparse_expand(lay, sp)
+    assert np.array_equal(back, dense_u8)
+    if density == 0.0:
+        assert sp.size < lay.coded_bytes // 15          # bitmap only
+    bad = sp.copy(); bad[0] ^= 1
+    with pytest.raises(pkg.CfbError):
+        pkg.sparse_expand(lay, bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,kind", [((704, 96), "natural"), ((704, 96), "random"), ((1920, 1080), "natural"), ((256, 64), "constant")])
+def test_gpu_sparse_matches_dense(pkg, size, kind):
+    w, h = size
+    rng = np.random.default_rng(w)
+    frames = [pu.synthetic_yuyv(rng, w, h, kind) for _ in range(3)]
+    desc = pkg.FrameDesc(w, h, pkg.PIXEL_YUYV)
+    quant = pkg.quant_for_quality(desc, 4)
+    with pkg.Context(0) as ctx, pkg.Codec(ctx, desc, 3) as codec:
+        dense = codec.forward_host(frames, quant)
+        sparse, sizes = codec.forward_host_sparse(frames, quant)
+        for d, s, n in zip(dense, sparse, sizes):
+            assert pkg.sparse_bytes(s) == n
+            assert np.array_equal(pkg.sparse_expand(codec.layout, s), d)                 # lossless
+            assert np.array_equal(pkg.sparse_compact(codec.layout, d), s[:n])            # same bytes as the host packer
+        out_d = [np.zeros((h, w * 2), np.uint8) for _ in frames]
+        out_s = [np.zeros((h, w * 2), np.uint8) for _ in frames]
+        codec.inverse_host(dense, quant, pkg.PIXEL_YUYV, out_d)
+        codec.inverse_host_sparse(sparse, quant, pkg.PIXEL_YUYV, out_s)
+        for a, b in zip(out_d, out_s):
+            assert np.array_equal(a, b)
+        if kind == "natural":
+            assert sizes[0] < codec.layout.coded_bytes // 2
