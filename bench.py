@@ -49,6 +49,48 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
+class Dist:
+    """torch.distributed plumbing of the benchmark: barrier + max-over-ranks of the device timing.  The data path
+    never uses it (frames are independent: SURVEY 8e).  backend "nccl" on GPUs, "gloo" in the CPU tests."""
+
+    def __init__(self, world, backend="nccl", local_rank=0):
+        self.world, self.backend, self.local_rank = world, backend, local_rank
+        self.dist = None
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            kw = {"device_id": torch.device("cuda", local_rank)} if backend == "nccl" else {}
+            dist.init_process_group(backend, **kw)
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+
+    def max(self, x):
+        if not self.dist:
+            return float(x)
+        import torch
+        t = torch.tensor([float(x)], device="cuda" if self.backend == "nccl" else "cpu")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def aggregate_fps(world, frames_per_rank, max_seconds):
+    """Whole-job throughput: every rank processed frames_per_rank frames within the slowest rank's time."""
+    return world * frames_per_rank / max_seconds
+
+
+def shard_seed(rank):
+    """Each rank/GPU encodes its own frames (weak scaling): distinct buffers per rank."""
+    return 1000 * rank
+
+
+# ------------------------------------------------------------------------------------------------
 class ClockSampler:
     def __init__(self, index):
         self.index, self.proc, self.path = index, None, None
@@ -119,7 +161,7 @@ def synthetic_frames(n, width, height, seed=0):
         rng = np.random.default_rng(seed)
         bases = [pu.synthetic_yuyv(rng, width, height, "natural")]
         DATA_NOTE = "synthetic (procedural gradients + texture + noise)"
-    return [np.ascontiguousarray(np.roll(bases[i % len(bases)], (16 * (i + seed)) % height, axis=0)) for i in range(n)]
+    return [np.ascontiguousarray(np.roll(bases[i % len(bases)], (16 * i + 6 * seed + 2 * (seed // 1000)) % height, axis=0)) for i in range(n)]
 
 
 def cpu_reference_run(width, height, quality, threads, iters):
@@ -165,11 +207,11 @@ def cpu_reference_run(width, height, quality, threads, iters):
 # ------------------------------------------------------------------------------------------------
 def best_reference_threads(iters):
     """The reference scales poorly past the physical cores (every DECODER owns worker threads and large scratch):
-    probe a few host-thread counts once and keep the fastest, so the baseline is the reference's best."""
+    probe a few host-thread counts and keep the fastest, so the baseline is the reference's best."""
     ncpu = os.cpu_count() or 1
     best = None
     for t in sorted({max(1, ncpu // 8), max(1, ncpu // 4), max(1, ncpu // 2), ncpu}):
-        fps, kind, desc = cpu_reference_run(WIDTH, HEIGHT, QUALITY, t, max(1, iters // 2))
+        fps = max(cpu_reference_run(WIDTH, HEIGHT, QUALITY, t, max(1, iters))[0] for _ in range(2))
         if best is None or fps > best[1]:
             best = (t, fps)
     return best[0]
@@ -208,12 +250,8 @@ def run_ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the transform path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    D = Dist(world, "nccl", local_rank)
+    barrier = D.barrier
 
     B = args.batch
     ctx = pkg.Context(local_rank)
@@ -222,7 +260,7 @@ def run_ours(args, rank, world, local_rank):
     codec = pkg.Codec(ctx, desc, B)
     lay = codec.layout
     stream = torch.cuda.ExternalStream(ctx.stream)
-    frames = synthetic_frames(B, WIDTH, HEIGHT, seed=rank)
+    frames = synthetic_frames(B, WIDTH, HEIGHT, seed=shard_seed(rank))
 
     # ---- device-resident working set: B frames in, B pyramids, B frames out (>> 126 MB L2) ----
     with torch.cuda.stream(stream):
@@ -246,12 +284,7 @@ def run_ours(args, rank, world, local_rank):
             fn()
         e1.record(stream)
         ctx.synchronize(); torch.cuda.synchronize(); barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return D.max(e0.elapsed_time(e1))
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -261,7 +294,7 @@ def run_ours(args, rank, world, local_rank):
     launches = ctx.stats()["kernel_launches"] - launches0 - 6 * args.warmup
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
-    value = world * B * args.steps / (total_ms / 1000.0)
+    value = aggregate_fps(world, B * args.steps, total_ms / 1000.0)
 
     # ---- parity spot check of what was just timed (decoded frame vs input, PSNR) ----
     with torch.cuda.stream(stream):
@@ -288,8 +321,8 @@ def run_ours(args, rank, world, local_rank):
     e2e = None
     if not args.no_e2e:
         nfr = B * args.e2e_steps
-        ring = min(nfr, 48)
-        pool = pkg.Pool([local_rank], desc, slots=args.pool_slots, batch=args.pool_batch, queue_length=32)
+        ring = min(nfr, 96)
+        pool = pkg.Pool([local_rank], desc, slots=args.pool_slots, batch=args.pool_batch, queue_length=64)
         h_in = [pkg.pinned_empty((HEIGHT, lay.frame_pitch)) for _ in range(ring)]
         h_cd = [pkg.pinned_empty(pkg.sparse_max_bytes(lay)) for _ in range(ring)]
         h_out = [pkg.pinned_empty((HEIGHT, lay.frame_pitch)) for _ in range(ring)]
@@ -303,7 +336,7 @@ def run_ours(args, rank, world, local_rank):
             next_f, done = 0, 0
             inflight = 0
             while done < total:
-                while next_f < total and inflight < 24 and next_f - done < ring - 8:
+                while next_f < total and inflight < args.pool_inflight and next_f - done < ring - 8:
                     sub_f(FWD | next_f, h_in[next_f % ring], quant, h_cd[next_f % ring])
                     next_f += 1; inflight += 1
                 r = pool.wait(); inflight -= 1
@@ -318,11 +351,7 @@ def run_ours(args, rank, world, local_rank):
             barrier()
             t0 = time.perf_counter()
             run_stream(nfr, sparse)
-            dt = time.perf_counter() - t0
-            if world > 1:
-                t = torch.tensor([dt], device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
+            dt = D.max(time.perf_counter() - t0)
             assert pu.psnr(h_out[0][:, 0::2], h_in[0][:, 0::2]) > 40.0
             return dt
 
@@ -330,14 +359,14 @@ def run_ours(args, rank, world, local_rank):
         dt_sparse = timed_stream(True)
         coded_sparse = int(np.mean([pkg.sparse_bytes(h_cd[i]) for i in range(min(ring, B))]))
         pool.close()
-        e2e = {"value": world * nfr / dt_sparse, "unit": "fps",
+        e2e = {"value": aggregate_fps(world, nfr, dt_sparse), "unit": "fps",
                "h2d_bytes_per_step": int(B * (lay.frame_bytes + coded_sparse)),
                "d2h_bytes_per_step": int(B * (coded_sparse + lay.frame_bytes)),
                "api": f"cfb_pool_submit_forward_sparse/inverse_sparse + cfb_pool_wait (C ABI), pinned host buffers, "
                       f"{args.pool_slots} slots x batch {args.pool_batch}, encode and decode jobs interleaved; coefficients cross "
                       f"PCIe in the lossless sparse format (bitmap + non-zero values, {coded_sparse} B/frame vs {lay.coded_bytes} dense)",
                "frames": nfr,
-               "dense_format": {"value": world * nfr / dt_dense, "unit": "fps",
+               "dense_format": {"value": aggregate_fps(world, nfr, dt_dense), "unit": "fps",
                                 "h2d_bytes_per_step": int(B * (lay.frame_bytes + lay.coded_bytes)),
                                 "d2h_bytes_per_step": int(B * (lay.coded_bytes + lay.frame_bytes))}}
 
@@ -368,8 +397,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    D.close()
 
 
 def main():
@@ -380,8 +408,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="frames per step per GPU")
     ap.add_argument("--e2e-steps", type=int, default=20)
-    ap.add_argument("--pool-slots", type=int, default=4)
-    ap.add_argument("--pool-batch", type=int, default=4)
+    ap.add_argument("--pool-slots", type=int, default=12)
+    ap.add_argument("--pool-batch", type=int, default=2)
+    ap.add_argument("--pool-inflight", type=int, default=48)
     ap.add_argument("--ref-iters", type=int, default=3, help="frames per host thread in the CPU baseline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

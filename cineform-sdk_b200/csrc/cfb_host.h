@@ -51,4 +51,5 @@ struct cfb_codec {
     unsigned *d_counts = nullptr;           // max_batch * (nseg + 1)
     unsigned *h_headers = nullptr;          // pinned, 4 u32 per slot
     size_t sparse_stride = 0;
+    unsigned value_guess = 0;               // running estimate of non-zero words per frame (speculative single-pass D2H)
 };

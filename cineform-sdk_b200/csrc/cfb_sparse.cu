@@ -259,16 +259,35 @@ cfb_error cfb_forward_host_sparse(cfb_codec *cd, int n, const void *const *h_fra
     if (err) return err;
     CFB_CUDA(launch_sparse_compact(sp, ctx->stream));
     ctx->kernel_launches += 3;
-    for (int i = 0; i < n; i++)
-        CFB_CUDA(cudaMemcpyAsync(cd->h_headers + 4 * i, sp.sparse[i], 16, cudaMemcpyDeviceToHost, ctx->stream));
-    CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // Speculative single-pass D2H: copy header + bitmap + as many values as recent frames needed (+12 %) right behind the
+    // kernels, without a host round trip; only if a frame turns out to hold more values is the remainder fetched.
+    const unsigned guess = cd->value_guess ? cd->value_guess : sp.nwords / 8;
     for (int i = 0; i < n; i++) {
-        const size_t bytes = (size_t)sp.values_off + (size_t)cd->h_headers[4 * i + 2] * 2;
+        size_t bytes = (size_t)sp.values_off + (size_t)guess * 2;
+        if (bytes > cd->sparse_stride) bytes = cd->sparse_stride;
         CFB_CUDA(cudaMemcpyAsync(h_sparse[i], sp.sparse[i], bytes, cudaMemcpyDeviceToHost, ctx->stream));
         ctx->d2h_bytes += (uint64_t)bytes;
-        if (sparse_bytes) sparse_bytes[i] = bytes;
     }
     CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    unsigned maxv = 0;
+    bool more = false;
+    for (int i = 0; i < n; i++) {
+        const unsigned nv = ((const unsigned *)h_sparse[i])[2];
+        if (nv > maxv) maxv = nv;
+        if (nv > guess) {
+            const size_t off = (size_t)sp.values_off + (size_t)guess * 2, rest = (size_t)(nv - guess) * 2;
+            CFB_CUDA(cudaMemcpyAsync((unsigned char *)h_sparse[i] + off, sp.sparse[i] + off, rest, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->d2h_bytes += (uint64_t)rest;
+            more = true;
+        }
+        if (sparse_bytes) sparse_bytes[i] = (size_t)sp.values_off + (size_t)nv * 2;
+    }
+    if (more) CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    {
+        unsigned g = maxv + maxv / 8 + 4096;
+        if (g > sp.nwords) g = sp.nwords;
+        cd->value_guess = (g + 63u) & ~63u;
+    }
     return CFB_OK;
 }
 
