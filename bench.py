@@ -205,10 +205,22 @@ def cpu_reference_run(width, height, quality, threads, iters):
 
 
 # ------------------------------------------------------------------------------------------------
+def usable_cpus():
+    """Host cores this process may actually use: affinity mask and cgroup CPU quota (containers), not just nproc."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def best_reference_threads(iters):
     """The reference scales poorly past the physical cores (every DECODER owns worker threads and large scratch):
     probe a few host-thread counts and keep the fastest, so the baseline is the reference's best."""
-    ncpu = os.cpu_count() or 1
+    ncpu = usable_cpus()
     best = None
     for t in sorted({max(1, ncpu // 8), max(1, ncpu // 4), max(1, ncpu // 2), ncpu}):
         fps = max(cpu_reference_run(WIDTH, HEIGHT, QUALITY, t, max(1, iters))[0] for _ in range(2))
@@ -408,7 +420,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="frames per step per GPU")
     ap.add_argument("--e2e-steps", type=int, default=20)
-    ap.add_argument("--pool-slots", type=int, default=12)
+    ap.add_argument("--pool-slots", type=int, default=8)
     ap.add_argument("--pool-batch", type=int, default=2)
     ap.add_argument("--pool-inflight", type=int, default=48)
     ap.add_argument("--ref-iters", type=int, default=3, help="frames per host thread in the CPU baseline")

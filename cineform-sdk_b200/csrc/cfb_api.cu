@@ -46,6 +46,13 @@ QuantParam make_quant_param(int divisor, int g)
     return q;
 }
 
+cudaError_t stream_wait(cfb_context *ctx)
+{
+    cudaError_t e = cudaEventRecord(ctx->done, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->done);
+}
+
 static inline int align16(int x) { return (x + 15) & ~15; }
 static inline int64_t align64(int64_t x) { return (x + 63) & ~(int64_t)63; }
 
@@ -258,7 +265,8 @@ cfb_error cfb_context_create(int device, cfb_context **out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete ctx; return cuda_fail(e, "cudaStreamCreate"); }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->done, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) { if (ctx->stream) cudaStreamDestroy(ctx->stream); delete ctx; return cuda_fail(e, "cudaStreamCreate"); }
     *out = ctx;
     return CFB_OK;
 }
@@ -267,6 +275,7 @@ void cfb_context_destroy(cfb_context *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->done) cudaEventDestroy(ctx->done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -275,7 +284,7 @@ cfb_error cfb_context_synchronize(cfb_context *ctx)
 {
     if (!ctx) return CFB_ERROR_INVALID_ARGUMENT;
     CFB_CUDA(cudaSetDevice(ctx->device));
-    CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    CFB_CUDA(stream_wait(ctx));
     return CFB_OK;
 }
 
@@ -462,7 +471,7 @@ cfb_error cfb_forward_host(cfb_codec *cd, int n, const void *const *h_frames, in
         CFB_CUDA(cudaMemcpyAsync(h_coded[i], dpy[i], (size_t)L.coded_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         ctx->d2h_bytes += (uint64_t)L.coded_bytes;
     }
-    CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    CFB_CUDA(stream_wait(ctx));
     return CFB_OK;
 }
 
@@ -579,7 +588,7 @@ cfb_error cfb_inverse_host(cfb_codec *cd, int n, const void *const *h_coded, con
         CFB_CUDA(cudaMemcpy2DAsync(h_frames[i], frame_pitch, dfr[i], dpitch, rowbytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
         ctx->d2h_bytes += (uint64_t)rowbytes * rows;
     }
-    CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    CFB_CUDA(stream_wait(ctx));
     return CFB_OK;
 }
 

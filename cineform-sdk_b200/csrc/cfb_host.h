@@ -20,6 +20,8 @@ cfb_error cuda_fail(cudaError_t e, const char *what);
     } while (0)
 
 QuantParam make_quant_param(int divisor, int midpoint_prequant);
+// wait for everything queued on the context's stream without busy-waiting on a CPU core
+cudaError_t stream_wait(cfb_context *ctx);
 
 // kernel launchers (cfb_forward.cu / cfb_inverse.cu)
 cudaError_t launch_fwd_plane(const FwdParams &p, int prescale, cudaStream_t stream);
@@ -32,6 +34,7 @@ cudaError_t launch_inv_422(const InvParams &p, cudaStream_t stream);
 struct cfb_context {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;             // blocking-sync event: host threads sleep instead of spinning
     int sm_count = 0;
     std::atomic<uint64_t> kernel_launches{0}, frames_forward{0}, frames_inverse{0}, h2d_bytes{0}, d2h_bytes{0};
 };

@@ -268,7 +268,7 @@ cfb_error cfb_forward_host_sparse(cfb_codec *cd, int n, const void *const *h_fra
         CFB_CUDA(cudaMemcpyAsync(h_sparse[i], sp.sparse[i], bytes, cudaMemcpyDeviceToHost, ctx->stream));
         ctx->d2h_bytes += (uint64_t)bytes;
     }
-    CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    CFB_CUDA(stream_wait(ctx));
     unsigned maxv = 0;
     bool more = false;
     for (int i = 0; i < n; i++) {
@@ -282,7 +282,7 @@ cfb_error cfb_forward_host_sparse(cfb_codec *cd, int n, const void *const *h_fra
         }
         if (sparse_bytes) sparse_bytes[i] = (size_t)sp.values_off + (size_t)nv * 2;
     }
-    if (more) CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (more) CFB_CUDA(stream_wait(ctx));
     {
         unsigned g = maxv + maxv / 8 + 4096;
         if (g > sp.nwords) g = sp.nwords;
@@ -322,7 +322,7 @@ cfb_error cfb_inverse_host_sparse(cfb_codec *cd, int n, const void *const *h_spa
         CFB_CUDA(cudaMemcpy2DAsync(h_frames[i], frame_pitch, dfr[i], dpitch, dpitch, cd->desc.height, cudaMemcpyDeviceToHost, ctx->stream));
         ctx->d2h_bytes += (uint64_t)dpitch * cd->desc.height;
     }
-    CFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    CFB_CUDA(stream_wait(ctx));
     return CFB_OK;
 }
 
