@@ -179,7 +179,9 @@ cfb_error cfb_quant_for_quality(const cfb_frame_desc *desc, int quality, cfb_qua
         {4, 6, 6, 8, 6, 6, 8, 5, 8, 8, 8, 8, 8, 16, 8, 8, 16}};
     memset(out, 0, sizeof(*out));
     const int precision = lay.precision;
-    const bool chroma_full = (desc->pixel_format == CFB_PIXEL_BYR4);   // format >= COLOR_FORMAT_BAYER (encoder.c:1139)
+    // ChromaFullRes = (format >= COLOR_FORMAT_BAYER) (encoder.c:1139): true for BYR4 (104) and RG48 (120)
+    const bool chroma_full = (desc->pixel_format == CFB_PIXEL_BYR4 || desc->pixel_format == CFB_PIXEL_RG48 ||
+                              desc->pixel_format == CFB_PIXEL_PLANAR16);
     int factor = quality & 0xff;
     const int detail = (quality & 0x0e0000) >> 17;
     int rgb_quality = (quality & 0x06000000) >> 25;
@@ -424,6 +426,21 @@ cfb_error cfb_forward_device(cfb_codec *cd, int n, const void *const *d_frames, 
         p.th = pick_th((p.ch[0].width + kStripIn - 1) / kStripIn, p.ch[0].height / 2, n * 3, ctx->sm_count);
         CFB_CUDA(launch_fwd_plane(p, quant->prescale[0], ctx->stream));
         ctx->kernel_launches++;
+    } else if (fmt == CFB_PIXEL_RG48) {
+        // channel order of the reference: plane 0 = G, 1 = R, 2 = B (Codec/frame.c:6155-6157); one launch per channel
+        static const int sel_of_channel[3] = {1, 0, 2};
+        for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_frames[i]; p.out_base[i] = (unsigned char *)d_pyramids[i]; }
+        p.shift = 16 - L.precision;
+        for (int c = 0; c < 3; c++) {
+            FwdParams q = p;
+            q.nchan = 1;
+            fill_level_geom(cd, quant, c, 0, q.ch[0]);
+            q.ch[0].in_off = 0; q.ch[0].in_pitch = frame_pitch;
+            q.ch[0].quant_ll = quant->divisor[c][0][0] > 1;
+            q.th = pick_th((q.ch[0].width + kStripIn - 1) / kStripIn, q.ch[0].height / 2, n, ctx->sm_count);
+            CFB_CUDA(launch_fwd_rg48(q, sel_of_channel[c], ctx->stream));
+            ctx->kernel_launches++;
+        }
     } else {
         set_error("forward level 1 for pixel format %d not implemented yet", fmt);
         return CFB_ERROR_UNSUPPORTED;

@@ -124,6 +124,45 @@ __device__ __forceinline__ void load_plane_row(const unsigned char *p, const Lan
     if (L.use_rh) r.halo = __ldg(reinterpret_cast<const unsigned *>(p + 16));
 }
 
+// ---- packed 16-bit RGB (RG48) input: a lane's 8 pixels are 48 contiguous bytes; one channel (word SEL of each
+// pixel: 0 = R, 1 = G, 2 = B) is extracted and reduced to the codec precision (>> shift), as
+// Codec/frame.c:5968 ConvertRGB48ToFrame16s (default branch :6130-6164) does on the host.
+struct RawRG48Row {
+    uint4 a, b, c;      // 24 words = 8 pixels x 3
+    unsigned halo;      // channel samples of pixels [-2,-1] (lane 0) or [+8,+9] (last lane), already packed
+};
+
+template <int SEL>
+__device__ __forceinline__ void load_rg48_row(const unsigned char *p, const LaneInfo &L, RawRG48Row &r)
+{
+    r.a = __ldg(reinterpret_cast<const uint4 *>(p));
+    r.b = __ldg(reinterpret_cast<const uint4 *>(p + 16));
+    r.c = __ldg(reinterpret_cast<const uint4 *>(p + 32));
+    r.halo = 0u;
+    if (L.use_lh) r.halo = (unsigned)__ldg(reinterpret_cast<const unsigned short *>(p - 12 + 2 * SEL)) |
+                           ((unsigned)__ldg(reinterpret_cast<const unsigned short *>(p - 6 + 2 * SEL)) << 16);
+    if (L.use_rh) r.halo = (unsigned)__ldg(reinterpret_cast<const unsigned short *>(p + 48 + 2 * SEL)) |
+                           ((unsigned)__ldg(reinterpret_cast<const unsigned short *>(p + 54 + 2 * SEL)) << 16);
+}
+
+// word index w (0..23) of the 48-byte group as a (register, half) pair -> PRMT selector nibble pair
+template <int SEL>
+__device__ __forceinline__ void rg48_extract(const RawRG48Row &r, int shift, RawPlaneRow &o)
+{
+    const unsigned w[12] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w, r.c.x, r.c.y, r.c.z, r.c.w};
+    unsigned out[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        const int w0 = 3 * (2 * m) + SEL, w1 = 3 * (2 * m + 1) + SEL;      // word indices of samples 2m, 2m+1
+        const unsigned lo = (w0 & 1) ? (w[w0 >> 1] >> 16) : (w[w0 >> 1] & 0xffffu);
+        const unsigned hi = (w1 & 1) ? (w[w1 >> 1] & 0xffff0000u) : (w[w1 >> 1] << 16);
+        out[m] = lo | hi;
+    }
+    const unsigned mask = (0xffffu >> shift) * 0x00010001u;
+    o.v = make_uint4((out[0] >> shift) & mask, (out[1] >> shift) & mask, (out[2] >> shift) & mask, (out[3] >> shift) & mask);
+    o.halo = (r.halo >> shift) & mask;
+}
+
 template <int PRESCALE>
 __device__ __forceinline__ int tap(int x) { return PRESCALE ? ((x + 3) >> 2) : x; }
 
@@ -235,6 +274,85 @@ __global__ void __launch_bounds__(128) k_fwd_plane(const __grid_constant__ FwdPa
         int a[8], b[8];
         hfilter_plane<PRESCALE>(c0, L, a);
         hfilter_plane<PRESCALE>(c1, L, b);
+        vstep<4>(st, a, b, g, out, off, j >= y0 && j < y1, j - 1 >= hlo);
+        off += (unsigned)g.out_pitch;
+        c0 = n0; c1 = n1;
+    }
+}
+
+// ----------------------------------------------------------------------------
+// level 1 of one channel of a packed RG48 frame (prescale 0, Codec/spatial.c:10026 on the 12-bit plane that
+// ConvertRGB48ToFrame16s would have produced).  One launch per channel: SEL picks the word of each pixel.
+template <int SEL>
+__global__ void __launch_bounds__(128) k_fwd_rg48(const __grid_constant__ FwdParams p)
+{
+    const int lane = threadIdx.x;
+    const int f = blockIdx.z;
+    const PlaneGeom &g = p.ch[0];
+    const int strip = blockIdx.x;
+    if (strip * kStripIn >= g.width) return;
+    const int oh = g.height >> 1;
+    LaneInfo L;
+    if (!lane_setup(strip, g.width, lane, L)) return;
+    const unsigned colbyte = (unsigned)((strip * kStripOut + lane * 4) * 2);
+    const unsigned char *in = p.in_base[f] + g.in_off + (long long)(strip * kStripIn + lane * 8) * 6;
+    unsigned char *out = p.out_base[f];
+    const int shift = p.shift;          // 16 - precision
+
+    if (blockIdx.y == gridDim.y - 1) {
+        if (threadIdx.y > 1) return;
+        const bool bottom = (threadIdx.y == 1);
+        const int j0 = bottom ? oh - 3 : 0;
+        int s[3][8], dsel[8];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            RawRG48Row q0, q1;
+            RawPlaneRow r0, r1;
+            int a[8], b[8];
+            load_rg48_row<SEL>(in + (long long)(2 * (j0 + k)) * g.in_pitch, L, q0);
+            load_rg48_row<SEL>(in + (long long)(2 * (j0 + k) + 1) * g.in_pitch, L, q1);
+            rg48_extract<SEL>(q0, shift, r0);
+            rg48_extract<SEL>(q1, shift, r1);
+            hfilter_plane<0>(r0, L, a);
+            hfilter_plane<0>(r1, L, b);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                s[k][i] = a[i] + b[i];
+                if (k == (bottom ? 2 : 0)) dsel[i] = a[i] - b[i];
+            }
+        }
+        border_emit<4>(s[0], s[1], s[2], dsel, bottom, g, out, (unsigned)((bottom ? oh - 1 : 0) * g.out_pitch) + colbyte);
+        return;
+    }
+
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * p.th;
+    if (y0 >= oh) return;
+    const int y1 = min(y0 + p.th, oh);
+    const int jfirst = max(y0 - 1, 0), jlast = min(y1, oh - 1);
+    const int hlo = max(y0, 1);
+
+    VState<4> st;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { st.llp[i] = st.llc[i] = st.dc[i] = 0; }
+
+    const unsigned char *rp = in + (long long)(2 * jfirst) * g.in_pitch;
+    RawRG48Row c0, c1, n0, n1;
+    load_rg48_row<SEL>(rp, L, c0);
+    load_rg48_row<SEL>(rp + g.in_pitch, L, c1);
+    n0 = c0; n1 = c1;
+    unsigned off = (unsigned)(jfirst * g.out_pitch) + colbyte;
+    for (int j = jfirst; j <= jlast; j++) {
+        rp += 2 * g.in_pitch;
+        if (j < jlast) {
+            load_rg48_row<SEL>(rp, L, n0);
+            load_rg48_row<SEL>(rp + g.in_pitch, L, n1);
+        }
+        RawPlaneRow r0, r1;
+        int a[8], b[8];
+        rg48_extract<SEL>(c0, shift, r0);
+        rg48_extract<SEL>(c1, shift, r1);
+        hfilter_plane<0>(r0, L, a);
+        hfilter_plane<0>(r1, L, b);
         vstep<4>(st, a, b, g, out, off, j >= y0 && j < y1, j - 1 >= hlo);
         off += (unsigned)g.out_pitch;
         c0 = n0; c1 = n1;
@@ -420,6 +538,17 @@ cudaError_t launch_fwd_plane(const FwdParams &p, int prescale, cudaStream_t stre
     dim3 grid(ceil_div(maxw, kStripIn), ceil_div(ceil_div(maxoh, p.th), (int)block.y) + 1, p.nframes * p.nchan);
     if (prescale) k_fwd_plane<2><<<grid, block, 0, stream>>>(p);
     else k_fwd_plane<0><<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// sel: word of each RGB pixel feeding this channel (0 = R, 1 = G, 2 = B); p.ch[0] describes the channel
+cudaError_t launch_fwd_rg48(const FwdParams &p, int sel, cudaStream_t stream)
+{
+    dim3 block(32, 4);
+    dim3 grid(ceil_div(p.ch[0].width, kStripIn), ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y) + 1, p.nframes);
+    if (sel == 0) k_fwd_rg48<0><<<grid, block, 0, stream>>>(p);
+    else if (sel == 1) k_fwd_rg48<1><<<grid, block, 0, stream>>>(p);
+    else k_fwd_rg48<2><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -168,3 +168,47 @@ def ref_decode_sample_bands(ref_lib, sample, width, height, decoded_format=COLOR
 
 
 UNIT_DIVISORS = [[[1, 1, 1, 1]] * 3] * 3
+
+
+# ---------------------------------------------------------------- RG48 (packed 16-bit RGB -> 4:4:4, 12 bit)
+CFHD_PIXEL_FORMAT_RG48 = (ord("R") << 24) | (ord("G") << 16) | (ord("4") << 8) | ord("8")
+
+
+def qbist_rg48(ref_lib, width, height, frame_number=1, seed=50):
+    pitch = width * 6
+    out = np.zeros((height, pitch), np.uint8)
+    ref_lib.ref_qbist_frames(seed, width, height, pitch, CFHD_PIXEL_FORMAT_RG48, frame_number, out.reshape(-1))
+    return out.view(np.uint16)          # (height, 3*width)
+
+
+def unpack_rg48(frame16, precision=12):
+    """Codec/frame.c:5968 ConvertRGB48ToFrame16s, default branch (:6130-6164): plane0 = G, plane1 = R, plane2 = B,
+    each `>> (16 - precision)`."""
+    sh = 16 - precision
+    r, g, b = frame16[:, 0::3], frame16[:, 1::3], frame16[:, 2::3]
+    return [np.ascontiguousarray((x >> sh).astype(np.int16)) for x in (g, r, b)]
+
+
+def forward_pyramid_planes(impl, planes, divisors, prescale, midpoint=2):
+    """3-level pyramid of already unpacked int16 planes (level 1 uses the plain / V210 variant by prescale[0])."""
+    out = {}
+    for c, ll in enumerate(planes):
+        for k in range(3):
+            variant = 1 if prescale[k] == 2 else 0
+            ll, lh, hl, hh = impl.fwd_level(ll, variant, divisors[c][k], midpoint)
+            out[(c, k + 1, "LL")], out[(c, k + 1, "LH")], out[(c, k + 1, "HL")], out[(c, k + 1, "HH")] = ll, lh, hl, hh
+    return out
+
+
+def synthetic_rg48(rng, width, height, kind="natural"):
+    if kind == "random":
+        return rng.integers(0, 65536, (height, width * 3)).astype(np.uint16)
+    if kind == "extreme":
+        return np.where(rng.integers(0, 2, (height, width * 3)) == 0, 0, 65535).astype(np.uint16)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
+    f = np.empty((height, width * 3), np.uint16)
+    for c, (a, b) in enumerate(((37.0, 23.0), (51.0, 31.0), (29.0, 47.0))):
+        v = 30000 + 20000 * np.sin(xx / a) * np.cos(yy / b) + 6000 * np.sin((xx + 2 * yy) / 5.0) * (xx > width / 2)
+        v += rng.normal(0, 300.0, v.shape)
+        f[:, c::3] = np.clip(v, 0, 65535).astype(np.uint16)
+    return f
