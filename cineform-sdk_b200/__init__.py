@@ -96,6 +96,7 @@ def lib():
     L.cfb_codec_device_pyramid.argtypes = [vp, i]
     L.cfb_codec_device_pyramid.restype = vp
     L.cfb_codec_set_level_mask.argtypes = [vp, i, i]
+    L.cfb_codec_set_bayer_phase.argtypes = [vp, i]
     L.cfb_forward_device.argtypes = [vp, i, C.POINTER(vp), i, C.POINTER(Quant), C.POINTER(vp)]
     L.cfb_forward_host.argtypes = [vp, i, C.POINTER(vp), i, C.POINTER(Quant), C.POINTER(vp)]
     L.cfb_inverse_device.argtypes = [vp, i, C.POINTER(vp), C.POINTER(Quant), i, C.POINTER(vp), i]
@@ -241,6 +242,9 @@ class Codec:
 
     def device_pyramid(self, slot):
         return lib().cfb_codec_device_pyramid(self.h, slot)
+
+    def set_bayer_phase(self, bayer_format):
+        _check(lib().cfb_codec_set_bayer_phase(self.h, bayer_format))
 
     def set_level_mask(self, forward_mask=7, inverse_mask=7):
         _check(lib().cfb_codec_set_level_mask(self.h, forward_mask, inverse_mask))

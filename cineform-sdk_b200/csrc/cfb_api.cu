@@ -182,6 +182,7 @@ cfb_error cfb_quant_for_quality(const cfb_frame_desc *desc, int quality, cfb_qua
     // ChromaFullRes = (format >= COLOR_FORMAT_BAYER) (encoder.c:1139): true for BYR4 (104) and RG48 (120)
     const bool chroma_full = (desc->pixel_format == CFB_PIXEL_BYR4 || desc->pixel_format == CFB_PIXEL_RG48 ||
                               desc->pixel_format == CFB_PIXEL_PLANAR16);
+    if (desc->pixel_format == CFB_PIXEL_BYR4) quality |= (3 << 25);     // encoder.c:2634: no extra quant on channels 1-3
     int factor = quality & 0xff;
     const int detail = (quality & 0x0e0000) >> 17;
     int rgb_quality = (quality & 0x06000000) >> 25;
@@ -352,6 +353,13 @@ cfb_error cfb_codec_layout(const cfb_codec *cd, cfb_layout *out)
     return CFB_OK;
 }
 
+cfb_error cfb_codec_set_bayer_phase(cfb_codec *cd, int bayer_format)
+{
+    if (!cd || bayer_format < 0 || bayer_format > 3) { set_error("bayer format %d out of range 0..3", bayer_format); return CFB_ERROR_INVALID_ARGUMENT; }
+    cd->bayer_phase = bayer_format;
+    return CFB_OK;
+}
+
 cfb_error cfb_codec_set_level_mask(cfb_codec *cd, int forward_mask, int inverse_mask)
 {
     if (!cd) return CFB_ERROR_INVALID_ARGUMENT;
@@ -441,6 +449,17 @@ cfb_error cfb_forward_device(cfb_codec *cd, int n, const void *const *d_frames, 
             CFB_CUDA(launch_fwd_rg48(q, sel_of_channel[c], ctx->stream));
             ctx->kernel_launches++;
         }
+    } else if (fmt == CFB_PIXEL_BYR4) {
+        for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_frames[i]; p.out_base[i] = (unsigned char *)d_pyramids[i]; }
+        for (int c = 0; c < 4; c++) {
+            fill_level_geom(cd, quant, c, 0, p.ch[c]);
+            p.ch[c].in_off = 0; p.ch[c].in_pitch = frame_pitch;      // bytes per Bayer line
+            p.ch[c].quant_ll = quant->divisor[c][0][0] > 1;
+        }
+        p.shift = 16 - L.precision; p.uyvy = cd->bayer_phase;
+        p.th = pick_th((p.ch[0].width + kStripIn - 1) / kStripIn * 4, p.ch[0].height / 2, n, ctx->sm_count);
+        CFB_CUDA(launch_fwd_byr4(p, ctx->stream));
+        ctx->kernel_launches++;
     } else {
         set_error("forward level 1 for pixel format %d not implemented yet", fmt);
         return CFB_ERROR_UNSUPPORTED;

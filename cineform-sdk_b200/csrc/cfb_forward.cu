@@ -360,6 +360,134 @@ __global__ void __launch_bounds__(128) k_fwd_rg48(const __grid_constant__ FwdPar
 }
 
 // ----------------------------------------------------------------------------
+// level 1 of one channel of a 16-bit Bayer frame (BYR4, curve already applied): the four half-resolution planes
+// G = (g1+g2)>>1, RG = (r-G+4096)>>1, BG = (b-G+4096)>>1, DG = (g1-g2+4096)>>1 at 12 bits
+// (Codec/frame.c:4993 ConvertBYR4ToFrame16s, encode_curve_preset branch :5040-5200) are formed on the fly from the
+// two Bayer lines of each plane row.  blockIdx.x = strip * 4 + channel, so the four channel jobs of a strip run
+// next to each other and share the Bayer lines through L1/L2.
+struct RawBYR4Row {
+    uint4 a0, a1;       // Bayer line 2r   : 16 pixels of this lane
+    uint4 b0, b1;       // Bayer line 2r+1
+    uint2 ha, hb;       // 4 pixels of each line just outside the strip (lane 0: left, last lane: right)
+};
+
+__device__ __forceinline__ void load_byr4_row(const unsigned char *p, int line_pitch, const LaneInfo &L, RawBYR4Row &r)
+{
+    r.a0 = __ldg(reinterpret_cast<const uint4 *>(p));
+    r.a1 = __ldg(reinterpret_cast<const uint4 *>(p + 16));
+    r.b0 = __ldg(reinterpret_cast<const uint4 *>(p + line_pitch));
+    r.b1 = __ldg(reinterpret_cast<const uint4 *>(p + line_pitch + 16));
+    r.ha = make_uint2(0u, 0u); r.hb = make_uint2(0u, 0u);
+    if (L.use_lh) { r.ha = __ldg(reinterpret_cast<const uint2 *>(p - 8)); r.hb = __ldg(reinterpret_cast<const uint2 *>(p + line_pitch - 8)); }
+    if (L.use_rh) { r.ha = __ldg(reinterpret_cast<const uint2 *>(p + 32)); r.hb = __ldg(reinterpret_cast<const uint2 *>(p + line_pitch + 32)); }
+}
+
+// one plane sample from the quad (w1 = two pixels of the first line, w2 = of the second line)
+__device__ __forceinline__ int byr4_sample(unsigned w1, unsigned w2, int shift, int fmt, int chan)
+{
+    const int q0 = (int)((w1 & 0xffffu) >> shift), q1 = (int)((w1 >> 16) >> shift);
+    const int q2 = (int)((w2 & 0xffffu) >> shift), q3 = (int)((w2 >> 16) >> shift);
+    const bool g_second = (fmt == 0) || (fmt == 3);             // RED_GRN / BLU_GRN: green is the 2nd pixel of line 1
+    const int g1 = g_second ? q1 : q0, g2 = g_second ? q2 : q3;
+    if (chan == 3) return (g1 - g2 + 4096) >> 1;
+    const int gg = (g1 + g2) >> 1;
+    if (chan == 0) return gg;
+    const int r = (fmt == 0) ? q0 : (fmt == 1) ? q1 : (fmt == 2) ? q2 : q3;
+    const int b = (fmt == 0) ? q3 : (fmt == 1) ? q2 : (fmt == 2) ? q1 : q0;
+    return (((chan == 1) ? r : b) - gg + 4096) >> 1;
+}
+
+__device__ __forceinline__ void byr4_extract(const RawBYR4Row &r, int shift, int fmt, int chan, RawPlaneRow &o)
+{
+    const unsigned l1[8] = {r.a0.x, r.a0.y, r.a0.z, r.a0.w, r.a1.x, r.a1.y, r.a1.z, r.a1.w};
+    const unsigned l2[8] = {r.b0.x, r.b0.y, r.b0.z, r.b0.w, r.b1.x, r.b1.y, r.b1.z, r.b1.w};
+    unsigned out[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+        out[m] = (unsigned)byr4_sample(l1[2 * m], l2[2 * m], shift, fmt, chan) |
+                 ((unsigned)byr4_sample(l1[2 * m + 1], l2[2 * m + 1], shift, fmt, chan) << 16);
+    o.v = make_uint4(out[0], out[1], out[2], out[3]);
+    o.halo = (unsigned)byr4_sample(r.ha.x, r.hb.x, shift, fmt, chan) | ((unsigned)byr4_sample(r.ha.y, r.hb.y, shift, fmt, chan) << 16);
+}
+
+__global__ void __launch_bounds__(128) k_fwd_byr4(const __grid_constant__ FwdParams p)
+{
+    const int lane = threadIdx.x;
+    const int f = blockIdx.z;
+    const int c = blockIdx.x & 3, strip = blockIdx.x >> 2;
+    const PlaneGeom &g = p.ch[c];
+    if (strip * kStripIn >= g.width) return;
+    const int oh = g.height >> 1;
+    LaneInfo L;
+    if (!lane_setup(strip, g.width, lane, L)) return;
+    const unsigned colbyte = (unsigned)((strip * kStripOut + lane * 4) * 2);
+    const int line_pitch = g.in_pitch;                      // bytes per Bayer line
+    const long long row_pitch = 2LL * line_pitch;           // one plane row = two Bayer lines
+    const unsigned char *in = p.in_base[f] + (long long)(strip * kStripIn + lane * 8) * 4;      // 2 pixels x 2 bytes per plane sample
+    unsigned char *out = p.out_base[f];
+    const int shift = p.shift, fmt = p.uyvy;                // uyvy field reused as the Bayer phase (0..3)
+
+    if (blockIdx.y == gridDim.y - 1) {
+        if (threadIdx.y > 1) return;
+        const bool bottom = (threadIdx.y == 1);
+        const int j0 = bottom ? oh - 3 : 0;
+        int s[3][8], dsel[8];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            RawBYR4Row q0, q1;
+            RawPlaneRow r0, r1;
+            int a[8], b[8];
+            load_byr4_row(in + (long long)(2 * (j0 + k)) * row_pitch, line_pitch, L, q0);
+            load_byr4_row(in + (long long)(2 * (j0 + k) + 1) * row_pitch, line_pitch, L, q1);
+            byr4_extract(q0, shift, fmt, c, r0);
+            byr4_extract(q1, shift, fmt, c, r1);
+            hfilter_plane<0>(r0, L, a);
+            hfilter_plane<0>(r1, L, b);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                s[k][i] = a[i] + b[i];
+                if (k == (bottom ? 2 : 0)) dsel[i] = a[i] - b[i];
+            }
+        }
+        border_emit<4>(s[0], s[1], s[2], dsel, bottom, g, out, (unsigned)((bottom ? oh - 1 : 0) * g.out_pitch) + colbyte);
+        return;
+    }
+
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * p.th;
+    if (y0 >= oh) return;
+    const int y1 = min(y0 + p.th, oh);
+    const int jfirst = max(y0 - 1, 0), jlast = min(y1, oh - 1);
+    const int hlo = max(y0, 1);
+
+    VState<4> st;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { st.llp[i] = st.llc[i] = st.dc[i] = 0; }
+
+    const unsigned char *rp = in + (long long)(2 * jfirst) * row_pitch;
+    RawBYR4Row c0, c1, n0, n1;
+    load_byr4_row(rp, line_pitch, L, c0);
+    load_byr4_row(rp + row_pitch, line_pitch, L, c1);
+    n0 = c0; n1 = c1;
+    unsigned off = (unsigned)(jfirst * g.out_pitch) + colbyte;
+    for (int j = jfirst; j <= jlast; j++) {
+        rp += 2 * row_pitch;
+        if (j < jlast) {
+            load_byr4_row(rp, line_pitch, L, n0);
+            load_byr4_row(rp + row_pitch, line_pitch, L, n1);
+        }
+        RawPlaneRow r0, r1;
+        int a[8], b[8];
+        byr4_extract(c0, shift, fmt, c, r0);
+        byr4_extract(c1, shift, fmt, c, r1);
+        hfilter_plane<0>(r0, L, a);
+        hfilter_plane<0>(r1, L, b);
+        vstep<4>(st, a, b, g, out, off, j >= y0 && j < y1, j - 1 >= hlo);
+        off += (unsigned)g.out_pitch;
+        c0 = n0; c1 = n1;
+    }
+}
+
+// ----------------------------------------------------------------------------
 // packed 8-bit 4:2:2 input: one warp produces the Y strip (128 columns) and the matching
 // U and V strips (64 columns each) from a single read of the packed rows.
 struct Raw422Row {
@@ -549,6 +677,15 @@ cudaError_t launch_fwd_rg48(const FwdParams &p, int sel, cudaStream_t stream)
     if (sel == 0) k_fwd_rg48<0><<<grid, block, 0, stream>>>(p);
     else if (sel == 1) k_fwd_rg48<1><<<grid, block, 0, stream>>>(p);
     else k_fwd_rg48<2><<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// all four Bayer-derived channels in one launch (blockIdx.x = strip * 4 + channel); p.uyvy carries the Bayer phase
+cudaError_t launch_fwd_byr4(const FwdParams &p, cudaStream_t stream)
+{
+    dim3 block(32, 4);
+    dim3 grid(ceil_div(p.ch[0].width, kStripIn) * 4, ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y) + 1, p.nframes);
+    k_fwd_byr4<<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -27,6 +27,7 @@ cudaError_t stream_wait(cfb_context *ctx);
 cudaError_t launch_fwd_plane(const FwdParams &p, int prescale, cudaStream_t stream);
 cudaError_t launch_fwd_422(const FwdParams &p, cudaStream_t stream);
 cudaError_t launch_fwd_rg48(const FwdParams &p, int sel, cudaStream_t stream);
+cudaError_t launch_fwd_byr4(const FwdParams &p, cudaStream_t stream);
 cudaError_t launch_inv_plane(const InvParams &p, int descale, cudaStream_t stream);
 cudaError_t launch_inv_422(const InvParams &p, cudaStream_t stream);
 
@@ -49,6 +50,7 @@ struct cfb_codec {
     unsigned char *d_pyramids = nullptr;    // max_batch pyramids
     size_t frame_stride = 0;                // bytes between device frame slots
     size_t pyramid_stride = 0;
+    int bayer_phase = 0;                    // BAYER_FORMAT_* (0 RED_GRN, 1 GRN_RED, 2 GRN_BLU, 3 BLU_GRN), DemoasicFrames.h:30
     int fwd_mask = 7, inv_mask = 7;         // profiling aid: levels to run
     // sparse transfer format staging (allocated on first use)
     unsigned char *d_sparse = nullptr;      // max_batch sparse buffers

@@ -144,6 +144,10 @@ CFB_API cfb_error cfb_codec_layout(const cfb_codec *codec, cfb_layout *out);
 CFB_API void *cfb_codec_device_frame(cfb_codec *codec, int slot);
 CFB_API void *cfb_codec_device_pyramid(cfb_codec *codec, int slot);
 
+/* BYR4 only: Bayer phase of the source (TAG_BAYER_FORMAT): 0 RED_GRN, 1 GRN_RED, 2 GRN_BLU, 3 BLU_GRN
+ * (Codec/DemoasicFrames.h:30-33).  The frame must already carry its encode curve (CFHD_ENCODING_FLAGS_CURVE_APPLIED). */
+CFB_API cfb_error cfb_codec_set_bayer_phase(cfb_codec *codec, int bayer_format);
+
 /* Profiling aid: restrict the following forward/inverse calls to a subset of pyramid levels
  * (bit k = level k+1; default 7 = all).  Used by bench.py to time one kernel in isolation. */
 CFB_API cfb_error cfb_codec_set_level_mask(cfb_codec *codec, int forward_mask, int inverse_mask);

@@ -176,6 +176,11 @@ void ref_qbist_frames(unsigned seed, int width, int height, int pitch, unsigned 
 //   bands: for c, for k (level 1..3), for b (LL,LH,HL,HH): height*width int16, dense, concatenated.
 // Returns the encoded sample size in bytes (0 on failure).
 
+static int g_probe_bayer_format = -1;
+// Bayer sources only: phase (BAYER_FORMAT_*, Codec/DemoasicFrames.h:30) used by the next ref_encode_frame_bands call;
+// the frame is treated as CFHD_ENCODING_FLAGS_CURVE_APPLIED (encode_curve_preset = 1, linear >> 4).  -1 disables.
+void ref_set_bayer_format(int fmt) { g_probe_bayer_format = fmt; }
+
 int ref_encode_frame_bands(const uint8_t *frame, int width, int height, int pitch, int color_format,
                            int sampling_444, int num_channels, int quality,
                            int32_t *dims, int32_t *quant, int32_t *prescale, int16_t *bands, int64_t bands_capacity,
@@ -191,9 +196,10 @@ int ref_encode_frame_bands(const uint8_t *frame, int width, int height, int pitc
     p.frame_sampling = sampling_444 ? FRAME_SAMPLING_444 : FRAME_SAMPLING_422;
     p.colorspace_yuv = 2; p.colorspace_rgb = 1;
     if (!InitializeEncoderWithParameters(NULL, enc, tr, num_channels, &p)) return 0;
+    if (g_probe_bayer_format >= 0) { enc->bayer.format = g_probe_bayer_format; enc->encode_curve_preset = 1; }
     size_t scratch_size = 0;
     PIXEL *scratch = CreateEncodingBuffer(NULL, width, height, pitch, color_format, 1, true, &scratch_size);
-    const size_t outcap = (size_t)width * height * 8 + 65536;
+    const size_t outcap = (size_t)width * height * 16 + 65536;
     Aligned out(outcap), fr((size_t)pitch * (height + 16) + 64);
     memcpy(fr.p, frame, (size_t)pitch * height);
     BITSTREAM bs;

@@ -212,3 +212,29 @@ def synthetic_rg48(rng, width, height, kind="natural"):
         v += rng.normal(0, 300.0, v.shape)
         f[:, c::3] = np.clip(v, 0, 65535).astype(np.uint16)
     return f
+
+
+# ---------------------------------------------------------------- BYR4 (16-bit Bayer, curve applied -> 4 planes, 12 bit)
+def mosaic_from_rg48(frame16, fmt=0):
+    """Bayer mosaic (height x width uint16) sampled from a packed RGB frame; fmt = BAYER_FORMAT_* phase."""
+    r, g, b = frame16[:, 0::3], frame16[:, 1::3], frame16[:, 2::3]
+    h, w = r.shape
+    m = np.empty((h, w), np.uint16)
+    # quad positions (line, col): RED_GRN: r g / g b ; GRN_RED: g r / b g ; GRN_BLU: g b / r g ; BLU_GRN: b g / g r
+    lay = {0: ("r", "g", "g", "b"), 1: ("g", "r", "b", "g"), 2: ("g", "b", "r", "g"), 3: ("b", "g", "g", "r")}[fmt]
+    src = {"r": r, "g": g, "b": b}
+    m[0::2, 0::2] = src[lay[0]][0::2, 0::2]; m[0::2, 1::2] = src[lay[1]][0::2, 1::2]
+    m[1::2, 0::2] = src[lay[2]][1::2, 0::2]; m[1::2, 1::2] = src[lay[3]][1::2, 1::2]
+    return m
+
+
+def unpack_byr4(bayer16, fmt=0, precision=12):
+    """Codec/frame.c:4993 ConvertBYR4ToFrame16s, encode_curve_preset branch (:5040-5200): planes G, R-G, B-G, dG."""
+    sh = 16 - precision
+    q0 = (bayer16[0::2, 0::2] >> sh).astype(np.int32); q1 = (bayer16[0::2, 1::2] >> sh).astype(np.int32)
+    q2 = (bayer16[1::2, 0::2] >> sh).astype(np.int32); q3 = (bayer16[1::2, 1::2] >> sh).astype(np.int32)
+    r, g1, g2, b = {0: (q0, q1, q2, q3), 1: (q1, q0, q3, q2), 2: (q2, q0, q3, q1), 3: (q3, q1, q2, q0)}[fmt]
+    mid = 1 << 12
+    gg = (g1 + g2) >> 1
+    planes = [gg, (r - gg + mid) >> 1, (b - gg + mid) >> 1, (g1 - g2 + mid) >> 1]
+    return [np.ascontiguousarray(p.astype(np.int16)) for p in planes]
