@@ -1,0 +1,116 @@
+// sdk_roundtrip.cpp -- our driver over the reference's PUBLIC C API only (Common/CFHDEncoder.h, CFHDDecoder.h).
+// It is what Example/TestCFHD.cpp does in -D (sync quality loop) and -E (encoder pool) modes, but with the frame
+// size, frame count and pool shape on the command line (TestCFHD hard-codes 1920x1080, TestCFHD.cpp:70-71).
+// Linked twice by integration/Makefile: against libCFHDCodec.so (CUDA transform interposed) and against the plain
+// reference, so the same program times both and their outputs can be compared.
+//
+//   sdk_roundtrip <width> <height> <frames> [pool_threads [queue]]
+// prints one JSON line: sync encode/decode ms, sample bytes, luma PSNR, FNV-1a hash of the decoded frames, pool fps.
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <vector>
+
+#include "CFHDDecoder.h"
+#include "CFHDEncoder.h"
+#include "qbist.h"
+
+static double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
+static void *aligned(size_t n) { void *p = nullptr; if (posix_memalign(&p, 64, n)) return nullptr; memset(p, 0, n); return p; }
+
+int main(int argc, char **argv)
+{
+    const int w = argc > 1 ? atoi(argv[1]) : 1920, h = argc > 2 ? atoi(argv[2]) : 1080, nframes = argc > 3 ? atoi(argv[3]) : 5;
+    const int pool_threads = argc > 4 ? atoi(argv[4]) : 0, queue = argc > 5 ? atoi(argv[5]) : 24;
+    const int pitch = w * 2;
+    const CFHD_PixelFormat fmt = CFHD_PIXEL_FORMAT_YUY2;
+    std::vector<uint8_t *> frames;
+    GetRand(50);                    // TestCFHD.cpp:1149 QBIST_SEED
+    initBaseTransform();
+    uint8_t *gen = (uint8_t *)aligned((size_t)w * h * 8);
+    const int distinct = nframes < 4 ? nframes : 4;
+    for (int i = 0; i < distinct; i++) {
+        RunQBist(w, h, pitch, fmt, 0, gen);
+        uint8_t *f = (uint8_t *)aligned((size_t)pitch * h);
+        memcpy(f, gen, (size_t)pitch * h);
+        frames.push_back(f);
+    }
+    CFHD_EncoderRef enc = nullptr;
+    CFHD_DecoderRef dec = nullptr;
+    CFHD_Error e = CFHD_OpenEncoder(&enc, nullptr);
+    if (!e) e = CFHD_PrepareToEncode(enc, w, h, fmt, CFHD_ENCODED_FORMAT_YUV_422, CFHD_ENCODING_FLAGS_NONE, CFHD_ENCODING_QUALITY_FILMSCAN1);
+    if (e) { fprintf(stderr, "encoder setup failed: %d\n", (int)e); return 1; }
+    e = CFHD_OpenDecoder(&dec, nullptr);
+    if (e) { fprintf(stderr, "decoder open failed: %d\n", (int)e); return 1; }
+    uint8_t *out = (uint8_t *)aligned((size_t)pitch * h);
+    double enc_s = 0, dec_s = 0, mse_sum = 0;
+    size_t bytes = 0;
+    uint64_t hash = 1469598103934665603ull;
+    bool prepared = false;
+    for (int i = 0; i < nframes; i++) {
+        uint8_t *f = frames[i % distinct];
+        double t0 = now_s();
+        e = CFHD_EncodeSample(enc, f, pitch);
+        enc_s += now_s() - t0;
+        if (e) { fprintf(stderr, "CFHD_EncodeSample failed: %d\n", (int)e); return 2; }
+        void *sample = nullptr; size_t size = 0;
+        CFHD_GetSampleData(enc, &sample, &size);
+        bytes += size;
+        if (!prepared) {
+            int aw, ah; CFHD_PixelFormat af;
+            e = CFHD_PrepareToDecode(dec, w, h, fmt, CFHD_DECODED_RESOLUTION_FULL, CFHD_DECODING_FLAGS_NONE, sample, size, &aw, &ah, &af);
+            if (e) { fprintf(stderr, "CFHD_PrepareToDecode failed: %d\n", (int)e); return 3; }
+            prepared = true;
+        }
+        t0 = now_s();
+        e = CFHD_DecodeSample(dec, sample, size, out, pitch);
+        dec_s += now_s() - t0;
+        if (e) { fprintf(stderr, "CFHD_DecodeSample failed: %d\n", (int)e); return 4; }
+        double mse = 0;
+        for (size_t k = 0; k < (size_t)pitch * h; k += 2) { const double d = (double)out[k] - (double)f[k]; mse += d * d; }
+        mse_sum += mse / ((double)w * h);
+        for (size_t k = 0; k < (size_t)pitch * h; k += 97) { hash ^= (uint64_t)(out[k] >> 1); hash *= 1099511628211ull; }     // dither-insensitive digest
+    }
+    const double psnr = 10.0 * log10(255.0 * 255.0 / (mse_sum / nframes + 1e-12));
+
+    // asynchronous encoder pool, exactly the TestCFHD -E call sequence (TestCFHD.cpp:783-1047)
+    double pool_fps = 0;
+    if (pool_threads > 0) {
+        CFHD_EncoderPoolRef pool = nullptr;
+        e = CFHD_CreateEncoderPool(&pool, pool_threads, queue, nullptr);
+        if (!e) e = CFHD_PrepareEncoderPool(pool, w, h, fmt, CFHD_ENCODED_FORMAT_YUV_422, CFHD_ENCODING_FLAGS_NONE, CFHD_ENCODING_QUALITY_FILMSCAN1);
+        if (!e) e = CFHD_StartEncoderPool(pool);
+        if (e) { fprintf(stderr, "encoder pool setup failed: %d\n", (int)e); return 5; }
+        const int total = nframes * 8;
+        int submitted = 0, received = 0;
+        const double t0 = now_s();
+        while (received < total) {
+            while (submitted < total && submitted - received < queue) {
+                e = CFHD_EncodeAsyncSample(pool, submitted, frames[submitted % distinct], pitch, nullptr);
+                if (e) { fprintf(stderr, "CFHD_EncodeAsyncSample failed: %d\n", (int)e); return 6; }
+                submitted++;
+            }
+            uint32_t frameNumber = 0; CFHD_SampleBufferRef sb = nullptr;
+            e = CFHD_WaitForSample(pool, &frameNumber, &sb);
+            if (e) { fprintf(stderr, "CFHD_WaitForSample failed: %d\n", (int)e); return 7; }
+            if ((int)frameNumber != received) { fprintf(stderr, "out-of-order delivery %u != %d\n", frameNumber, received); return 8; }
+            CFHD_ReleaseSampleBuffer(pool, sb);
+            received++;
+        }
+        pool_fps = total / (now_s() - t0);
+        CFHD_StopEncoderPool(pool);
+        CFHD_ReleaseEncoderPool(pool);
+    }
+    printf("{\"width\": %d, \"height\": %d, \"frames\": %d, \"enc_ms\": %.3f, \"dec_ms\": %.3f, \"sample_bytes\": %zu, "
+           "\"luma_psnr_db\": %.3f, \"decoded_digest\": \"%016llx\", \"pool_threads\": %d, \"pool_fps\": %.1f}\n",
+           w, h, nframes, 1e3 * enc_s / nframes, 1e3 * dec_s / nframes, bytes / nframes, psnr, (unsigned long long)hash,
+           pool_threads, pool_fps);
+    CFHD_CloseEncoder(enc);
+    CFHD_CloseDecoder(dec);
+    return 0;
+}

@@ -35,7 +35,7 @@ def test_oracle_rg48_pyramid_matches_reference_encoder(pkg, size):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("size", [(256, 64), (288, 48), (640, 96), (1920, 1080)])
-@pytest.mark.parametrize("kind", ["natural", "random"])
+@pytest.mark.parametrize("kind", ["natural", "random", "extreme"])
 def test_forward_rg48_vs_oracle(pkg, size, kind):
     w, h = size
     rng = np.random.default_rng(w + h)
