@@ -52,15 +52,15 @@ int main(int argc, char **argv)
     size_t bytes = 0;
     uint64_t hash = 1469598103934665603ull;
     bool prepared = false;
-    for (int i = 0; i < nframes; i++) {
-        uint8_t *f = frames[i % distinct];
+    for (int i = -1; i < nframes; i++) {          // i == -1: untimed warm-up (lazy allocations, CUDA context)
+        uint8_t *f = frames[(i + distinct) % distinct];
         double t0 = now_s();
         e = CFHD_EncodeSample(enc, f, pitch);
-        enc_s += now_s() - t0;
+        if (i >= 0) enc_s += now_s() - t0;
         if (e) { fprintf(stderr, "CFHD_EncodeSample failed: %d\n", (int)e); return 2; }
         void *sample = nullptr; size_t size = 0;
         CFHD_GetSampleData(enc, &sample, &size);
-        bytes += size;
+        if (i >= 0) bytes += size;
         if (!prepared) {
             int aw, ah; CFHD_PixelFormat af;
             e = CFHD_PrepareToDecode(dec, w, h, fmt, CFHD_DECODED_RESOLUTION_FULL, CFHD_DECODING_FLAGS_NONE, sample, size, &aw, &ah, &af);
@@ -69,8 +69,9 @@ int main(int argc, char **argv)
         }
         t0 = now_s();
         e = CFHD_DecodeSample(dec, sample, size, out, pitch);
-        dec_s += now_s() - t0;
+        if (i >= 0) dec_s += now_s() - t0;
         if (e) { fprintf(stderr, "CFHD_DecodeSample failed: %d\n", (int)e); return 4; }
+        if (i < 0) continue;
         double mse = 0;
         for (size_t k = 0; k < (size_t)pitch * h; k += 2) { const double d = (double)out[k] - (double)f[k]; mse += d * d; }
         mse_sum += mse / ((double)w * h);
@@ -86,11 +87,12 @@ int main(int argc, char **argv)
         if (!e) e = CFHD_PrepareEncoderPool(pool, w, h, fmt, CFHD_ENCODED_FORMAT_YUV_422, CFHD_ENCODING_FLAGS_NONE, CFHD_ENCODING_QUALITY_FILMSCAN1);
         if (!e) e = CFHD_StartEncoderPool(pool);
         if (e) { fprintf(stderr, "encoder pool setup failed: %d\n", (int)e); return 5; }
-        const int total = nframes * 8;
+        const int warm = 2 * pool_threads, total = warm + nframes * 16;
         int submitted = 0, received = 0;
-        const double t0 = now_s();
+        double t0 = now_s();
         while (received < total) {
-            while (submitted < total && submitted - received < queue) {
+            if (received == warm && submitted == warm) t0 = now_s();
+            while (submitted < (received < warm ? warm : total) && submitted - received < queue) {
                 e = CFHD_EncodeAsyncSample(pool, submitted, frames[submitted % distinct], pitch, nullptr);
                 if (e) { fprintf(stderr, "CFHD_EncodeAsyncSample failed: %d\n", (int)e); return 6; }
                 submitted++;
@@ -102,7 +104,7 @@ int main(int argc, char **argv)
             CFHD_ReleaseSampleBuffer(pool, sb);
             received++;
         }
-        pool_fps = total / (now_s() - t0);
+        pool_fps = (total - warm) / (now_s() - t0);
         CFHD_StopEncoderPool(pool);
         CFHD_ReleaseEncoderPool(pool);
     }
