@@ -119,9 +119,9 @@ struct RawPlaneRow {
 __device__ __forceinline__ void load_plane_row(const unsigned char *p, const LaneInfo &L, RawPlaneRow &r)
 {
     r.v = __ldg(reinterpret_cast<const uint4 *>(p));
+    // ONE predicated halo load per row (two loads into the same register would serialise on its scoreboard)
     r.halo = 0u;
-    if (L.use_lh) r.halo = __ldg(reinterpret_cast<const unsigned *>(p - 4));
-    if (L.use_rh) r.halo = __ldg(reinterpret_cast<const unsigned *>(p + 16));
+    if (L.use_lh | L.use_rh) r.halo = __ldg(reinterpret_cast<const unsigned *>(p + (L.use_lh ? -4 : 16)));
 }
 
 // ---- packed 16-bit RGB (RG48) input: a lane's 8 pixels are 48 contiguous bytes; one channel (word SEL of each
@@ -139,10 +139,11 @@ __device__ __forceinline__ void load_rg48_row(const unsigned char *p, const Lane
     r.b = __ldg(reinterpret_cast<const uint4 *>(p + 16));
     r.c = __ldg(reinterpret_cast<const uint4 *>(p + 32));
     r.halo = 0u;
-    if (L.use_lh) r.halo = (unsigned)__ldg(reinterpret_cast<const unsigned short *>(p - 12 + 2 * SEL)) |
-                           ((unsigned)__ldg(reinterpret_cast<const unsigned short *>(p - 6 + 2 * SEL)) << 16);
-    if (L.use_rh) r.halo = (unsigned)__ldg(reinterpret_cast<const unsigned short *>(p + 48 + 2 * SEL)) |
-                           ((unsigned)__ldg(reinterpret_cast<const unsigned short *>(p + 54 + 2 * SEL)) << 16);
+    if (L.use_lh | L.use_rh) {
+        const unsigned char *h = p + (L.use_lh ? -12 : 48) + 2 * SEL;
+        r.halo = (unsigned)__ldg(reinterpret_cast<const unsigned short *>(h)) |
+                 ((unsigned)__ldg(reinterpret_cast<const unsigned short *>(h + 6)) << 16);
+    }
 }
 
 // word index w (0..23) of the 48-byte group as a (register, half) pair -> PRMT selector nibble pair
@@ -378,8 +379,11 @@ __device__ __forceinline__ void load_byr4_row(const unsigned char *p, int line_p
     r.b0 = __ldg(reinterpret_cast<const uint4 *>(p + line_pitch));
     r.b1 = __ldg(reinterpret_cast<const uint4 *>(p + line_pitch + 16));
     r.ha = make_uint2(0u, 0u); r.hb = make_uint2(0u, 0u);
-    if (L.use_lh) { r.ha = __ldg(reinterpret_cast<const uint2 *>(p - 8)); r.hb = __ldg(reinterpret_cast<const uint2 *>(p + line_pitch - 8)); }
-    if (L.use_rh) { r.ha = __ldg(reinterpret_cast<const uint2 *>(p + 32)); r.hb = __ldg(reinterpret_cast<const uint2 *>(p + line_pitch + 32)); }
+    if (L.use_lh | L.use_rh) {
+        const unsigned char *h = p + (L.use_lh ? -8 : 32);
+        r.ha = __ldg(reinterpret_cast<const uint2 *>(h));
+        r.hb = __ldg(reinterpret_cast<const uint2 *>(h + line_pitch));
+    }
 }
 
 // one plane sample from the quad (w1 = two pixels of the first line, w2 = of the second line)
@@ -498,9 +502,9 @@ struct Raw422Row {
 __device__ __forceinline__ void load_422_row(const unsigned char *p, const LaneInfo &L, Raw422Row &r)
 {
     r.v = __ldg(reinterpret_cast<const uint4 *>(p));
+    // ONE predicated halo load per row (two loads into the same register would serialise on its scoreboard)
     r.halo = make_uint2(0u, 0u);
-    if (L.use_lh) r.halo = __ldg(reinterpret_cast<const uint2 *>(p - 8));
-    if (L.use_rh) r.halo = __ldg(reinterpret_cast<const uint2 *>(p + 16));
+    if (L.use_lh | L.use_rh) r.halo = __ldg(reinterpret_cast<const uint2 *>(p + (L.use_lh ? -8 : 16)));
 }
 
 struct Sel422 {     // dp4a coefficient words (already scaled by 1 << shift)
