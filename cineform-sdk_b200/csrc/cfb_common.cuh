@@ -76,6 +76,10 @@ struct InvParams {
     unsigned char *out_base[kMaxBatch];
 };
 
+// fire-and-forget prefetch into L2 (no destination register, no scoreboard): hides DRAM latency for rows that
+// will be loaded a few iterations later
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 __device__ __forceinline__ int clamp16(int v) { return max(-32768, min(32767, v)); }
 
 __device__ __forceinline__ int quant1(int x, const QuantParam &q) {

@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(128) k_fwd_plane(const __grid_constant__ FwdPa
             load_plane_row(rp, L, n0);
             load_plane_row(rp + g.in_pitch, L, n1);
         }
+        if (j + 2 < jlast) { prefetch_l2(rp + 4 * g.in_pitch); prefetch_l2(rp + 5 * g.in_pitch); }
         int a[8], b[8];
         hfilter_plane<PRESCALE>(c0, L, a);
         hfilter_plane<PRESCALE>(c1, L, b);
@@ -645,6 +646,7 @@ __global__ void __launch_bounds__(128) k_fwd_422(const __grid_constant__ FwdPara
             load_422_row(rp, L, n0);
             load_422_row(rp + gy.in_pitch, L, n1);
         }
+        if (j + 2 < jlast) { prefetch_l2(rp + 4 * gy.in_pitch); prefetch_l2(rp + 5 * gy.in_pitch); }
         int ay[8], by[8], au[4], bu[4], av[4], bv[4];
         hfilter_422(c0, sel, L, ay, au, av);
         hfilter_422(c1, sel, L, by, bu, bv);

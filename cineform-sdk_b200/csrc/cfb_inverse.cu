@@ -185,6 +185,11 @@ __device__ __forceinline__ void inv_step(InvChan<NC> &s, const InvGeom &g, const
         load_raw<NC>(in, g.band_off[2], rc, active, s.nhl);
         load_raw<NC>(in, g.band_off[3], rc, active, s.nhh);
     }
+    if (r + 3 < y1 && active) {     // L2 prefetch two more rows ahead (no register, no scoreboard)
+        const unsigned rn = (unsigned)min(r + 4, H - 1) * g.pitch + colbyte, rc = (unsigned)(r + 3) * g.pitch + colbyte;
+        prefetch_l2(in + g.band_off[0] + rn); prefetch_l2(in + g.band_off[1] + rn);
+        prefetch_l2(in + g.band_off[2] + rc); prefetch_l2(in + g.band_off[3] + rc);
+    }
     int el[NC], ol[NC], eh[NC], oh[NC];
     vinv_mid<NC>(s.lp, s.lc, ln, vhl, el, ol);
     vinv_mid<NC>(s.hp, s.hc, hn, vhh, eh, oh);
