@@ -38,6 +38,21 @@ METRIC = "4K YUY2 encode+decode fps"
 WORKLOAD = "TestCFHD -E/-D 3840x2160 YUY2 4:2:2 (BASELINE.json configs[2]), FILMSCAN1, GOP 1, progressive"
 
 
+def ncu_traffic_per_launch(kernel_summary):
+    """DRAM bytes (read + write) of one launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/<round>_prof_*_summary.csv, taken with the same 16-frame batch); None if the summary is absent."""
+    path = os.path.join(ROOT, "profiles", kernel_summary)
+    try:
+        vals = {}
+        for line in open(path):
+            k, unit, v = line.rstrip("\n").split(",")[:3]
+            if k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                vals[k] = float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        return int(vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"])
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -301,13 +316,14 @@ def run_ours(args, rank, world, local_rank):
         ctx.synchronize(); torch.cuda.synchronize(); barrier()
         return D.max(e0.elapsed_time(e1))
 
+    # nvidia-smi clock / throttle sampling runs from here until the end of the e2e section, i.e. across every timed
+    # region of this run (device-resident steps, per-kernel roofline timing, pooled e2e stream)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = ctx.stats()["kernel_launches"]
     total_ms = timed(step_device, args.warmup, args.steps)
     launches = ctx.stats()["kernel_launches"] - launches0 - 6 * args.warmup
-    clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = aggregate_fps(world, B * args.steps, total_ms / 1000.0)
 
@@ -385,6 +401,8 @@ def run_ours(args, rank, world, local_rank):
                                 "h2d_bytes_per_step": int(B * (lay.frame_bytes + lay.coded_bytes)),
                                 "d2h_bytes_per_step": int(B * (lay.coded_bytes + lay.frame_bytes))}}
 
+    clocks = sampler.stop() if rank == 0 else None
+
     # ---- CPU baseline (rank 0, N == 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -404,7 +422,10 @@ def run_ours(args, rank, world, local_rank):
                        "roundtrip_luma_psnr_db": round(float(psnr), 2)},
             "roofline": {"bound": "hbm", "kernel": "k_fwd_422 (level-1 forward, packed 4:2:2 -> 12 bands, fused quant)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": l1_bytes,
+                         "traffic": ncu_traffic_per_launch("r01_prof_fwd422_summary.csv") if B == 16 else None,
+                         "traffic_source": "profiles/r01_prof_fwd422_summary.csv (ncu --set full, dram__bytes_read.sum + "
+                                           "dram__bytes_write.sum, one launch of 16 frames)",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": l1_bytes,
                          "kernel_ms": k_ms,
                          "inverse_l1": {"kernel": "k_inv_422", "achieved": achieved_inv, "frac": achieved_inv / peak,
                                         "kernel_ms": ki_ms}},
