@@ -17,6 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcfhd_b200.so")
 
 PIXEL_YUYV, PIXEL_UYVY, PIXEL_RG48, PIXEL_BYR4, PIXEL_PLANAR16 = 0, 1, 2, 3, 4
+RESOLUTION_FULL, RESOLUTION_HALF, RESOLUTION_QUARTER = 1, 2, 3
 MAX_CHANNELS, NUM_LEVELS, NUM_BANDS, MAX_BATCH = 4, 3, 4, 16
 BAND_NAMES = ("LL", "LH", "HL", "HH")
 
@@ -97,6 +98,9 @@ def lib():
     L.cfb_codec_device_pyramid.restype = vp
     L.cfb_codec_set_level_mask.argtypes = [vp, i, i]
     L.cfb_codec_set_bayer_phase.argtypes = [vp, i]
+    L.cfb_codec_set_decode_resolution.argtypes = [vp, i]
+    L.cfb_codec_decoded_size.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
+    L.cfb_pool_set_decode_resolution.argtypes = [vp, i]
     L.cfb_forward_device.argtypes = [vp, i, C.POINTER(vp), i, C.POINTER(Quant), C.POINTER(vp)]
     L.cfb_forward_host.argtypes = [vp, i, C.POINTER(vp), i, C.POINTER(Quant), C.POINTER(vp)]
     L.cfb_inverse_device.argtypes = [vp, i, C.POINTER(vp), C.POINTER(Quant), i, C.POINTER(vp), i]
@@ -249,6 +253,15 @@ class Codec:
     def set_level_mask(self, forward_mask=7, inverse_mask=7):
         _check(lib().cfb_codec_set_level_mask(self.h, forward_mask, inverse_mask))
 
+    def set_decode_resolution(self, resolution):
+        """RESOLUTION_FULL / _HALF / _QUARTER (CFHD_PrepareToDecode's decodedResolution)."""
+        _check(lib().cfb_codec_set_decode_resolution(self.h, resolution))
+
+    def decoded_size(self):
+        w, h = C.c_int(0), C.c_int(0)
+        _check(lib().cfb_codec_decoded_size(self.h, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
     # -- forward -----------------------------------------------------------
     def forward_device(self, d_frames, frame_pitch, quant, d_pyramids):
         n = len(d_frames)
@@ -366,6 +379,9 @@ class Pool:
 
     def __exit__(self, *a):
         self.close()
+
+    def set_decode_resolution(self, resolution):
+        _check(lib().cfb_pool_set_decode_resolution(self.h, resolution))
 
     def submit_forward(self, frame_number, frame, quant, coded):
         _check(lib().cfb_pool_submit_forward(self.h, frame_number, frame.ctypes.data, frame.strides[0], C.byref(quant),

@@ -367,6 +367,28 @@ cfb_error cfb_codec_set_level_mask(cfb_codec *cd, int forward_mask, int inverse_
     return CFB_OK;
 }
 
+cfb_error cfb_codec_set_decode_resolution(cfb_codec *cd, int resolution)
+{
+    if (!cd) { set_error("null codec"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (resolution < CFB_RESOLUTION_FULL || resolution > CFB_RESOLUTION_QUARTER) {
+        set_error("decode resolution %d not in {full=1, half=2, quarter=3}", resolution);
+        return CFB_ERROR_INVALID_ARGUMENT;
+    }
+    cd->decode_res = resolution;
+    return CFB_OK;
+}
+
+cfb_error cfb_codec_decoded_size(const cfb_codec *cd, int *width, int *height)
+{
+    if (!cd || !width || !height) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (cd->decode_res == CFB_RESOLUTION_FULL) { *width = cd->desc.width; *height = cd->desc.height; }
+    else {      // the lowpass image of level (res - 1) of channel 0: decoder.c:26078 (half), :17000 (quarter)
+        const cfb_band_layout &ll = cd->layout.band[0][cd->decode_res - 2][0];
+        *width = ll.width; *height = ll.height;
+    }
+    return CFB_OK;
+}
+
 void *cfb_codec_device_frame(cfb_codec *cd, int slot)
 {
     return (cd && slot >= 0 && slot < cd->max_batch) ? cd->d_frames + cd->frame_stride * slot : nullptr;
@@ -536,11 +558,13 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
     const cfb_layout &L = cd->layout;
     const int fmt = cd->desc.pixel_format;
     const bool is422 = (fmt == CFB_PIXEL_YUYV || fmt == CFB_PIXEL_UYVY);
+    int out_w = 0, out_h = 0;
+    cfb_codec_decoded_size(cd, &out_w, &out_h);
     if (out_format == CFB_PIXEL_YUYV || out_format == CFB_PIXEL_UYVY) {
         if (!is422) { set_error("8-bit 4:2:2 output needs a 4:2:2 codec"); return CFB_ERROR_BADFORMAT; }
-        if (frame_pitch < cd->desc.width * 2 || (frame_pitch & 15)) { set_error("bad output pitch %d", frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
+        if (frame_pitch < out_w * 2 || (frame_pitch & 15)) { set_error("bad output pitch %d", frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
     } else if (out_format == CFB_PIXEL_PLANAR16) {
-        if (frame_pitch < cd->desc.width * 2 || (frame_pitch & 15)) { set_error("bad output pitch %d", frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
+        if (frame_pitch < out_w * 2 || (frame_pitch & 15)) { set_error("bad output pitch %d", frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
     } else { set_error("output format %d not implemented", out_format); return CFB_ERROR_UNSUPPORTED; }
     for (int i = 0; i < n; i++)
         if (!d_frames[i] || !d_pyramids[i] || ((uintptr_t)d_frames[i] & 15) || ((uintptr_t)d_pyramids[i] & 15)) {
@@ -553,7 +577,7 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
     memset(&p, 0, sizeof(p));
     p.nchan = L.num_channels; p.nframes = n;
     // levels 3 -> 2 -> 1: output = LL of the level below, inside the pyramid
-    for (int k = CFB_NUM_LEVELS - 1; k >= 1; k--) {
+    for (int k = CFB_NUM_LEVELS - 1; k >= 1 && k >= cd->decode_res - 1; k--) {
         if (!(cd->inv_mask & (1 << k))) continue;
         int maxw = 0, maxh = 0;
         for (int c = 0; c < L.num_channels; c++) {
@@ -565,6 +589,34 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
         p.th = pick_th((maxw + kInvStrip - 1) / kInvStrip, maxh, n * L.num_channels, ctx->sm_count);
         CFB_CUDA(launch_inv_plane(p, quant->prescale[k], ctx->stream));
         ctx->kernel_launches++;
+    }
+    if (cd->decode_res != CFB_RESOLUTION_FULL) {
+        // reduced resolution: the output is the lowpass image of level kk+1 (decoder.c:26078-26160 half,
+        // decoder.c:11818 + :17000 quarter); the levels below are never inverted
+        const int kk = cd->decode_res - 2;
+        for (int c = 0; c < L.num_channels; c++) fill_inv_geom(cd, quant, c, kk, p.ch[c]);
+        if (out_format == CFB_PIXEL_PLANAR16) {
+            for (int i = 0; i < n; i++) {
+                long long off = 0;
+                for (int c = 0; c < L.num_channels; c++) {
+                    const InvGeom &g = p.ch[c];
+                    CFB_CUDA(cudaMemcpy2DAsync((unsigned char *)d_frames[i] + off, frame_pitch,
+                                               (const unsigned char *)d_pyramids[i] + g.band_off[0], g.pitch,
+                                               (size_t)g.width * 2, g.height, cudaMemcpyDeviceToDevice, ctx->stream));
+                    off += (long long)frame_pitch * g.height;
+                }
+            }
+        } else {
+            for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_pyramids[i]; p.out_base[i] = (unsigned char *)d_frames[i]; }
+            p.ch[0].out_pitch = frame_pitch;
+            p.shift = 4;                                        // PRESCALE_LUMA10 / descale (frame.c:11742, temporal.c:11373)
+            p.pad = (cd->decode_res == CFB_RESOLUTION_QUARTER); // unsigned shift + packus in the quarter path
+            p.uyvy = (out_format == CFB_PIXEL_UYVY);
+            CFB_CUDA(launch_lowpass_422(p, ctx->stream));
+            ctx->kernel_launches++;
+        }
+        ctx->frames_inverse += n;
+        return CFB_OK;
     }
     // level 1 -> pixels
     if (!(cd->inv_mask & 1)) { ctx->frames_inverse += n; return CFB_OK; }
@@ -602,21 +654,38 @@ cfb_error cfb_inverse_host(cfb_codec *cd, int n, const void *const *h_coded, con
     const cfb_layout &L = cd->layout;
     CFB_CUDA(cudaSetDevice(ctx->device));
     int rows, rowbytes, dpitch;
+    int out_w = 0, out_h = 0;
+    cfb_codec_decoded_size(cd, &out_w, &out_h);
+    const int kk = cd->decode_res - 1;          // lowest level that is inverted (0 = all three)
     if (out_format == CFB_PIXEL_PLANAR16) {
         rows = 0;
-        for (int c = 0; c < L.num_channels; c++) rows += L.band[c][0][0].height * 2;
-        rowbytes = cd->desc.width * 2; dpitch = cd->desc.width * 2;
+        for (int c = 0; c < L.num_channels; c++) rows += kk ? L.band[c][kk - 1][0].height : L.band[c][0][0].height * 2;
+        rowbytes = out_w * 2; dpitch = (out_w * 2 + 15) & ~15;
         if ((size_t)dpitch * rows > cd->frame_stride) { set_error("planar16 output does not fit the codec's frame staging"); return CFB_ERROR_UNSUPPORTED; }
     } else {
-        rows = cd->desc.height; rowbytes = cd->desc.width * 2; dpitch = cd->desc.width * 2;
+        rows = out_h; rowbytes = out_w * 2; dpitch = (out_w * 2 + 15) & ~15;
     }
     void *dpy[kMaxBatch], *dfr[kMaxBatch];
     for (int i = 0; i < n; i++) {
         if (!h_coded[i] || !h_frames[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
         dpy[i] = cfb_codec_device_pyramid(cd, i);
         dfr[i] = cfb_codec_device_frame(cd, i);
-        CFB_CUDA(cudaMemcpyAsync(dpy[i], h_coded[i], (size_t)L.coded_bytes, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->h2d_bytes += (uint64_t)L.coded_bytes;
+        if (kk == 0) {
+            CFB_CUDA(cudaMemcpyAsync(dpy[i], h_coded[i], (size_t)L.coded_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d_bytes += (uint64_t)L.coded_bytes;
+        } else {
+            // reduced resolution: each channel's bands are laid out LL3, level 3, level 2, level 1, so the levels a
+            // half/quarter decode reads are one contiguous prefix per channel (the decoder skips the rest of the
+            // sample the same way: decoder.c:1965-1984 decoded_subband_mask_half / _quarter)
+            for (int c = 0; c < L.num_channels; c++) {
+                const int64_t lo = L.band[c][CFB_NUM_LEVELS - 1][0].offset;
+                const cfb_band_layout &last = L.band[c][kk][3];
+                const int64_t hi = last.offset + (int64_t)last.pitch * last.height;
+                CFB_CUDA(cudaMemcpyAsync((unsigned char *)dpy[i] + lo, (const unsigned char *)h_coded[i] + lo, (size_t)(hi - lo),
+                                         cudaMemcpyHostToDevice, ctx->stream));
+                ctx->h2d_bytes += (uint64_t)(hi - lo);
+            }
+        }
     }
     cfb_error err = cfb_inverse_device(cd, n, dpy, quant, out_format, dfr, dpitch);
     if (err) return err;

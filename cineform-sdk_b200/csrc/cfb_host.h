@@ -30,6 +30,7 @@ cudaError_t launch_fwd_rg48(const FwdParams &p, int sel, cudaStream_t stream);
 cudaError_t launch_fwd_byr4(const FwdParams &p, cudaStream_t stream);
 cudaError_t launch_inv_plane(const InvParams &p, int descale, cudaStream_t stream);
 cudaError_t launch_inv_422(const InvParams &p, cudaStream_t stream);
+cudaError_t launch_lowpass_422(const InvParams &p, cudaStream_t stream);
 
 }  // namespace cfb
 
@@ -52,6 +53,7 @@ struct cfb_codec {
     size_t pyramid_stride = 0;
     int bayer_phase = 0;                    // BAYER_FORMAT_* (0 RED_GRN, 1 GRN_RED, 2 GRN_BLU, 3 BLU_GRN), DemoasicFrames.h:30
     int fwd_mask = 7, inv_mask = 7;         // profiling aid: levels to run
+    int decode_res = 1;                     // CFB_RESOLUTION_*: 1 full, 2 half (LL1), 3 quarter (LL2)
     // sparse transfer format staging (allocated on first use)
     unsigned char *d_sparse = nullptr;      // max_batch sparse buffers
     unsigned *d_counts = nullptr;           // max_batch * (nseg + 1)

@@ -370,6 +370,42 @@ __global__ void __launch_bounds__(128) k_inv_422(const __grid_constant__ InvPara
 }
 
 // ----------------------------------------------------------------------------
+// Reduced-resolution decode: pack the lowpass images of the three 4:2:2 channels to 8-bit YUYV/UYVY.
+//   half    (LL1): Codec/frame.c:11742 ConvertLowpass16s10bitToYUV   out = sat_u8(ll >> 4)        (signed shift)
+//   quarter (LL2): Codec/temporal.c:11362 CopyQuarterRowToBuffer     out = packus((uint16)ll >> 4) (unsigned shift)
+// Byte order Y0 U Y1 V with U = channel 2, V = channel 1 (the reference's "u"/"v" names are swapped, the bytes are
+// these).  One thread = 8 luma + 4 + 4 chroma coefficients = 16 output bytes; purely streaming.
+__global__ void __launch_bounds__(256) k_lowpass_422(const __grid_constant__ InvParams p)
+{
+    const int frame = blockIdx.z;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const InvGeom &gy = p.ch[0], &gv = p.ch[1], &gu = p.ch[2];
+    if (y >= gy.height || x8 >= gy.width) return;
+    const unsigned char *in = p.in_base[frame];
+    const uint4 yr = *reinterpret_cast<const uint4 *>(in + gy.band_off[0] + (long long)y * gy.pitch + x8 * 2);
+    const uint2 ur = *reinterpret_cast<const uint2 *>(in + gu.band_off[0] + (long long)y * gu.pitch + x8);
+    const uint2 vr = *reinterpret_cast<const uint2 *>(in + gv.band_off[0] + (long long)y * gv.pitch + x8);
+    const unsigned yw[4] = {yr.x, yr.y, yr.z, yr.w}, uw[2] = {ur.x, ur.y}, vw[2] = {vr.x, vr.y};
+    const int sh = p.shift;
+    const bool uns = p.pad != 0;
+    auto lo = [&](unsigned w) { return uns ? (int)(w & 0xffffu) >> sh : lo16(w) >> sh; };
+    auto hi = [&](unsigned w) { return uns ? (int)(w >> 16) >> sh : hi16(w) >> sh; };
+    unsigned o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int ya = lo(yw[k]), yb = hi(yw[k]);
+        const int cu = (k & 1) ? hi(uw[k >> 1]) : lo(uw[k >> 1]);
+        const int cv = (k & 1) ? hi(vw[k >> 1]) : lo(vw[k >> 1]);
+        o[k] = p.uyvy ? pack_u8x4(cu, ya, cv, yb) : pack_u8x4(ya, cu, yb, cv);
+    }
+    unsigned char *out = p.out_base[frame] + (long long)y * gy.out_pitch + x8 * 2;
+    const int rem = gy.width - x8;          // widths are even; a ragged tail stores whole 4-byte pairs
+    if (rem >= 8) *reinterpret_cast<uint4 *>(out) = make_uint4(o[0], o[1], o[2], o[3]);
+    else for (int k = 0; k < rem / 2; k++) reinterpret_cast<unsigned *>(out)[k] = o[k];
+}
+
+// ----------------------------------------------------------------------------
 static inline int ceil_div_i(int a, int b) { return (a + b - 1) / b; }
 
 cudaError_t launch_inv_plane(const InvParams &p, int descale, cudaStream_t stream)
@@ -392,6 +428,14 @@ cudaError_t launch_inv_422(const InvParams &p, cudaStream_t stream)
     bool small = true;
     for (int c = 0; c < 3; c++) for (int b = 1; b < 4; b++) small = small && (p.ch[c].dq[b] >= 0 && p.ch[c].dq[b] <= 255);
     if (small) k_inv_422<true><<<grid, block, 0, stream>>>(p); else k_inv_422<false><<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lowpass_422(const InvParams &p, cudaStream_t stream)
+{
+    dim3 block(32, 8);
+    dim3 grid(ceil_div_i(ceil_div_i(p.ch[0].width, 8), 32), ceil_div_i(p.ch[0].height, 8), p.nframes);
+    k_lowpass_422<<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

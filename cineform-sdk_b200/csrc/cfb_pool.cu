@@ -150,6 +150,17 @@ cfb_error cfb_pool_create(const int *devices, int ndevices, const cfb_frame_desc
     return CFB_OK;
 }
 
+cfb_error cfb_pool_set_decode_resolution(cfb_pool *pool, int resolution)
+{
+    if (!pool) { set_error("null pool"); return CFB_ERROR_INVALID_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(pool->mu);          // applies to jobs submitted after this call returns
+    for (auto &s : pool->slots) {
+        cfb_error e = cfb_codec_set_decode_resolution(s->codec, resolution);
+        if (e) return e;
+    }
+    return CFB_OK;
+}
+
 void cfb_pool_destroy(cfb_pool *pool)
 {
     if (!pool) return;

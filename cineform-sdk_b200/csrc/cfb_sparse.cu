@@ -315,12 +315,14 @@ cfb_error cfb_inverse_host_sparse(cfb_codec *cd, int n, const void *const *h_spa
     }
     CFB_CUDA(launch_sparse_expand(sp, ctx->stream));
     ctx->kernel_launches += 3;
-    const int dpitch = cd->desc.width * 2;
+    int out_w = 0, out_h = 0;
+    cfb_codec_decoded_size(cd, &out_w, &out_h);     // reduced-resolution decodes return the LL1 / LL2 picture
+    const int rowbytes = out_w * 2, dpitch = (rowbytes + 15) & ~15;
     err = cfb_inverse_device(cd, n, dpy, quant, out_format, dfr, dpitch);
     if (err) return err;
     for (int i = 0; i < n; i++) {
-        CFB_CUDA(cudaMemcpy2DAsync(h_frames[i], frame_pitch, dfr[i], dpitch, dpitch, cd->desc.height, cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->d2h_bytes += (uint64_t)dpitch * cd->desc.height;
+        CFB_CUDA(cudaMemcpy2DAsync(h_frames[i], frame_pitch, dfr[i], dpitch, rowbytes, out_h, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h_bytes += (uint64_t)rowbytes * out_h;
     }
     CFB_CUDA(stream_wait(ctx));
     return CFB_OK;

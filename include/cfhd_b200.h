@@ -148,6 +148,22 @@ CFB_API void *cfb_codec_device_pyramid(cfb_codec *codec, int slot);
  * (Codec/DemoasicFrames.h:30-33).  The frame must already carry its encode curve (CFHD_ENCODING_FLAGS_CURVE_APPLIED). */
 CFB_API cfb_error cfb_codec_set_bayer_phase(cfb_codec *codec, int bayer_format);
 
+/* Decoded resolution of the following cfb_inverse_* calls: the decodedResolution argument of CFHD_PrepareToDecode
+ * (DecoderSDK/CFHDDecoder.cpp; Common/CFHDTypes.h:453-456, same numbering).  HALF stops after level 2 -> 1 and
+ * returns the lowpass image LL1 (Codec/decoder.c:26078-26160 -> CopyLowpass16sToBuffer :22883 ->
+ * ConvertLowpass16s10bitToYUV frame.c:11742: sat_u8(ll >> 4)); QUARTER stops after level 3 -> 2 and returns LL2
+ * (decoder.c:11818 -> ConvertQuarterFrameToBuffer :17000 -> CopyQuarterRowToBuffer temporal.c:11362:
+ * packus((uint16)ll >> 4)).  CFB_PIXEL_PLANAR16 output returns the raw int16 lowpass planes instead.  The host
+ * variants upload only the subbands the reduced decode reads (decoder.c:1965-1984 subband masks 0x7F / 0x0F). */
+typedef enum cfb_resolution {
+    CFB_RESOLUTION_FULL = 1,
+    CFB_RESOLUTION_HALF = 2,
+    CFB_RESOLUTION_QUARTER = 3
+} cfb_resolution;
+CFB_API cfb_error cfb_codec_set_decode_resolution(cfb_codec *codec, int resolution);
+/* width/height (pixels) of the frames cfb_inverse_* writes at the current decode resolution */
+CFB_API cfb_error cfb_codec_decoded_size(const cfb_codec *codec, int *width, int *height);
+
 /* Profiling aid: restrict the following forward/inverse calls to a subset of pyramid levels
  * (bit k = level k+1; default 7 = all).  Used by bench.py to time one kernel in isolation. */
 CFB_API cfb_error cfb_codec_set_level_mask(cfb_codec *codec, int forward_mask, int inverse_mask);
@@ -216,6 +232,8 @@ CFB_API void cfb_host_free(void *p);
  * A failed job is returned in order with its error; the pool keeps running. */
 CFB_API cfb_error cfb_pool_create(const int *devices, int ndevices, const cfb_frame_desc *desc,
                                   int slots, int batch, int queue_length, cfb_pool **out);
+/* decode resolution of every inverse job submitted afterwards (call with the pool idle) */
+CFB_API cfb_error cfb_pool_set_decode_resolution(cfb_pool *pool, int resolution);
 CFB_API void cfb_pool_destroy(cfb_pool *pool);
 /* forward: h_frame (frame_pitch bytes per row) -> h_coded (cfb_layout.coded_bytes) */
 CFB_API cfb_error cfb_pool_submit_forward(cfb_pool *pool, uint32_t frame_number, const void *h_frame, int frame_pitch,

@@ -17,6 +17,30 @@ static inline int16_t subs(int16_t a, int16_t b) { return sat16((int32_t)a - b);
 static inline int16_t wrap16(int32_t v) { return (int16_t)(uint16_t)(uint32_t)v; }
 static inline int16_t sra16(int16_t a, int s) { return (int16_t)(a >> s); }
 
+static uint8_t lowpass_px(int16_t c, int shift, int unsigned_shift)
+{
+    int v = unsigned_shift ? ((int)(uint16_t)c >> shift) : ((int)c >> shift);
+    return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+void orc_lowpass_to_422(const int16_t *y, int y_pitch, const int16_t *v, int v_pitch, const int16_t *u, int u_pitch,
+                        int width, int height, int shift, int unsigned_shift, int uyvy,
+                        uint8_t *out, int out_pitch)
+{
+    for (int r = 0; r < height; r++) {
+        const int16_t *yr = (const int16_t *)((const uint8_t *)y + (size_t)r * y_pitch);
+        const int16_t *vr = (const int16_t *)((const uint8_t *)v + (size_t)r * v_pitch);
+        const int16_t *ur = (const int16_t *)((const uint8_t *)u + (size_t)r * u_pitch);
+        uint8_t *o = out + (size_t)r * out_pitch;
+        for (int x = 0; x < width; x += 2) {
+            const uint8_t y0 = lowpass_px(yr[x], shift, unsigned_shift), y1 = lowpass_px(yr[x + 1], shift, unsigned_shift);
+            const uint8_t cu = lowpass_px(ur[x / 2], shift, unsigned_shift), cv = lowpass_px(vr[x / 2], shift, unsigned_shift);
+            if (uyvy) { o[2 * x] = cu; o[2 * x + 1] = y0; o[2 * x + 2] = cv; o[2 * x + 3] = y1; }
+            else      { o[2 * x] = y0; o[2 * x + 1] = cu; o[2 * x + 2] = y1; o[2 * x + 3] = cv; }
+        }
+    }
+}
+
 int orc_version(void) { return 1; }
 
 /* ------------------------------------------------------------------------- */

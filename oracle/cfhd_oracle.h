@@ -67,6 +67,18 @@ void orc_inv_level(const int16_t *ll, const int16_t *lh, const int16_t *hl, cons
                    int band_pitch, int width, int height, int descale,
                    int16_t *out, int out_pitch);
 
+/* Reduced-resolution decode, 4:2:2 sources, 8-bit packed output from the lowpass images of the three channels
+ * (y = channel 0, v = channel 1, u = channel 2 in the encoder's numbering; bytes Y0 U Y1 V or U Y0 V Y1):
+ *   half (unsigned_shift = 0): Codec/frame.c:11742 ConvertLowpass16s10bitToYUV scalar loop (:11880-11892; the MMX
+ *     dither branch is compiled out on x86-64):  sat_u8(ll >> shift), shift = PRESCALE_LUMA10 = 4;
+ *   quarter (unsigned_shift = 1): Codec/temporal.c:11362 CopyQuarterRowToBuffer: the coefficients are read as
+ *     uint16 and `_mm_srli_epi16(x, 4)` then `_mm_packus_epi16`.  (Its SIMD loop stores the first 8 pixels of every
+ *     16 in YUYV order even when UYVY is requested, :11395-11398; that quirk is NOT restated: uyvy=1 gives UYVY.)
+ * width/height = luma lowpass dimensions; pitches in bytes. */
+void orc_lowpass_to_422(const int16_t *y, int y_pitch, const int16_t *v, int v_pitch, const int16_t *u, int u_pitch,
+                        int width, int height, int shift, int unsigned_shift, int uyvy,
+                        uint8_t *out, int out_pitch);
+
 /* 3-level pyramid helpers are composed in Python (tests/) from the calls above. */
 
 int orc_version(void);

@@ -248,18 +248,42 @@ int ref_decode_sample(const uint8_t *sample, int64_t size, int width, int height
     return (int)err;
 }
 
+// Public-API decode at a reduced resolution (CFHD_DECODED_RESOLUTION_HALF = 2, _QUARTER = 3; SDK
+// CFHDTypes.h).  `out` must hold out_pitch * height bytes (full-size is always enough); the actual decoded
+// dimensions are returned in dims[0..1].
+int ref_decode_sample_res(const uint8_t *sample, int64_t size, int width, int height, unsigned pixel_format,
+                          int resolution, uint8_t *out, int out_pitch, int32_t *dims)
+{
+    CFHD_DecoderRef dec = NULL;
+    CFHD_Error err = CFHD_OpenDecoder(&dec, NULL);
+    if (err) return (int)err;
+    Aligned smp((size_t)size + 64), o((size_t)out_pitch * height + 64);
+    memcpy(smp.p, sample, (size_t)size);
+    int aw = 0, ah = 0;
+    CFHD_PixelFormat af = (CFHD_PixelFormat)0;
+    err = CFHD_PrepareToDecode(dec, 0, 0, (CFHD_PixelFormat)pixel_format, (CFHD_DecodedResolution)resolution,
+                               CFHD_DECODING_FLAGS_NONE, smp.p, (size_t)size, &aw, &ah, &af);
+    if (!err) err = CFHD_DecodeSample(dec, smp.p, (size_t)size, o.p, out_pitch);
+    if (!err) memcpy(out, o.p, (size_t)out_pitch * height);
+    dims[0] = aw; dims[1] = ah;
+    CFHD_CloseDecoder(dec);
+    return (int)err;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Codec-level decode (Codec/decoder.c:1497 DecodeInit + :10078 DecodeSample) that also copies out the
 // DECODER's wavelet bands as they stand after the decode: highpass bands hold the DEQUANTISED
 // coefficients produced by the FSM entropy decoder (decoder.c:20551), band[0] of level 3 the raw LL3
 // and band[0] of levels 2,1 the reconstructed lowpass images.  Same output conventions as
 // ref_encode_frame_bands.  decoded_format: DECODED_FORMAT_* (== COLOR_FORMAT_*).  Returns 0 on success.
+static int g_decode_resolution = DECODED_RESOLUTION_FULL;
+void ref_set_decode_resolution(int resolution) { g_decode_resolution = resolution ? resolution : DECODED_RESOLUTION_FULL; }
 int ref_decode_sample_bands(const uint8_t *sample, int64_t size, int width, int height, int decoded_format,
                             int num_channels, uint8_t *out, int out_pitch,
                             int32_t *dims, int32_t *quant, int16_t *bands, int64_t bands_capacity)
 {
     DECODER *dec = (DECODER *)calloc(1, DecoderSize());
-    if (!DecodeInit(NULL, dec, width, height, decoded_format, DECODED_RESOLUTION_FULL, NULL)) return 1;
+    if (!DecodeInit(NULL, dec, width, height, decoded_format, g_decode_resolution, NULL)) return 1;
     SetDecoderColorFlags(dec, COLOR_SPACE_CG_709);
     SetDecoderFlags(dec, DECODER_FLAGS_RENDER);      // as CSampleDecoder::DecodeSample does (SampleDecoder.cpp:1507)
     Aligned smp((size_t)size + 64), o((size_t)out_pitch * (height + 16) + 64);
@@ -272,7 +296,7 @@ int ref_decode_sample_bands(const uint8_t *sample, int64_t size, int width, int 
     for (int c = 0; c < num_channels; c++) {
         for (int k = 0; k < 3; k++) {
             IMAGE *w = dec->transform[c]->wavelet[k];
-            if (!w) return 3;
+            if (!w) { dims[(c * 3 + k) * 3 + 0] = dims[(c * 3 + k) * 3 + 1] = 0; continue; }   // reduced-resolution decode
             dims[(c * 3 + k) * 3 + 0] = w->width; dims[(c * 3 + k) * 3 + 1] = w->height; dims[(c * 3 + k) * 3 + 2] = w->pitch;
             for (int b = 0; b < 4; b++) {
                 quant[c * 12 + k * 4 + b] = w->quantization[b];

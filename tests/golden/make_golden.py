@@ -6,7 +6,8 @@ the unmodified reference compiled in place).  Run in the build container (needs 
 Each .npz holds a Qbist input frame (TestCFHD's generator, seed 50) and every wavelet band the
 reference's own EncodeSample produced for it (transform[c]->wavelet[k]->band[b]), the quantisation
 tables it used, the DEQUANTISED bands the reference's decoder holds after entropy-decoding that sample
-(d_*) and the 8-bit YUY2 frame its DecodeSample reconstructs from them.  tests/test_golden.py (CPU, oracle) and tests/test_forward_gpu.py
+(d_*), the lowpass images LL1/LL2 its inverse transform rebuilds (r_*), the 8-bit YUY2 frame its DecodeSample
+reconstructs from them, and the half- and quarter-resolution decodes of the same sample (decoded_half/quarter_yuy2).  tests/test_golden.py (CPU, oracle) and tests/test_forward_gpu.py
 (GPU, CUDA path) compare against these files, so the GPU box needs neither the reference tree
 nor oracle/_ref."""
 import os
@@ -31,13 +32,24 @@ def main():
         rc = ref_lib.ref_decode_sample(sample.ctypes.data_as(C.c_void_p), C.c_int64(sample.size), w, h,
                                        ol.CFHD_PIXEL_FORMAT_YUY2, decoded.ctypes.data_as(C.c_void_p), w * 2)
         assert rc == 0
-        arrays = {"frame": frame, "decoded_yuy2": decoded, "divisors": np.array(div, np.int32), "prescale": np.array(prescale[0], np.int32),
+        reduced = {}
+        for res, name in ((2, "half"), (3, "quarter")):                     # public API, reduced resolution
+            buf = np.zeros_like(frame)
+            dims = np.zeros(2, np.int32)
+            rc = ref_lib.ref_decode_sample_res(sample.ctypes.data_as(C.c_void_p), C.c_int64(sample.size), w, h,
+                                               ol.CFHD_PIXEL_FORMAT_YUY2, res, buf.ctypes.data_as(C.c_void_p), w * 2,
+                                               dims.ctypes.data_as(C.c_void_p))
+            assert rc == 0
+            reduced[f"decoded_{name}_yuy2"] = buf[:int(dims[1]), :int(dims[0]) * 2].copy()
+        arrays = {"frame": frame, "decoded_yuy2": decoded, **reduced, "divisors": np.array(div, np.int32), "prescale": np.array(prescale[0], np.int32),
                   "quality": np.array(quality), "sample_size": np.array(sample.size)}
         for (c, lvl, name), a in bands.items():
             arrays[f"b_{c}_{lvl}_{name}"] = a
         for (c, lvl, name), a in dec_bands.items():      # decoder side: dequantised, as the FSM decoder leaves them
             if name != "LL" or lvl == 3:
                 arrays[f"d_{c}_{lvl}_{name}"] = a
+            else:                                       # the decoder's reconstructed lowpass images LL1, LL2
+                arrays[f"r_{c}_{lvl}_LL"] = a
         path = os.path.join(HERE, f"qbist_yuy2_{w}x{h}_f{frame_no}_q{quality}.npz")
         np.savez_compressed(path, **arrays)
         print(path, os.path.getsize(path))

@@ -108,19 +108,36 @@ def dequantize(band, divisor):
     return (band.astype(np.int32) * divisor).astype(np.int16)
 
 
-def inverse_pyramid(impl, bands, divisors, prescale, nchan=3):
+def inverse_pyramid(impl, bands, divisors, prescale, nchan=3, stop_level=0):
     """bands: {(c, level, name)} QUANTISED coded-region bands (LL3 + highpass of levels 1..3).
-    Returns the reconstructed int16 plane of every channel at codec precision (list)."""
+    Returns the reconstructed int16 plane of every channel at codec precision (list); stop_level = 1 / 2 stops at
+    the lowpass image LL1 / LL2 (half / quarter resolution decode)."""
     planes = []
     for c in range(nchan):
         ll = bands[(c, 3, "LL")]
-        for k in (2, 1, 0):
+        for k in (2, 1, 0)[:3 - stop_level]:
             lh = dequantize(bands[(c, k + 1, "LH")], divisors[c][k][1])
             hl = dequantize(bands[(c, k + 1, "HL")], divisors[c][k][2])
             hh = dequantize(bands[(c, k + 1, "HH")], divisors[c][k][3])
             ll = impl.inv_level(ll, lh, hl, hh, 2 if prescale[k] == 2 else 0)
         planes.append(ll)
     return planes
+
+
+def lowpass_to_422(planes, unsigned_shift, uyvy=False, shift=4):
+    """oracle/cfhd_oracle.c orc_lowpass_to_422 on [y, v, u] lowpass planes -> packed 8-bit frame."""
+    import ctypes as C
+    import oracle_lib as ol
+    y, v, u = [np.ascontiguousarray(p, np.int16) for p in planes]
+    h, w = y.shape
+    out = np.zeros((h, w * 2), np.uint8)
+    lib = ol.load_oracle()
+    lib.orc_lowpass_to_422.restype = None
+    vp = C.c_void_p
+    lib.orc_lowpass_to_422(vp(y.ctypes.data), C.c_int(y.strides[0]), vp(v.ctypes.data), C.c_int(v.strides[0]),
+                           vp(u.ctypes.data), C.c_int(u.strides[0]), C.c_int(w), C.c_int(h), C.c_int(shift),
+                           C.c_int(int(unsigned_shift)), C.c_int(int(uyvy)), vp(out.ctypes.data), C.c_int(w * 2))
+    return out
 
 
 def yuyv_envelope(planes, shift=2, uyvy=False):

@@ -56,3 +56,27 @@ def test_oracle_inverse_inside_reference_decoder_envelope(path):
     ok = (dec == a) | (dec == b)
     assert ok.all(), f"{(~ok).sum()} bytes outside the dither envelope"
     assert pu.psnr(dec[:, 0::2], frame[:, 0::2]) > 45.0
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_oracle_reduced_resolution_decode(path):
+    """Half / quarter resolution decode (decoder.c:26078, :11818): the oracle's partial inverse pyramid must give the
+    reference decoder's own lowpass images LL1 / LL2 bit for bit, its half-resolution packing must equal the frame
+    CFHD_DecodeSample returned at CFHD_DECODED_RESOLUTION_HALF byte for byte, and the quarter-resolution packing
+    (CopyQuarterRowToBuffer, temporal.c:11362) must stay within the rounding of the SDK's quarter-resolution output,
+    which the public API renders through its 16-bit active-metadata path and re-dithers."""
+    z = np.load(path)
+    _, _, prescale, _, _ = load_golden(path)
+    bands, _ = load_golden_decoder_side(path)
+    for stop, name, unsigned in ((1, "half", False), (2, "quarter", True)):
+        planes = pu.inverse_pyramid(ol.oracle(), bands, pu.UNIT_DIVISORS, prescale, stop_level=stop)
+        for c in range(3):
+            assert np.array_equal(planes[c], z[f"r_{c}_{stop}_LL"]), f"LL{stop} channel {c}"
+        got = pu.lowpass_to_422(planes, unsigned)
+        want = z[f"decoded_{name}_yuy2"]
+        assert got.shape == want.shape
+        if name == "half":
+            assert np.array_equal(got, want)
+        else:
+            d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+            assert (d > 2).mean() < 2e-3 and d.max() <= 16 and d.mean() < 0.6, (d.max(), d.mean())

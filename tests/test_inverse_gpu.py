@@ -116,3 +116,68 @@ def test_roundtrip_4k_batch(pkg, ctx):
     for f, o, o2 in zip(frames, outs, outs2):
         assert np.array_equal(o, o2)
         assert pu.psnr(o[:, 0::2], f[:, 0::2]) > 45.0
+
+
+def _reduced(codec, pkg, coded, quant, res, fmt):
+    """Decode `coded` at a reduced resolution: returns (packed 8-bit frame, [Y, V, U] int16 lowpass planes)."""
+    codec.set_decode_resolution(res)
+    try:
+        w, h = codec.decoded_size()
+        out = np.zeros((h, w * 2), np.uint8)
+        codec.inverse_host([coded], quant, fmt, [out])
+        pl = np.zeros((3 * h, w), np.int16)
+        codec.inverse_host([coded], quant, pkg.PIXEL_PLANAR16, [pl])
+    finally:
+        codec.set_decode_resolution(pkg.RESOLUTION_FULL)
+    return out, [pl[0:h, :w], pl[h:2 * h, :w // 2], pl[2 * h:3 * h, :w // 2]]
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_reduced_resolution_golden(pkg, ctx, path):
+    """CFHD_DECODED_RESOLUTION_HALF / _QUARTER: lowpass images equal the reference decoder's own LL1 / LL2, the
+    half-resolution frame equals what CFHD_DecodeSample returned byte for byte, the quarter-resolution frame equals
+    the oracle's CopyQuarterRowToBuffer restatement."""
+    z = np.load(path)
+    frame, _, prescale, _, _ = load_golden(path)
+    bands, _ = load_golden_decoder_side(path)
+    h, w2 = frame.shape
+    desc = pkg.FrameDesc(w2 // 2, h, pkg.PIXEL_YUYV)
+    unit = pkg.make_quant(pu.UNIT_DIVISORS, prescale)
+    with pkg.Codec(ctx, desc, 1) as codec:
+        coded = codec.pack_coded(bands)
+        for res, stop, name in ((pkg.RESOLUTION_HALF, 1, "half"), (pkg.RESOLUTION_QUARTER, 2, "quarter")):
+            out, planes = _reduced(codec, pkg, coded, unit, res, pkg.PIXEL_YUYV)
+            _check_planes(planes, [z[f"r_{c}_{stop}_LL"] for c in range(3)])
+            assert np.array_equal(out, pu.lowpass_to_422(planes, unsigned_shift=(stop == 2)))
+            if name == "half":
+                assert np.array_equal(out, z["decoded_half_yuy2"])
+        # and the codec still decodes at full resolution afterwards
+        full = np.zeros((h, w2), np.uint8)
+        codec.inverse_host([coded], unit, pkg.PIXEL_YUYV, [full])
+        assert np.abs(full.astype(int) - z["decoded_yuy2"].astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("size", [(192, 48), (448, 120), (1920, 1080), (3840, 2160)])
+@pytest.mark.parametrize("fmt_name", ["YUYV", "UYVY"])
+def test_reduced_resolution_vs_oracle(pkg, ctx, size, fmt_name):
+    """Random (adversarial: negative and > 4095 lowpass values occur) coefficients: both shift rules and byte orders."""
+    w, h = size
+    fmt = getattr(pkg, "PIXEL_" + fmt_name)
+    rng = np.random.default_rng(w * 3 + h)
+    frame = pu.synthetic_yuyv(rng, w, h, "random")
+    desc = pkg.FrameDesc(w, h, pkg.PIXEL_YUYV)
+    quant = pkg.quant_for_quality(desc, 3)
+    orc = ol.oracle()
+    coded_bands = pu.oracle_forward_422(orc, frame, quant, 0)
+    # push the lowpass images out of the 8-bit range in places: scale LL3 of every channel
+    for c in range(3):
+        ll = coded_bands[(c, 3, "LL")].astype(np.int32)
+        coded_bands[(c, 3, "LL")] = np.clip((ll - 8000) * 3, -32768, 32767).astype(np.int16)
+    with pkg.Codec(ctx, desc, 1) as codec:
+        coded = codec.pack_coded(coded_bands)
+        for res, stop in ((pkg.RESOLUTION_HALF, 1), (pkg.RESOLUTION_QUARTER, 2)):
+            want = pu.inverse_pyramid(orc, coded_bands, quant.table(3), tuple(quant.prescale), stop_level=stop)
+            out, planes = _reduced(codec, pkg, coded, quant, res, fmt)
+            _check_planes(planes, want)
+            assert np.array_equal(out, pu.lowpass_to_422(want, unsigned_shift=(stop == 2), uyvy=(fmt_name == "UYVY")))
+            assert out.min() == 0 and out.max() == 255          # the saturating paths were exercised
