@@ -99,6 +99,8 @@ def lib():
     L.cfb_codec_set_level_mask.argtypes = [vp, i, i]
     L.cfb_codec_set_bayer_phase.argtypes = [vp, i]
     L.cfb_codec_set_decode_resolution.argtypes = [vp, i]
+    L.cfb_codec_set_interlaced.argtypes = [vp, i]
+    L.cfb_quant_for_source.argtypes = [C.POINTER(FrameDesc), i, i, C.POINTER(Quant)]
     L.cfb_codec_decoded_size.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
     L.cfb_pool_set_decode_resolution.argtypes = [vp, i]
     L.cfb_forward_device.argtypes = [vp, i, C.POINTER(vp), i, C.POINTER(Quant), C.POINTER(vp)]
@@ -145,9 +147,9 @@ def layout_for(desc):
     return out
 
 
-def quant_for_quality(desc, quality):
+def quant_for_quality(desc, quality, interlaced=False):
     out = Quant()
-    _check(lib().cfb_quant_for_quality(C.byref(desc), quality, C.byref(out)))
+    _check(lib().cfb_quant_for_source(C.byref(desc), quality, int(bool(interlaced)), C.byref(out)))
     return out
 
 
@@ -252,6 +254,10 @@ class Codec:
 
     def set_level_mask(self, forward_mask=7, inverse_mask=7):
         _check(lib().cfb_codec_set_level_mask(self.h, forward_mask, inverse_mask))
+
+    def set_interlaced(self, interlaced=True):
+        """Level 1 = field transform (CFHD_ENCODING_FLAGS_YUV_INTERLACED)."""
+        _check(lib().cfb_codec_set_interlaced(self.h, int(bool(interlaced))))
 
     def set_decode_resolution(self, resolution):
         """RESOLUTION_FULL / _HALF / _QUARTER (CFHD_PrepareToDecode's decodedResolution)."""

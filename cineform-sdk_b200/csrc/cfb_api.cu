@@ -33,12 +33,14 @@ cfb_error cuda_fail(cudaError_t e, const char *what)
 }
 
 // Codec/quantize.c:1395-1427: multiplier = 65536/d, midpoint = d/g (g in [2,9)), minus one when g == 2.
-QuantParam make_quant_param(int divisor, int g)
+QuantParam make_quant_param(int divisor, int g, bool plain_midpoint)
 {
     QuantParam q;
     if (divisor <= 1) { q.m = 65536; q.cpos = 0; q.cneg = 65535; q.pad = 0; return q; }
     int mid = 0;
-    if (g >= 2 && g < 9) { mid = divisor / g; if (g == 2 && mid) mid--; }
+    // plain_midpoint: the difference-filtered HL band of the field transform rounds with divisor / g and has no
+    // "-1" adjustment (spatial.c:5356-5358), unlike QuantizeRow16sTo16s (quantize.c:1415-1427)
+    if (g >= 2 && g < 9) { mid = divisor / g; if (g == 2 && mid && !plain_midpoint) mid--; }
     q.m = 65536 / divisor;
     q.cpos = mid * q.m;
     q.cneg = 65535 - mid * q.m;
@@ -163,6 +165,11 @@ cfb_error cfb_layout_compute(const cfb_frame_desc *desc, cfb_layout *out)
 // band scales {4,2,2,1}, {16,8,8,4}, {64,32,32,16}), Codec/wavelet.c:1710 (SetTransformPrescale).
 cfb_error cfb_quant_for_quality(const cfb_frame_desc *desc, int quality, cfb_quant *out)
 {
+    return cfb_quant_for_source(desc, quality, 0, out);
+}
+
+cfb_error cfb_quant_for_source(const cfb_frame_desc *desc, int quality, int interlaced, cfb_quant *out)
+{
     if (!desc || !out) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
     cfb_layout lay;
     cfb_error err = cfb_layout_compute(desc, &lay);
@@ -219,6 +226,10 @@ cfb_error cfb_quant_for_quality(const cfb_frame_desc *desc, int quality, cfb_qua
         static const int gains[4] = {8, 6, 4, 4};
         const int chromagain = gains[rgb_quality];
         for (int i = 11; i < 17; i++) { ql[i] *= 4; qc[i] *= chromagain; }
+    }
+    if (interlaced) {       // quantize.c:490-541 (!progressive): LH of the field transform * 3/2, HL * 2/3
+        ql[11] = ql[11] * 3 / 2; ql[12] = ql[12] * 2 / 3; ql[14] = ql[14] * 3 / 2; ql[15] = ql[15] * 2 / 3;
+        qc[11] = qc[11] * 3 / 2; qc[12] = qc[12] * 2 / 3; qc[14] = qc[14] * 3 / 2; qc[15] = qc[15] * 2 / 3;
     }
     // GOP length 1 (quantize.c:552-567)
     for (int i = 0; i < 3; i++) { ql[7 + i] = ql[11 + i]; qc[7 + i] = qc[11 + i]; }
@@ -340,6 +351,7 @@ void cfb_codec_destroy(cfb_codec *cd)
     if (cd->ctx) cudaSetDevice(cd->ctx->device);
     if (cd->d_frames) cudaFree(cd->d_frames);
     if (cd->d_pyramids) cudaFree(cd->d_pyramids);
+    if (cd->d_carry) cudaFree(cd->d_carry);
     if (cd->d_sparse) cudaFree(cd->d_sparse);
     if (cd->d_counts) cudaFree(cd->d_counts);
     if (cd->h_headers) cudaFreeHost(cd->h_headers);
@@ -375,6 +387,27 @@ cfb_error cfb_codec_set_decode_resolution(cfb_codec *cd, int resolution)
         return CFB_ERROR_INVALID_ARGUMENT;
     }
     cd->decode_res = resolution;
+    return CFB_OK;
+}
+
+cfb_error cfb_codec_set_interlaced(cfb_codec *cd, int interlaced)
+{
+    if (!cd) { set_error("null codec"); return CFB_ERROR_INVALID_ARGUMENT; }
+    const int fmt = cd->desc.pixel_format;
+    if (interlaced && fmt != CFB_PIXEL_YUYV && fmt != CFB_PIXEL_UYVY) {
+        set_error("the interlaced (field) transform is implemented for packed 8-bit 4:2:2 sources (CFHD_ENCODING_FLAGS_YUV_INTERLACED)");
+        return CFB_ERROR_UNSUPPORTED;
+    }
+    if (interlaced && !cd->d_carry) {
+        // per band row and strip carry-in of the difference-coded HL band, for up to kMaxBatch frames
+        const cfb_band_layout &ll = cd->layout.band[0][0][0];
+        cd->carry_strips = (ll.width + kInvStrip - 1) / kInvStrip;
+        const size_t bytes = (size_t)kMaxBatch * 3 * ll.height * cd->carry_strips * sizeof(int);
+        CFB_CUDA(cudaSetDevice(cd->ctx->device));
+        cudaError_t e = cudaMalloc((void **)&cd->d_carry, bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(field carries)");
+    }
+    cd->interlaced = interlaced ? 1 : 0;
     return CFB_OK;
 }
 
@@ -444,7 +477,13 @@ cfb_error cfb_forward_device(cfb_codec *cd, int n, const void *const *d_frames, 
         for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_frames[i]; p.out_base[i] = (unsigned char *)d_pyramids[i]; }
         p.shift = L.precision - 8; p.uyvy = (fmt == CFB_PIXEL_UYVY);
         p.th = pick_th((p.ch[0].width + kStripIn - 1) / kStripIn, p.ch[0].height / 2, n, ctx->sm_count);
-        CFB_CUDA(launch_fwd_422(p, ctx->stream));
+        if (cd->interlaced) {
+            for (int c = 0; c < 3; c++)
+                p.ch[c].q[2] = make_quant_param(quant->divisor[c][0][2], quant->midpoint_prequant, true);
+            CFB_CUDA(launch_fwd_422_fields(p, ctx->stream));
+        } else {
+            CFB_CUDA(launch_fwd_422(p, ctx->stream));
+        }
         ctx->kernel_launches++;
     } else if (fmt == CFB_PIXEL_PLANAR16) {
         for (int c = 0; c < 3; c++) {
@@ -622,7 +661,20 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
     if (!(cd->inv_mask & 1)) { ctx->frames_inverse += n; return CFB_OK; }
     for (int c = 0; c < L.num_channels; c++) fill_inv_geom(cd, quant, c, 0, p.ch[c]);
     for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_pyramids[i]; p.out_base[i] = (unsigned char *)d_frames[i]; }
-    if (out_format == CFB_PIXEL_PLANAR16) {
+    if (cd->interlaced) {
+        FieldsAux aux;
+        aux.carry = cd->d_carry; aux.nstrips = cd->carry_strips; aux.maxh = p.ch[0].height; aux.pad = 0;
+        long long off = 0;
+        for (int c = 0; c < 3; c++) {
+            p.ch[c].out_pitch = frame_pitch;
+            p.ch[c].out_off = (out_format == CFB_PIXEL_PLANAR16) ? off : 0;
+            off += (long long)frame_pitch * p.ch[c].height * 2;
+        }
+        p.shift = L.precision - 8; p.uyvy = (out_format == CFB_PIXEL_UYVY);
+        p.th = pick_th((p.ch[0].width + kInvStrip - 1) / kInvStrip, p.ch[0].height, n, ctx->sm_count);
+        CFB_CUDA(launch_inv_fields(p, aux, out_format == CFB_PIXEL_PLANAR16, ctx->stream));
+        ctx->kernel_launches++;
+    } else if (out_format == CFB_PIXEL_PLANAR16) {
         // planes stacked channel after channel, each channel at its own width, pitch = frame_pitch
         long long off = 0;
         int maxw = 0, maxh = 0;

@@ -76,6 +76,14 @@ struct InvParams {
     unsigned char *out_base[kMaxBatch];
 };
 
+// interlaced (field) inverse: per (frame, channel, band row, strip) carry-in of the difference-coded HL band
+struct FieldsAux {
+    int *carry;         // [(frame * nchan + c) * maxh + row] * nstrips + strip
+    int nstrips;        // strips of the luma band
+    int maxh;           // band rows
+    int pad;
+};
+
 // fire-and-forget prefetch into L2 (no destination register, no scoreboard): hides DRAM latency for rows that
 // will be loaded a few iterations later
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }

@@ -661,6 +661,167 @@ __global__ void __launch_bounds__(128) k_fwd_422(const __grid_constant__ FwdPara
 }
 
 // ----------------------------------------------------------------------------
+// Interlaced sources: level 1 is the frame (field) transform, Codec/wavelet.c:6076 TransformForwardFrameYUV
+// (Codec/filter.c:273 FilterFrameQuant16s is the planar form of the same transform):
+//   t_low = even + odd, t_high = odd - even (Codec/temporal.c:1568), then the horizontal 2-6 filter on both;
+//   LL = low(t_low), LH = Q(high(t_low)), HH = Q(high(t_high)) and HL = Q'(low(t_high)) difference coded along the
+//   row (Codec/spatial.c:5327: Q' uses the midpoint divisor/g without the "-1", out[i] = q[i] - q[i-1]).
+// The temporal step is linear in the packed bytes, so it is applied to the dp4a sums of the two rows before the
+// (non-linear) rounding of the highpass filter.  No vertical neighbourhood: no border warps, no carried state.
+struct Lin422 {
+    int S[4], d[4], cu[4], cv[4];
+    int hy, hu, hv;     // halo sums (lane 0 / last lane of strips with a neighbour strip)
+};
+
+__device__ __forceinline__ void hlinear_422(const Raw422Row &r, const Sel422 &sel, const LaneInfo &L, Lin422 &o)
+{
+    const unsigned w[4] = {r.v.x, r.v.y, r.v.z, r.v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        o.S[k] = dp4a_us(w[k], sel.ysum, 0);
+        o.d[k] = dp4a_us(w[k], sel.ydif, 0);
+        o.cu[k] = dp4a_us(w[k], sel.u, 0);
+        o.cv[k] = dp4a_us(w[k], sel.v, 0);
+    }
+    o.hy = dp4a_us(L.use_lh ? r.halo.y : r.halo.x, sel.ysum, 0);
+    o.hu = dp4a_us(r.halo.y, sel.u, dp4a_us(r.halo.x, sel.u, 0));
+    o.hv = dp4a_us(r.halo.y, sel.v, dp4a_us(r.halo.x, sel.v, 0));
+}
+
+// a + sgn * b on every member
+__device__ __forceinline__ void lin_combine(const Lin422 &a, const Lin422 &b, int sgn, Lin422 &o)
+{
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        o.S[k] = b.S[k] + sgn * a.S[k]; o.d[k] = b.d[k] + sgn * a.d[k];
+        o.cu[k] = b.cu[k] + sgn * a.cu[k]; o.cv[k] = b.cv[k] + sgn * a.cv[k];
+    }
+    o.hy = b.hy + sgn * a.hy; o.hu = b.hu + sgn * a.hu; o.hv = b.hv + sgn * a.hv;
+}
+
+// horizontal 2-6 on the (already temporally combined) sums.  Y: oy[0..3] low, oy[4..7] high; U/V: o[0..1], o[2..3].
+__device__ __forceinline__ void hfinish_422(const Lin422 &t, const LaneInfo &L, int *oy, int *ou, int *ov)
+{
+    const int *S = t.S, *d = t.d;
+    const int Su[2] = {t.cu[0] + t.cu[1], t.cu[2] + t.cu[3]}, du[2] = {t.cu[0] - t.cu[1], t.cu[2] - t.cu[3]};
+    const int Sv[2] = {t.cv[0] + t.cv[1], t.cv[2] + t.cv[3]}, dv[2] = {t.cv[0] - t.cv[1], t.cv[2] - t.cv[3]};
+    int Sp = __shfl_up_sync(L.amask, S[3], 1), Sn = __shfl_down_sync(L.amask, S[0], 1);
+    int Sup = __shfl_up_sync(L.amask, Su[1], 1), Sun = __shfl_down_sync(L.amask, Su[0], 1);
+    int Svp = __shfl_up_sync(L.amask, Sv[1], 1), Svn = __shfl_down_sync(L.amask, Sv[0], 1);
+    if (L.use_lh) { Sp = t.hy; Sup = t.hu; Svp = t.hv; }
+    if (L.use_rh) { Sn = t.hy; Sun = t.hu; Svn = t.hv; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) oy[k] = S[k];
+    oy[4] = ((S[1] - Sp + 4) >> 3) + d[0];
+    oy[5] = ((S[2] - S[0] + 4) >> 3) + d[1];
+    oy[6] = ((S[3] - S[1] + 4) >> 3) + d[2];
+    oy[7] = ((Sn - S[2] + 4) >> 3) + d[3];
+    ou[0] = Su[0]; ou[1] = Su[1];
+    ou[2] = ((Su[1] - Sup + 4) >> 3) + du[0];
+    ou[3] = ((Sun - Su[0] + 4) >> 3) + du[1];
+    ov[0] = Sv[0]; ov[1] = Sv[1];
+    ov[2] = ((Sv[1] - Svp + 4) >> 3) + dv[0];
+    ov[3] = ((Svn - Sv[0] + 4) >> 3) + dv[1];
+    if (L.has_border) {
+        if (L.left_border) {
+            oy[4] = clamp16((-3 * S[0] + 8 * d[0] + 4 * S[1] - S[2] + 4) >> 3);
+            ou[2] = clamp16((-3 * Su[0] + 8 * du[0] + 4 * Su[1] - Sun + 4) >> 3);
+            ov[2] = clamp16((-3 * Sv[0] + 8 * dv[0] + 4 * Sv[1] - Svn + 4) >> 3);
+        }
+        if (L.right_border) {
+            oy[7] = clamp16((3 * S[3] + 8 * d[3] - 4 * S[2] + S[1] + 4) >> 3);
+            ou[3] = clamp16((3 * Su[1] + 8 * du[1] - 4 * Su[0] + Sup + 4) >> 3);
+            ov[3] = clamp16((3 * Sv[1] + 8 * dv[1] - 4 * Sv[0] + Svp + 4) >> 3);
+        }
+    }
+}
+
+// quantise NC lowpass values of t_high and difference-code them along the row; prev_raw = the lowpass value of the
+// column left of the strip (halo), used by lane 0 of strips > 0
+template <int NC>
+__device__ __forceinline__ void store_diffq(unsigned char *p, const int *v, int prev_raw, const QuantParam &q, const LaneInfo &L)
+{
+    int Q[NC];
+#pragma unroll
+    for (int i = 0; i < NC; i++) Q[i] = quant1(v[i], q) >> 16;
+    int prev = __shfl_up_sync(L.amask, Q[NC - 1], 1);
+    if (L.use_lh) prev = quant1(prev_raw, q) >> 16;
+    if (L.left_border) prev = 0;
+    int o[NC];
+#pragma unroll
+    for (int i = 0; i < NC; i++) { o[i] = Q[i] - prev; prev = Q[i]; }
+    store_raw<NC>(p, o);
+}
+
+__global__ void __launch_bounds__(128) k_fwd_422_fields(const __grid_constant__ FwdParams p)
+{
+    const int lane = threadIdx.x;
+    const int f = blockIdx.z;
+    const PlaneGeom &gy = p.ch[0];
+    const PlaneGeom &gv = p.ch[1];
+    const PlaneGeom &gu = p.ch[2];
+    const int strip = blockIdx.x;
+    if (strip * kStripIn >= gy.width) return;
+    const int oh = gy.height >> 1;
+    LaneInfo L;
+    if (!lane_setup(strip, gy.width, lane, L)) return;
+    const unsigned colbyte_y = (unsigned)((strip * kStripOut + lane * 4) * 2);
+    const unsigned colbyte_c = (unsigned)((strip * (kStripOut / 2) + lane * 2) * 2);
+    const unsigned char *in = p.in_base[f] + gy.in_off + (strip * kStripIn + lane * 8) * 2;
+    unsigned char *out = p.out_base[f];
+
+    Sel422 sel;
+    {
+        const int m = 1 << p.shift;
+        const int neg = (-m) & 0xff;
+        if (!p.uyvy) { sel.ysum = m | (m << 16); sel.ydif = m | (neg << 16); sel.u = m << 8; sel.v = m << 24; }
+        else { sel.ysum = (m << 8) | (m << 24); sel.ydif = (m << 8) | (neg << 24); sel.u = m; sel.v = m << 16; }
+    }
+
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * p.th;
+    if (y0 >= oh) return;
+    const int y1 = min(y0 + p.th, oh);
+    const unsigned char *rp = in + (long long)(2 * y0) * gy.in_pitch;
+    Raw422Row c0, c1, n0, n1;
+    load_422_row(rp, L, c0);
+    load_422_row(rp + gy.in_pitch, L, c1);
+    n0 = c0; n1 = c1;
+    unsigned offy = (unsigned)(y0 * gy.out_pitch) + colbyte_y;
+    unsigned offc = (unsigned)(y0 * gu.out_pitch) + colbyte_c;
+    for (int j = y0; j < y1; j++) {
+        rp += 2 * gy.in_pitch;
+        if (j + 1 < y1) {
+            load_422_row(rp, L, n0);
+            load_422_row(rp + gy.in_pitch, L, n1);
+        }
+        if (j + 3 < y1) { prefetch_l2(rp + 4 * gy.in_pitch); prefetch_l2(rp + 5 * gy.in_pitch); }
+        Lin422 e, o, t;
+        hlinear_422(c0, sel, L, e);
+        hlinear_422(c1, sel, L, o);
+        int ay[8], au[4], av[4];
+        lin_combine(e, o, +1, t);               // temporal lowpass: even + odd
+        hfinish_422(t, L, ay, au, av);
+        store_raw<4>(out + (gy.band_off[0] + offy), ay);
+        store_quant<4>(out + (gy.band_off[1] + offy), ay + 4, gy.q[1]);
+        store_raw<2>(out + (gu.band_off[0] + offc), au);
+        store_quant<2>(out + (gu.band_off[1] + offc), au + 2, gu.q[1]);
+        store_raw<2>(out + (gv.band_off[0] + offc), av);
+        store_quant<2>(out + (gv.band_off[1] + offc), av + 2, gv.q[1]);
+        lin_combine(e, o, -1, t);               // temporal highpass: odd - even
+        hfinish_422(t, L, ay, au, av);
+        store_diffq<4>(out + (gy.band_off[2] + offy), ay, t.hy, gy.q[2], L);
+        store_quant<4>(out + (gy.band_off[3] + offy), ay + 4, gy.q[3]);
+        store_diffq<2>(out + (gu.band_off[2] + offc), au, t.hu, gu.q[2], L);
+        store_quant<2>(out + (gu.band_off[3] + offc), au + 2, gu.q[3]);
+        store_diffq<2>(out + (gv.band_off[2] + offc), av, t.hv, gv.q[2], L);
+        store_quant<2>(out + (gv.band_off[3] + offc), av + 2, gv.q[3]);
+        offy += (unsigned)gy.out_pitch;
+        offc += (unsigned)gu.out_pitch;
+        c0 = n0; c1 = n1;
+    }
+}
+
+// ----------------------------------------------------------------------------
 // host-side launchers (called from cfb_api.cu).  gridDim.y = row blocks + 1 border CTA row.
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -700,6 +861,14 @@ cudaError_t launch_fwd_422(const FwdParams &p, cudaStream_t stream)
     dim3 block(32, 4);
     dim3 grid(ceil_div(p.ch[0].width, kStripIn), ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y) + 1, p.nframes);
     k_fwd_422<<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fwd_422_fields(const FwdParams &p, cudaStream_t stream)
+{
+    dim3 block(32, 4);
+    dim3 grid(ceil_div(p.ch[0].width, kStripIn), ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y), p.nframes);
+    k_fwd_422_fields<<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -19,7 +19,7 @@ cfb_error cuda_fail(cudaError_t e, const char *what);
         if (e_ != cudaSuccess) return ::cfb::cuda_fail(e_, #call);      \
     } while (0)
 
-QuantParam make_quant_param(int divisor, int midpoint_prequant);
+QuantParam make_quant_param(int divisor, int midpoint_prequant, bool plain_midpoint = false);
 // wait for everything queued on the context's stream without busy-waiting on a CPU core
 cudaError_t stream_wait(cfb_context *ctx);
 
@@ -31,6 +31,8 @@ cudaError_t launch_fwd_byr4(const FwdParams &p, cudaStream_t stream);
 cudaError_t launch_inv_plane(const InvParams &p, int descale, cudaStream_t stream);
 cudaError_t launch_inv_422(const InvParams &p, cudaStream_t stream);
 cudaError_t launch_lowpass_422(const InvParams &p, cudaStream_t stream);
+cudaError_t launch_inv_fields(const InvParams &p, const FieldsAux &a, bool planar, cudaStream_t stream);
+cudaError_t launch_fwd_422_fields(const FwdParams &p, cudaStream_t stream);
 
 }  // namespace cfb
 
@@ -53,6 +55,9 @@ struct cfb_codec {
     size_t pyramid_stride = 0;
     int bayer_phase = 0;                    // BAYER_FORMAT_* (0 RED_GRN, 1 GRN_RED, 2 GRN_BLU, 3 BLU_GRN), DemoasicFrames.h:30
     int fwd_mask = 7, inv_mask = 7;         // profiling aid: levels to run
+    int interlaced = 0;                     // level 1 is the field transform (CFHD_ENCODING_FLAGS_YUV_INTERLACED)
+    int *d_carry = nullptr;                 // interlaced inverse: HL row carries, kMaxBatch frames
+    int carry_strips = 0;
     int decode_res = 1;                     // CFB_RESOLUTION_*: 1 full, 2 half (LL1), 3 quarter (LL2)
     // sparse transfer format staging (allocated on first use)
     unsigned char *d_sparse = nullptr;      // max_batch sparse buffers

@@ -370,6 +370,160 @@ __global__ void __launch_bounds__(128) k_inv_422(const __grid_constant__ InvPara
 }
 
 // ----------------------------------------------------------------------------
+// Interlaced sources: inverse of the frame (field) transform at level 1
+//   Codec/decoder.c:21493 TransformInverseFrameToYUV / :22027 TransformInverseFrameToRow16u:
+//   t_low = hinv(LL, LH), t_high = hinv(HL, HH) (InvertHorizontalRow16s8sTo16sBuffered), then
+//   even row = (t_low - t_high) >> 1, odd row = (t_low + t_high) >> 1 (Codec/temporal.c:3741 InvertInterlaced16s).
+// The coded HL band is difference coded along each row; the reference integrates it on the host after the FSM
+// decode (decoder.c:20822-20836 `line[x] += line[x-1]`, int16 wrap).  Here k_fields_carry computes, per band row
+// and strip, the sum of all coefficients left of the strip, and the inverse kernel finishes the prefix sum with a
+// warp scan, so the coded buffer keeps the exact format the forward path wrote.
+template <int NC>
+__device__ __forceinline__ int row_segment_sum(const unsigned char *row, int c0, int c1, int lane)
+{
+    const int col = c0 + NC * lane;
+    int v = 0;
+    if (col < c1) {
+        if (NC == 4) { const uint2 w = __ldg(reinterpret_cast<const uint2 *>(row + col * 2)); v = lo16(w.x) + hi16(w.x) + lo16(w.y) + hi16(w.y); }
+        else { const unsigned w = __ldg(reinterpret_cast<const unsigned *>(row + col * 2)); v = lo16(w) + hi16(w); }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d);
+    return v;
+}
+
+__global__ void __launch_bounds__(128) k_fields_carry(const __grid_constant__ InvParams p, const FieldsAux a)
+{
+    const int lane = threadIdx.x;
+    const int row = blockIdx.x * blockDim.y + threadIdx.y;
+    const int c = blockIdx.y, f = blockIdx.z;
+    const InvGeom &g = p.ch[c];
+    if (row >= g.height) return;
+    const unsigned char *hl = p.in_base[f] + g.band_off[2] + (long long)row * g.pitch;
+    int *out = a.carry + ((long long)(f * p.nchan + c) * a.maxh + row) * a.nstrips;
+    const int W = (c == 0) ? kInvStrip : kInvStrip / 2, halo = (c == 0) ? 4 : 2;
+    int total = 0;
+    for (int s = 0; s < a.nstrips; s++) {
+        const int c0 = max(s * W - halo, 0), c1 = min((s + 1) * W - halo, g.width);
+        if (lane == 0) out[s] = total;
+        if (c0 >= g.width) continue;
+        total += (c == 0) ? row_segment_sum<4>(hl, c0, c1, lane) : row_segment_sum<2>(hl, c0, c1, lane);
+    }
+}
+
+// inclusive prefix of the lane's NC raw HL values across the warp (lane order = column order) + carry-in
+template <int NC>
+__device__ __forceinline__ void integrate_row(int *h, int carry)
+{
+#pragma unroll
+    for (int i = 1; i < NC; i++) h[i] += h[i - 1];
+    int t = h[NC - 1];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(kFullMask, t, d);
+        if ((int)threadIdx.x >= d) t += u;
+    }
+    const int excl = t - h[NC - 1] + carry;
+#pragma unroll
+    for (int i = 0; i < NC; i++) h[i] += excl;
+}
+
+template <int NC>
+__device__ __forceinline__ void fields_channel(const InvGeom &g, const unsigned char *in, int r, unsigned colbyte, bool active,
+                                               int carry, bool has_border, bool left_border, bool right_border,
+                                               int *even, int *odd)
+{
+    RawCols<NC> a, b, c, d;
+    const unsigned off = (unsigned)r * g.pitch + colbyte;
+    load_raw<NC>(in, g.band_off[0], off, active, a);
+    load_raw<NC>(in, g.band_off[1], off, active, b);
+    load_raw<NC>(in, g.band_off[2], off, active, c);
+    load_raw<NC>(in, g.band_off[3], off, active, d);
+    int ll[NC], lh[NC], hl[NC], hh[NC];
+    Expand<false, NC>::ll(a, ll);
+    Expand<false, NC>::hp(b, g.dq[1], lh);
+    Expand<false, NC>::ll(c, hl);               // raw: integrate first, dequantise after (ring arithmetic, same result)
+    Expand<false, NC>::hp(d, g.dq[3], hh);
+    integrate_row<NC>(hl, carry);
+#pragma unroll
+    for (int i = 0; i < NC; i++) hl[i] = (int)(short)(hl[i] * g.dq[2]);     // int16 wrap as `line[x] += line[x-1]` on PIXEL
+    int tl[2 * NC], th[2 * NC];
+    hinv<NC>(ll, lh, has_border, left_border, right_border, tl);
+    hinv<NC>(hl, hh, has_border, left_border, right_border, th);
+#pragma unroll
+    for (int i = 0; i < 2 * NC; i++) {
+        const int lo = tl[i] >> 1, hi = th[i] >> 1;
+        even[i] = (lo - hi) >> 1;
+        odd[i] = (lo + hi) >> 1;
+    }
+}
+
+template <bool PLANAR>
+__global__ void __launch_bounds__(128) k_inv_fields(const __grid_constant__ InvParams p, const FieldsAux a)
+{
+    const int lane = threadIdx.x;
+    const int f = blockIdx.z;
+    const InvGeom &gy = p.ch[0];
+    const InvGeom &gv = p.ch[1];
+    const InvGeom &gu = p.ch[2];
+    const int strip = blockIdx.x;
+    if (strip * kInvStrip >= gy.width) return;
+    const int H = gy.height;
+    const int col0 = strip * kInvStrip - 4 + lane * 4;      // luma band column
+    const bool active = (col0 >= 0) && (col0 < gy.width);
+    const bool writer = active && lane >= 1 && lane <= 30;
+    const bool left_border = (col0 == 0);
+    const bool right_border = (col0 + 4 == gy.width);
+    const bool has_border = (strip == 0) || ((strip + 1) * kInvStrip + 4 >= gy.width);
+    const unsigned ycol = (unsigned)(col0 * 2), ccol = (unsigned)col0;
+    const unsigned char *in = p.in_base[f];
+    unsigned char *out = p.out_base[f];
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * p.th;
+    const int y1 = min(y0 + p.th, H);
+    const int sh = p.shift;         // precision - 8
+    const int *cy = a.carry + ((long long)(f * 3 + 0) * a.maxh) * a.nstrips + strip;
+    const int *cv = a.carry + ((long long)(f * 3 + 1) * a.maxh) * a.nstrips + strip;
+    const int *cu = a.carry + ((long long)(f * 3 + 2) * a.maxh) * a.nstrips + strip;
+    for (int r = y0; r < y1; r++) {
+        int ye[8], yo[8], ue[4], uo[4], ve[4], vo[4];
+        fields_channel<4>(gy, in, r, ycol, active, __ldg(cy + (long long)r * a.nstrips), has_border, left_border, right_border, ye, yo);
+        fields_channel<2>(gu, in, r, ccol, active, __ldg(cu + (long long)r * a.nstrips), has_border, left_border, right_border, ue, uo);
+        fields_channel<2>(gv, in, r, ccol, active, __ldg(cv + (long long)r * a.nstrips), has_border, left_border, right_border, ve, vo);
+        if (!writer) continue;
+        if (PLANAR) {
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const int *yy = rr ? yo : ye, *uu = rr ? uo : ue, *vv = rr ? vo : ve;
+                const long long row = 2 * r + rr;
+                *reinterpret_cast<uint4 *>(out + gy.out_off + row * gy.out_pitch + (long long)col0 * 4) =
+                    make_uint4(pack_sat16(yy[0], yy[1]), pack_sat16(yy[2], yy[3]), pack_sat16(yy[4], yy[5]), pack_sat16(yy[6], yy[7]));
+                *reinterpret_cast<uint2 *>(out + gu.out_off + row * gu.out_pitch + (long long)col0 * 2) =
+                    make_uint2(pack_sat16(uu[0], uu[1]), pack_sat16(uu[2], uu[3]));
+                *reinterpret_cast<uint2 *>(out + gv.out_off + row * gv.out_pitch + (long long)col0 * 2) =
+                    make_uint2(pack_sat16(vv[0], vv[1]), pack_sat16(vv[2], vv[3]));
+            }
+        } else {
+            // 8-bit reduction with the same ordered dither as k_inv_422: out = sat_u8((v + d) >> (precision - 8)),
+            // d = (x ^ y) & 1 scaled to the shift, inside the reference's {v >> 2, (v + 1) >> 2} envelope
+            unsigned char *o = out + gy.out_off + (long long)(2 * r) * gy.out_pitch + (long long)col0 * 4;
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const int *yy = rr ? yo : ye, *uu = rr ? uo : ue, *vv = rr ? vo : ve;
+                const int d0 = (rr ? 1 : 0) << (sh - 2), d1 = (rr ? 0 : 1) << (sh - 2);
+                unsigned w[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int ya = (yy[2 * k] + d0) >> sh, yb = (yy[2 * k + 1] + d1) >> sh;
+                    const int cu8 = (uu[k] + ((k & 1) ? d1 : d0)) >> sh, cv8 = (vv[k] + ((k & 1) ? d1 : d0)) >> sh;
+                    w[k] = p.uyvy ? pack_u8x4(cu8, ya, cv8, yb) : pack_u8x4(ya, cu8, yb, cv8);
+                }
+                *reinterpret_cast<uint4 *>(o + (rr ? gy.out_pitch : 0)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------
 // Reduced-resolution decode: pack the lowpass images of the three 4:2:2 channels to 8-bit YUYV/UYVY.
 //   half    (LL1): Codec/frame.c:11742 ConvertLowpass16s10bitToYUV   out = sat_u8(ll >> 4)        (signed shift)
 //   quarter (LL2): Codec/temporal.c:11362 CopyQuarterRowToBuffer     out = packus((uint16)ll >> 4) (unsigned shift)
@@ -428,6 +582,17 @@ cudaError_t launch_inv_422(const InvParams &p, cudaStream_t stream)
     bool small = true;
     for (int c = 0; c < 3; c++) for (int b = 1; b < 4; b++) small = small && (p.ch[c].dq[b] >= 0 && p.ch[c].dq[b] <= 255);
     if (small) k_inv_422<true><<<grid, block, 0, stream>>>(p); else k_inv_422<false><<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_inv_fields(const InvParams &p, const FieldsAux &a, bool planar, cudaStream_t stream)
+{
+    dim3 block(32, 4);
+    dim3 cgrid(ceil_div_i(p.ch[0].height, (int)block.y), 3, p.nframes);
+    k_fields_carry<<<cgrid, block, 0, stream>>>(p, a);
+    dim3 grid(ceil_div_i(p.ch[0].width, kInvStrip), ceil_div_i(ceil_div_i(p.ch[0].height, p.th), (int)block.y), p.nframes);
+    if (planar) k_inv_fields<true><<<grid, block, 0, stream>>>(p, a);
+    else k_inv_fields<false><<<grid, block, 0, stream>>>(p, a);
     return cudaGetLastError();
 }
 

@@ -132,6 +132,9 @@ CFB_API void *cfb_context_stream(cfb_context *ctx);           /* the cudaStream_
 CFB_API cfb_error cfb_layout_compute(const cfb_frame_desc *desc, cfb_layout *out);
 /* FILMSCAN-style fixed quality (CFHD_EncodingQuality low byte 1..6, Common/CFHDTypes.h:200-223). */
 CFB_API cfb_error cfb_quant_for_quality(const cfb_frame_desc *desc, int quality, cfb_quant *out);
+/* Same, for an interlaced source (parameters.progressive = 0): the level-1 LH divisor * 3/2 and HL * 2/3
+ * (Codec/quantize.c:490-541). */
+CFB_API cfb_error cfb_quant_for_source(const cfb_frame_desc *desc, int quality, int interlaced, cfb_quant *out);
 
 /* ---- codec plan ---------------------------------------------------------- */
 /* max_batch = frames processed per launch (1..CFB_MAX_BATCH). Allocates device staging for
@@ -147,6 +150,15 @@ CFB_API void *cfb_codec_device_pyramid(cfb_codec *codec, int slot);
 /* BYR4 only: Bayer phase of the source (TAG_BAYER_FORMAT): 0 RED_GRN, 1 GRN_RED, 2 GRN_BLU, 3 BLU_GRN
  * (Codec/DemoasicFrames.h:30-33).  The frame must already carry its encode curve (CFHD_ENCODING_FLAGS_CURVE_APPLIED). */
 CFB_API cfb_error cfb_codec_set_bayer_phase(cfb_codec *codec, int bayer_format);
+
+/* Interlaced sources (CFHD_ENCODING_FLAGS_YUV_INTERLACED, EncoderSDK/SampleEncoder.cpp:210 -> parameters.progressive = 0;
+ * on decode the sample's progressive flag): level 1 of the following forward/inverse calls is the frame (field)
+ * transform -- vertical Haar between the two fields + horizontal 2-6, HL band difference coded along each row --
+ * instead of the spatial transform.  Replaces Codec/encoder.c:2976 TransformForwardFrameYUV (wavelet.c:6076; planar
+ * form filter.c:273 FilterFrameQuant16s) and Codec/decoder.c:21493 TransformInverseFrameToYUV / :22027 ...ToRow16u
+ * (temporal.c:3741 InvertInterlaced16s) including the HL row integration of decoder.c:20822-20836.
+ * Packed 8-bit 4:2:2 codecs only; full-resolution decode. */
+CFB_API cfb_error cfb_codec_set_interlaced(cfb_codec *codec, int interlaced);
 
 /* Decoded resolution of the following cfb_inverse_* calls: the decodedResolution argument of CFHD_PrepareToDecode
  * (DecoderSDK/CFHDDecoder.cpp; Common/CFHDTypes.h:453-456, same numbering).  HALF stops after level 2 -> 1 and

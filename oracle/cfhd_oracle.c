@@ -384,3 +384,83 @@ void orc_inv_level(const int16_t *ll, const int16_t *lh, const int16_t *hl, cons
     }
     free(el); free(ol); free(eh); free(oh);
 }
+
+/* ------------------------------------------------------------------------- */
+/* Interlaced (field) transform, see cfhd_oracle.h. */
+static void fields_hrow(const int32_t *x, int width, int32_t *low, int32_t *high)
+{
+    const int m = width / 2;
+    int i;
+    for (i = 0; i < m; i++) low[i] = x[2 * i] + x[2 * i + 1];
+    for (i = 1; i < m - 1; i++)
+        high[i] = ((-x[2 * i - 2] - x[2 * i - 1] + x[2 * i + 2] + x[2 * i + 3] + 4) >> 3) + x[2 * i] - x[2 * i + 1];
+    high[0] = (5 * x[0] - 11 * x[1] + 4 * x[2] + 4 * x[3] - x[4] - x[5] + 4) >> 3;                      /* spatial.c:5371-5379 */
+    high[m - 1] = (11 * x[width - 2] - 5 * x[width - 1] - 4 * x[width - 3] - 4 * x[width - 4]
+                   + x[width - 5] + x[width - 6] + 4) >> 3;                                             /* spatial.c:5802-5810 */
+}
+
+void orc_fwd_fields_422(const uint8_t *frame, int frame_pitch, int width, int height, int channel,
+                        int format, int precision, const int quant[4], int midpoint_prequant,
+                        int16_t *ll, int16_t *lh, int16_t *hl, int16_t *hh, int out_pitch)
+{
+    const int m = width / 2, op = out_pitch / 2;
+    int16_t *e = (int16_t *)malloc((size_t)width * 2), *o = (int16_t *)malloc((size_t)width * 2);
+    int32_t *tl = (int32_t *)malloc((size_t)width * 4), *th = (int32_t *)malloc((size_t)width * 4);
+    int32_t *a = (int32_t *)malloc((size_t)m * 4), *b = (int32_t *)malloc((size_t)m * 4);
+    int16_t *tmp = (int16_t *)malloc((size_t)m * 2);
+    int r, i;
+    for (r = 0; r < height / 2; r++) {
+        orc_unpack_row_422(frame + (size_t)(2 * r) * frame_pitch, e, width, channel, format, precision - 8);
+        orc_unpack_row_422(frame + (size_t)(2 * r + 1) * frame_pitch, o, width, channel, format, precision - 8);
+        for (i = 0; i < width; i++) { tl[i] = (int32_t)e[i] + o[i]; th[i] = (int32_t)o[i] - e[i]; }
+        fields_hrow(tl, width, a, b);
+        for (i = 0; i < m; i++) { ll[(size_t)r * op + i] = wrap16(a[i]); tmp[i] = wrap16(b[i]); }
+        orc_quantize_row(tmp, lh + (size_t)r * op, m, quant[1], midpoint_prequant);
+        fields_hrow(th, width, a, b);
+        {
+            const int d = quant[2];
+            const int mid = (d > 1 && midpoint_prequant >= 2 && midpoint_prequant < 9) ? d / midpoint_prequant : 0;
+            const int mult = (d > 1) ? 65536 / d : 0;
+            int32_t prev = 0;
+            for (i = 0; i < m; i++) {
+                int32_t q = a[i];
+                if (d > 1) { const int32_t mag = ((q < 0 ? -q : q) + mid) * mult >> 16; q = q < 0 ? -mag : mag; }
+                hl[(size_t)r * op + i] = wrap16(q - prev);
+                prev = q;
+            }
+        }
+        for (i = 0; i < m; i++) tmp[i] = wrap16(b[i]);
+        orc_quantize_row(tmp, hh + (size_t)r * op, m, quant[3], midpoint_prequant);
+    }
+    free(e); free(o); free(tl); free(th); free(a); free(b); free(tmp);
+}
+
+static void fields_hinv(const int16_t *l, const int16_t *h, int n, int32_t *out)
+{
+    int i;
+    for (i = 1; i < n - 1; i++) {
+        out[2 * i] = ((((int32_t)l[i - 1] - l[i + 1] + 4) >> 3) + l[i] + h[i]) >> 1;
+        out[2 * i + 1] = (((-(int32_t)l[i - 1] + l[i + 1] + 4) >> 3) + l[i] - h[i]) >> 1;
+    }
+    out[0] = (((11 * (int32_t)l[0] - 4 * l[1] + l[2] + 4) >> 3) + h[0]) >> 1;
+    out[1] = (((5 * (int32_t)l[0] + 4 * l[1] - l[2] + 4) >> 3) - h[0]) >> 1;
+    out[2 * n - 2] = (((5 * (int32_t)l[n - 1] + 4 * l[n - 2] - l[n - 3] + 4) >> 3) + h[n - 1]) >> 1;
+    out[2 * n - 1] = (((11 * (int32_t)l[n - 1] - 4 * l[n - 2] + l[n - 3] + 4) >> 3) - h[n - 1]) >> 1;
+}
+
+void orc_inv_fields(const int16_t *ll, const int16_t *lh, const int16_t *hl, const int16_t *hh,
+                    int band_pitch, int width, int height, int16_t *out, int out_pitch)
+{
+    const int bp = band_pitch / 2, op = out_pitch / 2;
+    int32_t *tl = (int32_t *)malloc((size_t)width * 8), *th = (int32_t *)malloc((size_t)width * 8);
+    int r, i;
+    for (r = 0; r < height; r++) {
+        fields_hinv(ll + (size_t)r * bp, lh + (size_t)r * bp, width, tl);
+        fields_hinv(hl + (size_t)r * bp, hh + (size_t)r * bp, width, th);
+        for (i = 0; i < 2 * width; i++) {
+            out[(size_t)(2 * r) * op + i] = wrap16((tl[i] - th[i]) >> 1);
+            out[(size_t)(2 * r + 1) * op + i] = wrap16((tl[i] + th[i]) >> 1);
+        }
+    }
+    free(tl); free(th);
+}

@@ -79,6 +79,32 @@ void orc_lowpass_to_422(const int16_t *y, int y_pitch, const int16_t *v, int v_p
                         int width, int height, int shift, int unsigned_shift, int uyvy,
                         uint8_t *out, int out_pitch);
 
+/* ---- interlaced sources: the frame (field) transform replaces the spatial transform at level 1 ----
+ * Forward, packed 8-bit 4:2:2, one channel (Codec/wavelet.c:6076 TransformForwardFrameYUV, called from
+ * Codec/encoder.c:2976 when the encoder was opened with progressive = 0):
+ *   per row pair: temporal low = even + odd, temporal high = odd - even on the samples << (precision - 8)
+ *   (temporal.c:1568 FilterTemporalRowYUYVChannelTo16s), then the horizontal 2-6 filter on both rows
+ *   (spatial.c:253 FilterHorizontalRow16s):  LL = low(t_low) unquantised,  LH = Q(high(t_low)),
+ *   HH = Q(high(t_high)) with the ordinary quantiser (quantize.c:1395), and the HL band is
+ *   "difference filtered" (spatial.c:5327 FilterHorizontalRowScaled16sDifferenceFiltered, DIFFERENCE_CODING 1,
+ *   codec.h:161):  q[i] = sign * (((|low(t_high)[i]| + divisor / g) * (65536 / divisor)) >> 16)   (no "-1" on the
+ *   midpoint, :5356-5358)  and  HL[i] = q[i] - q[i-1], HL[0] = q[0].
+ * The arithmetic is restated in int32 and wrapped to int16 on store: identical to the reference's saturating SSE2
+ * chains for every 8-bit source (|t| <= 2040, far inside int16).  width/height = the CHANNEL's input dimensions. */
+void orc_fwd_fields_422(const uint8_t *frame, int frame_pitch, int width, int height, int channel,
+                        int format, int precision, const int quant[4], int midpoint_prequant,
+                        int16_t *ll, int16_t *lh, int16_t *hl, int16_t *hh, int out_pitch);
+
+/* Inverse of the above on DECODER-SIDE bands, i.e. dequantised and with HL already integrated along each row
+ * (Codec/decoder.c:20822-20836 `line[x] += line[x-1]` after the FSM decode):
+ *   t_low = hinv(LL, LH), t_high = hinv(HL, HH)  (Codec/decoder.c:21493 TransformInverseFrameToYUV ->
+ *   InvertHorizontalRow16s8sTo16sBuffered: interior ((l[i-1] - l[i+1] + 4) >> 3 + l[i] + h[i]) >> 1 etc., borders
+ *   (11,-4,1)/(5,4,-1)),  even row = (t_low - t_high) >> 1, odd row = (t_low + t_high) >> 1
+ *   (temporal.c:3741 InvertInterlaced16s / InvertInterlacedRow16s10bitToYUV).
+ * width/height = band dimensions; out is 2*width x 2*height int16 at the codec precision. */
+void orc_inv_fields(const int16_t *ll, const int16_t *lh, const int16_t *hl, const int16_t *hh,
+                    int band_pitch, int width, int height, int16_t *out, int out_pitch);
+
 /* 3-level pyramid helpers are composed in Python (tests/) from the calls above. */
 
 int orc_version(void);

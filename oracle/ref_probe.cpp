@@ -180,6 +180,10 @@ static int g_probe_bayer_format = -1;
 // Bayer sources only: phase (BAYER_FORMAT_*, Codec/DemoasicFrames.h:30) used by the next ref_encode_frame_bands call;
 // the frame is treated as CFHD_ENCODING_FLAGS_CURVE_APPLIED (encode_curve_preset = 1, linear >> 4).  -1 disables.
 void ref_set_bayer_format(int fmt) { g_probe_bayer_format = fmt; }
+static int g_probe_interlaced = 0;
+// Interlaced source (CFHD_ENCODING_FLAGS_YUV_INTERLACED -> parameters.progressive = 0, EncoderSDK/SampleEncoder.cpp:210,
+// :293): the next ref_encode_frame_bands calls use the frame (field) transform at level 1 (Codec/encoder.c:2949-2993).
+void ref_set_interlaced(int on) { g_probe_interlaced = on; }
 
 int ref_encode_frame_bands(const uint8_t *frame, int width, int height, int pitch, int color_format,
                            int sampling_444, int num_channels, int quality,
@@ -192,7 +196,7 @@ int ref_encode_frame_bands(const uint8_t *frame, int width, int height, int pitc
     ENCODING_PARAMETERS p;
     memset(&p, 0, sizeof(p));
     p.version = 1; p.gop_length = 1; p.encoded_width = width; p.encoded_height = height;
-    p.fixed_quality = quality; p.progressive = 1; p.format = color_format;
+    p.fixed_quality = quality; p.progressive = g_probe_interlaced ? 0 : 1; p.format = color_format;
     p.frame_sampling = sampling_444 ? FRAME_SAMPLING_444 : FRAME_SAMPLING_422;
     p.colorspace_yuv = 2; p.colorspace_rgb = 1;
     if (!InitializeEncoderWithParameters(NULL, enc, tr, num_channels, &p)) return 0;
@@ -334,7 +338,7 @@ int ref_time_transform_422(const uint8_t *frame, int width, int height, int pitc
     ENCODING_PARAMETERS p;
     memset(&p, 0, sizeof(p));
     p.version = 1; p.gop_length = 1; p.encoded_width = width; p.encoded_height = height;
-    p.fixed_quality = quality; p.progressive = 1; p.format = color_format;
+    p.fixed_quality = quality; p.progressive = g_probe_interlaced ? 0 : 1; p.format = color_format;
     p.frame_sampling = FRAME_SAMPLING_422; p.colorspace_yuv = 2; p.colorspace_rgb = 1;
     if (!InitializeEncoderWithParameters(NULL, enc, tr, num_channels, &p)) return 1;
     size_t scratch_size = 0;

@@ -55,5 +55,36 @@ def main():
         print(path, os.path.getsize(path))
 
 
+def interlaced():
+    """Interlaced source (CFHD_ENCODING_FLAGS_YUV_INTERLACED): level 1 is the field transform.  The odd field is
+    shifted horizontally so the two fields really differ (motion between fields)."""
+    import ctypes as C
+    ref_lib = ol.load_ref()
+    for (w, h, frame_no, quality, shift) in [(512, 128, 1, 4, 6), (448, 96, 2, 3, 10)]:
+        frame = pu.qbist_yuy2(ref_lib, w, h, frame_no).copy()
+        frame[1::2] = np.roll(frame[1::2], 2 * shift, axis=1)
+        ref_lib.ref_set_interlaced(1)
+        try:
+            bands, div, prescale, sample = pu.ref_encode_frame(ref_lib, frame, w, h, pu.COLOR_FORMAT_YUYV, 0, 3, quality)
+        finally:
+            ref_lib.ref_set_interlaced(0)
+        decoded, dec_bands = pu.ref_decode_sample_bands(ref_lib, sample, w, h)
+        api = np.zeros_like(frame)
+        rc = ref_lib.ref_decode_sample(sample.ctypes.data_as(C.c_void_p), C.c_int64(sample.size), w, h,
+                                       ol.CFHD_PIXEL_FORMAT_YUY2, api.ctypes.data_as(C.c_void_p), w * 2)
+        assert rc == 0
+        arrays = {"frame": frame, "decoded_yuy2": api, "divisors": np.array(div, np.int32),
+                  "prescale": np.array(prescale[0], np.int32), "quality": np.array(quality), "sample_size": np.array(sample.size)}
+        for (c, lvl, name), a in bands.items():
+            arrays[f"b_{c}_{lvl}_{name}"] = a
+        for (c, lvl, name), a in dec_bands.items():      # decoder side: dequantised, level-1 HL integrated along rows
+            if name != "LL" or lvl == 3:
+                arrays[f"d_{c}_{lvl}_{name}"] = a
+        path = os.path.join(HERE, f"interlaced_yuy2_{w}x{h}_f{frame_no}_q{quality}.npz")
+        np.savez_compressed(path, **arrays)
+        print(path, os.path.getsize(path))
+
+
 if __name__ == "__main__":
+    interlaced()
     main()

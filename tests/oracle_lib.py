@@ -100,6 +100,32 @@ class Impl:
         self._f("fwd_level_422")(frame, pitch, w, h, channel, fmt, precision, q, midpoint, *bands, (w // 2) * 2)
         return bands
 
+    def fwd_fields_422(self, frame, channel, fmt, quant, precision=10, midpoint=2):
+        """Interlaced (field) transform of level 1, oracle only (orc_fwd_fields_422)."""
+        frame = np.ascontiguousarray(frame, dtype=np.uint8)
+        h, pitch = frame.shape
+        fw = pitch // 2
+        w = fw if channel == 0 else fw // 2
+        bands = [np.zeros((h // 2, w // 2), np.int16) for _ in range(4)]
+        q = np.asarray(quant, dtype=np.int32)
+        f = self._f("fwd_fields_422")
+        f.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p, C.c_int,
+                      _i16p, _i16p, _i16p, _i16p, C.c_int]
+        f.restype = None
+        f(frame, pitch, w, h, channel, fmt, precision, q, midpoint, *bands, (w // 2) * 2)
+        return bands
+
+    def inv_fields(self, ll, lh, hl, hh):
+        """Inverse field transform on decoder-side (dequantised, HL integrated) bands (orc_inv_fields)."""
+        bands = [np.ascontiguousarray(b, dtype=np.int16) for b in (ll, lh, hl, hh)]
+        h, w = bands[0].shape
+        out = np.zeros((2 * h, 2 * w), np.int16)
+        f = self._f("inv_fields")
+        f.argtypes = [_i16p, _i16p, _i16p, _i16p, C.c_int, C.c_int, C.c_int, _i16p, C.c_int]
+        f.restype = None
+        f(*bands, w * 2, w, h, out, w * 4)
+        return out
+
     def inv_level(self, ll, lh, hl, hh, descale):
         bands = [np.ascontiguousarray(b, dtype=np.int16) for b in (ll, lh, hl, hh)]
         h, w = bands[0].shape

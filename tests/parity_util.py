@@ -51,13 +51,14 @@ def quant_table(quant, nchan=3):
     return [[[quant.divisor[c][k][b] for b in range(4)] for k in range(3)] for c in range(nchan)]
 
 
-def forward_pyramid_422(impl, frame, divisors, prescale=(0, 2, 0), fmt=0, midpoint=2):
+def forward_pyramid_422(impl, frame, divisors, prescale=(0, 2, 0), fmt=0, midpoint=2, interlaced=False):
     """3-level pyramid of a packed 4:2:2 frame with `impl` (oracle or reference building blocks).
     Returns {(c, level, band_name): array}, LL only for level 3 plus ('LL', level) intermediates under key
-    (c, level, 'LL')."""
+    (c, level, 'LL').  interlaced: level 1 is the field transform (encoder.c:2949-2993)."""
     out = {}
     for c in range(3):
-        ll, lh, hl, hh = impl.fwd_level_422(frame, c, fmt, divisors[c][0], precision=10, midpoint=midpoint)
+        level1 = impl.fwd_fields_422 if interlaced else impl.fwd_level_422
+        ll, lh, hl, hh = level1(frame, c, fmt, divisors[c][0], precision=10, midpoint=midpoint)
         out[(c, 1, "LL")], out[(c, 1, "LH")], out[(c, 1, "HL")], out[(c, 1, "HH")] = ll, lh, hl, hh
         for k in (1, 2):
             variant = 1 if prescale[k] == 2 else 0
@@ -66,9 +67,10 @@ def forward_pyramid_422(impl, frame, divisors, prescale=(0, 2, 0), fmt=0, midpoi
     return out
 
 
-def oracle_forward_422(orc, frame, quant, fmt=0):
+def oracle_forward_422(orc, frame, quant, fmt=0, interlaced=False):
     """Coded-region bands (LL3 + all highpass) the CUDA path must reproduce."""
-    pyr = forward_pyramid_422(orc, frame, quant_table(quant), tuple(quant.prescale), fmt, quant.midpoint_prequant)
+    pyr = forward_pyramid_422(orc, frame, quant_table(quant), tuple(quant.prescale), fmt, quant.midpoint_prequant,
+                              interlaced=interlaced)
     return {k: v for k, v in pyr.items() if not (k[2] == "LL" and k[1] != 3)}
 
 
@@ -108,7 +110,7 @@ def dequantize(band, divisor):
     return (band.astype(np.int32) * divisor).astype(np.int16)
 
 
-def inverse_pyramid(impl, bands, divisors, prescale, nchan=3, stop_level=0):
+def inverse_pyramid(impl, bands, divisors, prescale, nchan=3, stop_level=0, interlaced=False):
     """bands: {(c, level, name)} QUANTISED coded-region bands (LL3 + highpass of levels 1..3).
     Returns the reconstructed int16 plane of every channel at codec precision (list); stop_level = 1 / 2 stops at
     the lowpass image LL1 / LL2 (half / quarter resolution decode)."""
@@ -119,7 +121,13 @@ def inverse_pyramid(impl, bands, divisors, prescale, nchan=3, stop_level=0):
             lh = dequantize(bands[(c, k + 1, "LH")], divisors[c][k][1])
             hl = dequantize(bands[(c, k + 1, "HL")], divisors[c][k][2])
             hh = dequantize(bands[(c, k + 1, "HH")], divisors[c][k][3])
-            ll = impl.inv_level(ll, lh, hl, hh, 2 if prescale[k] == 2 else 0)
+            if k == 0 and interlaced:
+                # the coded HL band of the field transform is difference coded along each row; the decoder
+                # integrates it after dequantisation in int16 (decoder.c:20822-20836)
+                hl = np.cumsum(hl.astype(np.int64), axis=1).astype(np.int16)
+                ll = impl.inv_fields(ll, lh, hl, hh)
+            else:
+                ll = impl.inv_level(ll, lh, hl, hh, 2 if prescale[k] == 2 else 0)
         planes.append(ll)
     return planes
 

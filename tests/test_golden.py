@@ -9,7 +9,9 @@ import pytest
 import oracle_lib as ol
 import parity_util as pu
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+_ALL = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+GOLDEN = [p for p in _ALL if os.path.basename(p).startswith("qbist_")]                 # progressive
+GOLDEN_FIELDS = [p for p in _ALL if os.path.basename(p).startswith("interlaced_")]     # interlaced sources
 
 
 def load_golden(path):
@@ -80,3 +82,36 @@ def test_oracle_reduced_resolution_decode(path):
         else:
             d = np.abs(got.astype(np.int32) - want.astype(np.int32))
             assert (d > 2).mean() < 2e-3 and d.max() <= 16 and d.mean() < 0.6, (d.max(), d.mean())
+
+
+def test_interlaced_golden_present():
+    assert len(GOLDEN_FIELDS) >= 2
+
+
+@pytest.mark.parametrize("path", GOLDEN_FIELDS, ids=[os.path.basename(p) for p in GOLDEN_FIELDS])
+def test_oracle_reproduces_interlaced_golden(path):
+    """Field transform at level 1 (TransformForwardFrameYUV, wavelet.c:6076): every band the reference's EncodeSample
+    produced for an interlaced source, the HL band in its difference-coded form."""
+    frame, div, prescale, quality, bands = load_golden(path)
+    assert div[0][0][1] != div[0][0][2]          # the interlaced schedule (LH * 3/2, HL * 2/3) was in force
+    pyr = pu.forward_pyramid_422(ol.oracle(), frame, div, prescale, fmt=0, interlaced=True)
+    for key, want in bands.items():
+        assert np.array_equal(pyr[key], want), f"band {key}"
+
+
+@pytest.mark.parametrize("path", GOLDEN_FIELDS, ids=[os.path.basename(p) for p in GOLDEN_FIELDS])
+def test_oracle_interlaced_inverse_inside_reference_decoder_envelope(path):
+    frame, div, prescale, quality, enc_bands = load_golden(path)
+    bands, dec = load_golden_decoder_side(path)
+    for c in range(3):
+        # the decoder integrates HL after dequantising it (decoder.c:20822): its band is cumsum(coded) * divisor
+        want = (np.cumsum(enc_bands[(c, 1, "HL")].astype(np.int64), axis=1) * div[c][0][2]).astype(np.int16)
+        assert np.array_equal(bands[(c, 1, "HL")], want)
+        hl = bands[(c, 1, "HL")].astype(np.int32)
+        hl[:, 1:] -= hl[:, :-1].copy()
+        bands[(c, 1, "HL")] = hl.astype(np.int16)        # back to the coded (differenced) form inverse_pyramid expects
+    planes = pu.inverse_pyramid(ol.oracle(), bands, pu.UNIT_DIVISORS, prescale, interlaced=True)
+    a, b = pu.yuyv_envelope(planes)
+    ok = (dec == a) | (dec == b)
+    assert ok.all(), f"{(~ok).sum()} bytes outside the dither envelope"
+    assert pu.psnr(dec[:, 0::2], frame[:, 0::2]) > 45.0

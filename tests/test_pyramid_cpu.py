@@ -57,6 +57,64 @@ def test_quant_schedule_matches_reference(pkg, quality):
     assert list(q.prescale) == prescale[0]
 
 
+@needs_ref
+@pytest.mark.parametrize("quality", [1, 2, 3, 4, 5, 6, 4 | (1 << 17)])
+def test_interlaced_quant_schedule_matches_reference(pkg, quality):
+    """parameters.progressive = 0 (CFHD_ENCODING_FLAGS_YUV_INTERLACED): quantize.c:490-541 rescales level 1."""
+    w, h = 256, 64
+    ref_lib = ol.load_ref()
+    frame = pu.qbist_yuy2(ref_lib, w, h, 1)
+    ref_lib.ref_set_interlaced(1)
+    try:
+        _, div, prescale, _ = pu.ref_encode_frame(ref_lib, frame, w, h, pu.COLOR_FORMAT_YUYV, 0, 3, quality)
+    finally:
+        ref_lib.ref_set_interlaced(0)
+    q = pkg.quant_for_quality(pkg.FrameDesc(w, h, pkg.PIXEL_YUYV), quality, interlaced=True)
+    assert q.table(3) == div
+    assert list(q.prescale) == prescale[0]
+
+
+@needs_ref
+@pytest.mark.parametrize("size,quality,kind", [((640, 368), 4, "qbist"), ((256, 64), 3, "natural"), ((1920, 1080), 4, "qbist"),
+                                               ((320, 56), 1, "natural"), ((704, 96), 5, "random"), ((192, 48), 6, "random")])
+def test_oracle_field_transform_matches_reference_codec(size, quality, kind):
+    """Interlaced source through the reference's real encoder and decoder: the oracle's field transform reproduces
+    every band EncodeSample left behind (natural content; for full-range noise the entropy coder rewrites band values
+    in place, so the check goes through the sample instead: what the reference's DECODER recovered from the bitstream
+    must equal the oracle's bands, dequantised and with HL integrated), and the oracle's inverse of the decoder's
+    bands lies inside the dither envelope of the frame the decoder produced."""
+    w, h = size
+    ref_lib, orc = ol.load_ref(), ol.oracle()
+    rng = np.random.default_rng(w * 7 + h)
+    if kind == "qbist":
+        frame = pu.qbist_yuy2(ref_lib, w, h).copy()
+        frame[1::2] = np.roll(frame[1::2], 12, axis=1)
+    else:
+        frame = pu.synthetic_yuyv(rng, w, h, kind)
+    ref_lib.ref_set_interlaced(1)
+    try:
+        bands_ref, div, prescale, sample = pu.ref_encode_frame(ref_lib, frame, w, h, pu.COLOR_FORMAT_YUYV, 0, 3, quality)
+    finally:
+        ref_lib.ref_set_interlaced(0)
+    pyr = pu.forward_pyramid_422(orc, frame, div, tuple(prescale[0]), fmt=0, interlaced=True)
+    if kind != "random":
+        for key, want in bands_ref.items():
+            if not (key[2] == "LL" and key[1] != 3):
+                assert np.array_equal(pyr[key], want), f"band {key}"
+    dec, db = pu.ref_decode_sample_bands(ref_lib, sample, w, h)
+    for c in range(3):
+        hl = np.cumsum(pyr[(c, 1, "HL")].astype(np.int64), axis=1) * div[c][0][2]
+        assert np.array_equal(db[(c, 1, "HL")], hl.astype(np.int16)), f"channel {c}: decoder HL != integrated oracle HL"
+    coded = {k: v.copy() for k, v in db.items() if not (k[2] == "LL" and k[1] != 3)}
+    for c in range(3):
+        hl = coded[(c, 1, "HL")].astype(np.int32)
+        hl[:, 1:] -= hl[:, :-1].copy()
+        coded[(c, 1, "HL")] = hl.astype(np.int16)
+    planes = pu.inverse_pyramid(orc, coded, pu.UNIT_DIVISORS, tuple(prescale[0]), interlaced=True)
+    a, b = pu.yuyv_envelope(planes)
+    assert ((dec == a) | (dec == b)).all()
+
+
 def test_layout_rules(pkg):
     lay = pkg.layout_for(pkg.FrameDesc(3840, 2160, pkg.PIXEL_YUYV))
     assert lay.num_channels == 3 and lay.precision == 10
