@@ -21,13 +21,18 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--inverse", action="store_true")
+    ap.add_argument("--interlaced", action="store_true", help="field transform at level 1")
+    ap.add_argument("--resolution", type=int, default=1, help="decode resolution: 1 full, 2 half, 3 quarter")
     a = ap.parse_args()
     pkg = importlib.import_module("cineform-sdk_b200")
     torch.cuda.init()
     ctx = pkg.Context(0)
     desc = pkg.FrameDesc(a.width, a.height, pkg.PIXEL_YUYV)
-    quant = pkg.quant_for_quality(desc, 4)
+    quant = pkg.quant_for_quality(desc, 4, interlaced=a.interlaced)
     codec = pkg.Codec(ctx, desc, 1)
+    if a.interlaced:
+        codec.set_interlaced(True)
+    codec.set_decode_resolution(a.resolution)
     lay = codec.layout
     rng = np.random.default_rng(0)
     frame = pu.synthetic_yuyv(rng, a.width, a.height, "natural")
