@@ -100,6 +100,10 @@ def lib():
     L.cfb_codec_set_bayer_phase.argtypes = [vp, i]
     L.cfb_codec_set_decode_resolution.argtypes = [vp, i]
     L.cfb_codec_set_interlaced.argtypes = [vp, i]
+    L.cfb_temporal_forward_device.argtypes = [vp, vp, vp, i, vp, vp, i, i, i]
+    L.cfb_temporal_inverse_device.argtypes = [vp, vp, vp, i, vp, vp, i, i, i, i]
+    L.cfb_temporal_forward_host.argtypes = [vp, vp, vp, i, vp, vp, i, i, i]
+    L.cfb_temporal_inverse_host.argtypes = [vp, vp, vp, i, vp, vp, i, i, i, i]
     L.cfb_quant_for_source.argtypes = [C.POINTER(FrameDesc), i, i, C.POINTER(Quant)]
     L.cfb_codec_decoded_size.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
     L.cfb_pool_set_decode_resolution.argtypes = [vp, i]
@@ -217,6 +221,23 @@ class Context:
     @property
     def stream(self):
         return lib().cfb_context_stream(self.h)
+
+    # -- two-frame GOP building block (temporal Haar on int16 planes, host arrays) --
+    def temporal_forward(self, frame1, frame2):
+        a, b = np.ascontiguousarray(frame1, np.int16), np.ascontiguousarray(frame2, np.int16)
+        h, w = a.shape
+        low, high = np.zeros_like(a), np.zeros_like(a)
+        _check(lib().cfb_temporal_forward_host(self.h, a.ctypes.data, b.ctypes.data, a.strides[0], low.ctypes.data,
+                                               high.ctypes.data, low.strides[0], w, h))
+        return low, high
+
+    def temporal_inverse(self, low, high, precision=10):
+        lo, hi = np.ascontiguousarray(low, np.int16), np.ascontiguousarray(high, np.int16)
+        h, w = lo.shape
+        a, b = np.zeros_like(lo), np.zeros_like(lo)
+        _check(lib().cfb_temporal_inverse_host(self.h, lo.ctypes.data, hi.ctypes.data, lo.strides[0], a.ctypes.data,
+                                               b.ctypes.data, a.strides[0], w, h, precision))
+        return a, b
 
     def stats(self):
         s = Stats()

@@ -201,6 +201,25 @@ CFB_API cfb_error cfb_inverse_host(cfb_codec *codec, int n, const void *const *h
 
 
 
+/* ---- two-frame GOP building block: temporal Haar between two int16 planes --------------------
+ * In the reference's FIELDPLUS pyramid (CFHD_ENCODING_FLAGS_YUV_2FRAME_GOP; Codec/encoder.c:8431
+ * FinishFieldPlusTransformQuant, Codec/decoder.c:13109) wavelet[2] is the temporal transform of the level-1 lowpass
+ * images of frames A and B; the spatial levels above and below it are the same transforms as the intra-frame
+ * pyramid.  forward replaces Codec/temporal.c:498 FilterTemporal16s (low = adds(f1, f2), high = subs(f2, f1));
+ * inverse replaces Codec/temporal.c:9402 InvertTemporalQuant16s (f1 = subs(low, high) >> 1,
+ * f2 = adds(low, high) >> 1 on dequantised coefficients; precision 8 adds the reference's half-tone bit).
+ * Planes are int16, width a multiple of 16 (temporal.c:616), pitches in bytes, 16-byte aligned.
+ * The _device forms take device pointers and run asynchronously on cfb_context_stream(). */
+CFB_API cfb_error cfb_temporal_forward_device(cfb_context *ctx, const void *d_frame1, const void *d_frame2, int in_pitch,
+                                              void *d_low, void *d_high, int out_pitch, int width, int height);
+CFB_API cfb_error cfb_temporal_inverse_device(cfb_context *ctx, const void *d_low, const void *d_high, int in_pitch,
+                                              void *d_frame1, void *d_frame2, int out_pitch, int width, int height,
+                                              int precision);
+CFB_API cfb_error cfb_temporal_forward_host(cfb_context *ctx, const void *frame1, const void *frame2, int in_pitch,
+                                            void *low, void *high, int out_pitch, int width, int height);
+CFB_API cfb_error cfb_temporal_inverse_host(cfb_context *ctx, const void *low, const void *high, int in_pitch,
+                                            void *frame1, void *frame2, int out_pitch, int width, int height, int precision);
+
 /* ---- sparse transfer format of the coded region (lossless) ---- */
 /* Layout of a sparse buffer:  16-byte header {u32 'CFSP', u32 nwords, u32 nvalues, u32 0};
  * bitmap (nwords bits, bit i <=> int16 word i of the coded region [0, coded_bytes) is non-zero);

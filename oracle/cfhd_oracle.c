@@ -464,3 +464,41 @@ void orc_inv_fields(const int16_t *ll, const int16_t *lh, const int16_t *hl, con
     }
     free(tl); free(th);
 }
+
+/* ------------------------------------------------------------------------- */
+/* Two-frame GOP temporal Haar, see cfhd_oracle.h. */
+void orc_temporal_fwd(const int16_t *a, const int16_t *b, int in_pitch, int width, int height,
+                      int16_t *low, int16_t *high, int out_pitch)
+{
+    int r, c;
+    for (r = 0; r < height; r++) {
+        const int16_t *x = (const int16_t *)((const uint8_t *)a + (size_t)r * in_pitch);
+        const int16_t *y = (const int16_t *)((const uint8_t *)b + (size_t)r * in_pitch);
+        int16_t *l = (int16_t *)((uint8_t *)low + (size_t)r * out_pitch);
+        int16_t *h = (int16_t *)((uint8_t *)high + (size_t)r * out_pitch);
+        for (c = 0; c < width; c++) { l[c] = adds(x[c], y[c]); h[c] = subs(y[c], x[c]); }
+    }
+}
+
+void orc_temporal_inv(const int16_t *low, const int16_t *high, int in_pitch, int width, int height, int precision,
+                      int16_t *a, int16_t *b, int out_pitch)
+{
+    const int post = width - (width % 40);
+    int r, c;
+    for (r = 0; r < height; r++) {
+        const int16_t *l = (const int16_t *)((const uint8_t *)low + (size_t)r * in_pitch);
+        const int16_t *h = (const int16_t *)((const uint8_t *)high + (size_t)r * in_pitch);
+        int16_t *x = (int16_t *)((uint8_t *)a + (size_t)r * out_pitch);
+        int16_t *y = (int16_t *)((uint8_t *)b + (size_t)r * out_pitch);
+        for (c = 0; c < post; c++) {
+            const int16_t ht = (precision == 8) ? (int16_t)((c + r + 1) & 1) : 0;
+            x[c] = sra16(subs(l[c], h[c]), 1);
+            y[c] = sra16(adds(adds(l[c], h[c]), ht), 1);
+        }
+        for (; c < width; c++) {
+            const int t = (precision == 8) ? ((c + r) & 1) : 0;
+            x[c] = wrap16(((int32_t)l[c] - h[c]) >> 1);
+            y[c] = wrap16(((int32_t)l[c] + h[c] + t) >> 1);
+        }
+    }
+}

@@ -105,6 +105,19 @@ void orc_fwd_fields_422(const uint8_t *frame, int frame_pitch, int width, int he
 void orc_inv_fields(const int16_t *ll, const int16_t *lh, const int16_t *hl, const int16_t *hh,
                     int band_pitch, int width, int height, int16_t *out, int out_pitch);
 
+/* ---- two-frame GOP: temporal Haar between two int16 planes (the level-1 lowpass images of frames A and B) ----
+ * Forward, Codec/temporal.c:498 FilterTemporal16s (the 16-bit branch :603-645; the _HIGHPASS_8S branch is compiled
+ * out): low = adds(a, b), high = subs(b, a), saturating, width % 16 == 0 (asserted there). */
+void orc_temporal_fwd(const int16_t *a, const int16_t *b, int in_pitch, int width, int height,
+                      int16_t *low, int16_t *high, int out_pitch);
+/* Inverse, Codec/temporal.c:9402 InvertTemporalQuant16s (the coefficients arrive dequantised; its quantisation
+ * arguments are unused): SSE2 part, columns < width - width % 40: a = subs(low, high) >> 1,
+ * b = adds(adds(low, high), halftone) >> 1; scalar tail in int: a = (low - high) >> 1, b = (low + high + t) >> 1 stored
+ * as int16.  precision 8 only: halftone = (column + row + 1) & 1 in the SSE2 part (set_epi16 patterns :9437-9442) but
+ * t = (column + row) & 1 in the tail (:9625); 0 for precision >= 10. */
+void orc_temporal_inv(const int16_t *low, const int16_t *high, int in_pitch, int width, int height, int precision,
+                      int16_t *a, int16_t *b, int out_pitch);
+
 /* 3-level pyramid helpers are composed in Python (tests/) from the calls above. */
 
 int orc_version(void);

@@ -153,6 +153,40 @@ void ref_inv_level(const int16_t *ll, const int16_t *lh, const int16_t *hl, cons
     copy_in((uint8_t *)out, out_pitch, o.as<uint8_t>(), op, width * 4, height * 2);
 }
 
+// GOP-2 temporal Haar between two int16 planes (level-1 lowpass images of frame A and frame B):
+// Codec/temporal.c:498 FilterTemporal16s (live branch :603-645) and Codec/temporal.c:9402 InvertTemporalQuant16s.
+extern "C" void FilterTemporal16s(PIXEL *field1, int pitch1, PIXEL *field2, int pitch2,
+                                  PIXEL *lowpass, int lowpass_pitch, PIXEL *highpass, int highpass_pitch, ROI roi);
+extern "C" void InvertTemporalQuant16s(PIXEL *lowpass, int lowpass_quantization, int lowpass_pitch,
+                                       PIXEL *highpass, int highpass_quantization, int highpass_pitch,
+                                       PIXEL *field1, int pitch1, PIXEL *field2, int pitch2, ROI roi,
+                                       PIXEL *buffer, size_t buffer_size, int precision);
+void ref_temporal_fwd(const int16_t *a, const int16_t *b, int in_pitch, int width, int height,
+                      int16_t *low, int16_t *high, int out_pitch)
+{
+    const int pp = align16(width * 2) + 64;
+    Aligned x((size_t)pp * height + 64), y((size_t)pp * height + 64), l((size_t)pp * height + 64), h((size_t)pp * height + 64);
+    copy_in(x.as<uint8_t>(), pp, (const uint8_t *)a, in_pitch, width * 2, height);
+    copy_in(y.as<uint8_t>(), pp, (const uint8_t *)b, in_pitch, width * 2, height);
+    ROI roi = {width, height};
+    FilterTemporal16s(x.as<PIXEL>(), pp, y.as<PIXEL>(), pp, l.as<PIXEL>(), pp, h.as<PIXEL>(), pp, roi);
+    copy_in((uint8_t *)low, out_pitch, l.as<uint8_t>(), pp, width * 2, height);
+    copy_in((uint8_t *)high, out_pitch, h.as<uint8_t>(), pp, width * 2, height);
+}
+
+void ref_temporal_inv(const int16_t *low, const int16_t *high, int in_pitch, int width, int height, int precision,
+                      int16_t *a, int16_t *b, int out_pitch)
+{
+    const int pp = align16(width * 2) + 128;        // the software-pipelined loop loads 3 vectors ahead
+    Aligned x((size_t)pp * (height + 1) + 64), y((size_t)pp * (height + 1) + 64), l((size_t)pp * (height + 1) + 64), h((size_t)pp * (height + 1) + 64);
+    copy_in(l.as<uint8_t>(), pp, (const uint8_t *)low, in_pitch, width * 2, height);
+    copy_in(h.as<uint8_t>(), pp, (const uint8_t *)high, in_pitch, width * 2, height);
+    ROI roi = {width, height};
+    InvertTemporalQuant16s(l.as<PIXEL>(), 1, pp, h.as<PIXEL>(), 1, pp, x.as<PIXEL>(), pp, y.as<PIXEL>(), pp, roi, NULL, 0, precision);
+    copy_in((uint8_t *)a, out_pitch, x.as<uint8_t>(), pp, width * 2, height);
+    copy_in((uint8_t *)b, out_pitch, y.as<uint8_t>(), pp, width * 2, height);
+}
+
 // Example/qbist.cpp:252 RunQBist driven exactly like Example/TestCFHD.cpp:1149-1219:
 // GetRand(seed); initBaseTransform(); then one RunQBist() per frame; returns frame number `nframes` (1-based).
 void ref_qbist_frames(unsigned seed, int width, int height, int pitch, unsigned pixel_format, int nframes, uint8_t *out)
