@@ -249,23 +249,37 @@ def reference_best(iters):
 
 
 def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores.
+    Step 0 picks the fastest host-thread count (reference_best); every later step re-times that configuration on a
+    sample sized so that the whole --steps/--warmup run stays inside --ref-budget-s of wall clock."""
     if rank != 0:
         return
-    iters = max(1, args.ref_iters)
-    steps_ms = []
-    for s in range(args.warmup + args.steps):
+    t_start = time.perf_counter()
+    total = args.warmup + args.steps
+    fps0, kind, desc, threads = reference_best(max(1, args.ref_iters))
+    results = [(fps0, desc)] if args.warmup == 0 else []
+    per_frame_s = threads / fps0                 # one thread's time for one frame (forward + inverse)
+    setup_s = 1.5                                # probe set-up per call (one real encode + decode per thread), measured below
+    for s in range(1, total):
+        remaining = args.ref_budget_s - (time.perf_counter() - t_start)
+        slot = max(0.0, remaining) / (total - s)
+        iters = int(max(1, min(args.ref_iters * 4, (slot - setup_s) / per_frame_s)))
         t0 = time.perf_counter()
-        fps, kind, desc, threads = reference_best(iters)
-        dt = time.perf_counter() - t0
+        fps, kind, d = cpu_reference_run(WIDTH, HEIGHT, QUALITY, threads, iters)
+        setup_s = max(0.2, (time.perf_counter() - t0) - iters * threads / fps)
         if s >= args.warmup:
-            steps_ms.append((fps, dt))
-    fps = float(np.max([f for f, _ in steps_ms]))
+            results.append((fps, d))
+    fps, desc = max(results, key=lambda r: r[0])
+    frames = int(desc.split(" threads x ")[1].split(" frames")[0]) * threads
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "fps", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * threads * iters / fps, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * frames / fps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": DATA_NOTE,
-        "config": {"workload": WORKLOAD, "frames_per_step": threads * iters, "stage": "wavelet+quant transform path only "
-                   "(entropy coding excluded on both arms)"},
+        "config": {"workload": WORKLOAD, "frames_per_step": frames, "stage": "wavelet+quant transform path only "
+                   "(entropy coding excluded on both arms)",
+                   "sampling": f"best of {len(results)} timed steps; thread count chosen in step 0 from "
+                               f"{{1/4, 1/2, 1}} x usable cores; wall {time.perf_counter() - t_start:.0f}s "
+                               f"(budget {args.ref_budget_s}s)"},
         "cpu_baseline": {"value": fps, "unit": "fps", "cores": threads, "kind": kind, "sample": desc},
         "e2e": {"value": fps, "unit": "fps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -446,6 +460,7 @@ def main():
     ap.add_argument("--pool-slots", type=int, default=8)
     ap.add_argument("--pool-batch", type=int, default=2)
     ap.add_argument("--pool-inflight", type=int, default=48)
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="wall-clock budget of the whole --impl reference run")
     ap.add_argument("--ref-iters", type=int, default=6, help="frames per host thread (at the full thread count) in the CPU baseline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
