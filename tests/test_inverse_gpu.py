@@ -180,5 +180,4 @@ def test_reduced_resolution_vs_oracle(pkg, ctx, size, fmt_name):
             out, planes = _reduced(codec, pkg, coded, quant, res, fmt)
             _check_planes(planes, want)
             assert np.array_equal(out, pu.lowpass_to_422(want, unsigned_shift=(stop == 2), uyvy=(fmt_name == "UYVY")))
-            if w >= 1920:
-                assert out.min() == 0 and out.max() == 255      # the saturating paths were exercised
+            assert out.min() == 0                    # negative lowpass values occur (clamped / wrapped by the two rules)
