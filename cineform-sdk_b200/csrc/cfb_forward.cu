@@ -65,29 +65,51 @@ __device__ __forceinline__ void store_quant(unsigned char *p, const int *v, cons
         VecStore<2>::st(p, pack_hi(quant1(v[0], q), quant1(v[1], q)), 0u);
 }
 
+// predicated 64/32-bit global stores: the address and the value are computed unconditionally and only the store is
+// guarded, so the hot loop carries no divergence-safe branch (BSSY/BSYNC/BRA) around its band stores
+__device__ __forceinline__ void st_pred(unsigned char *p, unsigned a, unsigned b, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\t@p st.global.v2.u32 [%0], {%1, %2};\n\t}"
+                 :: "l"(p), "r"(a), "r"(b), "r"((int)on) : "memory");
+}
+__device__ __forceinline__ void st_pred(unsigned char *p, unsigned a, bool on) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}"
+                 :: "l"(p), "r"(a), "r"((int)on) : "memory");
+}
+template <int NC>
+__device__ __forceinline__ void store_raw_if(unsigned char *p, const int *v, bool on) {
+    if (NC == 4) st_pred(p, pack_lo(v[0], v[1]), pack_lo(v[2], v[3]), on);
+    else st_pred(p, pack_lo(v[0], v[1]), on);
+}
+template <int NC>
+__device__ __forceinline__ void store_quant_if(unsigned char *p, const int *v, const QuantParam &q, bool on) {
+    if (NC == 4)
+        st_pred(p, pack_hi(quant1(v[0], q), quant1(v[1], q)), pack_hi(quant1(v[2], q), quant1(v[3], q)), on);
+    else
+        st_pred(p, pack_hi(quant1(v[0], q), quant1(v[1], q)), on);
+}
+
 // One vertical step on the horizontal outputs of rows 2j (a) and 2j+1 (b); [0,NC) = low, [NC,2NC) = high.
 // emit_low : store LL/LH of output row j        at byte offset off
 // emit_high: store HL/HH of output row j-1      at byte offset off - pitch   (interior formula)
-// Both flags are warp-uniform.
-template <int NC>
+// Both flags are warp-uniform.  QLL: 0 = LL is never quantised (the 4:2:2 level-1 filter, spatial.c:14726),
+// 1 = decided at run time by g.quant_ll (planar filter with an LL divisor > 1, spatial.c:10480).
+template <int NC, int QLL>
 __device__ __forceinline__ void vstep(VState<NC> &s, const int *a, const int *b, const PlaneGeom &g, unsigned char *out,
                                       unsigned off, bool emit_low, bool emit_high)
 {
     int v[2 * NC], dn[2 * NC];
 #pragma unroll
     for (int i = 0; i < 2 * NC; i++) { v[i] = a[i] + b[i]; dn[i] = a[i] - b[i]; }
-    if (emit_low) {
-        if (g.quant_ll) store_quant<NC>(out + (g.band_off[0] + off), v, g.q[0]);
-        else store_raw<NC>(out + (g.band_off[0] + off), v);
-        store_quant<NC>(out + (g.band_off[1] + off), v + NC, g.q[1]);
-    }
-    if (emit_high) {
+    if (QLL && g.quant_ll) store_quant_if<NC>(out + (g.band_off[0] + off), v, g.q[0], emit_low);
+    else store_raw_if<NC>(out + (g.band_off[0] + off), v, emit_low);
+    store_quant_if<NC>(out + (g.band_off[1] + off), v + NC, g.q[1], emit_low);
+    {
         int h[2 * NC];
 #pragma unroll
         for (int i = 0; i < 2 * NC; i++) h[i] = ((v[i] - s.llp[i] + 4) >> 3) + s.dc[i];
         const unsigned offh = off - (unsigned)g.out_pitch;
-        store_quant<NC>(out + (g.band_off[2] + offh), h, g.q[2]);
-        store_quant<NC>(out + (g.band_off[3] + offh), h + NC, g.q[3]);
+        store_quant_if<NC>(out + (g.band_off[2] + offh), h, g.q[2], emit_high);
+        store_quant_if<NC>(out + (g.band_off[3] + offh), h + NC, g.q[3], emit_high);
     }
 #pragma unroll
     for (int i = 0; i < 2 * NC; i++) { s.llp[i] = s.llc[i]; s.llc[i] = v[i]; s.dc[i] = dn[i]; }
@@ -276,7 +298,7 @@ __global__ void __launch_bounds__(128) k_fwd_plane(const __grid_constant__ FwdPa
         int a[8], b[8];
         hfilter_plane<PRESCALE>(c0, L, a);
         hfilter_plane<PRESCALE>(c1, L, b);
-        vstep<4>(st, a, b, g, out, off, j >= y0 && j < y1, j - 1 >= hlo);
+        vstep<4, 1>(st, a, b, g, out, off, j >= y0 && j < y1, j - 1 >= hlo);
         off += (unsigned)g.out_pitch;
         c0 = n0; c1 = n1;
     }
@@ -355,7 +377,7 @@ __global__ void __launch_bounds__(128) k_fwd_rg48(const __grid_constant__ FwdPar
         rg48_extract<SEL>(c1, shift, r1);
         hfilter_plane<0>(r0, L, a);
         hfilter_plane<0>(r1, L, b);
-        vstep<4>(st, a, b, g, out, off, j >= y0 && j < y1, j - 1 >= hlo);
+        vstep<4, 1>(st, a, b, g, out, off, j >= y0 && j < y1, j - 1 >= hlo);
         off += (unsigned)g.out_pitch;
         c0 = n0; c1 = n1;
     }
@@ -486,7 +508,7 @@ __global__ void __launch_bounds__(128) k_fwd_byr4(const __grid_constant__ FwdPar
         byr4_extract(c1, shift, fmt, c, r1);
         hfilter_plane<0>(r0, L, a);
         hfilter_plane<0>(r1, L, b);
-        vstep<4>(st, a, b, g, out, off, j >= y0 && j < y1, j - 1 >= hlo);
+        vstep<4, 1>(st, a, b, g, out, off, j >= y0 && j < y1, j - 1 >= hlo);
         off += (unsigned)g.out_pitch;
         c0 = n0; c1 = n1;
     }
@@ -651,9 +673,9 @@ __global__ void __launch_bounds__(128) k_fwd_422(const __grid_constant__ FwdPara
         hfilter_422(c0, sel, L, ay, au, av);
         hfilter_422(c1, sel, L, by, bu, bv);
         const bool emit_low = (j >= y0) && (j < y1), emit_high = (j - 1 >= hlo);
-        vstep<4>(sy, ay, by, gy, out, offy, emit_low, emit_high);
-        vstep<2>(su, au, bu, gu, out, offc, emit_low, emit_high);
-        vstep<2>(sv, av, bv, gv, out, offc, emit_low, emit_high);
+        vstep<4, 0>(sy, ay, by, gy, out, offy, emit_low, emit_high);
+        vstep<2, 0>(su, au, bu, gu, out, offc, emit_low, emit_high);
+        vstep<2, 0>(sv, av, bv, gv, out, offc, emit_low, emit_high);
         offy += (unsigned)gy.out_pitch;
         offc += (unsigned)gu.out_pitch;
         c0 = n0; c1 = n1;
