@@ -142,6 +142,35 @@ __device__ __forceinline__ unsigned pack_sat16(int lo, int hi) {
 }
 
 // ----------------------------------------------------------------------------
+// Lane-distributed L2 prefetch.  A future band row of one strip touches <= 3 cache lines per luma band and <= 2 per
+// chroma band; instead of every lane prefetching its own 8 bytes of each of the 12 bands (12 address computations
+// per warp and row), each lane owns ONE (channel, band, 128-byte line) and the whole set costs one prefetch
+// instruction per row.  LL/LH are fetched 4 rows ahead (the vertical window reads row r+1), HL/HH 3 rows ahead.
+struct LanePrefetch {
+    const unsigned char *base;      // in + band offset + line start (row 0)
+    int pitch;
+    int ahead;
+    bool valid;
+    __device__ __forceinline__ void issue(int r, int y1, int H) const {
+        if (valid && r + 3 < y1) prefetch_l2(base + (long long)min(r + ahead, H - 1) * pitch);
+    }
+};
+
+// chan_of_lane < 0: lane idle.  bytes_per_col = 2 for a full-width band, 1 for the half-width chroma bands of 4:2:2
+// (their columns are addressed as luma_column / 2).
+__device__ __forceinline__ LanePrefetch make_prefetch(const InvGeom &g, const unsigned char *in, int strip, int band, int line,
+                                                      int bytes_per_col, bool on)
+{
+    LanePrefetch pf;
+    const int col = ((max(strip * kInvStrip - 4, 0) * bytes_per_col) & ~127) + line * 128;
+    pf.valid = on && col < g.pitch;
+    pf.base = in + g.band_off[band] + col;
+    pf.pitch = g.pitch;
+    pf.ahead = (band < 2) ? 4 : 3;
+    return pf;
+}
+
+// ----------------------------------------------------------------------------
 // Per-channel inverse engine: a three-row window of LL and LH (already expanded to int32) plus a
 // one-iteration-ahead prefetch of the raw band rows.
 template <int NC>
@@ -184,11 +213,6 @@ __device__ __forceinline__ void inv_step(InvChan<NC> &s, const InvGeom &g, const
         load_raw<NC>(in, g.band_off[1], rn, active, s.nlh);
         load_raw<NC>(in, g.band_off[2], rc, active, s.nhl);
         load_raw<NC>(in, g.band_off[3], rc, active, s.nhh);
-    }
-    if (r + 3 < y1 && active) {     // L2 prefetch two more rows ahead (no register, no scoreboard)
-        const unsigned rn = (unsigned)min(r + 4, H - 1) * g.pitch + colbyte, rc = (unsigned)(r + 3) * g.pitch + colbyte;
-        prefetch_l2(in + g.band_off[0] + rn); prefetch_l2(in + g.band_off[1] + rn);
-        prefetch_l2(in + g.band_off[2] + rc); prefetch_l2(in + g.band_off[3] + rc);
     }
     int el[NC], ol[NC], eh[NC], oh[NC];
     vinv_mid<NC>(s.lp, s.lc, ln, vhl, el, ol);
@@ -275,9 +299,11 @@ __global__ void __launch_bounds__(128) k_inv_plane(const __grid_constant__ InvPa
     const int y1 = min((int)(blockIdx.y * blockDim.y + threadIdx.y + 1) * p.th, H - 1);
     if (y0 >= y1) return;
 
+    const LanePrefetch pf = make_prefetch(g, in, strip, lane / 3, lane % 3, 2, lane < 12);
     InvChan<4> st;
     inv_prologue<4, SMALLDQ>(st, g, in, y0, H, colbyte, active);
     for (int r = y0; r < y1; r++) {
+        pf.issue(r, y1, H);
         int te[8], to[8];
         inv_step<4, SMALLDQ>(st, g, in, r, y1, H, colbyte, active, has_border, left_border, right_border, te, to);
         if (writer) emit(r, te, to);
@@ -355,12 +381,17 @@ __global__ void __launch_bounds__(128) k_inv_422(const __grid_constant__ InvPara
     const int y1 = min((int)(blockIdx.y * blockDim.y + threadIdx.y + 1) * p.th, H - 1);
     if (y0 >= y1) return;
 
+    // lanes 0-11: luma (band = lane / 3, line = lane % 3); lanes 12-27: chroma (channel 1 + i / 8, band (i % 8) / 2, line i % 2)
+    const int pi = lane - 12;
+    const LanePrefetch pf = (lane < 12) ? make_prefetch(gy, in, strip, lane / 3, lane % 3, 2, true)
+                                        : make_prefetch((pi & 8) ? gu : gv, in, strip, (pi & 7) >> 1, pi & 1, 1, lane < 28);
     InvChan<4> sy;
     InvChan<2> su, sv;
     inv_prologue<4, SMALLDQ>(sy, gy, in, y0, H, ycol, active);
     inv_prologue<2, SMALLDQ>(su, gu, in, y0, H, ccol, active);
     inv_prologue<2, SMALLDQ>(sv, gv, in, y0, H, ccol, active);
     for (int r = y0; r < y1; r++) {
+        pf.issue(r, y1, H);
         int ye[8], yo[8], ue[4], uo[4], ve[4], vo[4];
         inv_step<4, SMALLDQ>(sy, gy, in, r, y1, H, ycol, active, has_border, left_border, right_border, ye, yo);
         inv_step<2, SMALLDQ>(su, gu, in, r, y1, H, ccol, active, has_border, left_border, right_border, ue, uo);
