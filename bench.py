@@ -297,6 +297,14 @@ def run_ours(args, rank, world, local_rank):
     D = Dist(world, "nccl", local_rank)
     barrier = D.barrier
 
+    # one process per GPU, placed on the GPU's own NUMA node (as `numactl --cpunodebind` would): pinned buffers
+    # allocated below and the pool's copy threads are then local to the PCIe root of this rank's GPU.  The original mask
+    # is restored before the CPU baseline so that the reference arm keeps every host core.
+    full_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa_node = pkg.device_numa_node(local_rank)
+    if not args.no_numa_bind:
+        pkg.bind_thread_to_device(local_rank)
+
     B = args.batch
     ctx = pkg.Context(local_rank)
     desc = pkg.FrameDesc(WIDTH, HEIGHT, pkg.PIXEL_YUYV)
@@ -408,7 +416,7 @@ def run_ours(args, rank, world, local_rank):
                "h2d_bytes_per_step": int(B * (lay.frame_bytes + coded_sparse)),
                "d2h_bytes_per_step": int(B * (coded_sparse + lay.frame_bytes)),
                "api": f"cfb_pool_submit_forward_sparse/inverse_sparse + cfb_pool_wait (C ABI), pinned host buffers, "
-                      f"{args.pool_slots} slots x batch {args.pool_batch}, encode and decode jobs interleaved; coefficients cross "
+                      f"{args.pool_slots} slots x batch {args.pool_batch}, encode and decode jobs interleaved{'' if args.no_numa_bind else f', rank bound to NUMA node {numa_node} of its GPU'}; coefficients cross "
                       f"PCIe in the lossless sparse format (bitmap + non-zero values, {coded_sparse} B/frame vs {lay.coded_bytes} dense)",
                "frames": nfr,
                "dense_format": {"value": aggregate_fps(world, nfr, dt_dense), "unit": "fps",
@@ -416,6 +424,8 @@ def run_ours(args, rank, world, local_rank):
                                 "d2h_bytes_per_step": int(B * (lay.coded_bytes + lay.frame_bytes))}}
 
     clocks = sampler.stop() if rank == 0 else None
+    if full_affinity is not None:
+        os.sched_setaffinity(0, full_affinity)
 
     # ---- CPU baseline (rank 0, N == 1 only) ----
     cpu = None
@@ -460,6 +470,7 @@ def main():
     ap.add_argument("--pool-slots", type=int, default=8)
     ap.add_argument("--pool-batch", type=int, default=2)
     ap.add_argument("--pool-inflight", type=int, default=48)
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not restrict the rank to its GPU's NUMA node")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="wall-clock budget of the whole --impl reference run")
     ap.add_argument("--ref-iters", type=int, default=6, help="frames per host thread (at the full thread count) in the CPU baseline")
     ap.add_argument("--no-e2e", action="store_true")

@@ -79,6 +79,8 @@ def lib():
     L.cfb_version.restype = i
     L.cfb_last_error_string.restype = C.c_char_p
     L.cfb_device_count.restype = i
+    L.cfb_device_numa_node.argtypes = [i]
+    L.cfb_bind_thread_to_device.argtypes = [i]
     L.cfb_context_create.argtypes = [i, C.POINTER(vp)]
     L.cfb_context_destroy.argtypes = [vp]
     L.cfb_context_destroy.restype = None
@@ -149,6 +151,15 @@ def layout_for(desc):
     out = Layout()
     _check(lib().cfb_layout_compute(C.byref(desc), C.byref(out)))
     return out
+
+
+def device_numa_node(device):
+    return int(lib().cfb_device_numa_node(device))
+
+
+def bind_thread_to_device(device):
+    """Restrict the calling thread to the CPUs of the GPU's NUMA node (pinned allocations that follow are local)."""
+    _check(lib().cfb_bind_thread_to_device(device))
 
 
 def quant_for_quality(desc, quality, interlaced=False):

@@ -11,6 +11,9 @@
 #include <new>
 
 #include "cfb_host.h"
+#include <ctype.h>
+#include <sched.h>
+#include <stdio.h>
 
 namespace cfb {
 
@@ -91,6 +94,53 @@ int cfb_device_count(void)
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+// NUMA placement.  Host<->device copies run at full PCIe rate only from memory (and threads) on the GPU's own NUMA
+// node; the reference pins its worker threads too (Codec/thread.c SetThreadAffinityMask / the SDK's thread
+// "capabilities" masks).  Linux sysfs only: /sys/bus/pci/devices/<bdf>/numa_node, /sys/devices/system/node/nodeN/cpulist.
+int cfb_device_numa_node(int device)
+{
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char *c = bdf; *c; c++) *c = (char)tolower((unsigned char)*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bdf);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+cfb_error cfb_bind_thread_to_device(int device)
+{
+    const int node = cfb_device_numa_node(device);
+    if (node < 0) return CFB_OK;                    // no NUMA information (single node, container without sysfs): leave as is
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    FILE *f = fopen(path, "r");
+    if (!f) return CFB_OK;
+    char list[4096] = {0};
+    const size_t n = fread(list, 1, sizeof(list) - 1, f);
+    fclose(f);
+    list[n] = 0;
+    cpu_set_t allowed, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return CFB_OK;
+    int count = 0;
+    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k == 1) b = a;
+        if (k < 1) continue;
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++)
+            if (CPU_ISSET(c, &allowed)) { CPU_SET(c, &want); count++; }
+    }
+    if (count == 0) return CFB_OK;                  // the node's CPUs are outside this process's mask: keep the mask
+    if (sched_setaffinity(0, sizeof(want), &want) != 0) { set_error("sched_setaffinity failed"); return CFB_ERROR_INVALID_ARGUMENT; }
+    return CFB_OK;
 }
 
 // ---------------------------------------------------------------------------

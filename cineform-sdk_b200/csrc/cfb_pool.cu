@@ -61,6 +61,7 @@ void cfb_pool::worker(int slot_index, int device_index)
 {
     Slot &s = *slots[slot_index];
     cudaSetDevice(s.ctx->device);
+    cfb_bind_thread_to_device(s.ctx->device);       // copies are issued from the GPU's own NUMA node
     std::vector<std::shared_ptr<Job>> mine;
     for (;;) {
         mine.clear();

@@ -122,6 +122,12 @@ typedef struct cfb_pool cfb_pool;           /* async, in-order, multi-GPU frame 
 CFB_API int cfb_version(void);
 CFB_API const char *cfb_last_error_string(void);              /* thread-local */
 CFB_API int cfb_device_count(void);                           /* 0 when no usable GPU */
+/* NUMA placement (Linux): node of the GPU's PCIe root (-1 if unknown) and a helper that restricts the CALLING thread to
+ * that node's CPUs, so that pinned buffers it allocates afterwards (cfb_host_alloc) and the copies it issues are local
+ * to the GPU.  The pool binds its own worker threads.  The reference sets worker-thread affinity likewise
+ * (Codec/thread.c:SetThreadAffinityMask). */
+CFB_API int cfb_device_numa_node(int device);
+CFB_API cfb_error cfb_bind_thread_to_device(int device);
 
 CFB_API cfb_error cfb_context_create(int device, cfb_context **out);
 CFB_API void cfb_context_destroy(cfb_context *ctx);
