@@ -844,6 +844,133 @@ __global__ void __launch_bounds__(128) k_fwd_422_fields(const __grid_constant__ 
 }
 
 // ----------------------------------------------------------------------------
+// 16-bit packed 4:2:2 sources (YU64: Y0 C1 Y1 C3, 16 bits each).  The reference converts them to 10-bit planes on the
+// host first (Codec/frame.c:1556 ConvertYU64ToFrame16s: `(word >> 6) & 0x03ff03ff`, convert.c:3345, then
+// convert.c:14370 de-interleave: position 1 -> channel 1, position 3 -> channel 2) and runs the planar level-1 filter on
+// each plane (Codec/encoder.c:3180-3193 TransformForwardSpatial -> spatial.c:10026 FilterSpatialQuant16s).  Here the
+// conversion is fused into the load of the same one-pass kernel structure as k_fwd_422.
+struct RawYU64Row {
+    uint4 a, b;         // 8 luma + 4 + 4 chroma samples of this lane (32 bytes)
+    uint4 halo;         // lane 0: previous 16 bytes; last lane: next 16 bytes
+};
+
+struct SrcYU64 {
+    typedef RawYU64Row Row;
+    static constexpr int kBytesPerLumaPair = 8;     // Y0 C1 Y1 C3
+    static __device__ __forceinline__ void load(const unsigned char *p, const LaneInfo &L, Row &r) {
+        r.a = __ldg(reinterpret_cast<const uint4 *>(p));
+        r.b = __ldg(reinterpret_cast<const uint4 *>(p + 16));
+        r.halo = make_uint4(0u, 0u, 0u, 0u);
+        if (L.use_lh | L.use_rh) r.halo = __ldg(reinterpret_cast<const uint4 *>(p + (L.use_lh ? -16 : 32)));
+    }
+    // cu = the position-1 chroma sample, cv = the position-3 sample of every 4-sample group
+    static __device__ __forceinline__ void linear(const Row &r, int shift, const LaneInfo &L, Lin422 &o) {
+        const unsigned M = (0xffffu >> shift) * 0x00010001u;
+        const unsigned w[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned t0 = (w[2 * k] >> shift) & M, t1 = (w[2 * k + 1] >> shift) & M;
+            const int y0 = (int)(t0 & 0xffffu), y1 = (int)(t1 & 0xffffu);
+            o.S[k] = y0 + y1; o.d[k] = y0 - y1;
+            o.cu[k] = (int)(t0 >> 16); o.cv[k] = (int)(t1 >> 16);
+        }
+        const unsigned h0 = (r.halo.x >> shift) & M, h1 = (r.halo.y >> shift) & M, h2 = (r.halo.z >> shift) & M, h3 = (r.halo.w >> shift) & M;
+        o.hy = L.use_lh ? (int)((h2 & 0xffffu) + (h3 & 0xffffu)) : (int)((h0 & 0xffffu) + (h1 & 0xffffu));
+        o.hu = (int)((h0 >> 16) + (h2 >> 16));
+        o.hv = (int)((h1 >> 16) + (h3 >> 16));
+    }
+};
+
+// Generic one-pass level 1 of a packed 4:2:2 source: SRC supplies the row load and the linear (pre-rounding) sums.
+// p.ch[0] = luma, p.ch[1] receives the position-1 chroma, p.ch[2] the position-3 chroma.
+template <class SRC>
+__global__ void __launch_bounds__(128) k_fwd_422_src(const __grid_constant__ FwdParams p)
+{
+    const int lane = threadIdx.x;
+    const int f = blockIdx.z;
+    const PlaneGeom &gy = p.ch[0];
+    const PlaneGeom &g1 = p.ch[1];
+    const PlaneGeom &g3 = p.ch[2];
+    const int strip = blockIdx.x;
+    if (strip * kStripIn >= gy.width) return;
+    const int oh = gy.height >> 1;
+    LaneInfo L;
+    if (!lane_setup(strip, gy.width, lane, L)) return;
+    const unsigned colbyte_y = (unsigned)((strip * kStripOut + lane * 4) * 2);
+    const unsigned colbyte_c = (unsigned)((strip * (kStripOut / 2) + lane * 2) * 2);
+    const unsigned char *in = p.in_base[f] + gy.in_off + (long long)(strip * kStripIn + lane * 8) / 2 * SRC::kBytesPerLumaPair;
+    unsigned char *out = p.out_base[f];
+    const int shift = p.shift;
+
+    if (blockIdx.y == gridDim.y - 1) {      // border warps: first / last HL,HH row of all three channels
+        if (threadIdx.y > 1) return;
+        const bool bottom = (threadIdx.y == 1);
+        const int j0 = bottom ? oh - 3 : 0;
+        int sy[3][8], s1[3][4], s3[3][4], dy[8], d1[4], d3[4];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            typename SRC::Row r0, r1;
+            Lin422 t;
+            int ay[8], by[8], a1[4], b1[4], a3[4], b3[4];
+            SRC::load(in + (long long)(2 * (j0 + k)) * gy.in_pitch, L, r0);
+            SRC::load(in + (long long)(2 * (j0 + k) + 1) * gy.in_pitch, L, r1);
+            SRC::linear(r0, shift, L, t); hfinish_422(t, L, ay, a1, a3);
+            SRC::linear(r1, shift, L, t); hfinish_422(t, L, by, b1, b3);
+            const bool keep = (k == (bottom ? 2 : 0));
+#pragma unroll
+            for (int i = 0; i < 8; i++) { sy[k][i] = ay[i] + by[i]; if (keep) dy[i] = ay[i] - by[i]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                s1[k][i] = a1[i] + b1[i]; s3[k][i] = a3[i] + b3[i];
+                if (keep) { d1[i] = a1[i] - b1[i]; d3[i] = a3[i] - b3[i]; }
+            }
+        }
+        const int row = bottom ? oh - 1 : 0;
+        border_emit<4>(sy[0], sy[1], sy[2], dy, bottom, gy, out, (unsigned)(row * gy.out_pitch) + colbyte_y);
+        border_emit<2>(s1[0], s1[1], s1[2], d1, bottom, g1, out, (unsigned)(row * g1.out_pitch) + colbyte_c);
+        border_emit<2>(s3[0], s3[1], s3[2], d3, bottom, g3, out, (unsigned)(row * g3.out_pitch) + colbyte_c);
+        return;
+    }
+
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * p.th;
+    if (y0 >= oh) return;
+    const int y1 = min(y0 + p.th, oh);
+    const int jfirst = max(y0 - 1, 0), jlast = min(y1, oh - 1);
+    const int hlo = max(y0, 1);
+    VState<4> sy;
+    VState<2> s1, s3;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { sy.llp[i] = sy.llc[i] = sy.dc[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { s1.llp[i] = s1.llc[i] = s1.dc[i] = 0; s3.llp[i] = s3.llc[i] = s3.dc[i] = 0; }
+    const unsigned char *rp = in + (long long)(2 * jfirst) * gy.in_pitch;
+    typename SRC::Row c0, c1, n0, n1;
+    SRC::load(rp, L, c0);
+    SRC::load(rp + gy.in_pitch, L, c1);
+    n0 = c0; n1 = c1;
+    unsigned offy = (unsigned)(jfirst * gy.out_pitch) + colbyte_y;
+    unsigned offc = (unsigned)(jfirst * g1.out_pitch) + colbyte_c;
+    for (int j = jfirst; j <= jlast; j++) {
+        rp += 2 * gy.in_pitch;
+        if (j < jlast) {
+            SRC::load(rp, L, n0);
+            SRC::load(rp + gy.in_pitch, L, n1);
+        }
+        Lin422 t;
+        int ay[8], by[8], a1[4], b1[4], a3[4], b3[4];
+        SRC::linear(c0, shift, L, t); hfinish_422(t, L, ay, a1, a3);
+        SRC::linear(c1, shift, L, t); hfinish_422(t, L, by, b1, b3);
+        const bool emit_low = (j >= y0) && (j < y1), emit_high = (j - 1 >= hlo);
+        vstep<4, 1>(sy, ay, by, gy, out, offy, emit_low, emit_high);
+        vstep<2, 1>(s1, a1, b1, g1, out, offc, emit_low, emit_high);
+        vstep<2, 1>(s3, a3, b3, g3, out, offc, emit_low, emit_high);
+        offy += (unsigned)gy.out_pitch;
+        offc += (unsigned)g1.out_pitch;
+        c0 = n0; c1 = n1;
+    }
+}
+
+// ----------------------------------------------------------------------------
 // host-side launchers (called from cfb_api.cu).  gridDim.y = row blocks + 1 border CTA row.
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -883,6 +1010,14 @@ cudaError_t launch_fwd_422(const FwdParams &p, cudaStream_t stream)
     dim3 block(32, 4);
     dim3 grid(ceil_div(p.ch[0].width, kStripIn), ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y) + 1, p.nframes);
     k_fwd_422<<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fwd_yu64(const FwdParams &p, cudaStream_t stream)
+{
+    dim3 block(32, 4);
+    dim3 grid(ceil_div(p.ch[0].width, kStripIn), ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y) + 1, p.nframes);
+    k_fwd_422_src<SrcYU64><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

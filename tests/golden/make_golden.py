@@ -85,6 +85,23 @@ def interlaced():
         print(path, os.path.getsize(path))
 
 
+def yu64():
+    """16-bit packed 4:2:2 source (CFHD_PIXEL_FORMAT_YU64): frame + every band of the reference's EncodeSample."""
+    ref_lib = ol.load_ref()
+    w, h, quality = 448, 96, 4
+    frame16 = pu.yu64_from_yuyv(pu.qbist_yuy2(ref_lib, w, h, 2), np.random.default_rng(7))
+    bands, div, prescale, sample = pu.ref_encode_frame(ref_lib, frame16.view(np.uint8).reshape(h, w * 4), w, h,
+                                                       pu.COLOR_FORMAT_YU64, 0, 3, quality)
+    arrays = {"frame16": frame16, "divisors": np.array(div, np.int32), "prescale": np.array(prescale[0], np.int32),
+              "quality": np.array(quality), "sample_size": np.array(sample.size)}
+    for (c, lvl, name), a in bands.items():
+        arrays[f"b_{c}_{lvl}_{name}"] = a
+    path = os.path.join(HERE, f"yu64_{w}x{h}_f2_q{quality}.npz")
+    np.savez_compressed(path, **arrays)
+    print(path, os.path.getsize(path))
+
+
 if __name__ == "__main__":
     interlaced()
+    yu64()
     main()

@@ -263,3 +263,19 @@ def unpack_byr4(bayer16, fmt=0, precision=12):
     gg = (g1 + g2) >> 1
     planes = [gg, (r - gg + mid) >> 1, (b - gg + mid) >> 1, (g1 - g2 + mid) >> 1]
     return [np.ascontiguousarray(p.astype(np.int16)) for p in planes]
+
+
+# ---------------------------------------------------------------- YU64 (16-bit packed 4:2:2 -> 10-bit planes)
+COLOR_FORMAT_YU64 = 12
+
+
+def yu64_from_yuyv(frame8, rng):
+    """16-bit packed Y0 C1 Y1 C3 frame whose top 8 bits are the given 8-bit frame and whose low bits are random."""
+    f16 = (frame8.astype(np.uint16) << 8) | rng.integers(0, 256, frame8.shape).astype(np.uint16)
+    return f16                                   # (height, 2 * width) uint16
+
+
+def unpack_yu64(frame16, precision=10):
+    """Codec/frame.c:1556 ConvertYU64ToFrame16s: sample >> (16 - precision); position 1 -> channel 1, position 3 -> channel 2."""
+    s = (frame16 >> (16 - precision)).astype(np.int16)
+    return [np.ascontiguousarray(s[:, 0::2]), np.ascontiguousarray(s[:, 1::4]), np.ascontiguousarray(s[:, 3::4])]

@@ -115,6 +115,24 @@ def test_oracle_field_transform_matches_reference_codec(size, quality, kind):
     assert ((dec == a) | (dec == b)).all()
 
 
+@needs_ref
+@pytest.mark.parametrize("size,quality", [((512, 128), 4), ((256, 64), 2), ((1920, 1080), 4)])
+def test_oracle_yu64_matches_reference_encoder(pkg, size, quality):
+    """YU64 source through the reference's EncodeSample: planes = sample >> 6 (position 1 -> channel 1, position 3 ->
+    channel 2), then the planar pyramid; same schedule as 8-bit 4:2:2."""
+    w, h = size
+    ref_lib, orc = ol.load_ref(), ol.oracle()
+    frame16 = pu.yu64_from_yuyv(pu.qbist_yuy2(ref_lib, w, h), np.random.default_rng(w))
+    bands_ref, div, prescale, _ = pu.ref_encode_frame(ref_lib, frame16.view(np.uint8).reshape(h, w * 4), w, h,
+                                                      pu.COLOR_FORMAT_YU64, 0, 3, quality)
+    q = pkg.quant_for_quality(pkg.FrameDesc(w, h, pkg.PIXEL_YU64), quality)
+    assert q.table(3) == div and list(q.prescale) == prescale[0]
+    pyr = pu.forward_pyramid_planes(orc, pu.unpack_yu64(frame16), div, tuple(prescale[0]))
+    for key, want in bands_ref.items():
+        if not (key[2] == "LL" and key[1] != 3):
+            assert np.array_equal(pyr[key], want), f"band {key}"
+
+
 def test_layout_rules(pkg):
     lay = pkg.layout_for(pkg.FrameDesc(3840, 2160, pkg.PIXEL_YUYV))
     assert lay.num_channels == 3 and lay.precision == 10
