@@ -374,8 +374,9 @@ def run_ours(args, rank, world, local_rank):
     e2e = None
     if not args.no_e2e:
         nfr = B * args.e2e_steps
-        ring = min(nfr, 96)
-        pool = pkg.Pool([local_rank], desc, slots=args.pool_slots, batch=args.pool_batch, queue_length=64)
+        ring = min(nfr, max(96, args.pool_inflight + 32))
+        pool = pkg.Pool([local_rank], desc, slots=args.pool_slots, batch=args.pool_batch,
+                        queue_length=args.pool_inflight + 16)     # the bounded queue must never block this single submit/wait thread
         h_in = [pkg.pinned_empty((HEIGHT, lay.frame_pitch)) for _ in range(ring)]
         h_cd = [pkg.pinned_empty(pkg.sparse_max_bytes(lay)) for _ in range(ring)]
         h_out = [pkg.pinned_empty((HEIGHT, lay.frame_pitch)) for _ in range(ring)]
@@ -467,9 +468,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="frames per step per GPU")
     ap.add_argument("--e2e-steps", type=int, default=20)
-    ap.add_argument("--pool-slots", type=int, default=8)
+    ap.add_argument("--pool-slots", type=int, default=16)
     ap.add_argument("--pool-batch", type=int, default=2)
-    ap.add_argument("--pool-inflight", type=int, default=48)
+    ap.add_argument("--pool-inflight", type=int, default=64)
     ap.add_argument("--no-numa-bind", action="store_true", help="do not restrict the rank to its GPU's NUMA node")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="wall-clock budget of the whole --impl reference run")
     ap.add_argument("--ref-iters", type=int, default=6, help="frames per host thread (at the full thread count) in the CPU baseline")

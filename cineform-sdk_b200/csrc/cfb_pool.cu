@@ -120,7 +120,7 @@ cfb_error cfb_pool_create(const int *devices, int ndevices, const cfb_frame_desc
 {
     if (!devices || !desc || !out || ndevices < 1) { set_error("null/empty argument"); return CFB_ERROR_INVALID_ARGUMENT; }
     *out = nullptr;
-    if (slots < 1 || slots > 16 || batch < 1 || batch > CFB_MAX_BATCH || queue_length < 1) {
+    if (slots < 1 || slots > 32 || batch < 1 || batch > CFB_MAX_BATCH || queue_length < 1) {
         set_error("slots %d (1..16), batch %d (1..%d), queue_length %d (>=1) out of range", slots, batch, CFB_MAX_BATCH, queue_length);
         return CFB_ERROR_INVALID_ARGUMENT;
     }
