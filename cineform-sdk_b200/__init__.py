@@ -58,6 +58,11 @@ class Quant(C.Structure):
         return [[[self.divisor[c][k][b] for b in range(4)] for k in range(3)] for c in range(nchan)]
 
 
+class LevelDesc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("plane_pitch", C.c_int32), ("band_pitch", C.c_int32),
+                ("prescale", C.c_int32), ("midpoint_prequant", C.c_int32), ("divisor", C.c_int32 * 4)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("frames_forward", C.c_uint64), ("frames_inverse", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
@@ -102,6 +107,10 @@ def lib():
     L.cfb_codec_set_bayer_phase.argtypes = [vp, i]
     L.cfb_codec_set_decode_resolution.argtypes = [vp, i]
     L.cfb_codec_set_interlaced.argtypes = [vp, i]
+    L.cfb_level_forward_device.argtypes = [vp, C.POINTER(LevelDesc), vp, C.POINTER(vp)]
+    L.cfb_level_inverse_device.argtypes = [vp, C.POINTER(LevelDesc), C.POINTER(vp), vp]
+    L.cfb_level_forward_host.argtypes = [vp, C.POINTER(LevelDesc), vp, C.POINTER(vp)]
+    L.cfb_level_inverse_host.argtypes = [vp, C.POINTER(LevelDesc), C.POINTER(vp), vp]
     L.cfb_temporal_forward_device.argtypes = [vp, vp, vp, i, vp, vp, i, i, i]
     L.cfb_temporal_inverse_device.argtypes = [vp, vp, vp, i, vp, vp, i, i, i, i]
     L.cfb_temporal_forward_host.argtypes = [vp, vp, vp, i, vp, vp, i, i, i]
@@ -232,6 +241,44 @@ class Context:
     @property
     def stream(self):
         return lib().cfb_context_stream(self.h)
+
+    # -- single wavelet level on a free-standing int16 plane (host arrays) --
+    @staticmethod
+    def _level_desc(w, h, plane_pitch, band_pitch, prescale, divisor, midpoint):
+        d = LevelDesc(w, h, plane_pitch, band_pitch, prescale, midpoint)
+        for b in range(4):
+            d.divisor[b] = int(divisor[b])
+        return d
+
+    def level_forward(self, plane, prescale, divisor, midpoint=2):
+        plane = np.ascontiguousarray(plane, np.int16)
+        h, w = plane.shape
+        bands = [np.zeros((h // 2, w // 2), np.int16) for _ in range(4)]
+        d = self._level_desc(w, h, plane.strides[0], bands[0].strides[0], prescale, divisor, midpoint)
+        _check(lib().cfb_level_forward_host(self.h, C.byref(d), plane.ctypes.data, _ptr_array([b.ctypes.data for b in bands])))
+        return bands
+
+    def level_inverse(self, bands, prescale, divisor):
+        bands = [np.ascontiguousarray(b, np.int16) for b in bands]
+        h2, w2 = bands[0].shape
+        plane = np.zeros((2 * h2, 2 * w2), np.int16)
+        d = self._level_desc(2 * w2, 2 * h2, plane.strides[0], bands[0].strides[0], prescale, divisor, 2)
+        _check(lib().cfb_level_inverse_host(self.h, C.byref(d), _ptr_array([b.ctypes.data for b in bands]), plane.ctypes.data))
+        return plane
+
+    def level_forward_device(self, w, h, plane_pitch, band_pitch, prescale, divisor, midpoint, d_plane, d_bands):
+        d = self._level_desc(w, h, plane_pitch, band_pitch, prescale, divisor, midpoint)
+        _check(lib().cfb_level_forward_device(self.h, C.byref(d), d_plane, _ptr_array(d_bands)))
+
+    def level_inverse_device(self, w, h, plane_pitch, band_pitch, prescale, divisor, d_bands, d_plane):
+        d = self._level_desc(w, h, plane_pitch, band_pitch, prescale, divisor, 2)
+        _check(lib().cfb_level_inverse_device(self.h, C.byref(d), _ptr_array(d_bands), d_plane))
+
+    def temporal_forward_device(self, d_a, d_b, in_pitch, d_low, d_high, out_pitch, w, h):
+        _check(lib().cfb_temporal_forward_device(self.h, d_a, d_b, in_pitch, d_low, d_high, out_pitch, w, h))
+
+    def temporal_inverse_device(self, d_low, d_high, in_pitch, d_a, d_b, out_pitch, w, h, precision=10):
+        _check(lib().cfb_temporal_inverse_device(self.h, d_low, d_high, in_pitch, d_a, d_b, out_pitch, w, h, precision))
 
     # -- two-frame GOP building block (temporal Haar on int16 planes, host arrays) --
     def temporal_forward(self, frame1, frame2):

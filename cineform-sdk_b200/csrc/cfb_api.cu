@@ -79,6 +79,8 @@ static int pick_th(int strips, int oh, int planes, int sm_count)
     return 4;
 }
 
+int pick_rows_per_warp(int strips, int rows, int planes, int sm_count) { return pick_th(strips, rows, planes, sm_count); }
+
 }  // namespace cfb
 
 using namespace cfb;

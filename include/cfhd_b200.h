@@ -228,6 +228,28 @@ CFB_API cfb_error cfb_temporal_forward_host(cfb_context *ctx, const void *frame1
 CFB_API cfb_error cfb_temporal_inverse_host(cfb_context *ctx, const void *low, const void *high, int in_pitch,
                                             void *frame1, void *frame2, int out_pitch, int width, int height, int precision);
 
+/* ---- single wavelet level on a free-standing int16 plane ----------------------------------------
+ * forward = Codec/wavelet.c:2420 TransformForwardSpatial (spatial.c:10026 FilterSpatialQuant16s for prescale 0,
+ * spatial.c:12942 FilterSpatialV210Quant16s for prescale 2); inverse = Codec/wavelet.c:5685
+ * TransformInverseSpatialQuantLowpass (spatial.c:21877 / :22414, dequantisation fused).  With cfb_temporal_* these
+ * compose the reference's other transform graphs, e.g. the two-frame-GOP FIELDPLUS pyramid (Codec/encoder.c:8431):
+ *   wavelet[2] = temporal(LL1 of frame A, LL1 of frame B); wavelet[3] = level(temporal high);
+ *   wavelet[4] = level(temporal low); wavelet[5] = level(LL of wavelet[4]).
+ * width/height: the PLANE's dimensions (bands are width/2 x height/2); pitches in bytes, 16-byte aligned; bands[] in
+ * the order LL, LH, HL, HH.  divisor[0] > 1 quantises LL in the forward direction only when prescale == 0, as the
+ * reference does; the inverse carries LL undequantised. */
+typedef struct cfb_level_desc {
+    int32_t width, height;
+    int32_t plane_pitch, band_pitch;
+    int32_t prescale;               /* 0 or 2 (wavelet.c:1710 SetTransformPrescale) */
+    int32_t midpoint_prequant;      /* quantiser midpoint rule, as cfb_quant */
+    int32_t divisor[4];
+} cfb_level_desc;
+CFB_API cfb_error cfb_level_forward_device(cfb_context *ctx, const cfb_level_desc *desc, const void *d_plane, void *const *d_bands);
+CFB_API cfb_error cfb_level_inverse_device(cfb_context *ctx, const cfb_level_desc *desc, const void *const *d_bands, void *d_plane);
+CFB_API cfb_error cfb_level_forward_host(cfb_context *ctx, const cfb_level_desc *desc, const void *plane, void *const *bands);
+CFB_API cfb_error cfb_level_inverse_host(cfb_context *ctx, const cfb_level_desc *desc, const void *const *bands, void *plane);
+
 /* ---- sparse transfer format of the coded region (lossless) ---- */
 /* Layout of a sparse buffer:  16-byte header {u32 'CFSP', u32 nwords, u32 nvalues, u32 0};
  * bitmap (nwords bits, bit i <=> int16 word i of the coded region [0, coded_bytes) is non-zero);

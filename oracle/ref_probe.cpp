@@ -266,6 +266,59 @@ int ref_encode_frame_bands(const uint8_t *frame, int width, int height, int pitc
 }
 
 // ---------------------------------------------------------------------------------------------
+// Two-frame GOP (CFHD_ENCODING_FLAGS_YUV_2FRAME_GOP -> parameters.gop_length = 2, EncoderSDK/SampleEncoder.cpp:211):
+// run the reference's EncodeSample on frame A then frame B and copy out all six wavelets of every channel of the
+// FIELDPLUS transform (Codec/encoder.c:8431 FinishFieldPlusTransformQuant): wavelet 0/1 = level 1 of frame A/B,
+// 2 = temporal (bands 0 = low, 1 = high), 3 = spatial of the temporal highpass, 4 = spatial of the temporal lowpass,
+// 5 = spatial of wavelet 4's lowpass.  dims[(c*6+k)*4] = {width, height, pitch, num_bands}; quant[(c*6+k)*4+b];
+// prescale[c*8+k]; bands dense, concatenated in (c, k, b) order.  Returns the number of int16 written (0 on failure).
+int64_t ref_encode_gop2_bands(const uint8_t *frame_a, const uint8_t *frame_b, int width, int height, int pitch,
+                              int color_format, int num_channels, int quality,
+                              int32_t *dims, int32_t *quant, int32_t *prescale, int16_t *bands, int64_t bands_capacity)
+{
+    ENCODER *enc = (ENCODER *)calloc(1, sizeof(ENCODER));
+    TRANSFORM *tr[FRAME_MAX_CHANNELS];
+    for (int c = 0; c < FRAME_MAX_CHANNELS; c++) { tr[c] = (TRANSFORM *)calloc(1, sizeof(TRANSFORM)); InitTransform(tr[c]); }
+    ENCODING_PARAMETERS p;
+    memset(&p, 0, sizeof(p));
+    p.version = 1; p.gop_length = 2; p.encoded_width = width; p.encoded_height = height;
+    p.fixed_quality = quality; p.progressive = g_probe_interlaced ? 0 : 1; p.format = color_format;
+    p.frame_sampling = FRAME_SAMPLING_422;
+    p.colorspace_yuv = 2; p.colorspace_rgb = 1;
+    if (!InitializeEncoderWithParameters(NULL, enc, tr, num_channels, &p)) return 0;
+    size_t scratch_size = 0;
+    PIXEL *scratch = CreateEncodingBuffer(NULL, width, height, pitch, color_format, 2, true, &scratch_size);
+    const size_t outcap = (size_t)width * height * 32 + 65536;
+    Aligned out(outcap), fr((size_t)pitch * (height + 16) + 64);
+    BITSTREAM bs;
+    InitBitstreamBuffer(&bs, out.as<uint8_t>(), outcap, BITSTREAM_ACCESS_WRITE);
+    const uint8_t *src[2] = {frame_a, frame_b};
+    for (int i = 0; i < 2; i++) {
+        memcpy(fr.p, src[i], (size_t)pitch * height);
+        if (!EncodeSample(enc, fr.as<uint8_t>(), width, height, pitch, color_format, tr, num_channels, &bs,
+                          scratch, scratch_size, quality, 0, NULL, 0.0f, NULL)) return 0;
+    }
+    int64_t pos = 0;
+    for (int c = 0; c < num_channels; c++) {
+        for (int k = 0; k < 8; k++) prescale[c * 8 + k] = tr[c]->prescale[k];
+        for (int k = 0; k < 6; k++) {
+            IMAGE *w = tr[c]->wavelet[k];
+            int32_t *d = dims + (c * 6 + k) * 4;
+            if (!w) { d[0] = d[1] = d[2] = d[3] = 0; continue; }
+            d[0] = w->width; d[1] = w->height; d[2] = w->pitch; d[3] = w->num_bands;
+            for (int b = 0; b < w->num_bands && b < 4; b++) {
+                quant[(c * 6 + k) * 4 + b] = w->quant[b];
+                if (pos + (int64_t)w->width * w->height > bands_capacity) return 0;
+                for (int r = 0; r < w->height; r++)
+                    memcpy(bands + pos + (int64_t)r * w->width, (uint8_t *)w->band[b] + (size_t)r * w->pitch, (size_t)w->width * 2);
+                pos += (int64_t)w->width * w->height;
+            }
+        }
+    }
+    return pos;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Decode a sample with the reference's public API (DecoderSDK/CFHDDecoder.cpp:716 CFHD_DecodeSample)
 // at full resolution into `pixel_format` (FOURCC). Returns 0 on success, else the CFHD_Error.
 int ref_decode_sample(const uint8_t *sample, int64_t size, int width, int height, unsigned pixel_format,

@@ -101,7 +101,24 @@ def yu64():
     print(path, os.path.getsize(path))
 
 
+def gop2():
+    """Two-frame GOP (CFHD_ENCODING_FLAGS_YUV_2FRAME_GOP): both frames and all six wavelets of every channel."""
+    ref_lib = ol.load_ref()
+    w, h, quality = 512, 128, 4
+    fa, fb = pu.qbist_yuy2(ref_lib, w, h, 1), pu.qbist_yuy2(ref_lib, w, h, 2)
+    bands, quant, prescale = pu.ref_encode_gop2(ref_lib, fa, fb, w, h, quality)
+    arrays = {"frame_a": fa, "frame_b": fb, "quant": np.array(quant, np.int32), "prescale": np.array(prescale, np.int32),
+              "quality": np.array(quality)}
+    for (c, k, b), a in bands.items():
+        if not (b == 0 and k in (0, 1, 4)):              # lowpass images that only feed the next wavelet
+            arrays[f"g_{c}_{k}_{b}"] = a
+    path = os.path.join(HERE, f"gop2_yuy2_{w}x{h}_q{quality}.npz")
+    np.savez_compressed(path, **arrays)
+    print(path, os.path.getsize(path))
+
+
 if __name__ == "__main__":
     interlaced()
     yu64()
+    gop2()
     main()

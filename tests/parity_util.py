@@ -279,3 +279,52 @@ def unpack_yu64(frame16, precision=10):
     """Codec/frame.c:1556 ConvertYU64ToFrame16s: sample >> (16 - precision); position 1 -> channel 1, position 3 -> channel 2."""
     s = (frame16 >> (16 - precision)).astype(np.int16)
     return [np.ascontiguousarray(s[:, 0::2]), np.ascontiguousarray(s[:, 1::4]), np.ascontiguousarray(s[:, 3::4])]
+
+
+# ---------------------------------------------------------------- two-frame GOP (FIELDPLUS pyramid)
+def ref_encode_gop2(ref_lib, frame_a, frame_b, width, height, quality, num_channels=3, color_format=COLOR_FORMAT_YUYV):
+    """The reference's EncodeSample on frame A then frame B with gop_length = 2; returns
+    ({(c, wavelet 0..5, band): array}, quant[c][k][b], prescale[c][k])  (oracle/ref_probe.cpp ref_encode_gop2_bands)."""
+    fn = ref_lib.ref_encode_gop2_bands
+    fn.restype = C.c_int64
+    fa, fb = np.ascontiguousarray(frame_a), np.ascontiguousarray(frame_b)
+    dims = np.zeros(num_channels * 24, np.int32)
+    quant = np.zeros(num_channels * 24, np.int32)
+    prescale = np.zeros(num_channels * 8, np.int32)
+    cap = width * height * 8 * num_channels
+    bands = np.zeros(cap, np.int16)
+    vp = C.c_void_p
+    n = fn(vp(fa.ctypes.data), vp(fb.ctypes.data), width, height, fa.strides[0], color_format, num_channels, quality,
+           vp(dims.ctypes.data), vp(quant.ctypes.data), vp(prescale.ctypes.data), vp(bands.ctypes.data), C.c_int64(cap))
+    assert n > 0, "reference two-frame-GOP encode failed"
+    d = dims.reshape(num_channels, 6, 4)
+    out, pos = {}, 0
+    for c in range(num_channels):
+        for k in range(6):
+            w, h, _, nb = (int(v) for v in d[c, k])
+            for b in range(nb):
+                out[(c, k, b)] = bands[pos:pos + w * h].reshape(h, w).copy()
+                pos += w * h
+    return out, quant.reshape(num_channels, 6, 4).tolist(), prescale.reshape(num_channels, 8).tolist()
+
+
+def gop2_pyramid(level1, temporal, level, frame_a, frame_b, quant, prescale, nchan=3, midpoint=2):
+    """FIELDPLUS composition (Codec/encoder.c:8431 FinishFieldPlusTransformQuant) from three callables:
+    level1(frame, c, divisors) -> 4 bands, temporal(a, b) -> (low, high), level(plane, prescale, divisors) -> 4 bands.
+    Returns {(c, wavelet, band)} with the same keys the reference dump has (LL of wavelets 0, 1, 4 omitted)."""
+    out = {}
+    for c in range(nchan):
+        a = level1(frame_a, c, quant[c][0])
+        b = level1(frame_b, c, quant[c][1])
+        for i in range(1, 4):
+            out[(c, 0, i)], out[(c, 1, i)] = a[i], b[i]
+        low, high = temporal(a[0], b[0])
+        out[(c, 2, 0)], out[(c, 2, 1)] = low, high
+        w3 = level(high, prescale[c][3], quant[c][3])
+        w4 = level(low, prescale[c][4], quant[c][4])
+        w5 = level(w4[0], prescale[c][5], quant[c][5])
+        for i in range(4):
+            out[(c, 3, i)], out[(c, 5, i)] = w3[i], w5[i]
+        for i in range(1, 4):
+            out[(c, 4, i)] = w4[i]
+    return out
