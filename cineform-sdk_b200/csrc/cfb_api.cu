@@ -162,19 +162,19 @@ cfb_error cfb_layout_compute(const cfb_frame_desc *desc, cfb_layout *out)
         out->precision = 10;
         cw[0] = W; cw[1] = cw[2] = W / 2; ch[0] = ch[1] = ch[2] = H;
         out->frame_pitch = (fmt == CFB_PIXEL_YU64) ? W * 4 : W * 2;
-        if (W % 64) { set_error("4:2:2 width %d must be a multiple of 64", W); return CFB_ERROR_UNSUPPORTED; }
+        if (W % 16) { set_error("4:2:2 width %d must be a multiple of 16 (the reference's own row unpackers need it, convert.c:4701)", W); return CFB_ERROR_UNSUPPORTED; }
         break;
     case CFB_PIXEL_RG48: case CFB_PIXEL_PLANAR16:
         out->precision = 12;
         for (int c = 0; c < 3; c++) { cw[c] = W; ch[c] = H; }
         out->frame_pitch = (fmt == CFB_PIXEL_RG48) ? W * 6 : W * 2;
-        if (W % 32) { set_error("4:4:4 width %d must be a multiple of 32", W); return CFB_ERROR_UNSUPPORTED; }
+        if (W % 8) { set_error("4:4:4 width %d must be a multiple of 8", W); return CFB_ERROR_UNSUPPORTED; }
         break;
     case CFB_PIXEL_BYR4:
         out->precision = 12;
         for (int c = 0; c < 4; c++) { cw[c] = W / 2; ch[c] = H / 2; }
         out->frame_pitch = W * 2;
-        if (W % 64 || H % 2) { set_error("Bayer width %d must be a multiple of 64", W); return CFB_ERROR_UNSUPPORTED; }
+        if (W % 16 || H % 2) { set_error("Bayer width %d must be a multiple of 16", W); return CFB_ERROR_UNSUPPORTED; }
         break;
     }
     for (int c = 0; c < nc; c++)

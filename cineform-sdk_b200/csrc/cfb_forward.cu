@@ -221,15 +221,18 @@ __device__ __forceinline__ void hfilter_plane(const RawPlaneRow &r, const LaneIn
 
 __device__ __forceinline__ bool lane_setup(int strip, int width, int lane, LaneInfo &L)
 {
+    // A lane is active only when all of its 8 input columns exist.  When the width is not a multiple of 8 the last
+    // 2-6 columns (1-3 output columns, the right border among them) are produced by k_fwd_plane_edge; the last full
+    // lane then takes its right neighbour value from a halo word like the last lane of an interior strip does.
     const int col0 = strip * kStripIn + lane * 8;
-    const bool active = col0 < width;
+    const bool active = col0 + 8 <= width;
     L.amask = __ballot_sync(0xffffffffu, active);
     if (!active) return false;
     L.left_border = (col0 == 0);
     L.right_border = (col0 + 8 == width);
     L.has_border = (strip == 0) || ((strip + 1) * kStripIn >= width);
     L.use_lh = (lane == 0) && (strip > 0);
-    L.use_rh = (lane == 31) && (col0 + 8 < width);
+    L.use_rh = (col0 + 8 < width) && (lane == 31 || col0 + 16 > width);
     return true;
 }
 
@@ -302,6 +305,55 @@ __global__ void __launch_bounds__(128) k_fwd_plane(const __grid_constant__ FwdPa
         off += (unsigned)g.out_pitch;
         c0 = n0; c1 = n1;
     }
+}
+
+// ----------------------------------------------------------------------------
+// Ragged widths: output columns [4 * (width / 8), width / 2) of a plane level, one thread per coefficient position,
+// written exactly as the formulas read (spatial.c:253-570 rows, :10166-10558 columns).  At most 3 columns per row, so
+// the cost is nil; it keeps the lane-granular main kernel free of partial-lane cases.
+template <int PRESCALE>
+__global__ void __launch_bounds__(128) k_fwd_plane_edge(const __grid_constant__ FwdParams p)
+{
+    const int f = blockIdx.z / p.nchan, c = blockIdx.z - f * p.nchan;
+    const PlaneGeom &g = p.ch[c];
+    const int w = g.width, ow = w >> 1, oh = g.height >> 1;
+    const int col = (w >> 3) * 4 + blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ow || j >= oh) return;
+    const unsigned char *in = p.in_base[f] + g.in_off;
+    auto px = [&](int r, int i) { return (int)*reinterpret_cast<const short *>(in + (long long)r * g.in_pitch + 2 * i); };
+    auto hrow = [&](int r, int &lo, int &hi) {
+        auto t = [&](int i) { return tap<PRESCALE>(px(r, i)); };
+        const int i0 = 2 * col;
+        lo = PRESCALE ? ((px(r, i0) + px(r, i0 + 1) + 3) >> 2) : (px(r, i0) + px(r, i0 + 1));
+        if (col == ow - 1)
+            hi = clamp16((11 * t(w - 2) - 5 * t(w - 1) - 4 * t(w - 3) - 4 * t(w - 4) + t(w - 5) + t(w - 6) + 4) >> 3);
+        else
+            hi = ((-t(i0 - 2) - t(i0 - 1) + t(i0 + 2) + t(i0 + 3) + 4) >> 3) + t(i0) - t(i0 + 1);
+    };
+    int l[6], h[6];
+    const int r0 = (j == 0) ? 0 : ((j == oh - 1) ? g.height - 6 : 2 * j - 2);
+#pragma unroll
+    for (int k = 0; k < 6; k++) hrow(r0 + k, l[k], h[k]);
+    int ll, lh, hl, hh;
+    if (j == 0) {
+        ll = l[0] + l[1]; lh = h[0] + h[1];
+        hl = clamp16((5 * l[0] - 11 * l[1] + 4 * l[2] + 4 * l[3] - l[4] - l[5] + 4) >> 3);
+        hh = clamp16((5 * h[0] - 11 * h[1] + 4 * h[2] + 4 * h[3] - h[4] - h[5] + 4) >> 3);
+    } else if (j == oh - 1) {
+        ll = l[4] + l[5]; lh = h[4] + h[5];
+        hl = clamp16((11 * l[4] - 5 * l[5] - 4 * l[3] - 4 * l[2] + l[1] + l[0] + 4) >> 3);
+        hh = clamp16((11 * h[4] - 5 * h[5] - 4 * h[3] - 4 * h[2] + h[1] + h[0] + 4) >> 3);
+    } else {
+        ll = l[2] + l[3]; lh = h[2] + h[3];
+        hl = ((-l[0] - l[1] + l[4] + l[5] + 4) >> 3) + l[2] - l[3];
+        hh = ((-h[0] - h[1] + h[4] + h[5] + 4) >> 3) + h[2] - h[3];
+    }
+    unsigned char *out = p.out_base[f] + (long long)j * g.out_pitch + 2 * col;
+    *reinterpret_cast<short *>(out + g.band_off[0]) = (short)(g.quant_ll ? (quant1(ll, g.q[0]) >> 16) : ll);
+    *reinterpret_cast<short *>(out + g.band_off[1]) = (short)(quant1(lh, g.q[1]) >> 16);
+    *reinterpret_cast<short *>(out + g.band_off[2]) = (short)(quant1(hl, g.q[2]) >> 16);
+    *reinterpret_cast<short *>(out + g.band_off[3]) = (short)(quant1(hh, g.q[3]) >> 16);
 }
 
 // ----------------------------------------------------------------------------
@@ -977,7 +1029,15 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 cudaError_t launch_fwd_plane(const FwdParams &p, int prescale, cudaStream_t stream)
 {
     int maxw = 0, maxoh = 0;
-    for (int c = 0; c < p.nchan; c++) { maxw = max(maxw, p.ch[c].width); maxoh = max(maxoh, p.ch[c].height / 2); }
+    bool ragged = false;
+    for (int c = 0; c < p.nchan; c++) {
+        maxw = max(maxw, p.ch[c].width); maxoh = max(maxoh, p.ch[c].height / 2);
+        ragged = ragged || (p.ch[c].width & 7);
+    }
+    if (ragged) {       // the 1-3 output columns right of the last full lane (they include the right border)
+        dim3 eblock(128), egrid(ceil_div(maxoh, 128), 3, p.nframes * p.nchan);
+        if (prescale) k_fwd_plane_edge<2><<<egrid, eblock, 0, stream>>>(p); else k_fwd_plane_edge<0><<<egrid, eblock, 0, stream>>>(p);
+    }
     dim3 block(32, 4);
     dim3 grid(ceil_div(maxw, kStripIn), ceil_div(ceil_div(maxoh, p.th), (int)block.y) + 1, p.nframes * p.nchan);
     if (prescale) k_fwd_plane<2><<<grid, block, 0, stream>>>(p);

@@ -261,7 +261,9 @@ __global__ void __launch_bounds__(128) k_inv_plane(const __grid_constant__ InvPa
 
     const int col0 = strip * kInvStrip - 4 + lane * 4;          // first band column of this lane
     const bool active = (col0 >= 0) && (col0 < g.width);
-    const bool writer = active && lane >= 1 && lane <= 30;
+    // a lane whose 4 columns are not all inside the band (width % 4 != 0) still loads (its first column is its left
+    // neighbour's right tap) but does not write: those 1-3 columns, the right border among them, are k_inv_plane_edge's
+    const bool writer = active && lane >= 1 && lane <= 30 && (col0 + 4 <= g.width);
     const bool left_border = (col0 == 0);
     const bool right_border = (col0 + 4 == g.width);
     const bool has_border = (strip == 0) || ((strip + 1) * kInvStrip + 4 >= g.width);
@@ -307,6 +309,68 @@ __global__ void __launch_bounds__(128) k_inv_plane(const __grid_constant__ InvPa
         int te[8], to[8];
         inv_step<4, SMALLDQ>(st, g, in, r, y1, H, colbyte, active, has_border, left_border, right_border, te, to);
         if (writer) emit(r, te, to);
+    }
+}
+
+// ----------------------------------------------------------------------------
+// Ragged widths: band columns [4 * (width / 4), width) of an inverse level, one thread per band coefficient position
+// (-> a 2x2 block of output samples), written as the formulas read (spatial.c:21980-22400 vertical,
+// InvertHorizontalStrip16s.c:459-896 / :1700-2166 horizontal).
+template <int DESCALE>
+__global__ void __launch_bounds__(128) k_inv_plane_edge(const __grid_constant__ InvParams p)
+{
+    const int f = blockIdx.z / p.nchan, c = blockIdx.z - f * p.nchan;
+    const InvGeom &g = p.ch[c];
+    const int W = g.width, H = g.height;
+    const int col = (W >> 2) * 4 + blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= W || r >= H) return;
+    const unsigned char *in = p.in_base[f];
+    auto coef = [&](int b, int row, int cc) {
+        return (int)*reinterpret_cast<const short *>(in + g.band_off[b] + (long long)row * g.pitch + 2 * cc) * (b ? g.dq[b] : 1);
+    };
+    // vertical inverse of (low band lb, high band hb) at band column cc -> even / odd intermediate rows
+    auto vinv = [&](int lb, int hb, int cc, int &e, int &o) {
+        const int hv = coef(hb, r, cc);
+        if (r == 0 || r == H - 1) {
+            const bool bottom = (r != 0);
+            const int a0 = coef(lb, bottom ? H - 1 : 0, cc), a1 = coef(lb, bottom ? H - 2 : 1, cc), a2 = coef(lb, bottom ? H - 3 : 2, cc);
+            const int x = (11 * a0 - 4 * a1 + a2 + 4) >> 3, y = (5 * a0 + 4 * a1 - a2 + 4) >> 3;
+            e = ((bottom ? y : x) + hv) >> 1;
+            o = ((bottom ? x : y) - hv) >> 1;
+        } else {
+            const int pv = coef(lb, r - 1, cc), cv = coef(lb, r, cc), nv = coef(lb, r + 1, cc);
+            e = (((pv - nv + 4) >> 3) + cv + hv) >> 1;
+            o = (((nv - pv + 4) >> 3) + cv - hv) >> 1;
+        }
+    };
+    // columns col-2 .. col+1 of the vertically inverted lowpass (LL/HL) and column col of the highpass (LH/HH)
+    int le[4], lo[4], he, ho;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int cc = min(max(col - 2 + k, 0), W - 1);
+        vinv(0, 2, cc, le[k], lo[k]);
+    }
+    vinv(1, 3, col, he, ho);
+    auto hpair = [&](const int *l, int hv, int &t0, int &t1) {      // l[0..3] = columns col-2 .. col+1
+        if (col == W - 1) {
+            t0 = ((5 * l[2] + 4 * l[1] - l[0] + 4) >> 3) + hv;
+            t1 = ((11 * l[2] - 4 * l[1] + l[0] + 4) >> 3) - hv;
+        } else {
+            t0 = ((l[1] - l[3] + 4) >> 3) + l[2] + hv;
+            t1 = ((l[3] - l[1] + 4) >> 3) + l[2] - hv;
+        }
+    };
+    int e0, e1, o0, o1;
+    hpair(le, he, e0, e1);
+    hpair(lo, ho, o0, o1);
+    unsigned char *out = p.out_base[f] + g.out_off + (long long)(2 * r) * g.out_pitch + (long long)col * 4;
+    if (DESCALE) {
+        *reinterpret_cast<unsigned *>(out) = pack_sat16(e0 << 1, e1 << 1);
+        *reinterpret_cast<unsigned *>(out + g.out_pitch) = pack_sat16(o0 << 1, o1 << 1);
+    } else {
+        *reinterpret_cast<unsigned *>(out) = pack_sat16(e0 >> 1, e1 >> 1);
+        *reinterpret_cast<unsigned *>(out + g.out_pitch) = pack_sat16(o0 >> 1, o1 >> 1);
     }
 }
 
@@ -603,6 +667,12 @@ cudaError_t launch_inv_plane(const InvParams &p, int descale, cudaStream_t strea
     for (int c = 0; c < p.nchan; c++) for (int b = 1; b < 4; b++) small = small && (p.ch[c].dq[b] >= 0 && p.ch[c].dq[b] <= 255);
     if (descale) { if (small) k_inv_plane<2, true><<<grid, block, 0, stream>>>(p); else k_inv_plane<2, false><<<grid, block, 0, stream>>>(p); }
     else { if (small) k_inv_plane<0, true><<<grid, block, 0, stream>>>(p); else k_inv_plane<0, false><<<grid, block, 0, stream>>>(p); }
+    bool ragged = false;
+    for (int c = 0; c < p.nchan; c++) ragged = ragged || (p.ch[c].width & 3);
+    if (ragged) {       // the 1-3 band columns right of the last full lane (they include the right border)
+        dim3 eblock(128), egrid(ceil_div_i(maxh, 128), 3, p.nframes * p.nchan);
+        if (descale) k_inv_plane_edge<2><<<egrid, eblock, 0, stream>>>(p); else k_inv_plane_edge<0><<<egrid, eblock, 0, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 

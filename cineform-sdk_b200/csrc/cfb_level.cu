@@ -19,8 +19,8 @@ using namespace cfb;
 static cfb_error check_level(const cfb_level_desc *d, const void *plane, const void *const *bands)
 {
     if (!d || !plane || !bands) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
-    if (d->width < 16 || d->height < 6 || (d->width & 7) || (d->height & 1)) {
-        set_error("level plane %dx%d: width must be a multiple of 8 (>= 16), height even (>= 6)", d->width, d->height);
+    if (d->width < 16 || d->height < 6 || (d->width & 1) || (d->height & 1)) {
+        set_error("level plane %dx%d: width even (>= 16), height even (>= 6)", d->width, d->height);
         return CFB_ERROR_UNSUPPORTED;
     }
     if (d->prescale != 0 && d->prescale != 2) { set_error("prescale %d not in {0, 2}", d->prescale); return CFB_ERROR_INVALID_ARGUMENT; }

@@ -72,8 +72,10 @@ enum { CFB_MAX_CHANNELS = 4, CFB_NUM_LEVELS = 3, CFB_NUM_BANDS = 4 };
 
 /* Geometry of one frame. width/height are the FRAME dimensions in pixels.
  * Requirements (else CFB_ERROR_UNSUPPORTED): height % 8 == 0 (the reference rounds
- * up to 8, encoder.c:2236); every channel's level-3 input width % 8 == 0
- * (4:2:2: width % 64 == 0; 4:4:4: width % 32 == 0; Bayer: width % 64 == 0). */
+ * up to 8, encoder.c:2236)
+ * (4:2:2: width % 16 == 0, as the reference's row unpackers require; 4:4:4: width % 8 == 0; Bayer: width % 16 == 0;
+ * channel heights % 8 == 0 and >= 48).  Band widths that are not a multiple of the kernels' lane granularity (e.g. 720 or
+ * 1440 wide sources: chroma LL3 is 45 / 90 wide) are handled by small edge kernels. */
 typedef struct cfb_frame_desc {
     int32_t width;
     int32_t height;
