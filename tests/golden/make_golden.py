@@ -21,9 +21,13 @@ import oracle_lib as ol  # noqa: E402
 import parity_util as pu  # noqa: E402
 
 
-def main():
+def main(only=None):
+    """only: restrict to one width (the 8-bit decoded frames are dithered with rand(), so regenerating a fixture changes
+    its decoded_yuy2 array; tests treat it through the dither envelope)."""
     ref_lib = ol.load_ref()
-    for (w, h, frame_no, quality) in [(256, 64, 1, 4), (512, 128, 2, 4), (704, 96, 1, 3)]:
+    for (w, h, frame_no, quality) in [(256, 64, 1, 4), (512, 128, 2, 4), (704, 96, 1, 3), (208, 48, 1, 4)]:    # 208: ragged band widths (13 at level 3)
+        if only is not None and w != only:
+            continue
         frame = pu.qbist_yuy2(ref_lib, w, h, frame_no)
         bands, div, prescale, sample = pu.ref_encode_frame(ref_lib, frame, w, h, pu.COLOR_FORMAT_YUYV, 0, 3, quality)
         import ctypes as C

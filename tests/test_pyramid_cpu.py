@@ -22,7 +22,8 @@ def pkg():
 
 
 @needs_ref
-@pytest.mark.parametrize("size,frame_no", [((256, 64), 1), ((512, 128), 3), ((1920, 1080), 1)])
+@pytest.mark.parametrize("size,frame_no", [((256, 64), 1), ((512, 128), 3), ((1920, 1080), 1),
+                                           ((720, 480), 1), ((1440, 1080), 2), ((208, 48), 1), ((400, 56), 1)])     # ragged band widths
 def test_oracle_pyramid_matches_reference_encoder(size, frame_no):
     w, h = size
     ref_lib = ol.load_ref()
