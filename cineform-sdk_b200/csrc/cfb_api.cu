@@ -459,7 +459,7 @@ cfb_error cfb_codec_set_interlaced(cfb_codec *cd, int interlaced)
         cudaError_t e = cudaMalloc((void **)&cd->d_carry, bytes);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(field carries)");
     }
-    cd->interlaced = interlaced ? 1 : 0;
+    cd->interlaced = (interlaced == CFB_INTERLACED_HL_INTEGRATED) ? 2 : (interlaced ? 1 : 0);
     return CFB_OK;
 }
 
@@ -725,7 +725,7 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
     for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_pyramids[i]; p.out_base[i] = (unsigned char *)d_frames[i]; }
     if (cd->interlaced) {
         FieldsAux aux;
-        aux.carry = cd->d_carry; aux.nstrips = cd->carry_strips; aux.maxh = p.ch[0].height; aux.pad = 0;
+        aux.carry = cd->d_carry; aux.nstrips = cd->carry_strips; aux.maxh = p.ch[0].height; aux.pad = (cd->interlaced == 2);
         long long off = 0;
         for (int c = 0; c < 3; c++) {
             p.ch[c].out_pitch = frame_pitch;

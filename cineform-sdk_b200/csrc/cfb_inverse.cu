@@ -525,7 +525,7 @@ __device__ __forceinline__ void integrate_row(int *h, int carry)
 
 template <int NC>
 __device__ __forceinline__ void fields_channel(const InvGeom &g, const unsigned char *in, int r, unsigned colbyte, bool active,
-                                               int carry, bool has_border, bool left_border, bool right_border,
+                                               int carry, bool integrate, bool has_border, bool left_border, bool right_border,
                                                int *even, int *odd)
 {
     RawCols<NC> a, b, c, d;
@@ -539,7 +539,7 @@ __device__ __forceinline__ void fields_channel(const InvGeom &g, const unsigned 
     Expand<false, NC>::hp(b, g.dq[1], lh);
     Expand<false, NC>::ll(c, hl);               // raw: integrate first, dequantise after (ring arithmetic, same result)
     Expand<false, NC>::hp(d, g.dq[3], hh);
-    integrate_row<NC>(hl, carry);
+    if (integrate) integrate_row<NC>(hl, carry);     // warp-uniform: off when the host already integrated the band
 #pragma unroll
     for (int i = 0; i < NC; i++) hl[i] = (int)(short)(hl[i] * g.dq[2]);     // int16 wrap as `line[x] += line[x-1]` on PIXEL
     int tl[2 * NC], th[2 * NC];
@@ -581,9 +581,10 @@ __global__ void __launch_bounds__(128) k_inv_fields(const __grid_constant__ InvP
     const int *cu = a.carry + ((long long)(f * 3 + 2) * a.maxh) * a.nstrips + strip;
     for (int r = y0; r < y1; r++) {
         int ye[8], yo[8], ue[4], uo[4], ve[4], vo[4];
-        fields_channel<4>(gy, in, r, ycol, active, __ldg(cy + (long long)r * a.nstrips), has_border, left_border, right_border, ye, yo);
-        fields_channel<2>(gu, in, r, ccol, active, __ldg(cu + (long long)r * a.nstrips), has_border, left_border, right_border, ue, uo);
-        fields_channel<2>(gv, in, r, ccol, active, __ldg(cv + (long long)r * a.nstrips), has_border, left_border, right_border, ve, vo);
+        const bool integ = (a.pad == 0);
+        fields_channel<4>(gy, in, r, ycol, active, integ ? __ldg(cy + (long long)r * a.nstrips) : 0, integ, has_border, left_border, right_border, ye, yo);
+        fields_channel<2>(gu, in, r, ccol, active, integ ? __ldg(cu + (long long)r * a.nstrips) : 0, integ, has_border, left_border, right_border, ue, uo);
+        fields_channel<2>(gv, in, r, ccol, active, integ ? __ldg(cv + (long long)r * a.nstrips) : 0, integ, has_border, left_border, right_border, ve, vo);
         if (!writer) continue;
         if (PLANAR) {
 #pragma unroll
@@ -690,7 +691,7 @@ cudaError_t launch_inv_fields(const InvParams &p, const FieldsAux &a, bool plana
 {
     dim3 block(32, 4);
     dim3 cgrid(ceil_div_i(p.ch[0].height, (int)block.y), 3, p.nframes);
-    k_fields_carry<<<cgrid, block, 0, stream>>>(p, a);
+    if (a.pad == 0) k_fields_carry<<<cgrid, block, 0, stream>>>(p, a);     // pad != 0: HL arrives integrated (decoder.c:20822)
     dim3 grid(ceil_div_i(p.ch[0].width, kInvStrip), ceil_div_i(ceil_div_i(p.ch[0].height, p.th), (int)block.y), p.nframes);
     if (planar) k_inv_fields<true><<<grid, block, 0, stream>>>(p, a);
     else k_inv_fields<false><<<grid, block, 0, stream>>>(p, a);

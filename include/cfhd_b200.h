@@ -168,6 +168,10 @@ CFB_API cfb_error cfb_codec_set_bayer_phase(cfb_codec *codec, int bayer_format);
  * form filter.c:273 FilterFrameQuant16s) and Codec/decoder.c:21493 TransformInverseFrameToYUV / :22027 ...ToRow16u
  * (temporal.c:3741 InvertInterlaced16s) including the HL row integration of decoder.c:20822-20836.
  * Packed 8-bit 4:2:2 codecs only; full-resolution decode. */
+enum { CFB_PROGRESSIVE = 0, CFB_INTERLACED = 1,
+       /* inverse only: the level-1 HL band arrives already integrated along its rows, i.e. exactly as the reference's
+        * entropy decoder leaves it (decoder.c:20822-20836); the GPU then skips its own prefix sum */
+       CFB_INTERLACED_HL_INTEGRATED = 2 };
 CFB_API cfb_error cfb_codec_set_interlaced(cfb_codec *codec, int interlaced);
 
 /* Decoded resolution of the following cfb_inverse_* calls: the decodedResolution argument of CFHD_PrepareToDecode

@@ -82,12 +82,13 @@ struct Plan {
     bool tried = false;
 };
 
-Plan *get_plan(int width, int height, int pixel_format)
+// interlaced: CFB_PROGRESSIVE, CFB_INTERLACED (encoder: coded HL band) or CFB_INTERLACED_HL_INTEGRATED (decoder bands)
+Plan *get_plan(int width, int height, int pixel_format, int interlaced = CFB_PROGRESSIVE)
 {
     static thread_local std::map<uint64_t, Plan> plans;
     static std::mutex mu;
     static int next_device = 0;
-    const uint64_t key = ((uint64_t)width << 40) | ((uint64_t)height << 16) | (uint64_t)pixel_format;
+    const uint64_t key = ((uint64_t)width << 40) | ((uint64_t)height << 16) | ((uint64_t)interlaced << 8) | (uint64_t)pixel_format;
     Plan &p = plans[key];
     if (p.tried) return p.codec ? &p : nullptr;
     p.tried = true;
@@ -97,6 +98,9 @@ Plan *get_plan(int width, int height, int pixel_format)
     { std::lock_guard<std::mutex> lk(mu); dev = next_device++ % cfb_device_count(); }      // frames sharded over the GPUs
     if (cfb_context_create(dev, &p.ctx) != CFB_OK) return nullptr;
     if (cfb_codec_create(p.ctx, &d, 1, &p.codec) != CFB_OK) { cfb_context_destroy(p.ctx); p.ctx = nullptr; return nullptr; }
+    if (interlaced && cfb_codec_set_interlaced(p.codec, interlaced) != CFB_OK) {
+        cfb_codec_destroy(p.codec); p.codec = nullptr; cfb_context_destroy(p.ctx); p.ctx = nullptr; return nullptr;
+    }
     if (cfb_host_alloc((size_t)p.layout.coded_bytes, &p.coded) != CFB_OK) { cfb_codec_destroy(p.codec); p.codec = nullptr; return nullptr; }
     return &p;
 }
@@ -113,20 +117,19 @@ bool spatial3(TRANSFORM *t)
 extern "C" {
 
 // ------------------------------------------------------------------------------------------------ encoder
-void TransformForwardSpatialYUV(uint8_t *input, int input_pitch, FRAME_INFO *frame, TRANSFORM *transform[], int frame_index,
-                                int num_channels, PIXEL *buffer, size_t buffer_size, int chroma_offset, int IFrame,
-                                int precision, int limit_yuv, int conv_601_709)
+// The whole 3-level pyramid of one packed 4:2:2 frame on the GPU (level 1 = spatial or field transform); false = not
+// taken (geometry / options outside the CUDA path, or a CUDA error): the caller then runs the reference's own function.
+static bool forward_pyramid_on_gpu(uint8_t *input, int input_pitch, FRAME_INFO *frame, TRANSFORM *transform[], int frame_index,
+                                   int num_channels, int precision, int limit_yuv, int conv_601_709, int interlaced)
 {
-    typedef void (*fn_t)(uint8_t *, int, FRAME_INFO *, TRANSFORM *[], int, int, PIXEL *, size_t, int, int, int, int, int);
-    static fn_t ref = next_symbol<fn_t>("TransformForwardSpatialYUV");
     t_pyramid_done_for = nullptr;
     const bool fmt_ok = frame && (frame->format == COLOR_FORMAT_YUYV || frame->format == COLOR_FORMAT_UYVY);
     Plan *plan = nullptr;
     if (gpu_enabled() && fmt_ok && frame_index == 0 && num_channels == 3 && precision == 10 && !limit_yuv && !conv_601_709 &&
         input_pitch > 0 && (input_pitch & 15) == 0 && ((uintptr_t)input & 15) == 0 &&
         spatial3(transform[0]) && spatial3(transform[1]) && spatial3(transform[2]))
-        plan = get_plan(frame->width, frame->height, frame->format == COLOR_FORMAT_YUYV ? CFB_PIXEL_YUYV : CFB_PIXEL_UYVY);
-    if (!plan) { g_fwd_ref++; ref(input, input_pitch, frame, transform, frame_index, num_channels, buffer, buffer_size, chroma_offset, IFrame, precision, limit_yuv, conv_601_709); return; }
+        plan = get_plan(frame->width, frame->height, frame->format == COLOR_FORMAT_YUYV ? CFB_PIXEL_YUYV : CFB_PIXEL_UYVY, interlaced);
+    if (!plan) return false;
 
     cfb_quant q;
     memset(&q, 0, sizeof(q));
@@ -142,10 +145,7 @@ void TransformForwardSpatialYUV(uint8_t *input, int input_pitch, FRAME_INFO *fra
         }
     const void *frames[1] = {input};
     void *coded[1] = {plan->coded};
-    if (!ok || cfb_forward_host(plan->codec, 1, frames, input_pitch, &q, coded) != CFB_OK) {
-        ref(input, input_pitch, frame, transform, frame_index, num_channels, buffer, buffer_size, chroma_offset, IFrame, precision, limit_yuv, conv_601_709);
-        return;
-    }
+    if (!ok || cfb_forward_host(plan->codec, 1, frames, input_pitch, &q, coded) != CFB_OK) return false;
     // hand the bands to the host entropy coder exactly where it expects them
     for (int c = 0; c < 3; c++)
         for (int k = 0; k < 3; k++) {
@@ -158,6 +158,30 @@ void TransformForwardSpatialYUV(uint8_t *input, int input_pitch, FRAME_INFO *fra
         }
     t_pyramid_done_for = transform[0];
     g_fwd_frames++;
+    return true;
+}
+
+void TransformForwardSpatialYUV(uint8_t *input, int input_pitch, FRAME_INFO *frame, TRANSFORM *transform[], int frame_index,
+                                int num_channels, PIXEL *buffer, size_t buffer_size, int chroma_offset, int IFrame,
+                                int precision, int limit_yuv, int conv_601_709)
+{
+    typedef void (*fn_t)(uint8_t *, int, FRAME_INFO *, TRANSFORM *[], int, int, PIXEL *, size_t, int, int, int, int, int);
+    static fn_t ref = next_symbol<fn_t>("TransformForwardSpatialYUV");
+    if (forward_pyramid_on_gpu(input, input_pitch, frame, transform, frame_index, num_channels, precision, limit_yuv, conv_601_709, CFB_PROGRESSIVE)) return;
+    g_fwd_ref++;
+    ref(input, input_pitch, frame, transform, frame_index, num_channels, buffer, buffer_size, chroma_offset, IFrame, precision, limit_yuv, conv_601_709);
+}
+
+// interlaced sources (CFHD_ENCODING_FLAGS_YUV_INTERLACED): Codec/encoder.c:2976 -> Codec/wavelet.c:6076
+void TransformForwardFrameYUV(uint8_t *input, int input_pitch, FRAME_INFO *frame, TRANSFORM *transform[], int frame_index,
+                              int num_channels, char *buffer, size_t buffer_size, int chroma_offset,
+                              int precision, int limit_yuv, int conv_601_709)
+{
+    typedef void (*fn_t)(uint8_t *, int, FRAME_INFO *, TRANSFORM *[], int, int, char *, size_t, int, int, int, int);
+    static fn_t ref = next_symbol<fn_t>("TransformForwardFrameYUV");
+    if (forward_pyramid_on_gpu(input, input_pitch, frame, transform, frame_index, num_channels, precision, limit_yuv, conv_601_709, CFB_INTERLACED)) return;
+    g_fwd_ref++;
+    ref(input, input_pitch, frame, transform, frame_index, num_channels, buffer, buffer_size, chroma_offset, precision, limit_yuv, conv_601_709);
 }
 
 void ComputeGroupTransformQuant(ENCODER *encoder, TRANSFORM *transform[], int num_transforms)
@@ -183,7 +207,7 @@ static bool decoder_on_gpu(DECODER *d)
 {
     if (!gpu_enabled() || !d) return false;
     const CODEC_STATE *cs = &d->codec;
-    if (!cs->progressive || cs->num_channels != 3 || cs->precision != 10) return false;
+    if (cs->num_channels != 3 || cs->precision != 10) return false;     // progressive or interlaced (field transform at level 1)
     if (cs->encoded_format != ENCODED_FORMAT_YUV_422) return false;
     if (d->frame.resolution != DECODED_RESOLUTION_FULL) return false;
     if (d->frame.format != DECODED_FORMAT_YUYV && d->frame.format != DECODED_FORMAT_UYVY) return false;
@@ -219,7 +243,9 @@ void ReconstructSampleFrameToBuffer(DECODER *decoder, int frame, uint8_t *output
         (decoder->flags & DECODER_FLAGS_RENDER)) {
         WaitForTransformThread(decoder);        // all entropy / bookkeeping jobs of this sample have finished
         IMAGE *y1 = decoder->transform[0]->wavelet[0];
-        if (y1) plan = get_plan(y1->width * 2, y1->height * 2, decoder->frame.format == DECODED_FORMAT_YUYV ? CFB_PIXEL_YUYV : CFB_PIXEL_UYVY);
+        // interlaced samples: the entropy decoder has already integrated the level-1 HL band (decoder.c:20822)
+        if (y1) plan = get_plan(y1->width * 2, y1->height * 2, decoder->frame.format == DECODED_FORMAT_YUYV ? CFB_PIXEL_YUYV : CFB_PIXEL_UYVY,
+                                decoder->codec.progressive ? CFB_PROGRESSIVE : CFB_INTERLACED_HL_INTEGRATED);
     }
     bool ok = plan != nullptr;
     for (int c = 0; c < 3 && ok; c++)

@@ -27,6 +27,8 @@ int main(int argc, char **argv)
 {
     const int w = argc > 1 ? atoi(argv[1]) : 1920, h = argc > 2 ? atoi(argv[2]) : 1080, nframes = argc > 3 ? atoi(argv[3]) : 5;
     const int pool_threads = argc > 4 ? atoi(argv[4]) : 0, queue = argc > 5 ? atoi(argv[5]) : 24;
+    const bool interlaced = argc > 6 && atoi(argv[6]) != 0;     // CFHD_ENCODING_FLAGS_YUV_INTERLACED: field transform at level 1
+    const CFHD_EncodingFlags eflags = interlaced ? CFHD_ENCODING_FLAGS_YUV_INTERLACED : CFHD_ENCODING_FLAGS_NONE;
     const int pitch = w * 2;
     const CFHD_PixelFormat fmt = CFHD_PIXEL_FORMAT_YUY2;
     std::vector<uint8_t *> frames;
@@ -38,12 +40,14 @@ int main(int argc, char **argv)
         RunQBist(w, h, pitch, fmt, 0, gen);
         uint8_t *f = (uint8_t *)aligned((size_t)pitch * h);
         memcpy(f, gen, (size_t)pitch * h);
+        if (interlaced)             // make the two fields differ: shift the odd field by 8 pixels
+            for (int y = 1; y < h; y += 2) memmove(f + (size_t)y * pitch + 16, gen + (size_t)y * pitch, (size_t)pitch - 16);
         frames.push_back(f);
     }
     CFHD_EncoderRef enc = nullptr;
     CFHD_DecoderRef dec = nullptr;
     CFHD_Error e = CFHD_OpenEncoder(&enc, nullptr);
-    if (!e) e = CFHD_PrepareToEncode(enc, w, h, fmt, CFHD_ENCODED_FORMAT_YUV_422, CFHD_ENCODING_FLAGS_NONE, CFHD_ENCODING_QUALITY_FILMSCAN1);
+    if (!e) e = CFHD_PrepareToEncode(enc, w, h, fmt, CFHD_ENCODED_FORMAT_YUV_422, eflags, CFHD_ENCODING_QUALITY_FILMSCAN1);
     if (e) { fprintf(stderr, "encoder setup failed: %d\n", (int)e); return 1; }
     e = CFHD_OpenDecoder(&dec, nullptr);
     if (e) { fprintf(stderr, "decoder open failed: %d\n", (int)e); return 1; }
@@ -84,7 +88,7 @@ int main(int argc, char **argv)
     if (pool_threads > 0) {
         CFHD_EncoderPoolRef pool = nullptr;
         e = CFHD_CreateEncoderPool(&pool, pool_threads, queue, nullptr);
-        if (!e) e = CFHD_PrepareEncoderPool(pool, w, h, fmt, CFHD_ENCODED_FORMAT_YUV_422, CFHD_ENCODING_FLAGS_NONE, CFHD_ENCODING_QUALITY_FILMSCAN1);
+        if (!e) e = CFHD_PrepareEncoderPool(pool, w, h, fmt, CFHD_ENCODED_FORMAT_YUV_422, eflags, CFHD_ENCODING_QUALITY_FILMSCAN1);
         if (!e) e = CFHD_StartEncoderPool(pool);
         if (e) { fprintf(stderr, "encoder pool setup failed: %d\n", (int)e); return 5; }
         const int warm = 2 * pool_threads, total = warm + nframes * 16;
@@ -109,9 +113,9 @@ int main(int argc, char **argv)
         CFHD_ReleaseEncoderPool(pool);
     }
     printf("{\"width\": %d, \"height\": %d, \"frames\": %d, \"enc_ms\": %.3f, \"dec_ms\": %.3f, \"sample_bytes\": %zu, "
-           "\"luma_psnr_db\": %.3f, \"decoded_digest\": \"%016llx\", \"pool_threads\": %d, \"pool_fps\": %.1f}\n",
+           "\"luma_psnr_db\": %.3f, \"decoded_digest\": \"%016llx\", \"pool_threads\": %d, \"pool_fps\": %.1f, \"interlaced\": %d}\n",
            w, h, nframes, 1e3 * enc_s / nframes, 1e3 * dec_s / nframes, bytes / nframes, psnr, (unsigned long long)hash,
-           pool_threads, pool_fps);
+           pool_threads, pool_fps, interlaced ? 1 : 0);
     CFHD_CloseEncoder(enc);
     CFHD_CloseDecoder(dec);
     return 0;

@@ -24,7 +24,7 @@ def run(exe, *args, env=None):
 
 
 @needs_build
-@pytest.mark.parametrize("size", [(1920, 1080), (3840, 2160)])
+@pytest.mark.parametrize("size", [(1920, 1080), (3840, 2160), (1440, 1080)])
 def test_public_api_roundtrip_matches_reference(size):
     w, h = size
     gpu = run("sdk_roundtrip", w, h, 4, 4)
@@ -48,3 +48,22 @@ def test_testcfhd_runs_unchanged():
     assert "forward frames on GPU" in p.stderr
     fwd_gpu = int(p.stderr.split("cfhd_gpu_shim: forward frames on GPU")[-1].split()[0])
     assert fwd_gpu >= 500                               # at least the YUY2 row of the table ran on the GPU
+
+
+@needs_build
+@pytest.mark.parametrize("size", [(1920, 1080), (720, 480)])
+def test_public_api_interlaced_roundtrip_matches_reference(size):
+    """CFHD_ENCODING_FLAGS_YUV_INTERLACED through the unmodified SDK: the field transform (forward incl. the
+    difference-coded HL band, inverse on the decoder's already-integrated band) runs on the GPU and the entropy coder
+    produces byte-for-byte the same sample size as with the reference's CPU transform.  720x480: ragged band widths."""
+    w, h = size
+    gpu = run("sdk_roundtrip", w, h, 3, 2, 24, 1)
+    ref = run("sdk_roundtrip_ref", w, h, 3, 2, 24, 1)
+    g, r = json.loads(gpu.stdout.strip().splitlines()[-1]), json.loads(ref.stdout.strip().splitlines()[-1])
+    assert g["interlaced"] == 1
+    stats = gpu.stderr.split("cfhd_gpu_shim: forward frames on GPU")[-1]
+    fwd_gpu = int(stats.split()[0])
+    inv_gpu = int(stats.split("inverse frames on GPU")[1].split()[0])
+    assert fwd_gpu >= 3 + 32 and inv_gpu >= 3
+    assert g["sample_bytes"] == r["sample_bytes"]
+    assert abs(g["luma_psnr_db"] - r["luma_psnr_db"]) < 0.1
