@@ -152,17 +152,18 @@ cfb_error cfb_layout_compute(const cfb_frame_desc *desc, cfb_layout *out)
     if (!desc || !out) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
     const int W = desc->width, H = desc->height, fmt = desc->pixel_format;
     if (W <= 0 || H <= 0) { set_error("bad dimensions %dx%d", W, H); return CFB_ERROR_INVALID_ARGUMENT; }
-    if (fmt < CFB_PIXEL_YUYV || fmt > CFB_PIXEL_YU64) { set_error("bad pixel format %d", fmt); return CFB_ERROR_BADFORMAT; }
+    if (fmt < CFB_PIXEL_YUYV || fmt > CFB_PIXEL_V210) { set_error("bad pixel format %d", fmt); return CFB_ERROR_BADFORMAT; }
     memset(out, 0, sizeof(*out));
     int cw[CFB_MAX_CHANNELS], ch[CFB_MAX_CHANNELS];
     const int nc = channels_of(fmt);
     out->num_channels = nc;
     switch (fmt) {
-    case CFB_PIXEL_YUYV: case CFB_PIXEL_UYVY: case CFB_PIXEL_YU64:
+    case CFB_PIXEL_YUYV: case CFB_PIXEL_UYVY: case CFB_PIXEL_YU64: case CFB_PIXEL_V210:
         out->precision = 10;
         cw[0] = W; cw[1] = cw[2] = W / 2; ch[0] = ch[1] = ch[2] = H;
-        out->frame_pitch = (fmt == CFB_PIXEL_YU64) ? W * 4 : W * 2;
+        out->frame_pitch = (fmt == CFB_PIXEL_YU64) ? W * 4 : (fmt == CFB_PIXEL_V210) ? ((W + 47) / 48) * 128 : W * 2;
         if (W % 16) { set_error("4:2:2 width %d must be a multiple of 16 (the reference's own row unpackers need it, convert.c:4701)", W); return CFB_ERROR_UNSUPPORTED; }
+        if (fmt == CFB_PIXEL_V210 && W % 48) { set_error("V210 width %d must be a multiple of 48 (whole 6-pixel groups and 16-pixel lanes; the reference's unpacker reads row padding otherwise)", W); return CFB_ERROR_UNSUPPORTED; }
         break;
     case CFB_PIXEL_RG48: case CFB_PIXEL_PLANAR16:
         out->precision = 12;
@@ -537,7 +538,7 @@ cfb_error cfb_forward_device(cfb_codec *cd, int n, const void *const *d_frames, 
             CFB_CUDA(launch_fwd_422(p, ctx->stream));
         }
         ctx->kernel_launches++;
-    } else if (fmt == CFB_PIXEL_YU64) {
+    } else if (fmt == CFB_PIXEL_YU64 || fmt == CFB_PIXEL_V210) {
         for (int c = 0; c < 3; c++) {
             fill_level_geom(cd, quant, c, 0, p.ch[c]); p.ch[c].in_off = 0; p.ch[c].in_pitch = frame_pitch;
             p.ch[c].quant_ll = quant->divisor[c][0][0] > 1;         // planar filter: LL quantised when its divisor > 1
@@ -545,7 +546,7 @@ cfb_error cfb_forward_device(cfb_codec *cd, int n, const void *const *d_frames, 
         for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_frames[i]; p.out_base[i] = (unsigned char *)d_pyramids[i]; }
         p.shift = 16 - L.precision;
         p.th = pick_th((p.ch[0].width + kStripIn - 1) / kStripIn, p.ch[0].height / 2, n, ctx->sm_count);
-        CFB_CUDA(launch_fwd_yu64(p, ctx->stream));
+        CFB_CUDA(fmt == CFB_PIXEL_V210 ? launch_fwd_v210(p, ctx->stream) : launch_fwd_yu64(p, ctx->stream));
         ctx->kernel_launches++;
     } else if (fmt == CFB_PIXEL_PLANAR16) {
         for (int c = 0; c < 3; c++) {
@@ -658,7 +659,7 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
     cfb_context *ctx = cd->ctx;
     const cfb_layout &L = cd->layout;
     const int fmt = cd->desc.pixel_format;
-    const bool is422 = (fmt == CFB_PIXEL_YUYV || fmt == CFB_PIXEL_UYVY || fmt == CFB_PIXEL_YU64);
+    const bool is422 = (fmt == CFB_PIXEL_YUYV || fmt == CFB_PIXEL_UYVY || fmt == CFB_PIXEL_YU64 || fmt == CFB_PIXEL_V210);
     int out_w = 0, out_h = 0;
     cfb_codec_decoded_size(cd, &out_w, &out_h);
     if (out_format == CFB_PIXEL_YUYV || out_format == CFB_PIXEL_UYVY) {

@@ -908,8 +908,9 @@ struct RawYU64Row {
 
 struct SrcYU64 {
     typedef RawYU64Row Row;
-    static constexpr int kBytesPerLumaPair = 8;     // Y0 C1 Y1 C3
-    static __device__ __forceinline__ void load(const unsigned char *p, const LaneInfo &L, Row &r) {
+    // byte offset of global lane lg (8 luma pixels = 4 groups of Y0 C1 Y1 C3, 8 bytes each) inside a row
+    static __device__ __forceinline__ long long offset(int lg) { return (long long)lg * 32; }
+    static __device__ __forceinline__ void load(const unsigned char *p, int, const LaneInfo &L, Row &r) {
         r.a = __ldg(reinterpret_cast<const uint4 *>(p));
         r.b = __ldg(reinterpret_cast<const uint4 *>(p + 16));
         r.halo = make_uint4(0u, 0u, 0u, 0u);
@@ -933,6 +934,79 @@ struct SrcYU64 {
     }
 };
 
+// 10-bit packed 4:2:2 (V210): the row is a stream of 10-bit components Cb Y Cr Y Cb Y ... packed three per 32-bit
+// word at bits 0, 10, 20 (Codec/convert.c:3365 ConvertYUVRowToV210 shows the layout; rows are padded to 128 bytes).  The
+// reference unpacks it on the host into 10-bit planes (Codec/encoder.c:2518-2534 ConvertV210ToFrame16s: first chroma ->
+// channel 2, second chroma -> channel 1, values unshifted) and runs the planar filter per plane (encoder.c:3180-3193).
+// A lane's 8 pixels are 16 consecutive components starting at component 16 * lg, i.e. at word (16 * lg) / 3 with a
+// phase of lg % 3 components into that word: six words always cover them.
+struct RawV210Row {
+    unsigned w[6];      // words (16 * lg) / 3 ... + 5
+    unsigned hw[4];     // halo: the words holding the 8 components before (lane 0) / after (last lane) this lane's
+    int phase;          // (16 * lg) % 3
+};
+
+// 60 useful bits of two consecutive words
+__device__ __forceinline__ unsigned long long v210_pair(unsigned a, unsigned b) {
+    return (unsigned long long)(a & 0x3fffffffu) | ((unsigned long long)(b & 0x3fffffffu) << 30);
+}
+// drop `sh` (0, 10 or 20) bits from the front of the 60-bit pair lo, refilling from the next pair hi
+__device__ __forceinline__ unsigned long long v210_shift(unsigned long long lo, unsigned long long hi, int sh) {
+    const unsigned long long m60 = (1ull << 60) - 1;
+    return sh ? (((lo >> sh) | (hi << (60 - sh))) & m60) : lo;
+}
+__device__ __forceinline__ int v210_field(unsigned long long x, int i) { return (int)((x >> (10 * i)) & 0x3ffu); }
+
+struct SrcV210 {
+    typedef RawV210Row Row;
+    static __device__ __forceinline__ long long offset(int lg) { return (long long)((16 * lg) / 3) * 4; }
+    static __device__ __forceinline__ void load(const unsigned char *p, int lg, const LaneInfo &L, Row &r) {
+        const unsigned *wp = reinterpret_cast<const unsigned *>(p);
+#pragma unroll
+        for (int i = 0; i < 6; i++) r.w[i] = __ldg(wp + i);
+        r.phase = (16 * lg) % 3;
+#pragma unroll
+        for (int i = 0; i < 4; i++) r.hw[i] = 0u;
+        if (L.use_lh | L.use_rh) {
+            // the 8 components before this lane start at component 16 lg - 8, the 8 after it at 16 lg + 16
+            const int c0 = 16 * lg + (L.use_lh ? -8 : 16);
+            const unsigned *hp = wp + (c0 / 3 - (16 * lg) / 3);
+#pragma unroll
+            for (int i = 0; i < 4; i++) r.hw[i] = __ldg(hp + i);
+        }
+    }
+    // cu = the chroma that goes to channel 1 (the SECOND chroma component, Cr), cv = the one for channel 2 (Cb)
+    static __device__ __forceinline__ void linear(const Row &r, int, const LaneInfo &L, Lin422 &o) {
+        const int sh = 10 * r.phase;
+        const unsigned long long A = v210_pair(r.w[0], r.w[1]), B = v210_pair(r.w[2], r.w[3]), C = v210_pair(r.w[4], r.w[5]);
+        const unsigned long long a = v210_shift(A, B, sh), b = v210_shift(B, C, sh), c = v210_shift(C, 0ull, sh);
+        int comp[16];
+#pragma unroll
+        for (int i = 0; i < 6; i++) { comp[i] = v210_field(a, i); comp[6 + i] = v210_field(b, i); }
+#pragma unroll
+        for (int i = 0; i < 4; i++) comp[12 + i] = v210_field(c, i);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int y0 = comp[4 * k + 1], y1 = comp[4 * k + 3];
+            o.S[k] = y0 + y1; o.d[k] = y0 - y1;
+            o.cv[k] = comp[4 * k]; o.cu[k] = comp[4 * k + 2];
+        }
+        // halo: 8 components starting at phase (phase + 1) % 3 of hw[0] (16 lg - 8 and 16 lg + 16 are both = 16 lg + 1 mod 3)
+        const int hsh = 10 * ((r.phase + 1) % 3);
+        const unsigned long long HA = v210_pair(r.hw[0], r.hw[1]), HB = v210_pair(r.hw[2], r.hw[3]);
+        const unsigned long long ha = v210_shift(HA, HB, hsh), hb = v210_shift(HB, 0ull, hsh);
+        int hc[8];
+#pragma unroll
+        for (int i = 0; i < 6; i++) hc[i] = v210_field(ha, i);
+        hc[6] = v210_field(hb, 0); hc[7] = v210_field(hb, 1);
+        // components: Cb Y Cr Y | Cb Y Cr Y ; the luma pair adjacent to this lane is the second group on the left
+        // side and the first group on the right side
+        o.hy = L.use_lh ? (hc[5] + hc[7]) : (hc[1] + hc[3]);
+        o.hv = hc[0] + hc[4];
+        o.hu = hc[2] + hc[6];
+    }
+};
+
 // Generic one-pass level 1 of a packed 4:2:2 source: SRC supplies the row load and the linear (pre-rounding) sums.
 // p.ch[0] = luma, p.ch[1] receives the position-1 chroma, p.ch[2] the position-3 chroma.
 template <class SRC>
@@ -950,7 +1024,8 @@ __global__ void __launch_bounds__(128) k_fwd_422_src(const __grid_constant__ Fwd
     if (!lane_setup(strip, gy.width, lane, L)) return;
     const unsigned colbyte_y = (unsigned)((strip * kStripOut + lane * 4) * 2);
     const unsigned colbyte_c = (unsigned)((strip * (kStripOut / 2) + lane * 2) * 2);
-    const unsigned char *in = p.in_base[f] + gy.in_off + (long long)(strip * kStripIn + lane * 8) / 2 * SRC::kBytesPerLumaPair;
+    const int lg = strip * 32 + lane;           // global lane index: 8 luma pixels each
+    const unsigned char *in = p.in_base[f] + gy.in_off + SRC::offset(lg);
     unsigned char *out = p.out_base[f];
     const int shift = p.shift;
 
@@ -964,8 +1039,8 @@ __global__ void __launch_bounds__(128) k_fwd_422_src(const __grid_constant__ Fwd
             typename SRC::Row r0, r1;
             Lin422 t;
             int ay[8], by[8], a1[4], b1[4], a3[4], b3[4];
-            SRC::load(in + (long long)(2 * (j0 + k)) * gy.in_pitch, L, r0);
-            SRC::load(in + (long long)(2 * (j0 + k) + 1) * gy.in_pitch, L, r1);
+            SRC::load(in + (long long)(2 * (j0 + k)) * gy.in_pitch, lg, L, r0);
+            SRC::load(in + (long long)(2 * (j0 + k) + 1) * gy.in_pitch, lg, L, r1);
             SRC::linear(r0, shift, L, t); hfinish_422(t, L, ay, a1, a3);
             SRC::linear(r1, shift, L, t); hfinish_422(t, L, by, b1, b3);
             const bool keep = (k == (bottom ? 2 : 0));
@@ -997,16 +1072,16 @@ __global__ void __launch_bounds__(128) k_fwd_422_src(const __grid_constant__ Fwd
     for (int i = 0; i < 4; i++) { s1.llp[i] = s1.llc[i] = s1.dc[i] = 0; s3.llp[i] = s3.llc[i] = s3.dc[i] = 0; }
     const unsigned char *rp = in + (long long)(2 * jfirst) * gy.in_pitch;
     typename SRC::Row c0, c1, n0, n1;
-    SRC::load(rp, L, c0);
-    SRC::load(rp + gy.in_pitch, L, c1);
+    SRC::load(rp, lg, L, c0);
+    SRC::load(rp + gy.in_pitch, lg, L, c1);
     n0 = c0; n1 = c1;
     unsigned offy = (unsigned)(jfirst * gy.out_pitch) + colbyte_y;
     unsigned offc = (unsigned)(jfirst * g1.out_pitch) + colbyte_c;
     for (int j = jfirst; j <= jlast; j++) {
         rp += 2 * gy.in_pitch;
         if (j < jlast) {
-            SRC::load(rp, L, n0);
-            SRC::load(rp + gy.in_pitch, L, n1);
+            SRC::load(rp, lg, L, n0);
+            SRC::load(rp + gy.in_pitch, lg, L, n1);
         }
         Lin422 t;
         int ay[8], by[8], a1[4], b1[4], a3[4], b3[4];
@@ -1078,6 +1153,14 @@ cudaError_t launch_fwd_yu64(const FwdParams &p, cudaStream_t stream)
     dim3 block(32, 4);
     dim3 grid(ceil_div(p.ch[0].width, kStripIn), ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y) + 1, p.nframes);
     k_fwd_422_src<SrcYU64><<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fwd_v210(const FwdParams &p, cudaStream_t stream)
+{
+    dim3 block(32, 4);
+    dim3 grid(ceil_div(p.ch[0].width, kStripIn), ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y) + 1, p.nframes);
+    k_fwd_422_src<SrcV210><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -34,6 +34,7 @@ cudaError_t launch_lowpass_422(const InvParams &p, cudaStream_t stream);
 cudaError_t launch_inv_fields(const InvParams &p, const FieldsAux &a, bool planar, cudaStream_t stream);
 cudaError_t launch_fwd_422_fields(const FwdParams &p, cudaStream_t stream);
 cudaError_t launch_fwd_yu64(const FwdParams &p, cudaStream_t stream);
+cudaError_t launch_fwd_v210(const FwdParams &p, cudaStream_t stream);
 
 }  // namespace cfb
 

@@ -64,8 +64,11 @@ typedef enum cfb_pixel_format {
     CFB_PIXEL_RG48 = 2,     /* 16-bit packed R,G,B -> 3 planes G,R,B at 12 bits (frame.c:5968)  */
     CFB_PIXEL_BYR4 = 3,     /* 16-bit Bayer -> 4 half-size planes at 12 bits   (frame.c:4993)  */
     CFB_PIXEL_PLANAR16 = 4, /* channels already unpacked to int16 planes (testing / chaining)   */
-    CFB_PIXEL_YU64 = 5      /* 16-bit packed 4:2:2  Y0 C1 Y1 C3 -> 10-bit planes, C1 -> channel 1, C3 -> channel 2
+    CFB_PIXEL_YU64 = 5,     /* 16-bit packed 4:2:2  Y0 C1 Y1 C3 -> 10-bit planes, C1 -> channel 1, C3 -> channel 2
                              * (CFHD_PIXEL_FORMAT_YU64; frame.c:1556 ConvertYU64ToFrame16s); input only */
+    CFB_PIXEL_V210 = 6      /* 10-bit packed 4:2:2, components Cb Y Cr Y ... three per 32-bit word, rows padded to
+                             * 128 bytes (CFHD_PIXEL_FORMAT_V210; encoder.c:2518 ConvertV210ToFrame16s: Cb -> channel 2,
+                             * Cr -> channel 1); input only */
 } cfb_pixel_format;
 
 enum { CFB_MAX_CHANNELS = 4, CFB_NUM_LEVELS = 3, CFB_NUM_BANDS = 4 };

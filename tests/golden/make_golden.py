@@ -121,7 +121,24 @@ def gop2():
     print(path, os.path.getsize(path))
 
 
+def v210():
+    """10-bit packed 4:2:2 source (CFHD_PIXEL_FORMAT_V210): packed words + every band of the reference's EncodeSample."""
+    ref_lib = ol.load_ref()
+    w, h, quality = 480, 96, 4
+    words, _ = pu.v210_from_yuyv(pu.qbist_yuy2(ref_lib, w, h, 1), np.random.default_rng(11))
+    bands, div, prescale, sample = pu.ref_encode_frame(ref_lib, words.view(np.uint8).reshape(h, -1), w, h,
+                                                       pu.COLOR_FORMAT_V210, 0, 3, quality)
+    arrays = {"words": words, "width": np.array(w), "divisors": np.array(div, np.int32), "prescale": np.array(prescale[0], np.int32),
+              "quality": np.array(quality), "sample_size": np.array(sample.size)}
+    for (c, lvl, name), a in bands.items():
+        arrays[f"b_{c}_{lvl}_{name}"] = a
+    path = os.path.join(HERE, f"v210_{w}x{h}_f1_q{quality}.npz")
+    np.savez_compressed(path, **arrays)
+    print(path, os.path.getsize(path))
+
+
 if __name__ == "__main__":
+    v210()
     interlaced()
     yu64()
     gop2()

@@ -328,3 +328,30 @@ def gop2_pyramid(level1, temporal, level, frame_a, frame_b, quant, prescale, nch
         for i in range(1, 4):
             out[(c, 4, i)] = w4[i]
     return out
+
+
+# ---------------------------------------------------------------- V210 (10-bit packed 4:2:2)
+COLOR_FORMAT_V210 = 10
+
+
+def pack_v210(y, cb, cr):
+    """y (h, w), cb / cr (h, w/2) 10-bit -> (h, pitch/4) uint32: component stream Cb Y Cr Y ..., three per word at bits
+    0, 10, 20 (Codec/convert.c:3365), rows padded to a multiple of 128 bytes (48 pixels)."""
+    h, w = y.shape
+    comp = np.zeros((h, 2 * w), np.uint32)
+    comp[:, 0::4], comp[:, 1::4], comp[:, 2::4], comp[:, 3::4] = cb, y[:, 0::2], cr, y[:, 1::2]
+    nwords = ((w + 47) // 48) * 32
+    padded = np.zeros((h, nwords * 3), np.uint32)
+    padded[:, :2 * w] = comp
+    return (padded[:, 0::3] | (padded[:, 1::3] << 10) | (padded[:, 2::3] << 20)).astype(np.uint32)
+
+
+def v210_from_yuyv(frame8, rng):
+    """10-bit planes whose top 8 bits are the given 8-bit YUYV frame (random low bits) and their V210 packing.
+    Returns (words, [Y, ch1, ch2]) with ch1 = Cr (second chroma), ch2 = Cb as ConvertV210ToFrame16s assigns them."""
+    h, w2 = frame8.shape
+    w = w2 // 2
+    y = (frame8[:, 0::2].astype(np.uint32) << 2) | rng.integers(0, 4, (h, w)).astype(np.uint32)
+    cb = (frame8[:, 1::4].astype(np.uint32) << 2) | rng.integers(0, 4, (h, w // 2)).astype(np.uint32)
+    cr = (frame8[:, 3::4].astype(np.uint32) << 2) | rng.integers(0, 4, (h, w // 2)).astype(np.uint32)
+    return pack_v210(y, cb, cr), [y.astype(np.int16), cr.astype(np.int16), cb.astype(np.int16)]

@@ -134,6 +134,24 @@ def test_oracle_yu64_matches_reference_encoder(pkg, size, quality):
             assert np.array_equal(pyr[key], want), f"band {key}"
 
 
+@needs_ref
+@pytest.mark.parametrize("size,quality", [((480, 96), 4), ((240, 64), 2), ((1920, 1080), 4), ((720, 480), 3)])
+def test_oracle_v210_matches_reference_encoder(pkg, size, quality):
+    """V210 source through the reference's EncodeSample: 10-bit components used as they are, first chroma -> channel 2,
+    second chroma -> channel 1, then the planar pyramid."""
+    w, h = size
+    ref_lib, orc = ol.load_ref(), ol.oracle()
+    words, planes = pu.v210_from_yuyv(pu.qbist_yuy2(ref_lib, w, h), np.random.default_rng(w))
+    bands_ref, div, prescale, _ = pu.ref_encode_frame(ref_lib, words.view(np.uint8).reshape(h, -1), w, h,
+                                                      pu.COLOR_FORMAT_V210, 0, 3, quality)
+    q = pkg.quant_for_quality(pkg.FrameDesc(w, h, pkg.PIXEL_V210), quality)
+    assert q.table(3) == div and list(q.prescale) == prescale[0]
+    pyr = pu.forward_pyramid_planes(orc, planes, div, tuple(prescale[0]))
+    for key, want in bands_ref.items():
+        if not (key[2] == "LL" and key[1] != 3):
+            assert np.array_equal(pyr[key], want), f"band {key}"
+
+
 def test_layout_rules(pkg):
     lay = pkg.layout_for(pkg.FrameDesc(3840, 2160, pkg.PIXEL_YUYV))
     assert lay.num_channels == 3 and lay.precision == 10
