@@ -152,7 +152,7 @@ cfb_error cfb_layout_compute(const cfb_frame_desc *desc, cfb_layout *out)
     if (!desc || !out) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
     const int W = desc->width, H = desc->height, fmt = desc->pixel_format;
     if (W <= 0 || H <= 0) { set_error("bad dimensions %dx%d", W, H); return CFB_ERROR_INVALID_ARGUMENT; }
-    if (fmt < CFB_PIXEL_YUYV || fmt > CFB_PIXEL_V210) { set_error("bad pixel format %d", fmt); return CFB_ERROR_BADFORMAT; }
+    if (fmt < CFB_PIXEL_YUYV || fmt > CFB_PIXEL_DPX0) { set_error("bad pixel format %d", fmt); return CFB_ERROR_BADFORMAT; }
     memset(out, 0, sizeof(*out));
     int cw[CFB_MAX_CHANNELS], ch[CFB_MAX_CHANNELS];
     const int nc = channels_of(fmt);
@@ -166,9 +166,10 @@ cfb_error cfb_layout_compute(const cfb_frame_desc *desc, cfb_layout *out)
         if (fmt == CFB_PIXEL_V210 && W % 48) { set_error("V210 width %d must be a multiple of 48 (whole 6-pixel groups and 16-pixel lanes; the reference's unpacker reads row padding otherwise)", W); return CFB_ERROR_UNSUPPORTED; }
         break;
     case CFB_PIXEL_RG48: case CFB_PIXEL_PLANAR16:
+    case CFB_PIXEL_RG30: case CFB_PIXEL_AB10: case CFB_PIXEL_AR10: case CFB_PIXEL_R210: case CFB_PIXEL_DPX0:
         out->precision = 12;
         for (int c = 0; c < 3; c++) { cw[c] = W; ch[c] = H; }
-        out->frame_pitch = (fmt == CFB_PIXEL_RG48) ? W * 6 : W * 2;
+        out->frame_pitch = (fmt == CFB_PIXEL_RG48) ? W * 6 : (fmt >= CFB_PIXEL_RG30 ? W * 4 : W * 2);
         if (W % 8) { set_error("4:4:4 width %d must be a multiple of 8", W); return CFB_ERROR_UNSUPPORTED; }
         break;
     case CFB_PIXEL_BYR4:
@@ -241,7 +242,7 @@ cfb_error cfb_quant_for_source(const cfb_frame_desc *desc, int quality, int inte
     const int precision = lay.precision;
     // ChromaFullRes = (format >= COLOR_FORMAT_BAYER) (encoder.c:1139): true for BYR4 (104) and RG48 (120)
     const bool chroma_full = (desc->pixel_format == CFB_PIXEL_BYR4 || desc->pixel_format == CFB_PIXEL_RG48 ||
-                              desc->pixel_format == CFB_PIXEL_PLANAR16);
+                              desc->pixel_format == CFB_PIXEL_PLANAR16 || desc->pixel_format >= CFB_PIXEL_RG30);
     if (desc->pixel_format == CFB_PIXEL_BYR4) quality |= (3 << 25);     // encoder.c:2634: no extra quant on channels 1-3
     int factor = quality & 0xff;
     const int detail = (quality & 0x0e0000) >> 17;
@@ -571,6 +572,24 @@ cfb_error cfb_forward_device(cfb_codec *cd, int n, const void *const *d_frames, 
             q.ch[0].quant_ll = quant->divisor[c][0][0] > 1;
             q.th = pick_th((q.ch[0].width + kStripIn - 1) / kStripIn, q.ch[0].height / 2, n, ctx->sm_count);
             CFB_CUDA(launch_fwd_rg48(q, sel_of_channel[c], ctx->stream));
+            ctx->kernel_launches++;
+        }
+    } else if (fmt >= CFB_PIXEL_RG30 && fmt <= CFB_PIXEL_DPX0) {
+        // planes G, R, B; field position of each inside the (possibly byte-swapped) word: spatial.c:2118-2268
+        static const int pos_rgb[5][3] = {{0, 10, 20}, {0, 10, 20}, {20, 10, 0}, {20, 10, 0}, {22, 12, 2}};   // R, G, B of RG30 AB10 AR10 R210 DPX0
+        static const int chan_is[3] = {1, 0, 2};                                                              // channel 0 = G, 1 = R, 2 = B
+        for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_frames[i]; p.out_base[i] = (unsigned char *)d_pyramids[i]; }
+        for (int c = 0; c < 3; c++) {
+            FwdParams q = p;
+            q.nchan = 1;
+            fill_level_geom(cd, quant, c, 0, q.ch[0]);
+            q.ch[0].in_off = 0; q.ch[0].in_pitch = frame_pitch;
+            q.ch[0].quant_ll = quant->divisor[c][0][0] > 1;
+            q.shift = L.precision - 10;
+            q.uyvy = (fmt == CFB_PIXEL_R210 || fmt == CFB_PIXEL_DPX0);
+            q.pad = pos_rgb[fmt - CFB_PIXEL_RG30][chan_is[c]];
+            q.th = pick_th((q.ch[0].width + kStripIn - 1) / kStripIn, q.ch[0].height / 2, n, ctx->sm_count);
+            CFB_CUDA(launch_fwd_rgb30(q, ctx->stream));
             ctx->kernel_launches++;
         }
     } else if (fmt == CFB_PIXEL_BYR4) {

@@ -735,6 +735,115 @@ __global__ void __launch_bounds__(128) k_fwd_422(const __grid_constant__ FwdPara
 }
 
 // ----------------------------------------------------------------------------
+// 10-bit packed RGB (RG30 / AB10 / AR10 / R210 / DPX0: one 32-bit word per pixel).  The reference transforms these
+// frames directly (Codec/encoder.c:3158-3176 -> wavelet.c:3597 TransformForwardSpatialRGB30 ->
+// spatial.c:2080 FilterHorizontalRowRGB30_16s): the 10-bit fields are filtered after `<< (precision - 10)`, planes in
+// the order G, R, B like RG48.  One launch per channel: p.pad = bit position of the channel's field, p.uyvy != 0 when
+// the word is stored byte-swapped (R210, DPX0), p.shift = precision - 10.
+struct RawRGB30Row {
+    uint4 a, b;         // 8 pixels
+    uint2 halo;         // pixels [-2,-1] (lane 0) or [+8,+9] (last lane)
+};
+
+__device__ __forceinline__ void load_rgb30_row(const unsigned char *p, const LaneInfo &L, RawRGB30Row &r)
+{
+    r.a = __ldg(reinterpret_cast<const uint4 *>(p));
+    r.b = __ldg(reinterpret_cast<const uint4 *>(p + 16));
+    r.halo = make_uint2(0u, 0u);
+    if (L.use_lh | L.use_rh) r.halo = __ldg(reinterpret_cast<const uint2 *>(p + (L.use_lh ? -8 : 32)));
+}
+
+__device__ __forceinline__ unsigned rgb30_field(unsigned w, int swap, int pos, int shift)
+{
+    if (swap) w = __byte_perm(w, 0u, 0x0123);
+    return ((w >> pos) & 0x3ffu) << shift;
+}
+
+__device__ __forceinline__ void rgb30_extract(const RawRGB30Row &r, int swap, int pos, int shift, RawPlaneRow &o)
+{
+    const unsigned w[8] = {r.a.x, r.a.y, r.a.z, r.a.w, r.b.x, r.b.y, r.b.z, r.b.w};
+    unsigned out[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+        out[m] = rgb30_field(w[2 * m], swap, pos, shift) | (rgb30_field(w[2 * m + 1], swap, pos, shift) << 16);
+    o.v = make_uint4(out[0], out[1], out[2], out[3]);
+    o.halo = rgb30_field(r.halo.x, swap, pos, shift) | (rgb30_field(r.halo.y, swap, pos, shift) << 16);
+}
+
+__global__ void __launch_bounds__(128) k_fwd_rgb30(const __grid_constant__ FwdParams p)
+{
+    const int lane = threadIdx.x;
+    const int f = blockIdx.z;
+    const PlaneGeom &g = p.ch[0];
+    const int strip = blockIdx.x;
+    if (strip * kStripIn >= g.width) return;
+    const int oh = g.height >> 1;
+    LaneInfo L;
+    if (!lane_setup(strip, g.width, lane, L)) return;
+    const unsigned colbyte = (unsigned)((strip * kStripOut + lane * 4) * 2);
+    const unsigned char *in = p.in_base[f] + g.in_off + (long long)(strip * kStripIn + lane * 8) * 4;
+    unsigned char *out = p.out_base[f];
+    const int shift = p.shift, swap = p.uyvy, pos = p.pad;
+
+    if (blockIdx.y == gridDim.y - 1) {
+        if (threadIdx.y > 1) return;
+        const bool bottom = (threadIdx.y == 1);
+        const int j0 = bottom ? oh - 3 : 0;
+        int s[3][8], dsel[8];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            RawRGB30Row q0, q1;
+            RawPlaneRow r0, r1;
+            int a[8], b[8];
+            load_rgb30_row(in + (long long)(2 * (j0 + k)) * g.in_pitch, L, q0);
+            load_rgb30_row(in + (long long)(2 * (j0 + k) + 1) * g.in_pitch, L, q1);
+            rgb30_extract(q0, swap, pos, shift, r0);
+            rgb30_extract(q1, swap, pos, shift, r1);
+            hfilter_plane<0>(r0, L, a);
+            hfilter_plane<0>(r1, L, b);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                s[k][i] = a[i] + b[i];
+                if (k == (bottom ? 2 : 0)) dsel[i] = a[i] - b[i];
+            }
+        }
+        border_emit<4>(s[0], s[1], s[2], dsel, bottom, g, out, (unsigned)((bottom ? oh - 1 : 0) * g.out_pitch) + colbyte);
+        return;
+    }
+
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * p.th;
+    if (y0 >= oh) return;
+    const int y1 = min(y0 + p.th, oh);
+    const int jfirst = max(y0 - 1, 0), jlast = min(y1, oh - 1);
+    const int hlo = max(y0, 1);
+    VState<4> st;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { st.llp[i] = st.llc[i] = st.dc[i] = 0; }
+    const unsigned char *rp = in + (long long)(2 * jfirst) * g.in_pitch;
+    RawRGB30Row c0, c1, n0, n1;
+    load_rgb30_row(rp, L, c0);
+    load_rgb30_row(rp + g.in_pitch, L, c1);
+    n0 = c0; n1 = c1;
+    unsigned off = (unsigned)(jfirst * g.out_pitch) + colbyte;
+    for (int j = jfirst; j <= jlast; j++) {
+        rp += 2 * g.in_pitch;
+        if (j < jlast) {
+            load_rgb30_row(rp, L, n0);
+            load_rgb30_row(rp + g.in_pitch, L, n1);
+        }
+        RawPlaneRow r0, r1;
+        int a[8], b[8];
+        rgb30_extract(c0, swap, pos, shift, r0);
+        rgb30_extract(c1, swap, pos, shift, r1);
+        hfilter_plane<0>(r0, L, a);
+        hfilter_plane<0>(r1, L, b);
+        vstep<4, 1>(st, a, b, g, out, off, j >= y0 && j < y1, j - 1 >= hlo);
+        off += (unsigned)g.out_pitch;
+        c0 = n0; c1 = n1;
+    }
+}
+
+// ----------------------------------------------------------------------------
 // Interlaced sources: level 1 is the frame (field) transform, Codec/wavelet.c:6076 TransformForwardFrameYUV
 // (Codec/filter.c:273 FilterFrameQuant16s is the planar form of the same transform):
 //   t_low = even + odd, t_high = odd - even (Codec/temporal.c:1568), then the horizontal 2-6 filter on both;
@@ -1128,6 +1237,14 @@ cudaError_t launch_fwd_rg48(const FwdParams &p, int sel, cudaStream_t stream)
     if (sel == 0) k_fwd_rg48<0><<<grid, block, 0, stream>>>(p);
     else if (sel == 1) k_fwd_rg48<1><<<grid, block, 0, stream>>>(p);
     else k_fwd_rg48<2><<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fwd_rgb30(const FwdParams &p, cudaStream_t stream)
+{
+    dim3 block(32, 4);
+    dim3 grid(ceil_div(p.ch[0].width, kStripIn), ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y) + 1, p.nframes);
+    k_fwd_rgb30<<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -66,9 +66,16 @@ typedef enum cfb_pixel_format {
     CFB_PIXEL_PLANAR16 = 4, /* channels already unpacked to int16 planes (testing / chaining)   */
     CFB_PIXEL_YU64 = 5,     /* 16-bit packed 4:2:2  Y0 C1 Y1 C3 -> 10-bit planes, C1 -> channel 1, C3 -> channel 2
                              * (CFHD_PIXEL_FORMAT_YU64; frame.c:1556 ConvertYU64ToFrame16s); input only */
-    CFB_PIXEL_V210 = 6      /* 10-bit packed 4:2:2, components Cb Y Cr Y ... three per 32-bit word, rows padded to
+    CFB_PIXEL_V210 = 6,     /* 10-bit packed 4:2:2, components Cb Y Cr Y ... three per 32-bit word, rows padded to
                              * 128 bytes (CFHD_PIXEL_FORMAT_V210; encoder.c:2518 ConvertV210ToFrame16s: Cb -> channel 2,
                              * Cr -> channel 1); input only */
+    /* 10-bit packed RGB, one 32-bit word per pixel -> 3 planes G, R, B at 12 bits like RG48 (encoder.c:3158-3176
+     * TransformForwardSpatialRGB30, field layouts spatial.c:2118-2268); input only */
+    CFB_PIXEL_RG30 = 7,     /* R bits 0-9, G 10-19, B 20-29 (CFHD_PIXEL_FORMAT_RG30)                       */
+    CFB_PIXEL_AB10 = 8,     /* same layout (A2B10G10R10)                                                   */
+    CFB_PIXEL_AR10 = 9,     /* B bits 0-9, G 10-19, R 20-29 (A2R10G10B10)                                   */
+    CFB_PIXEL_R210 = 10,    /* big-endian word: R 20-29, G 10-19, B 0-9 after the byte swap               */
+    CFB_PIXEL_DPX0 = 11     /* big-endian word: R 22-31, G 12-21, B 2-11 after the byte swap              */
 } cfb_pixel_format;
 
 enum { CFB_MAX_CHANNELS = 4, CFB_NUM_LEVELS = 3, CFB_NUM_BANDS = 4 };

@@ -355,3 +355,26 @@ def v210_from_yuyv(frame8, rng):
     cb = (frame8[:, 1::4].astype(np.uint32) << 2) | rng.integers(0, 4, (h, w // 2)).astype(np.uint32)
     cr = (frame8[:, 3::4].astype(np.uint32) << 2) | rng.integers(0, 4, (h, w // 2)).astype(np.uint32)
     return pack_v210(y, cb, cr), [y.astype(np.int16), cr.astype(np.int16), cb.astype(np.int16)]
+
+
+# ---------------------------------------------------------------- 10-bit packed RGB (one 32-bit word per pixel)
+RGB30_FORMATS = {          # name: (COLOR_FORMAT_* of Codec/color.h, byte swapped, bit position of R, G, B)
+    "RG30": (122, False, (0, 10, 20)),
+    "R210": (123, True, (20, 10, 0)),
+    "AR10": (124, False, (20, 10, 0)),
+    "AB10": (125, False, (0, 10, 20)),
+    "DPX0": (128, True, (22, 12, 2)),
+}
+
+
+def pack_rgb30(name, r, g, b):
+    """10-bit r, g, b planes (h, w) -> (h, w) uint32 words in the layout of Codec/spatial.c:2118-2268."""
+    _, swap, (pr, pg, pb) = RGB30_FORMATS[name]
+    words = ((r.astype(np.uint32) << pr) | (g.astype(np.uint32) << pg) | (b.astype(np.uint32) << pb)).astype(np.uint32)
+    return words.byteswap() if swap else words
+
+
+def rgb30_planes(r, g, b, precision=12):
+    """planes the reference transforms: G, R, B at `precision` bits (value << (precision - 10))."""
+    sh = precision - 10
+    return [(g.astype(np.int32) << sh).astype(np.int16), (r.astype(np.int32) << sh).astype(np.int16), (b.astype(np.int32) << sh).astype(np.int16)]
