@@ -119,6 +119,7 @@ def lib():
     L.cfb_quant_for_source.argtypes = [C.POINTER(FrameDesc), i, i, C.POINTER(Quant)]
     L.cfb_codec_decoded_size.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
     L.cfb_pool_set_decode_resolution.argtypes = [vp, i]
+    L.cfb_pool_set_interlaced.argtypes = [vp, i]
     L.cfb_forward_device.argtypes = [vp, i, C.POINTER(vp), i, C.POINTER(Quant), C.POINTER(vp)]
     L.cfb_forward_host.argtypes = [vp, i, C.POINTER(vp), i, C.POINTER(Quant), C.POINTER(vp)]
     L.cfb_inverse_device.argtypes = [vp, i, C.POINTER(vp), C.POINTER(Quant), i, C.POINTER(vp), i]
@@ -468,6 +469,9 @@ class Pool:
 
     def set_decode_resolution(self, resolution):
         _check(lib().cfb_pool_set_decode_resolution(self.h, resolution))
+
+    def set_interlaced(self, interlaced=1):
+        _check(lib().cfb_pool_set_interlaced(self.h, int(interlaced)))
 
     def submit_forward(self, frame_number, frame, quant, coded):
         _check(lib().cfb_pool_submit_forward(self.h, frame_number, frame.ctypes.data, frame.strides[0], C.byref(quant),

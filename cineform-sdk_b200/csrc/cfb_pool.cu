@@ -151,6 +151,17 @@ cfb_error cfb_pool_create(const int *devices, int ndevices, const cfb_frame_desc
     return CFB_OK;
 }
 
+cfb_error cfb_pool_set_interlaced(cfb_pool *pool, int interlaced)
+{
+    if (!pool) { set_error("null pool"); return CFB_ERROR_INVALID_ARGUMENT; }
+    std::lock_guard<std::mutex> lk(pool->mu);          // applies to jobs submitted after this call returns
+    for (auto &s : pool->slots) {
+        cfb_error e = cfb_codec_set_interlaced(s->codec, interlaced);
+        if (e) return e;
+    }
+    return CFB_OK;
+}
+
 cfb_error cfb_pool_set_decode_resolution(cfb_pool *pool, int resolution)
 {
     if (!pool) { set_error("null pool"); return CFB_ERROR_INVALID_ARGUMENT; }

@@ -309,6 +309,8 @@ CFB_API void cfb_host_free(void *p);
  * A failed job is returned in order with its error; the pool keeps running. */
 CFB_API cfb_error cfb_pool_create(const int *devices, int ndevices, const cfb_frame_desc *desc,
                                   int slots, int batch, int queue_length, cfb_pool **out);
+/* progressive / interlaced mode (cfb_codec_set_interlaced) of every job submitted afterwards (call with the pool idle) */
+CFB_API cfb_error cfb_pool_set_interlaced(cfb_pool *pool, int interlaced);
 /* decode resolution of every inverse job submitted afterwards (call with the pool idle) */
 CFB_API cfb_error cfb_pool_set_decode_resolution(cfb_pool *pool, int resolution);
 CFB_API void cfb_pool_destroy(cfb_pool *pool);

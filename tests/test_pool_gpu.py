@@ -78,3 +78,44 @@ def test_pool_test_returns_not_finished_then_result(pkg):
         assert r == 7
         with pytest.raises(pkg.CfbError):
             pool.wait()             # nothing outstanding -> invalid argument, as the reference's empty queue
+
+
+def test_pool_interlaced_and_half_resolution(pkg):
+    """Pool-wide modes: interlaced sources (field transform at level 1) and half-resolution decode through the
+    asynchronous queue give the same bytes as the synchronous codec."""
+    w, h, n = 448, 96, 6
+    desc = pkg.FrameDesc(w, h, pkg.PIXEL_YUYV)
+    quant = pkg.quant_for_quality(desc, 4, interlaced=True)
+    rng = np.random.default_rng(11)
+    frames = []
+    for i in range(n):
+        f = pu.synthetic_yuyv(rng, w, h, "natural")
+        f[1::2] = np.roll(f[1::2], 4 + 2 * i, axis=1)
+        frames.append(f)
+    with pkg.Pool([0], desc, slots=2, batch=2, queue_length=8) as pool, pkg.Context(0) as ctx, pkg.Codec(ctx, desc, 1) as codec:
+        pool.set_interlaced(1)
+        codec.set_interlaced(True)
+        lay = pool.layout
+        pf = [pkg.pinned_empty((h, w * 2)) for _ in range(n)]
+        pc = [pkg.pinned_empty(lay.coded_bytes) for _ in range(n)]
+        for a, f in zip(pf, frames):
+            a[:] = f
+        for i in range(n):
+            pool.submit_forward(i, pf[i], quant, pc[i])
+        assert [pool.wait() for _ in range(n)] == list(range(n))
+        for i in range(n):
+            one = np.zeros(lay.coded_bytes, np.uint8)
+            codec.forward_host([frames[i]], quant, [one])
+            assert np.array_equal(np.asarray(pc[i]), one), f"frame {i}"
+        # half-resolution decode of the interlaced samples (LL1 does not depend on the level-1 transform type)
+        pool.set_decode_resolution(pkg.RESOLUTION_HALF)
+        codec.set_decode_resolution(pkg.RESOLUTION_HALF)
+        rw, rh = codec.decoded_size()
+        po = [pkg.pinned_empty((rh, rw * 2)) for _ in range(n)]
+        for i in range(n):
+            pool.submit_inverse(i, pc[i], quant, pkg.PIXEL_YUYV, po[i])
+        assert [pool.wait() for _ in range(n)] == list(range(n))
+        for i in range(n):
+            want = np.zeros((rh, rw * 2), np.uint8)
+            codec.inverse_host([np.asarray(pc[i])], quant, pkg.PIXEL_YUYV, [want])
+            assert np.array_equal(np.asarray(po[i]), want), f"frame {i}"
