@@ -6,9 +6,11 @@ A "step" = one pass of the hot path (forward 3-level 2-6 wavelet + quantise, the
 
   value   : whole-job throughput, frames (encode+decode pairs) per second, inputs resident in HBM,
             kernels only, CUDA events on the launching stream, max over ranks.
-  e2e     : the same metric through the C ABI with HOST buffers (cfb_forward_host + cfb_inverse_host):
-            every step copies the frames H2D, the coded coefficients D2H, then H2D again and the decoded
-            frames D2H, from/to pinned host memory.
+  e2e     : the same metric through the C ABI with HOST buffers: the asynchronous in-order frame pool
+            (cfb_pool_submit_forward_sparse / _inverse_sparse + cfb_pool_wait).  Every frame is copied H2D from
+            pinned host memory, its coefficients come back D2H (lossless sparse format), go H2D again for the
+            decode and the decoded frame is copied D2H; all copies are inside the timed region.  The dense
+            int16 format (cfb_pool_submit_forward / _inverse) is reported next to it.
   roofline: the dominant kernel (level-1 forward, k_fwd_422) timed alone, live, with CUDA events.
   cpu_baseline / --impl reference: the reference's own calls for this path (oracle/_ref, the unmodified
             reference compiled in place) on the box's host cores.
