@@ -59,6 +59,19 @@ class Quant(C.Structure):
         return [[[self.divisor[c][k][b] for b in range(4)] for k in range(3)] for c in range(nchan)]
 
 
+GOP2_WAVELETS = 6
+
+
+class Gop2Layout(C.Structure):
+    _fields_ = [("num_channels", C.c_int32), ("reserved", C.c_int32), ("coded_bytes", C.c_int64), ("total_bytes", C.c_int64),
+                ("band", BandLayout * NUM_BANDS * GOP2_WAVELETS * MAX_CHANNELS)]
+
+
+class Gop2Quant(C.Structure):
+    _fields_ = [("midpoint_prequant", C.c_int32), ("prescale", C.c_int32 * GOP2_WAVELETS), ("reserved", C.c_int32),
+                ("divisor", C.c_int32 * NUM_BANDS * GOP2_WAVELETS * MAX_CHANNELS)]
+
+
 class LevelDesc(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("plane_pitch", C.c_int32), ("band_pitch", C.c_int32),
                 ("prescale", C.c_int32), ("midpoint_prequant", C.c_int32), ("divisor", C.c_int32 * 4)]
@@ -108,6 +121,9 @@ def lib():
     L.cfb_codec_set_bayer_phase.argtypes = [vp, i]
     L.cfb_codec_set_decode_resolution.argtypes = [vp, i]
     L.cfb_codec_set_interlaced.argtypes = [vp, i]
+    L.cfb_gop2_layout_compute.argtypes = [C.POINTER(FrameDesc), C.POINTER(Gop2Layout)]
+    L.cfb_gop2_forward_host.argtypes = [vp, vp, vp, i, C.POINTER(Gop2Quant), vp]
+    L.cfb_gop2_inverse_host.argtypes = [vp, vp, C.POINTER(Gop2Quant), i, vp, vp, i]
     L.cfb_level_forward_device.argtypes = [vp, C.POINTER(LevelDesc), vp, C.POINTER(vp)]
     L.cfb_level_inverse_device.argtypes = [vp, C.POINTER(LevelDesc), C.POINTER(vp), vp]
     L.cfb_level_forward_host.argtypes = [vp, C.POINTER(LevelDesc), vp, C.POINTER(vp)]
@@ -199,6 +215,19 @@ def sparse_compact(layout, dense):
     n = C.c_size_t()
     _check(lib().cfb_sparse_compact(C.byref(layout), dense.ctypes.data, out.ctypes.data, C.byref(n)))
     return out[:n.value]
+
+
+def make_gop2_quant(divisors, prescale, midpoint_prequant=2):
+    """divisors[c][wavelet 0..5][b], prescale[wavelet] (transform->prescale of the reference)."""
+    q = Gop2Quant()
+    q.midpoint_prequant = midpoint_prequant
+    for k in range(GOP2_WAVELETS):
+        q.prescale[k] = int(prescale[k])
+    for c, per_c in enumerate(divisors):
+        for k, per_k in enumerate(per_c):
+            for b, d in enumerate(per_k):
+                q.divisor[c][k][b] = int(d)
+    return q
 
 
 def make_quant(divisors, prescale, midpoint_prequant=2):
@@ -335,6 +364,30 @@ class Codec:
 
     def set_level_mask(self, forward_mask=7, inverse_mask=7):
         _check(lib().cfb_codec_set_level_mask(self.h, forward_mask, inverse_mask))
+
+    # -- two-frame GOP (FIELDPLUS pyramid) as one call --
+    def gop2_layout(self):
+        g = Gop2Layout()
+        _check(lib().cfb_gop2_layout_compute(C.byref(self.desc), C.byref(g)))
+        return g
+
+    def gop2_forward_host(self, frame_a, frame_b, gquant):
+        g = self.gop2_layout()
+        a, b = np.ascontiguousarray(frame_a), np.ascontiguousarray(frame_b)
+        coded = np.zeros(g.coded_bytes, np.uint8)
+        _check(lib().cfb_gop2_forward_host(self.h, a.ctypes.data, b.ctypes.data, a.strides[0], C.byref(gquant), coded.ctypes.data))
+        return coded
+
+    def gop2_inverse_host(self, coded, gquant, out_format, shape):
+        a, b = np.zeros(shape, np.uint8), np.zeros(shape, np.uint8)
+        _check(lib().cfb_gop2_inverse_host(self.h, coded.ctypes.data, C.byref(gquant), out_format, a.ctypes.data, b.ctypes.data, a.strides[0]))
+        return a, b
+
+    @staticmethod
+    def gop2_band_view(glayout, buf, c, k, b):
+        bl = glayout.band[c][k][b]
+        flat = buf[bl.offset: bl.offset + bl.pitch * bl.height].view(np.int16)
+        return flat.reshape(bl.height, bl.pitch // 2)[:, :bl.width]
 
     def set_interlaced(self, interlaced=True):
         """Level 1 = field transform (CFHD_ENCODING_FLAGS_YUV_INTERLACED)."""

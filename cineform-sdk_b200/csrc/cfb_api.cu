@@ -406,6 +406,7 @@ void cfb_codec_destroy(cfb_codec *cd)
     if (cd->d_frames) cudaFree(cd->d_frames);
     if (cd->d_pyramids) cudaFree(cd->d_pyramids);
     if (cd->d_carry) cudaFree(cd->d_carry);
+    if (cd->d_gop) cudaFree(cd->d_gop);
     if (cd->d_sparse) cudaFree(cd->d_sparse);
     if (cd->d_counts) cudaFree(cd->d_counts);
     if (cd->h_headers) cudaFreeHost(cd->h_headers);

@@ -266,6 +266,35 @@ CFB_API cfb_error cfb_level_inverse_device(cfb_context *ctx, const cfb_level_des
 CFB_API cfb_error cfb_level_forward_host(cfb_context *ctx, const cfb_level_desc *desc, const void *plane, void *const *bands);
 CFB_API cfb_error cfb_level_inverse_host(cfb_context *ctx, const cfb_level_desc *desc, const void *const *bands, void *plane);
 
+/* ---- two-frame GOP as one call (CFHD_ENCODING_FLAGS_YUV_2FRAME_GOP; packed 8-bit 4:2:2) ------------
+ * The FIELDPLUS pyramid of Codec/encoder.c:8431 FinishFieldPlusTransformQuant: wavelet 0 / 1 = level 1 of frame A / B
+ * (spatial, or the field transform when the codec is interlaced), 2 = temporal (band 0 low, band 1 high),
+ * 3 = level(temporal high), 4 = level(temporal low), 5 = level(LL of 4).  The coded region holds the 17 subbands the
+ * entropy coder walks (quantize.c:3480): per channel wavelet 5 (LL, LH, HL, HH), 4 (LH, HL, HH), 3 (LL, LH, HL, HH),
+ * 1 (LH, HL, HH), 0 (LH, HL, HH); LL of wavelets 0, 1, 4 and the temporal bands live in device scratch.
+ * prescale[k] / divisor[c][k][b] are transform->prescale[k] and wavelet[k]->quant[b] of the reference (its schedule
+ * for this transform type is not restated here).  The codec must have been created with max_batch >= 2 and a width
+ * that is a multiple of 64.  decoder side: Codec/decoder.c:13052-13170 + the level-1 inverse of both frames. */
+enum { CFB_GOP2_WAVELETS = 6 };
+typedef struct cfb_gop2_layout {
+    int32_t num_channels;
+    int32_t reserved;
+    int64_t coded_bytes;
+    int64_t total_bytes;
+    cfb_band_layout band[CFB_MAX_CHANNELS][CFB_GOP2_WAVELETS][CFB_NUM_BANDS];
+} cfb_gop2_layout;
+typedef struct cfb_gop2_quant {
+    int32_t midpoint_prequant;
+    int32_t prescale[CFB_GOP2_WAVELETS];
+    int32_t reserved;
+    int32_t divisor[CFB_MAX_CHANNELS][CFB_GOP2_WAVELETS][CFB_NUM_BANDS];
+} cfb_gop2_quant;
+CFB_API cfb_error cfb_gop2_layout_compute(const cfb_frame_desc *desc, cfb_gop2_layout *out);
+CFB_API cfb_error cfb_gop2_forward_host(cfb_codec *codec, const void *frame_a, const void *frame_b, int frame_pitch,
+                                        const cfb_gop2_quant *quant, void *coded);
+CFB_API cfb_error cfb_gop2_inverse_host(cfb_codec *codec, const void *coded, const cfb_gop2_quant *quant, int out_format,
+                                        void *frame_a, void *frame_b, int frame_pitch);
+
 /* ---- sparse transfer format of the coded region (lossless) ---- */
 /* Layout of a sparse buffer:  16-byte header {u32 'CFSP', u32 nwords, u32 nvalues, u32 0};
  * bitmap (nwords bits, bit i <=> int16 word i of the coded region [0, coded_bytes) is non-zero);

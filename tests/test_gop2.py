@@ -174,3 +174,64 @@ def test_cuda_gop2_device_resident(path):
             lib.orc_temporal_inv(vp(o_tl.ctypes.data), vp(o_th.ctypes.data), lw * 2, lw, lh, 10, vp(oa.ctypes.data), vp(ob.ctypes.data), lw * 2)
             assert np.array_equal(fetch(ra, lh, lw), oa) and np.array_equal(fetch(rb, lh, lw), ob)
         _compare(got, bands)
+
+
+def test_gop2_layout_host_only():
+    """cfb_gop2_layout_compute needs no GPU: 17 coded subbands per channel, 64-byte aligned, scratch after the coded region."""
+    pkg = importlib.import_module("cineform-sdk_b200")
+    with_desc = pkg.FrameDesc(1920, 1080, pkg.PIXEL_YUYV)
+    g = pkg.Gop2Layout()
+    assert pkg.lib().cfb_gop2_layout_compute(C.byref(with_desc), C.byref(g)) == 0
+    coded = [(c, k, b) for c in range(3) for k, bs in ((5, range(4)), (4, range(1, 4)), (3, range(4)), (1, range(1, 4)), (0, range(1, 4))) for b in bs]
+    assert len(coded) == 3 * 17
+    for (c, k, b) in coded:
+        bl = g.band[c][k][b]
+        assert bl.offset % 64 == 0 and bl.pitch % 16 == 0 and bl.offset + bl.pitch * bl.height <= g.coded_bytes
+    for c in range(3):
+        for (k, b) in ((0, 0), (1, 0), (2, 0), (2, 1), (4, 0)):
+            assert g.band[c][k][b].offset >= g.coded_bytes
+    assert g.band[0][5][0].width == 1920 // 8 and g.band[1][3][0].width == 1920 // 8
+    bad = pkg.FrameDesc(720, 480, pkg.PIXEL_YUYV)          # chroma level-1 band 180 wide: not a multiple of 16
+    assert pkg.lib().cfb_gop2_layout_compute(C.byref(bad), C.byref(g)) != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_cuda_gop2_single_call(path):
+    """cfb_gop2_forward_host / cfb_gop2_inverse_host: every coded band equals the reference's two-frame encode; the
+    decoded frames lie inside the dither envelope of the oracle's inverse composition."""
+    pkg = importlib.import_module("cineform-sdk_b200")
+    fa, fb, quant, prescale, quality, bands = _load(path)
+    h, w2 = fa.shape
+    desc = pkg.FrameDesc(w2 // 2, h, pkg.PIXEL_YUYV)
+    gq = pkg.make_gop2_quant(quant, prescale[0][:6])
+    orc, lib = ol.oracle(), ol.load_oracle()
+    with pkg.Context(0) as ctx, pkg.Codec(ctx, desc, 2) as codec:
+        g = codec.gop2_layout()
+        coded = codec.gop2_forward_host(fa, fb, gq)
+        for (c, k, b), want in sorted(bands.items()):
+            if k == 2:
+                continue                                    # temporal bands are device scratch, not coded
+            got = codec.gop2_band_view(g, coded, c, k, b)
+            assert np.array_equal(got, want), f"(channel, wavelet, band) {(c, k, b)}"
+        out_a, out_b = codec.gop2_inverse_host(coded, gq, pkg.PIXEL_YUYV, fa.shape)
+
+    def inv(bands4, c, k):
+        deq = [bands4[0]] + [pu.dequantize(bands4[b], quant[c][k][b]) for b in (1, 2, 3)]
+        return orc.inv_level(*deq, 2 if prescale[c][k] == 2 else 0)
+
+    planes_a, planes_b = [], []
+    vp = C.c_void_p
+    for c in range(3):
+        ll4 = inv([bands[(c, 5, b)] for b in range(4)], c, 5)
+        tl = inv([ll4] + [bands[(c, 4, b)] for b in (1, 2, 3)], c, 4)
+        th = inv([bands[(c, 3, b)] for b in range(4)], c, 3)
+        la, lb = np.zeros_like(tl), np.zeros_like(tl)
+        hh, ww = tl.shape
+        lib.orc_temporal_inv(vp(tl.ctypes.data), vp(th.ctypes.data), ww * 2, ww, hh, 10, vp(la.ctypes.data), vp(lb.ctypes.data), ww * 2)
+        planes_a.append(inv([la] + [bands[(c, 0, b)] for b in (1, 2, 3)], c, 0))
+        planes_b.append(inv([lb] + [bands[(c, 1, b)] for b in (1, 2, 3)], c, 1))
+    for out, planes, src in ((out_a, planes_a, fa), (out_b, planes_b, fb)):
+        a, b = pu.yuyv_envelope(planes)
+        assert ((out == a) | (out == b)).all()
+        assert pu.psnr(out[:, 0::2], src[:, 0::2]) > 45.0
