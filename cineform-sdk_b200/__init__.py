@@ -122,6 +122,7 @@ def lib():
     L.cfb_codec_set_decode_resolution.argtypes = [vp, i]
     L.cfb_codec_set_interlaced.argtypes = [vp, i]
     L.cfb_gop2_layout_compute.argtypes = [C.POINTER(FrameDesc), C.POINTER(Gop2Layout)]
+    L.cfb_gop2_quant_for_quality.argtypes = [C.POINTER(FrameDesc), i, i, C.POINTER(Gop2Quant)]
     L.cfb_gop2_forward_host.argtypes = [vp, vp, vp, i, C.POINTER(Gop2Quant), vp]
     L.cfb_gop2_inverse_host.argtypes = [vp, vp, C.POINTER(Gop2Quant), i, vp, vp, i]
     L.cfb_level_forward_device.argtypes = [vp, C.POINTER(LevelDesc), vp, C.POINTER(vp)]
@@ -215,6 +216,12 @@ def sparse_compact(layout, dense):
     n = C.c_size_t()
     _check(lib().cfb_sparse_compact(C.byref(layout), dense.ctypes.data, out.ctypes.data, C.byref(n)))
     return out[:n.value]
+
+
+def gop2_quant_for_quality(desc, quality, interlaced=False):
+    out = Gop2Quant()
+    _check(lib().cfb_gop2_quant_for_quality(C.byref(desc), quality, int(bool(interlaced)), C.byref(out)))
+    return out
 
 
 def make_gop2_quant(divisors, prescale, midpoint_prequant=2):

@@ -222,9 +222,12 @@ cfb_error cfb_quant_for_quality(const cfb_frame_desc *desc, int quality, cfb_qua
     return cfb_quant_for_source(desc, quality, 0, out);
 }
 
-cfb_error cfb_quant_for_source(const cfb_frame_desc *desc, int quality, int interlaced, cfb_quant *out)
+// Subband divisor tables of one frame BEFORE they are mapped onto a transform: quantize.c:186 QuantizationSetQuality
+// (tables, precision scaling, !progressive rescaling).  ql / qc: luma / chroma, index = subband number.
+static cfb_error quant_tables(const cfb_frame_desc *desc, int quality, int interlaced, int *ql_out, int *qc_out, int *g_out,
+                              int *precision_out, int *nchan_out)
 {
-    if (!desc || !out) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (!desc) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
     cfb_layout lay;
     cfb_error err = cfb_layout_compute(desc, &lay);
     if (err) return err;
@@ -238,7 +241,6 @@ cfb_error cfb_quant_for_source(const cfb_frame_desc *desc, int quality, int inte
         {4, 8, 8, 12, 8, 8, 12, 9, 12, 12, 16, 32, 32, 48, 32, 32, 48},
         {4, 6, 6, 8, 6, 6, 8, 5, 8, 8, 12, 16, 16, 32, 16, 16, 32},
         {4, 6, 6, 8, 6, 6, 8, 5, 8, 8, 8, 8, 8, 16, 8, 8, 16}};
-    memset(out, 0, sizeof(*out));
     const int precision = lay.precision;
     // ChromaFullRes = (format >= COLOR_FORMAT_BAYER) (encoder.c:1139): true for BYR4 (104) and RG48 (120)
     const bool chroma_full = (desc->pixel_format == CFB_PIXEL_BYR4 || desc->pixel_format == CFB_PIXEL_RG48 ||
@@ -285,13 +287,25 @@ cfb_error cfb_quant_for_source(const cfb_frame_desc *desc, int quality, int inte
         ql[11] = ql[11] * 3 / 2; ql[12] = ql[12] * 2 / 3; ql[14] = ql[14] * 3 / 2; ql[15] = ql[15] * 2 / 3;
         qc[11] = qc[11] * 3 / 2; qc[12] = qc[12] * 2 / 3; qc[14] = qc[14] * 3 / 2; qc[15] = qc[15] * 2 / 3;
     }
+    memcpy(ql_out, ql, sizeof(ql)); memcpy(qc_out, qc, sizeof(qc));
+    *g_out = g; *precision_out = precision; *nchan_out = lay.num_channels;
+    return CFB_OK;
+}
+
+cfb_error cfb_quant_for_source(const cfb_frame_desc *desc, int quality, int interlaced, cfb_quant *out)
+{
+    if (!desc || !out) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    int ql[17], qc[17], g = 0, precision = 0, nchan = 0;
+    cfb_error err = quant_tables(desc, quality, interlaced, ql, qc, &g, &precision, &nchan);
+    if (err) return err;
+    memset(out, 0, sizeof(*out));
     // GOP length 1 (quantize.c:552-567)
     for (int i = 0; i < 3; i++) { ql[7 + i] = ql[11 + i]; qc[7 + i] = qc[11 + i]; }
 
     static const int scale[3][4] = {{4, 2, 2, 1}, {16, 8, 8, 4}, {64, 32, 32, 16}};
     out->midpoint_prequant = g;
     out->prescale[0] = 0; out->prescale[1] = 2; out->prescale[2] = (precision == 12) ? 2 : 0;
-    for (int c = 0; c < lay.num_channels; c++) {
+    for (int c = 0; c < nchan; c++) {
         const int *q = (c > 0) ? qc : ql;
         int subband = 1;
         for (int k = 2; k >= 0; k--) {
@@ -301,6 +315,41 @@ cfb_error cfb_quant_for_source(const cfb_frame_desc *desc, int quality, int inte
                 if (g) { d *= g; d /= (g - 1) * 2; } else d /= 2;
                 out->divisor[c][k][b] = d;
                 subband++;
+            }
+        }
+    }
+    return CFB_OK;
+}
+
+// Two-frame GOP (TRANSFORM_TYPE_FIELDPLUS): quantize.c:3480-3640 maps the subbands onto the six wavelets as
+// 1-3 -> wavelet 5, 4-6 -> wavelet 4, 7 -> LL of wavelet 3 (forced to 1 for >= 10 bit, encoder.c:8487), 8-10 -> wavelet 3,
+// 11-13 -> wavelet 1, 14-16 -> wavelet 0, with the band scales of wavelet.c:7135-7180 (SetTransformScale, FIELDPLUS):
+// wavelet 3 {16,8,8,4}, wavelet 4 {32,16,16,8}, wavelet 5 {128,64,64,32}; frame wavelets take the table value itself.
+// No GOP-1 copy of subbands 11-13 into 7-9 (quantize.c:552).  Prescale {0,0,0,0,2,0} (wavelet.c:1710, 10 bit).
+cfb_error cfb_gop2_quant_for_quality(const cfb_frame_desc *desc, int quality, int interlaced, cfb_gop2_quant *out)
+{
+    if (!desc || !out) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    int ql[17], qc[17], g = 0, precision = 0, nchan = 0;
+    cfb_error err = quant_tables(desc, quality, interlaced, ql, qc, &g, &precision, &nchan);
+    if (err) return err;
+    if (precision != 10) { set_error("two-frame GOP: 10-bit 4:2:2 sources"); return CFB_ERROR_UNSUPPORTED; }
+    memset(out, 0, sizeof(*out));
+    out->midpoint_prequant = g;
+    out->prescale[4] = 2;
+    static const int wavelet_of[5] = {5, 4, 3, 1, 0};
+    static const int first_subband[5] = {1, 4, 8, 11, 14};
+    static const int scale[6][4] = {{4, 2, 2, 1}, {4, 2, 2, 1}, {8, 4, 0, 0}, {16, 8, 8, 4}, {32, 16, 16, 8}, {128, 64, 64, 32}};
+    for (int c = 0; c < nchan; c++) {
+        const int *q = (c > 0) ? qc : ql;
+        for (int k = 0; k < CFB_GOP2_WAVELETS; k++) out->divisor[c][k][0] = 1;
+        out->divisor[c][2][1] = 1;
+        for (int i = 0; i < 5; i++) {
+            const int k = wavelet_of[i];
+            for (int b = 1; b < 4; b++) {
+                const int v = q[first_subband[i] + b - 1];
+                int d = (k <= 1) ? v : ((v * scale[k][b]) >> 2);
+                if (g) { d *= g; d /= (g - 1) * 2; } else d /= 2;
+                out->divisor[c][k][b] = d;
             }
         }
     }

@@ -272,8 +272,8 @@ CFB_API cfb_error cfb_level_inverse_host(cfb_context *ctx, const cfb_level_desc 
  * 3 = level(temporal high), 4 = level(temporal low), 5 = level(LL of 4).  The coded region holds the 17 subbands the
  * entropy coder walks (quantize.c:3480): per channel wavelet 5 (LL, LH, HL, HH), 4 (LH, HL, HH), 3 (LL, LH, HL, HH),
  * 1 (LH, HL, HH), 0 (LH, HL, HH); LL of wavelets 0, 1, 4 and the temporal bands live in device scratch.
- * prescale[k] / divisor[c][k][b] are transform->prescale[k] and wavelet[k]->quant[b] of the reference (its schedule
- * for this transform type is not restated here).  The codec must have been created with max_batch >= 2 and a width
+ * prescale[k] / divisor[c][k][b] are transform->prescale[k] and wavelet[k]->quant[b] of the reference
+ * (cfb_gop2_quant_for_quality restates its schedule).  The codec must have been created with max_batch >= 2 and a width
  * that is a multiple of 64.  decoder side: Codec/decoder.c:13052-13170 + the level-1 inverse of both frames. */
 enum { CFB_GOP2_WAVELETS = 6 };
 typedef struct cfb_gop2_layout {
@@ -290,6 +290,8 @@ typedef struct cfb_gop2_quant {
     int32_t divisor[CFB_MAX_CHANNELS][CFB_GOP2_WAVELETS][CFB_NUM_BANDS];
 } cfb_gop2_quant;
 CFB_API cfb_error cfb_gop2_layout_compute(const cfb_frame_desc *desc, cfb_gop2_layout *out);
+/* the reference's schedule for this transform type (quantize.c:3480-3640, wavelet.c:7135-7180), host only */
+CFB_API cfb_error cfb_gop2_quant_for_quality(const cfb_frame_desc *desc, int quality, int interlaced, cfb_gop2_quant *out);
 CFB_API cfb_error cfb_gop2_forward_host(cfb_codec *codec, const void *frame_a, const void *frame_b, int frame_pitch,
                                         const cfb_gop2_quant *quant, void *coded);
 CFB_API cfb_error cfb_gop2_inverse_host(cfb_codec *codec, const void *coded, const cfb_gop2_quant *quant, int out_format,

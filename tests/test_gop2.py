@@ -235,3 +235,83 @@ def test_cuda_gop2_single_call(path):
         a, b = pu.yuyv_envelope(planes)
         assert ((out == a) | (out == b)).all()
         assert pu.psnr(out[:, 0::2], src[:, 0::2]) > 45.0
+
+
+@needs_ref
+@pytest.mark.parametrize("quality", [1, 2, 3, 4, 5, 6, 4 | (1 << 17)])
+@pytest.mark.parametrize("interlaced", [False, True])
+def test_gop2_quant_schedule_matches_reference(quality, interlaced):
+    """cfb_gop2_quant_for_quality == the divisors / prescale the reference's encoder really used (quantize.c:3480)."""
+    pkg = importlib.import_module("cineform-sdk_b200")
+    w, h = 256, 64
+    ref_lib = ol.load_ref()
+    fa, fb = pu.qbist_yuy2(ref_lib, w, h, 1), pu.qbist_yuy2(ref_lib, w, h, 2)
+    ref_lib.ref_set_interlaced(1 if interlaced else 0)
+    try:
+        _, quant, prescale = pu.ref_encode_gop2(ref_lib, fa, fb, w, h, quality)
+    finally:
+        ref_lib.ref_set_interlaced(0)
+    q = pkg.gop2_quant_for_quality(pkg.FrameDesc(w, h, pkg.PIXEL_YUYV), quality, interlaced)
+    assert [int(v) for v in q.prescale] == prescale[0][:6]
+    for c in range(3):
+        for k in range(6):
+            nb = 2 if k == 2 else 4
+            got = [int(q.divisor[c][k][b]) for b in range(nb)]
+            want = quant[c][k][:nb]
+            if k in (0, 1, 4):
+                got, want = got[1:], want[1:]            # their LL is never coded
+            assert got == want, (c, k, got, want)
+
+
+@needs_ref
+@pytest.mark.parametrize("size,quality", [((256, 64), 4), ((704, 96), 3)])
+def test_oracle_gop2_interlaced_matches_reference_encoder(size, quality):
+    """Interlaced two-frame GOP: level 1 of both frames is the field transform, everything above is unchanged."""
+    w, h = size
+    ref_lib, orc = ol.load_ref(), ol.oracle()
+    fa, fb = pu.qbist_yuy2(ref_lib, w, h, 1).copy(), pu.qbist_yuy2(ref_lib, w, h, 3).copy()
+    for f in (fa, fb):
+        f[1::2] = np.roll(f[1::2], 8, axis=1)
+    ref_lib.ref_set_interlaced(1)
+    try:
+        bands, quant, prescale = pu.ref_encode_gop2(ref_lib, fa, fb, w, h, quality)
+    finally:
+        ref_lib.ref_set_interlaced(0)
+    _, temporal, level = _oracle_blocks()
+    got = pu.gop2_pyramid(lambda f, c, q: orc.fwd_fields_422(f, c, 0, q, 10, 2), temporal, level, fa, fb, quant, prescale)
+    _compare(got, {k: v for k, v in bands.items() if k in got})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("interlaced", [False, True])
+@pytest.mark.parametrize("size", [(256, 64), (704, 96), (1920, 1080)])
+def test_cuda_gop2_vs_oracle(size, interlaced):
+    """cfb_gop2_* with the restated schedule, progressive and interlaced level 1, against the oracle composition."""
+    pkg = importlib.import_module("cineform-sdk_b200")
+    w, h = size
+    rng = np.random.default_rng(w + h + int(interlaced))
+    fa = pu.synthetic_yuyv(rng, w, h, "natural")
+    fb = np.roll(fa, 2, axis=0).copy()
+    fb[:, 0::2] = np.clip(fb[:, 0::2].astype(np.int32) + rng.integers(-3, 4, (h, w)), 16, 235).astype(np.uint8)
+    if interlaced:
+        for f in (fa, fb):
+            f[1::2] = np.roll(f[1::2], 8, axis=1)
+    desc = pkg.FrameDesc(w, h, pkg.PIXEL_YUYV)
+    gq = pkg.gop2_quant_for_quality(desc, 4, interlaced)
+    quant = [[[int(gq.divisor[c][k][b]) for b in range(4)] for k in range(6)] for c in range(3)]
+    prescale = [[int(v) for v in gq.prescale] + [0, 0]] * 3
+    orc = ol.oracle()
+    _, temporal, level = _oracle_blocks()
+    level1 = (lambda f, c, q: orc.fwd_fields_422(f, c, 0, q, 10, 2)) if interlaced else (lambda f, c, q: orc.fwd_level_422(f, c, 0, q, 10, 2))
+    want = pu.gop2_pyramid(level1, temporal, level, fa, fb, quant, prescale)
+    with pkg.Context(0) as ctx, pkg.Codec(ctx, desc, 2) as codec:
+        if interlaced:
+            codec.set_interlaced(True)
+        g = codec.gop2_layout()
+        coded = codec.gop2_forward_host(fa, fb, gq)
+        for (c, k, b), wv in sorted(want.items()):
+            if k == 2:
+                continue
+            assert np.array_equal(codec.gop2_band_view(g, coded, c, k, b), wv), f"(channel, wavelet, band) {(c, k, b)}"
+        out_a, out_b = codec.gop2_inverse_host(coded, gq, pkg.PIXEL_YUYV, fa.shape)
+    assert pu.psnr(out_a[:, 0::2], fa[:, 0::2]) > 40.0 and pu.psnr(out_b[:, 0::2], fb[:, 0::2]) > 40.0
