@@ -172,3 +172,23 @@ def test_no_cpu_fallback_without_device(pkg):
     with pytest.raises(pkg.CfbError) as ei:
         pkg.Context(0)
     assert ei.value.code == 100
+
+
+def test_product_does_not_depend_on_the_checker():
+    """oracle/ and tests/ are test infrastructure: the shipped library must not link against them and neither the package
+    nor bench.py's product arm may import them (bench.py may, inside its CPU-baseline / --impl reference leg only)."""
+    import subprocess
+    lib = os.path.join(ROOT, "cineform-sdk_b200", "libcfhd_b200.so")
+    needed = subprocess.run(["readelf", "-d", lib], capture_output=True, text=True).stdout
+    assert "oracle" not in needed and "cfhd_ref" not in needed and "CFHDCodec" not in needed
+    pkg_src = open(os.path.join(ROOT, "cineform-sdk_b200", "__init__.py")).read()
+    assert "oracle" not in pkg_src and "parity_util" not in pkg_src
+    for name in sorted(os.listdir(os.path.join(ROOT, "cineform-sdk_b200", "csrc"))):
+        if not name.endswith((".cu", ".cuh", ".h")):
+            continue
+        src = open(os.path.join(ROOT, "cineform-sdk_b200", "csrc", name)).read()
+        assert "oracle/" not in src and "cfhd_oracle" not in src, name
+    bench_src = open(os.path.join(ROOT, "bench.py")).read()
+    # the only function of bench.py that imports the checker is the CPU baseline / reference-arm timer
+    importing = [seg.split("(")[0] for seg in bench_src.split("\ndef ")[1:] if "import oracle_lib" in seg or "import parity_util" in seg]
+    assert importing == ["cpu_reference_run"], importing
