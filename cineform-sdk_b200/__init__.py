@@ -119,6 +119,7 @@ def lib():
     L.cfb_codec_device_pyramid.restype = vp
     L.cfb_codec_set_level_mask.argtypes = [vp, i, i]
     L.cfb_codec_set_bayer_phase.argtypes = [vp, i]
+    L.cfb_codec_set_bayer_curve.argtypes = [vp, vp, i]
     L.cfb_codec_set_decode_resolution.argtypes = [vp, i]
     L.cfb_codec_set_interlaced.argtypes = [vp, i]
     L.cfb_gop2_layout_compute.argtypes = [C.POINTER(FrameDesc), C.POINTER(Gop2Layout)]
@@ -368,6 +369,14 @@ class Codec:
 
     def set_bayer_phase(self, bayer_format):
         _check(lib().cfb_codec_set_bayer_phase(self.h, bayer_format))
+
+    def set_bayer_curve(self, curve):
+        """curve: uint16 array of 1 << 14 entries (the reference's per-call encode curve), or None = already applied."""
+        if curve is None:
+            _check(lib().cfb_codec_set_bayer_curve(self.h, None, 0))
+        else:
+            c = np.ascontiguousarray(curve, np.uint16)
+            _check(lib().cfb_codec_set_bayer_curve(self.h, c.ctypes.data, c.size))
 
     def set_level_mask(self, forward_mask=7, inverse_mask=7):
         _check(lib().cfb_codec_set_level_mask(self.h, forward_mask, inverse_mask))

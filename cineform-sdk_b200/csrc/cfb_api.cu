@@ -456,6 +456,7 @@ void cfb_codec_destroy(cfb_codec *cd)
     if (cd->d_pyramids) cudaFree(cd->d_pyramids);
     if (cd->d_carry) cudaFree(cd->d_carry);
     if (cd->d_gop) cudaFree(cd->d_gop);
+    if (cd->d_curve) cudaFree(cd->d_curve);
     if (cd->d_sparse) cudaFree(cd->d_sparse);
     if (cd->d_counts) cudaFree(cd->d_counts);
     if (cd->h_headers) cudaFreeHost(cd->h_headers);
@@ -473,6 +474,22 @@ cfb_error cfb_codec_set_bayer_phase(cfb_codec *cd, int bayer_format)
 {
     if (!cd || bayer_format < 0 || bayer_format > 3) { set_error("bayer format %d out of range 0..3", bayer_format); return CFB_ERROR_INVALID_ARGUMENT; }
     cd->bayer_phase = bayer_format;
+    return CFB_OK;
+}
+
+cfb_error cfb_codec_set_bayer_curve(cfb_codec *cd, const uint16_t *curve, int entries)
+{
+    if (!cd) { set_error("null codec"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (cd->desc.pixel_format != CFB_PIXEL_BYR4) { set_error("the encode curve applies to Bayer (BYR4) codecs"); return CFB_ERROR_BADFORMAT; }
+    CFB_CUDA(cudaSetDevice(cd->ctx->device));
+    if (!curve) {                                   // back to "curve already applied" (encode_curve_preset)
+        if (cd->d_curve) { CFB_CUDA(stream_wait(cd->ctx)); cudaFree(cd->d_curve); cd->d_curve = nullptr; }
+        return CFB_OK;
+    }
+    if (entries != (1 << 14)) { set_error("Bayer encode curve must have 1 << 14 entries (MAX_INPUT_PRECISION, frame.c:4843)"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (!cd->d_curve) CFB_CUDA(cudaMalloc((void **)&cd->d_curve, sizeof(uint16_t) << 14));
+    CFB_CUDA(cudaMemcpyAsync(cd->d_curve, curve, sizeof(uint16_t) << 14, cudaMemcpyHostToDevice, cd->ctx->stream));
+    CFB_CUDA(stream_wait(cd->ctx));                 // the caller's table may go away after this call
     return CFB_OK;
 }
 
@@ -649,7 +666,7 @@ cfb_error cfb_forward_device(cfb_codec *cd, int n, const void *const *d_frames, 
             p.ch[c].in_off = 0; p.ch[c].in_pitch = frame_pitch;      // bytes per Bayer line
             p.ch[c].quant_ll = quant->divisor[c][0][0] > 1;
         }
-        p.shift = 16 - L.precision; p.uyvy = cd->bayer_phase;
+        p.shift = 16 - L.precision; p.uyvy = cd->bayer_phase; p.lut = cd->d_curve;
         p.th = pick_th((p.ch[0].width + kStripIn - 1) / kStripIn * 4, p.ch[0].height / 2, n, ctx->sm_count);
         CFB_CUDA(launch_fwd_byr4(p, ctx->stream));
         ctx->kernel_launches++;

@@ -50,6 +50,7 @@ struct FwdParams {
     PlaneGeom ch[kMaxChannels];
     const unsigned char *in_base[kMaxBatch];
     unsigned char *out_base[kMaxBatch];
+    const unsigned short *lut;      // Bayer only: encode curve, 1 << 14 entries (frame.c:5208), null = samples >> shift
 };
 
 constexpr int kInvStrip = 120;    // band columns written per warp-row by the inverse kernels (30 lanes x 4)

@@ -462,10 +462,19 @@ __device__ __forceinline__ void load_byr4_row(const unsigned char *p, int line_p
 }
 
 // one plane sample from the quad (w1 = two pixels of the first line, w2 = of the second line)
-__device__ __forceinline__ int byr4_sample(unsigned w1, unsigned w2, int shift, int fmt, int chan)
+// LUT: the encode curve of Codec/frame.c:5208-5330 (default: log base 90), indexed by the 14 most significant bits
+// (MAX_INPUT_PRECISION, frame.c:4843); without it the frame is taken as already curved (`>> shift`, encode_curve_preset).
+template <bool LUT>
+__device__ __forceinline__ int byr4_sample(unsigned w1, unsigned w2, int shift, int fmt, int chan, const unsigned short *lut)
 {
-    const int q0 = (int)((w1 & 0xffffu) >> shift), q1 = (int)((w1 >> 16) >> shift);
-    const int q2 = (int)((w2 & 0xffffu) >> shift), q3 = (int)((w2 >> 16) >> shift);
+    int q0, q1, q2, q3;
+    if (LUT) {
+        q0 = __ldg(lut + ((w1 & 0xffffu) >> 2)); q1 = __ldg(lut + (w1 >> 18));
+        q2 = __ldg(lut + ((w2 & 0xffffu) >> 2)); q3 = __ldg(lut + (w2 >> 18));
+    } else {
+        q0 = (int)((w1 & 0xffffu) >> shift); q1 = (int)((w1 >> 16) >> shift);
+        q2 = (int)((w2 & 0xffffu) >> shift); q3 = (int)((w2 >> 16) >> shift);
+    }
     const bool g_second = (fmt == 0) || (fmt == 3);             // RED_GRN / BLU_GRN: green is the 2nd pixel of line 1
     const int g1 = g_second ? q1 : q0, g2 = g_second ? q2 : q3;
     if (chan == 3) return (g1 - g2 + 4096) >> 1;
@@ -476,19 +485,21 @@ __device__ __forceinline__ int byr4_sample(unsigned w1, unsigned w2, int shift, 
     return (((chan == 1) ? r : b) - gg + 4096) >> 1;
 }
 
-__device__ __forceinline__ void byr4_extract(const RawBYR4Row &r, int shift, int fmt, int chan, RawPlaneRow &o)
+template <bool LUT>
+__device__ __forceinline__ void byr4_extract(const RawBYR4Row &r, int shift, int fmt, int chan, const unsigned short *lut, RawPlaneRow &o)
 {
     const unsigned l1[8] = {r.a0.x, r.a0.y, r.a0.z, r.a0.w, r.a1.x, r.a1.y, r.a1.z, r.a1.w};
     const unsigned l2[8] = {r.b0.x, r.b0.y, r.b0.z, r.b0.w, r.b1.x, r.b1.y, r.b1.z, r.b1.w};
     unsigned out[4];
 #pragma unroll
     for (int m = 0; m < 4; m++)
-        out[m] = (unsigned)byr4_sample(l1[2 * m], l2[2 * m], shift, fmt, chan) |
-                 ((unsigned)byr4_sample(l1[2 * m + 1], l2[2 * m + 1], shift, fmt, chan) << 16);
+        out[m] = (unsigned)byr4_sample<LUT>(l1[2 * m], l2[2 * m], shift, fmt, chan, lut) |
+                 ((unsigned)byr4_sample<LUT>(l1[2 * m + 1], l2[2 * m + 1], shift, fmt, chan, lut) << 16);
     o.v = make_uint4(out[0], out[1], out[2], out[3]);
-    o.halo = (unsigned)byr4_sample(r.ha.x, r.hb.x, shift, fmt, chan) | ((unsigned)byr4_sample(r.ha.y, r.hb.y, shift, fmt, chan) << 16);
+    o.halo = (unsigned)byr4_sample<LUT>(r.ha.x, r.hb.x, shift, fmt, chan, lut) | ((unsigned)byr4_sample<LUT>(r.ha.y, r.hb.y, shift, fmt, chan, lut) << 16);
 }
 
+template <bool LUT>
 __global__ void __launch_bounds__(128) k_fwd_byr4(const __grid_constant__ FwdParams p)
 {
     const int lane = threadIdx.x;
@@ -518,8 +529,8 @@ __global__ void __launch_bounds__(128) k_fwd_byr4(const __grid_constant__ FwdPar
             int a[8], b[8];
             load_byr4_row(in + (long long)(2 * (j0 + k)) * row_pitch, line_pitch, L, q0);
             load_byr4_row(in + (long long)(2 * (j0 + k) + 1) * row_pitch, line_pitch, L, q1);
-            byr4_extract(q0, shift, fmt, c, r0);
-            byr4_extract(q1, shift, fmt, c, r1);
+            byr4_extract<LUT>(q0, shift, fmt, c, p.lut, r0);
+            byr4_extract<LUT>(q1, shift, fmt, c, p.lut, r1);
             hfilter_plane<0>(r0, L, a);
             hfilter_plane<0>(r1, L, b);
 #pragma unroll
@@ -556,8 +567,8 @@ __global__ void __launch_bounds__(128) k_fwd_byr4(const __grid_constant__ FwdPar
         }
         RawPlaneRow r0, r1;
         int a[8], b[8];
-        byr4_extract(c0, shift, fmt, c, r0);
-        byr4_extract(c1, shift, fmt, c, r1);
+        byr4_extract<LUT>(c0, shift, fmt, c, p.lut, r0);
+        byr4_extract<LUT>(c1, shift, fmt, c, p.lut, r1);
         hfilter_plane<0>(r0, L, a);
         hfilter_plane<0>(r1, L, b);
         vstep<4, 1>(st, a, b, g, out, off, j >= y0 && j < y1, j - 1 >= hlo);
@@ -1253,7 +1264,7 @@ cudaError_t launch_fwd_byr4(const FwdParams &p, cudaStream_t stream)
 {
     dim3 block(32, 4);
     dim3 grid(ceil_div(p.ch[0].width, kStripIn) * 4, ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y) + 1, p.nframes);
-    k_fwd_byr4<<<grid, block, 0, stream>>>(p);
+    if (p.lut) k_fwd_byr4<true><<<grid, block, 0, stream>>>(p); else k_fwd_byr4<false><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -168,8 +168,12 @@ CFB_API void *cfb_codec_device_frame(cfb_codec *codec, int slot);
 CFB_API void *cfb_codec_device_pyramid(cfb_codec *codec, int slot);
 
 /* BYR4 only: Bayer phase of the source (TAG_BAYER_FORMAT): 0 RED_GRN, 1 GRN_RED, 2 GRN_BLU, 3 BLU_GRN
- * (Codec/DemoasicFrames.h:30-33).  The frame must already carry its encode curve (CFHD_ENCODING_FLAGS_CURVE_APPLIED). */
+ * (Codec/DemoasicFrames.h:30-33). */
 CFB_API cfb_error cfb_codec_set_bayer_phase(cfb_codec *codec, int bayer_format);
+/* BYR4 only: the encode curve the reference builds per call (Codec/frame.c:5208-5330, default log base 90) as a table of
+ * 1 << 14 12-bit values indexed by sample >> 2; the kernel applies it while loading.  NULL (default) = the frame already
+ * carries its curve (CFHD_ENCODING_FLAGS_CURVE_APPLIED / encode_curve_preset): samples >> 4. */
+CFB_API cfb_error cfb_codec_set_bayer_curve(cfb_codec *codec, const uint16_t *curve, int entries);
 
 /* Interlaced sources (CFHD_ENCODING_FLAGS_YUV_INTERLACED, EncoderSDK/SampleEncoder.cpp:210 -> parameters.progressive = 0;
  * on decode the sample's progressive flag): level 1 of the following forward/inverse calls is the frame (field)

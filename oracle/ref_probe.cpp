@@ -214,6 +214,10 @@ static int g_probe_bayer_format = -1;
 // Bayer sources only: phase (BAYER_FORMAT_*, Codec/DemoasicFrames.h:30) used by the next ref_encode_frame_bands call;
 // the frame is treated as CFHD_ENCODING_FLAGS_CURVE_APPLIED (encode_curve_preset = 1, linear >> 4).  -1 disables.
 void ref_set_bayer_format(int fmt) { g_probe_bayer_format = fmt; }
+static int g_probe_bayer_preset = 1;
+// 1 (default): the frame already carries its curve (encode_curve_preset = 1, samples >> 4); 0: the encoder builds and
+// applies its default encode curve (log base 90, Codec/frame.c:5208-5245) itself.
+void ref_set_bayer_curve_preset(int preset) { g_probe_bayer_preset = preset; }
 static int g_probe_interlaced = 0;
 // Interlaced source (CFHD_ENCODING_FLAGS_YUV_INTERLACED -> parameters.progressive = 0, EncoderSDK/SampleEncoder.cpp:210,
 // :293): the next ref_encode_frame_bands calls use the frame (field) transform at level 1 (Codec/encoder.c:2949-2993).
@@ -234,7 +238,7 @@ int ref_encode_frame_bands(const uint8_t *frame, int width, int height, int pitc
     p.frame_sampling = sampling_444 ? FRAME_SAMPLING_444 : FRAME_SAMPLING_422;
     p.colorspace_yuv = 2; p.colorspace_rgb = 1;
     if (!InitializeEncoderWithParameters(NULL, enc, tr, num_channels, &p)) return 0;
-    if (g_probe_bayer_format >= 0) { enc->bayer.format = g_probe_bayer_format; enc->encode_curve_preset = 1; }
+    if (g_probe_bayer_format >= 0) { enc->bayer.format = g_probe_bayer_format; enc->encode_curve_preset = g_probe_bayer_preset; }
     size_t scratch_size = 0;
     PIXEL *scratch = CreateEncodingBuffer(NULL, width, height, pitch, color_format, 1, true, &scratch_size);
     const size_t outcap = (size_t)width * height * 16 + 65536;

@@ -253,11 +253,26 @@ def mosaic_from_rg48(frame16, fmt=0):
     return m
 
 
-def unpack_byr4(bayer16, fmt=0, precision=12):
-    """Codec/frame.c:4993 ConvertBYR4ToFrame16s, encode_curve_preset branch (:5040-5200): planes G, R-G, B-G, dG."""
+def bayer_log90_curve(precision=12):
+    """The default encode curve of Codec/frame.c:5208-5245: curve[i] = (int)(lin2log((float)i / 16384, 90) * 4095) with
+    lin2log (Common/AVIExtendedHeader.h:153) evaluated in double and rounded to float, 1 << 14 entries, curve[0] = 0."""
+    i = np.arange(1 << 14, dtype=np.float32) / np.float32(1 << 14)
+    v = (np.log10(i.astype(np.float64) * (np.float64(np.float32(90.0)) - 1.0) + 1.0) / np.log10(np.float64(np.float32(90.0)))).astype(np.float32)
+    curve = (v * np.float32((1 << precision) - 1)).astype(np.int32)
+    curve[0] = 0
+    return curve.astype(np.uint16)
+
+
+def unpack_byr4(bayer16, fmt=0, precision=12, curve=None):
+    """Codec/frame.c:4993 ConvertBYR4ToFrame16s: planes G, R-G, B-G, dG.  curve=None: encode_curve_preset branch
+    (:5040-5200, samples >> 4); else the table branch (:5206-5420): sample -> curve[sample >> 2]."""
     sh = 16 - precision
-    q0 = (bayer16[0::2, 0::2] >> sh).astype(np.int32); q1 = (bayer16[0::2, 1::2] >> sh).astype(np.int32)
-    q2 = (bayer16[1::2, 0::2] >> sh).astype(np.int32); q3 = (bayer16[1::2, 1::2] >> sh).astype(np.int32)
+    if curve is None:
+        conv = lambda a: (a >> sh).astype(np.int32)
+    else:
+        conv = lambda a: curve[(a >> 2).astype(np.int64)].astype(np.int32)
+    q0 = conv(bayer16[0::2, 0::2]); q1 = conv(bayer16[0::2, 1::2])
+    q2 = conv(bayer16[1::2, 0::2]); q3 = conv(bayer16[1::2, 1::2])
     r, g1, g2, b = {0: (q0, q1, q2, q3), 1: (q1, q0, q3, q2), 2: (q2, q0, q3, q1), 3: (q3, q1, q2, q0)}[fmt]
     mid = 1 << 12
     gg = (g1 + g2) >> 1

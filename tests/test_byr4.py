@@ -68,3 +68,52 @@ def test_forward_byr4_vs_oracle(pkg, size, fmt):
         codec.inverse_host([coded], quant, pkg.PIXEL_PLANAR16, [out])
         for c in range(4):
             assert np.array_equal(out[c * ph:(c + 1) * ph, :pw], want_planes[c]), f"inverse channel {c}"
+
+
+@needs_ref
+@pytest.mark.parametrize("fmt", [0, 1, 2, 3])
+def test_oracle_byr4_default_curve_matches_reference_encoder(pkg, fmt):
+    """BYR4 WITHOUT the curve-applied flag: the reference builds its default encode curve (log base 90, frame.c:5208-5245)
+    and maps every sample through it; parity_util.bayer_log90_curve restates the table."""
+    w, h = 512, 128
+    ref_lib = ol.load_ref()
+    rng = np.random.default_rng(fmt)
+    bayer = pu.mosaic_from_rg48(pu.qbist_rg48(ref_lib, w, h, 1), fmt)
+    bayer = (bayer.astype(np.uint32) | rng.integers(0, 16, bayer.shape).astype(np.uint32)).astype(np.uint16)   # use the low bits too
+    ref_lib.ref_set_bayer_format(fmt)
+    ref_lib.ref_set_bayer_curve_preset(0)
+    try:
+        two_lines_per_row = np.ascontiguousarray(bayer).reshape(h // 2, 2 * w)
+        bands_ref, div, prescale, _ = pu.ref_encode_frame(ref_lib, two_lines_per_row.view(np.uint8), w // 2, h // 2,
+                                                          pu.COLOR_FORMAT_BYR4, 1, 4, 4)
+    finally:
+        ref_lib.ref_set_bayer_curve_preset(1)
+        ref_lib.ref_set_bayer_format(-1)
+    curve = pu.bayer_log90_curve()
+    assert curve[0] == 0 and curve[-1] <= 4095 and np.all(np.diff(curve.astype(np.int32)) >= 0)
+    pyr = pu.forward_pyramid_planes(ol.oracle(), pu.unpack_byr4(bayer, fmt, curve=curve), div, tuple(prescale[0]))
+    for key, want in bands_ref.items():
+        assert np.array_equal(pyr[key], want), f"band {key}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,fmt", [((512, 128), 0), ((1152, 192), 1), ((512, 128), 2), ((3840, 2160), 3)])
+def test_forward_byr4_with_encode_curve(pkg, size, fmt):
+    """cfb_codec_set_bayer_curve: the table lookup fused into the load == oracle planes built with the same table;
+    clearing the curve restores the curve-applied path."""
+    w, h = size
+    rng = np.random.default_rng(w + 10 * fmt)
+    bayer = rng.integers(0, 65536, (h, w)).astype(np.uint16)
+    desc = pkg.FrameDesc(w, h, pkg.PIXEL_BYR4)
+    quant = pkg.quant_for_quality(desc, 4)
+    curve = pu.bayer_log90_curve()
+    with pkg.Context(0) as ctx, pkg.Codec(ctx, desc, 1) as codec:
+        codec.set_bayer_phase(fmt)
+        for cv in (curve, None):
+            codec.set_bayer_curve(cv)
+            got = codec.unpack_coded(codec.forward_host([bayer], quant)[0])
+            pyr = pu.forward_pyramid_planes(ol.oracle(), pu.unpack_byr4(bayer, fmt, curve=cv), quant.table(4), tuple(quant.prescale))
+            for key, want in pyr.items():
+                if key[2] == "LL" and key[1] != 3:
+                    continue
+                assert np.array_equal(got[key], want), f"curve {'on' if cv is not None else 'off'} band {key}"
