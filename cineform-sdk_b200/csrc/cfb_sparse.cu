@@ -202,12 +202,11 @@ static cfb_error sparse_prepare(cfb_codec *cd, SparseParams &p, int n)
     p.nseg = (p.nwords + kSeg - 1) / kSeg;
     p.bitmap_off = sp_bitmap_off();
     p.values_off = sp_values_off(p.nwords);
-    if (!cd->d_sparse) {
-        cd->sparse_stride = (cfb_sparse_max_bytes(&L) + 255) & ~(size_t)255;
-        CFB_CUDA(cudaMalloc((void **)&cd->d_sparse, cd->sparse_stride * cd->max_batch));
-        CFB_CUDA(cudaMalloc((void **)&cd->d_counts, sizeof(unsigned) * (size_t)(p.nseg + 1) * cd->max_batch));
-        CFB_CUDA(cudaHostAlloc((void **)&cd->h_headers, 16 * (size_t)cd->max_batch, cudaHostAllocPortable));
-    }
+    // each staging buffer under its own check: a failed allocation leaves the others usable for the retry
+    cd->sparse_stride = (cfb_sparse_max_bytes(&L) + 255) & ~(size_t)255;
+    if (!cd->d_sparse) CFB_CUDA(cudaMalloc((void **)&cd->d_sparse, cd->sparse_stride * cd->max_batch));
+    if (!cd->d_counts) CFB_CUDA(cudaMalloc((void **)&cd->d_counts, sizeof(unsigned) * (size_t)(p.nseg + 1) * cd->max_batch));
+    if (!cd->h_headers) CFB_CUDA(cudaHostAlloc((void **)&cd->h_headers, 16 * (size_t)cd->max_batch, cudaHostAllocPortable));
     for (int i = 0; i < n; i++) {
         p.dense[i] = cd->d_pyramids + cd->pyramid_stride * i;
         p.sparse[i] = cd->d_sparse + cd->sparse_stride * i;
@@ -261,10 +260,11 @@ cfb_error cfb_forward_host_sparse(cfb_codec *cd, int n, const void *const *h_fra
     ctx->kernel_launches += 3;
     // Speculative single-pass D2H: copy header + bitmap + as many values as recent frames needed (+12 %) right behind the
     // kernels, without a host round trip; only if a frame turns out to hold more values is the remainder fetched.
-    const unsigned guess = cd->value_guess ? cd->value_guess : sp.nwords / 8;
+    // (never more than the caller's buffer holds: cfb_sparse_max_bytes = values_off + nwords * 2)
+    unsigned guess = cd->value_guess ? cd->value_guess : sp.nwords / 8;
+    if (guess > sp.nwords) guess = sp.nwords;
     for (int i = 0; i < n; i++) {
-        size_t bytes = (size_t)sp.values_off + (size_t)guess * 2;
-        if (bytes > cd->sparse_stride) bytes = cd->sparse_stride;
+        const size_t bytes = (size_t)sp.values_off + (size_t)guess * 2;
         CFB_CUDA(cudaMemcpyAsync(h_sparse[i], sp.sparse[i], bytes, cudaMemcpyDeviceToHost, ctx->stream));
         ctx->d2h_bytes += (uint64_t)bytes;
     }
@@ -284,9 +284,9 @@ cfb_error cfb_forward_host_sparse(cfb_codec *cd, int n, const void *const *h_fra
     }
     if (more) CFB_CUDA(stream_wait(ctx));
     {
-        unsigned g = maxv + maxv / 8 + 4096;
-        if (g > sp.nwords) g = sp.nwords;
-        cd->value_guess = (g + 63u) & ~63u;
+        unsigned g = (maxv + maxv / 8 + 4096 + 63u) & ~63u;
+        if (g > sp.nwords) g = sp.nwords;           // clamp AFTER the rounding: the copy must stay inside cfb_sparse_max_bytes
+        cd->value_guess = g;
     }
     return CFB_OK;
 }
@@ -340,7 +340,12 @@ cfb_error cfb_sparse_expand(const cfb_layout *L, const void *sparse, void *dense
     size_t pos = 0;
     for (unsigned w = 0; w < nwords; w += 32) {
         unsigned m = bm[w >> 5];
-        for (int k = 0; k < 32 && w + k < nwords; k++) out[w + k] = (m >> k) & 1u ? vals[pos++] : (int16_t)0;
+        for (int k = 0; k < 32 && w + k < nwords; k++) {
+            if ((m >> k) & 1u) {
+                if (pos >= h[2]) { set_error("sparse bitmap has more set bits than the header's value count"); return CFB_ERROR_BADFORMAT; }
+                out[w + k] = vals[pos++];
+            } else out[w + k] = 0;
+        }
     }
     if (pos != h[2]) { set_error("sparse value count mismatch"); return CFB_ERROR_BADFORMAT; }
     return CFB_OK;

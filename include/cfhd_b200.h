@@ -181,7 +181,10 @@ CFB_API cfb_error cfb_codec_set_bayer_curve(cfb_codec *codec, const uint16_t *cu
  * instead of the spatial transform.  Replaces Codec/encoder.c:2976 TransformForwardFrameYUV (wavelet.c:6076; planar
  * form filter.c:273 FilterFrameQuant16s) and Codec/decoder.c:21493 TransformInverseFrameToYUV / :22027 ...ToRow16u
  * (temporal.c:3741 InvertInterlaced16s) including the HL row integration of decoder.c:20822-20836.
- * Packed 8-bit 4:2:2 codecs only; full-resolution decode. */
+ * Packed 8-bit 4:2:2 codecs only.  Reduced-resolution decodes of an interlaced sample (cfb_codec_set_decode_resolution)
+ * return the lowpass image LL1 / LL2 exactly as the reference does: its half- and quarter-resolution paths
+ * (Codec/decoder.c:26078 and :11818) run before / outside the progressive-vs-interlaced split of
+ * ReconstructSampleFrameToBuffer, so the level-1 transform type does not enter. */
 enum { CFB_PROGRESSIVE = 0, CFB_INTERLACED = 1,
        /* inverse only: the level-1 HL band arrives already integrated along its rows, i.e. exactly as the reference's
         * entropy decoder leaves it (decoder.c:20822-20836); the GPU then skips its own prefix sum */

@@ -79,6 +79,7 @@ struct Plan {
     cfb_codec *codec = nullptr;
     cfb_layout layout{};
     void *coded = nullptr;          // pinned staging for the coded region
+    void *frame = nullptr;          // pinned staging for a decoded frame at the ENCODED size (allocated on first use)
     bool tried = false;
 };
 
@@ -271,9 +272,27 @@ void ReconstructSampleFrameToBuffer(DECODER *decoder, int frame, uint8_t *output
             }
         }
     const void *coded[1] = {plan->coded};
-    void *frames[1] = {output};
     const int fmt = decoder->frame.format == DECODED_FORMAT_YUYV ? CFB_PIXEL_YUYV : CFB_PIXEL_UYVY;
-    if (cfb_inverse_host(plan->codec, 1, coded, &q, fmt, frames, pitch) != CFB_OK) {
+    // The pyramid has the ENCODED size (height rounded up to a multiple of 8, encoder.c:2232: 720x486 is coded as 488
+    // rows) while the caller's buffer holds the DISPLAY size (decoder->frame): the reference writes info->height rows of
+    // info->width pixels only.  When the two differ the frame is decoded into a staging buffer and the display window is
+    // copied out, so nothing is ever written past the caller's last row.
+    const int enc_w = plan->layout.band[0][0][0].width * 2, enc_h = plan->layout.band[0][0][0].height * 2;
+    const int out_w = decoder->frame.width, out_h = decoder->frame.height;
+    if (out_w <= 0 || out_h <= 0 || out_w > enc_w || out_h > enc_h || pitch < out_w * 2) { g_inv_ref++; ref(decoder, frame, output, pitch); return; }
+    cfb_error err;
+    if (out_w == enc_w && out_h == enc_h) {
+        void *frames[1] = {output};
+        err = cfb_inverse_host(plan->codec, 1, coded, &q, fmt, frames, pitch);
+    } else {
+        if (!plan->frame && cfb_host_alloc((size_t)plan->layout.frame_bytes, &plan->frame) != CFB_OK) plan->frame = nullptr;
+        void *frames[1] = {plan->frame};
+        err = plan->frame ? cfb_inverse_host(plan->codec, 1, coded, &q, fmt, frames, plan->layout.frame_pitch) : CFB_ERROR_OUTOFMEMORY;
+        if (err == CFB_OK)
+            for (int r = 0; r < out_h; r++)
+                memcpy(output + (size_t)r * pitch, (const char *)plan->frame + (size_t)r * plan->layout.frame_pitch, (size_t)out_w * 2);
+    }
+    if (err != CFB_OK) {
         fprintf(stderr, "cfhd_gpu_shim: CUDA inverse failed: %s\n", cfb_last_error_string());
         decoder->error = CODEC_ERROR_BAD_FRAME;
     }

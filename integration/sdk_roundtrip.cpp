@@ -51,7 +51,11 @@ int main(int argc, char **argv)
     if (e) { fprintf(stderr, "encoder setup failed: %d\n", (int)e); return 1; }
     e = CFHD_OpenDecoder(&dec, nullptr);
     if (e) { fprintf(stderr, "decoder open failed: %d\n", (int)e); return 1; }
-    uint8_t *out = (uint8_t *)aligned((size_t)pitch * h);
+    // 16 guard rows behind the decoded frame: a decoder that writes the ENCODED height (rounded up to a multiple of 8,
+    // e.g. 488 rows for a 720x486 source) instead of the display height would trample them
+    const size_t guard_bytes = (size_t)pitch * 16;
+    uint8_t *out = (uint8_t *)aligned((size_t)pitch * h + guard_bytes);
+    memset(out + (size_t)pitch * h, 0xA5, guard_bytes);
     double enc_s = 0, dec_s = 0, mse_sum = 0;
     size_t bytes = 0;
     uint64_t hash = 1469598103934665603ull;
@@ -81,6 +85,8 @@ int main(int argc, char **argv)
         mse_sum += mse / ((double)w * h);
         for (size_t k = 0; k < (size_t)pitch * h; k += 97) { hash ^= (uint64_t)(out[k] >> 1); hash *= 1099511628211ull; }     // dither-insensitive digest
     }
+    bool guard_ok = true;
+    for (size_t k = 0; k < guard_bytes; k++) guard_ok = guard_ok && out[(size_t)pitch * h + k] == 0xA5;
     const double psnr = 10.0 * log10(255.0 * 255.0 / (mse_sum / nframes + 1e-12));
 
     // asynchronous encoder pool, exactly the TestCFHD -E call sequence (TestCFHD.cpp:783-1047)
@@ -113,9 +119,9 @@ int main(int argc, char **argv)
         CFHD_ReleaseEncoderPool(pool);
     }
     printf("{\"width\": %d, \"height\": %d, \"frames\": %d, \"enc_ms\": %.3f, \"dec_ms\": %.3f, \"sample_bytes\": %zu, "
-           "\"luma_psnr_db\": %.3f, \"decoded_digest\": \"%016llx\", \"pool_threads\": %d, \"pool_fps\": %.1f, \"interlaced\": %d}\n",
+           "\"luma_psnr_db\": %.3f, \"decoded_digest\": \"%016llx\", \"pool_threads\": %d, \"pool_fps\": %.1f, \"interlaced\": %d, \"guard_ok\": %d}\n",
            w, h, nframes, 1e3 * enc_s / nframes, 1e3 * dec_s / nframes, bytes / nframes, psnr, (unsigned long long)hash,
-           pool_threads, pool_fps, interlaced ? 1 : 0);
+           pool_threads, pool_fps, interlaced ? 1 : 0, guard_ok ? 1 : 0);
     CFHD_CloseEncoder(enc);
     CFHD_CloseDecoder(dec);
     return 0;

@@ -41,6 +41,20 @@ def test_public_api_roundtrip_matches_reference(size):
 
 
 @needs_build
+def test_public_api_roundtrip_height_not_multiple_of_8():
+    """720x486 (NTSC) is coded as 488 rows (encoder.c:2232) but the caller's buffer holds 486: the interposed decoder
+    must write the display window only (guard rows behind the frame stay untouched), with the reference's sample size."""
+    gpu = run("sdk_roundtrip", 720, 486, 3, 2)
+    ref = run("sdk_roundtrip_ref", 720, 486, 3, 2)
+    g, r = json.loads(gpu.stdout.strip().splitlines()[-1]), json.loads(ref.stdout.strip().splitlines()[-1])
+    assert g["guard_ok"] == 1 and r["guard_ok"] == 1
+    stats = gpu.stderr.split("cfhd_gpu_shim: forward frames on GPU")[-1]
+    assert int(stats.split("inverse frames on GPU")[1].split()[0]) >= 3      # the decode did run on the GPU
+    assert g["sample_bytes"] == r["sample_bytes"]
+    assert abs(g["luma_psnr_db"] - r["luma_psnr_db"]) < 0.1
+
+
+@needs_build
 def test_testcfhd_runs_unchanged():
     """Example/TestCFHD.cpp -E (encoder pool speed test over its format table) against libCFHDCodec.so."""
     p = run("TestCFHD", "-E")
