@@ -200,6 +200,18 @@ void ref_qbist_frames(unsigned seed, int width, int height, int pitch, unsigned 
     memcpy(out, buf.p, (size_t)pitch * height);
 }
 
+// Frames 1 .. nframes of the same sequence in one pass (out: nframes consecutive buffers of pitch * height bytes).
+void ref_qbist_sequence(unsigned seed, int width, int height, int pitch, unsigned pixel_format, int nframes, uint8_t *out)
+{
+    Aligned buf((size_t)width * height * 8 + 64);
+    GetRand(seed);
+    initBaseTransform();
+    for (int i = 0; i < nframes; i++) {
+        RunQBist(width, height, pitch, (CFHD_PixelFormat)pixel_format, 0, buf.as<unsigned char>());
+        memcpy(out + (size_t)i * pitch * height, buf.p, (size_t)pitch * height);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Whole-frame probe: run the reference's own Codec/encoder.c:1897 EncodeSample on one frame and copy
 // out every wavelet band plus the quantisation / prescale tables it used.

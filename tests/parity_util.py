@@ -46,6 +46,17 @@ def qbist_yuy2(ref_lib, width, height, frame_number=1, seed=50):
     return out
 
 
+def qbist_yuy2_sequence(ref_lib, width, height, nframes, seed=50):
+    """Frames 1 .. nframes of the TestCFHD Qbist sequence (seed 50, Example/TestCFHD.cpp:41), generated in one pass."""
+    pitch = width * 2
+    out = np.zeros((nframes, height, pitch), np.uint8)
+    fn = ref_lib.ref_qbist_sequence
+    fn.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_void_p]
+    fn.restype = None
+    fn(seed, width, height, pitch, ol.CFHD_PIXEL_FORMAT_YUY2, nframes, out.ctypes.data_as(C.c_void_p))
+    return [out[i] for i in range(nframes)]
+
+
 # ---------------------------------------------------------------- oracle pyramids
 def quant_table(quant, nchan=3):
     return [[[quant.divisor[c][k][b] for b in range(4)] for k in range(3)] for c in range(nchan)]
