@@ -23,6 +23,10 @@
 // last output row, which use the 6-tap border filters) are produced by dedicated
 // border warps in an extra CTA row, so the hot loop carries no border code.
 #include "cfb_common.cuh"
+#include "cfb_tma.cuh"
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
 
 namespace cfb {
 
@@ -746,6 +750,92 @@ __global__ void __launch_bounds__(128) k_fwd_422(const __grid_constant__ FwdPara
 }
 
 // ----------------------------------------------------------------------------
+// Building blocks of the second-generation level-1 kernel (k_fwd_422_tma, cfb_forward_tma.inl).  The first version
+// (k_fwd_422 above, kept selectable with CFB_FWD422=r1 for the A/B in profiles/) spent ~12 % of its issue slots on
+// register moves (vertical state shuffle llp <- llc <- v, row double buffer c <- n), ~4 % on constant reloads (LDC)
+// and a few per cent on divergence-safe branches around the border code.  Here the vertical state is two values per
+// column instead of three, and strips with an image border run their own instantiation of the row loop, so interior
+// strips carry no border code (the choice is warp-uniform and made once).  Results are bit-identical.
+// (Measured and rejected, profiles/r02_ab_fwd422.txt: unrolling the row loop by two to rotate register roles instead
+// of moving values -- fewer instructions but 168-214 registers, 173 us against 160 us.)
+// Vertical state per column: two values instead of three.  With t_j = 8 D_j - S_{j-1} the interior highpass row is
+//   high_{j-1} = ((S_j - S_{j-2} + 4) >> 3) + D_{j-1} = (S_j + t_{j-1} + 4) >> 3      (8 D is a multiple of 8: exact)
+// so a step needs t_{j-1} and S_{j-1} only (to form t_j); S_{j-2} and D_{j-1} are never kept separately.
+template <int NC> struct RotState {
+    int t[2 * NC];      // t_{j-1} = 8 D_{j-1} - S_{j-2}
+    int s[2 * NC];      // S_{j-1}
+};
+
+template <int NC, int QLL>
+__device__ __forceinline__ void vstep_rot(RotState<NC> &st, const int *a, const int *b, const PlaneGeom &g, unsigned char *out,
+                                          unsigned off, bool emit_low, bool emit_high)
+{
+    int v[2 * NC], h[2 * NC];
+#pragma unroll
+    for (int i = 0; i < 2 * NC; i++) {
+        v[i] = a[i] + b[i];
+        h[i] = (v[i] + st.t[i] + 4) >> 3;
+        st.t[i] = ((a[i] - b[i]) << 3) - st.s[i];
+        st.s[i] = v[i];
+    }
+    if (QLL && g.quant_ll) store_quant_if<NC>(out + (g.band_off[0] + off), v, g.q[0], emit_low);
+    else store_raw_if<NC>(out + (g.band_off[0] + off), v, emit_low);
+    store_quant_if<NC>(out + (g.band_off[1] + off), v + NC, g.q[1], emit_low);
+    const unsigned offh = off - (unsigned)g.out_pitch;
+    store_quant_if<NC>(out + (g.band_off[2] + offh), h, g.q[2], emit_high);
+    store_quant_if<NC>(out + (g.band_off[3] + offh), h + NC, g.q[3], emit_high);
+}
+
+// hfilter_422 with the border decision lifted to a template parameter
+template <bool BORDER>
+__device__ __forceinline__ void hfilter_422_t(const Raw422Row &r, const Sel422 &sel, const LaneInfo &L, int *oy, int *ou, int *ov)
+{
+    const unsigned w[4] = {r.v.x, r.v.y, r.v.z, r.v.w};
+    int S[4], d[4], cu[4], cv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        S[k] = dp4a_us(w[k], sel.ysum, 0);
+        d[k] = dp4a_us(w[k], sel.ydif, 0);
+        cu[k] = dp4a_us(w[k], sel.u, 0);
+        cv[k] = dp4a_us(w[k], sel.v, 0);
+        oy[k] = S[k];
+    }
+    const int Su[2] = {cu[0] + cu[1], cu[2] + cu[3]}, du[2] = {cu[0] - cu[1], cu[2] - cu[3]};
+    const int Sv[2] = {cv[0] + cv[1], cv[2] + cv[3]}, dv[2] = {cv[0] - cv[1], cv[2] - cv[3]};
+    int Sp = __shfl_up_sync(L.amask, S[3], 1), Sn = __shfl_down_sync(L.amask, S[0], 1);
+    int Sup = __shfl_up_sync(L.amask, Su[1], 1), Sun = __shfl_down_sync(L.amask, Su[0], 1);
+    int Svp = __shfl_up_sync(L.amask, Sv[1], 1), Svn = __shfl_down_sync(L.amask, Sv[0], 1);
+    if (L.use_lh | L.use_rh) {
+        const int hy = dp4a_us(L.use_lh ? r.halo.y : r.halo.x, sel.ysum, 0);
+        const int hu = dp4a_us(r.halo.y, sel.u, dp4a_us(r.halo.x, sel.u, 0));
+        const int hv = dp4a_us(r.halo.y, sel.v, dp4a_us(r.halo.x, sel.v, 0));
+        if (L.use_lh) { Sp = hy; Sup = hu; Svp = hv; } else { Sn = hy; Sun = hu; Svn = hv; }
+    }
+    oy[4] = ((S[1] - Sp + 4) >> 3) + d[0];
+    oy[5] = ((S[2] - S[0] + 4) >> 3) + d[1];
+    oy[6] = ((S[3] - S[1] + 4) >> 3) + d[2];
+    oy[7] = ((Sn - S[2] + 4) >> 3) + d[3];
+    ou[0] = Su[0]; ou[1] = Su[1];
+    ou[2] = ((Su[1] - Sup + 4) >> 3) + du[0];
+    ou[3] = ((Sun - Su[0] + 4) >> 3) + du[1];
+    ov[0] = Sv[0]; ov[1] = Sv[1];
+    ov[2] = ((Sv[1] - Svp + 4) >> 3) + dv[0];
+    ov[3] = ((Svn - Sv[0] + 4) >> 3) + dv[1];
+    if (BORDER) {
+        if (L.left_border) {
+            oy[4] = clamp16((-3 * S[0] + 8 * d[0] + 4 * S[1] - S[2] + 4) >> 3);
+            ou[2] = clamp16((-3 * Su[0] + 8 * du[0] + 4 * Su[1] - Sun + 4) >> 3);
+            ov[2] = clamp16((-3 * Sv[0] + 8 * dv[0] + 4 * Sv[1] - Svn + 4) >> 3);
+        }
+        if (L.right_border) {
+            oy[7] = clamp16((3 * S[3] + 8 * d[3] - 4 * S[2] + S[1] + 4) >> 3);
+            ou[3] = clamp16((3 * Su[1] + 8 * du[1] - 4 * Su[0] + Sup + 4) >> 3);
+            ov[3] = clamp16((3 * Sv[1] + 8 * dv[1] - 4 * Sv[0] + Svp + 4) >> 3);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------
 // 10-bit packed RGB (RG30 / AB10 / AR10 / R210 / DPX0: one 32-bit word per pixel).  The reference transforms these
 // frames directly (Codec/encoder.c:3158-3176 -> wavelet.c:3597 TransformForwardSpatialRGB30 ->
 // spatial.c:2080 FilterHorizontalRowRGB30_16s): the 10-bit fields are filtered after `<< (precision - 10)`, planes in
@@ -1217,6 +1307,8 @@ __global__ void __launch_bounds__(128) k_fwd_422_src(const __grid_constant__ Fwd
     }
 }
 
+#include "cfb_forward_tma.inl"
+
 // ----------------------------------------------------------------------------
 // host-side launchers (called from cfb_api.cu).  gridDim.y = row blocks + 1 border CTA row.
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -1268,11 +1360,27 @@ cudaError_t launch_fwd_byr4(const FwdParams &p, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+// CFB_FWD422 = r1 selects the first-generation kernel (direct LDG into registers; kept for the A/B evidence in profiles/)
+static int fwd422_variant()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CFB_FWD422"); v = (e && !strcmp(e, "r1")) ? 1 : 0; }
+    return v;
+}
+
 cudaError_t launch_fwd_422(const FwdParams &p, cudaStream_t stream)
 {
     dim3 block(32, 4);
     dim3 grid(ceil_div(p.ch[0].width, kStripIn), ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y) + 1, p.nframes);
-    k_fwd_422<<<grid, block, 0, stream>>>(p);
+    if (fwd422_variant() == 1) { k_fwd_422<<<grid, block, 0, stream>>>(p); return cudaGetLastError(); }
+    // one tensor map per frame of the batch: rows of 2 * width bytes, `height` rows, the caller's pitch
+    FwdTmaMaps tm;
+    for (int i = 0; i < p.nframes; i++) {
+        cudaError_t e = tmap_encode_2d(&tm.in_map[i], p.in_base[i] + p.ch[0].in_off, (uint64_t)p.ch[0].width * 2, (uint64_t)p.ch[0].height,
+                                       (uint64_t)p.ch[0].in_pitch, kTmaRowBytes, 2);
+        if (e != cudaSuccess) return e;
+    }
+    k_fwd_422_tma<3><<<grid, block, 4 * kTmaWarpBytes + 4 * kTmaStages * 8, stream>>>(p, tm);
     return cudaGetLastError();
 }
 
