@@ -696,30 +696,55 @@ cfb_error cfb_forward_host(cfb_codec *cd, int n, const void *const *h_frames, in
                            const cfb_quant *quant, void *const *h_coded)
 {
     if (!cd || !h_frames || !quant || !h_coded) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
-    if (n < 1 || n > cd->max_batch) { set_error("batch %d exceeds codec max_batch %d", n, cd->max_batch); return CFB_ERROR_INVALID_ARGUMENT; }
     cfb_context *ctx = cd->ctx;
-    const cfb_layout &L = cd->layout;
-    CFB_CUDA(cudaSetDevice(ctx->device));
-    const int rows = (int)(L.frame_bytes / L.frame_pitch);
-    const void *dfr[kMaxBatch];
-    void *dpy[kMaxBatch];
-    for (int i = 0; i < n; i++) {
-        if (!h_frames[i] || !h_coded[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
-        dfr[i] = cfb_codec_device_frame(cd, i);
-        dpy[i] = cfb_codec_device_pyramid(cd, i);
-        CFB_CUDA(cudaMemcpy2DAsync((void *)dfr[i], L.frame_pitch, h_frames[i], frame_pitch, L.frame_pitch, rows,
-                                   cudaMemcpyHostToDevice, ctx->stream));
-        ctx->h2d_bytes += (uint64_t)L.frame_bytes;
-    }
-    cfb_error err = cfb_forward_device(cd, n, dfr, L.frame_pitch, quant, dpy);
+    cfb_error err = stage_fwd_upload(cd, n, h_frames, frame_pitch, ctx->stream);
+    if (!err) err = stage_fwd_compute(cd, n, quant, false);
+    if (!err) err = stage_fwd_download(cd, n, h_coded, false, 0, ctx->stream);
     if (err) return err;
-    for (int i = 0; i < n; i++) {
-        CFB_CUDA(cudaMemcpyAsync(h_coded[i], dpy[i], (size_t)L.coded_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->d2h_bytes += (uint64_t)L.coded_bytes;
-    }
     CFB_CUDA(stream_wait(ctx));
     return CFB_OK;
 }
+
+}  // extern "C"
+
+namespace cfb {
+
+cfb_error stage_fwd_upload(cfb_codec *cd, int n, const void *const *h_frames, int frame_pitch, cudaStream_t s)
+{
+    if (!cd || !h_frames) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (n < 1 || n > cd->max_batch) { set_error("batch %d exceeds codec max_batch %d", n, cd->max_batch); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_context *ctx = cd->ctx;
+    const cfb_layout &L = cd->layout;
+    if (frame_pitch < L.frame_pitch || (frame_pitch & 15)) { set_error("frame pitch %d must be >= %d and 16-byte aligned", frame_pitch, L.frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
+    CFB_CUDA(cudaSetDevice(ctx->device));
+    const int rows = (int)(L.frame_bytes / L.frame_pitch);
+    for (int i = 0; i < n; i++) {
+        if (!h_frames[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
+        if (frame_pitch == L.frame_pitch)       // contiguous on both sides: one linear copy
+            CFB_CUDA(cudaMemcpyAsync(cfb_codec_device_frame(cd, i), h_frames[i], (size_t)L.frame_pitch * rows, cudaMemcpyHostToDevice, s));
+        else
+            CFB_CUDA(cudaMemcpy2DAsync(cfb_codec_device_frame(cd, i), L.frame_pitch, h_frames[i], frame_pitch, L.frame_pitch, rows,
+                                       cudaMemcpyHostToDevice, s));
+        ctx->h2d_bytes += (uint64_t)L.frame_bytes;
+    }
+    return CFB_OK;
+}
+
+cfb_error stage_fwd_compute(cfb_codec *cd, int n, const cfb_quant *quant, bool sparse)
+{
+    if (!cd || !quant) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (n < 1 || n > cd->max_batch) { set_error("batch %d exceeds codec max_batch %d", n, cd->max_batch); return CFB_ERROR_INVALID_ARGUMENT; }
+    const void *dfr[kMaxBatch];
+    void *dpy[kMaxBatch];
+    for (int i = 0; i < n; i++) { dfr[i] = cfb_codec_device_frame(cd, i); dpy[i] = cfb_codec_device_pyramid(cd, i); }
+    cfb_error err = cfb_forward_device(cd, n, dfr, cd->layout.frame_pitch, quant, dpy);
+    if (!err && sparse) err = sparse_compact_device(cd, n);
+    return err;
+}
+
+}  // namespace cfb
+
+extern "C" {
 
 // ---------------------------------------------------------------------------
 // inverse
@@ -850,29 +875,51 @@ cfb_error cfb_inverse_host(cfb_codec *cd, int n, const void *const *h_coded, con
                            int out_format, void *const *h_frames, int frame_pitch)
 {
     if (!cd || !h_coded || !quant || !h_frames) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_context *ctx = cd->ctx;
+    cfb_error err = stage_inv_upload(cd, n, h_coded, false, ctx->stream);
+    if (!err) err = stage_inv_compute(cd, n, quant, out_format, false);
+    if (!err) err = stage_inv_download(cd, n, h_frames, frame_pitch, out_format, ctx->stream);
+    if (err) return err;
+    CFB_CUDA(stream_wait(ctx));
+    return CFB_OK;
+}
+
+}  // extern "C"
+
+namespace cfb {
+
+// geometry of what the inverse writes into the device frame staging / the caller's buffer at the current resolution
+static cfb_error inv_output_geometry(const cfb_codec *cd, int out_format, int *rows, int *rowbytes, int *dpitch)
+{
+    const cfb_layout &L = cd->layout;
+    int out_w = 0, out_h = 0;
+    cfb_codec_decoded_size(cd, &out_w, &out_h);
+    const int kk = cd->decode_res - 1;          // lowest level that is inverted (0 = all three)
+    *rowbytes = out_w * 2; *dpitch = (out_w * 2 + 15) & ~15;
+    if (out_format == CFB_PIXEL_PLANAR16) {
+        *rows = 0;
+        for (int c = 0; c < L.num_channels; c++) *rows += kk ? L.band[c][kk - 1][0].height : L.band[c][0][0].height * 2;
+        if ((size_t)*dpitch * *rows > cd->frame_stride) { set_error("planar16 output does not fit the codec's frame staging"); return CFB_ERROR_UNSUPPORTED; }
+    } else {
+        *rows = out_h;
+    }
+    return CFB_OK;
+}
+
+cfb_error stage_inv_upload(cfb_codec *cd, int n, const void *const *h_in, bool sparse, cudaStream_t s)
+{
+    if (!cd || !h_in) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
     if (n < 1 || n > cd->max_batch) { set_error("batch %d exceeds codec max_batch %d", n, cd->max_batch); return CFB_ERROR_INVALID_ARGUMENT; }
     cfb_context *ctx = cd->ctx;
     const cfb_layout &L = cd->layout;
     CFB_CUDA(cudaSetDevice(ctx->device));
-    int rows, rowbytes, dpitch;
-    int out_w = 0, out_h = 0;
-    cfb_codec_decoded_size(cd, &out_w, &out_h);
-    const int kk = cd->decode_res - 1;          // lowest level that is inverted (0 = all three)
-    if (out_format == CFB_PIXEL_PLANAR16) {
-        rows = 0;
-        for (int c = 0; c < L.num_channels; c++) rows += kk ? L.band[c][kk - 1][0].height : L.band[c][0][0].height * 2;
-        rowbytes = out_w * 2; dpitch = (out_w * 2 + 15) & ~15;
-        if ((size_t)dpitch * rows > cd->frame_stride) { set_error("planar16 output does not fit the codec's frame staging"); return CFB_ERROR_UNSUPPORTED; }
-    } else {
-        rows = out_h; rowbytes = out_w * 2; dpitch = (out_w * 2 + 15) & ~15;
-    }
-    void *dpy[kMaxBatch], *dfr[kMaxBatch];
+    if (sparse) return sparse_upload(cd, n, h_in, s);
+    const int kk = cd->decode_res - 1;
     for (int i = 0; i < n; i++) {
-        if (!h_coded[i] || !h_frames[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
-        dpy[i] = cfb_codec_device_pyramid(cd, i);
-        dfr[i] = cfb_codec_device_frame(cd, i);
+        if (!h_in[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
+        void *dpy = cfb_codec_device_pyramid(cd, i);
         if (kk == 0) {
-            CFB_CUDA(cudaMemcpyAsync(dpy[i], h_coded[i], (size_t)L.coded_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            CFB_CUDA(cudaMemcpyAsync(dpy, h_in[i], (size_t)L.coded_bytes, cudaMemcpyHostToDevice, s));
             ctx->h2d_bytes += (uint64_t)L.coded_bytes;
         } else {
             // reduced resolution: each channel's bands are laid out LL3, level 3, level 2, level 1, so the levels a
@@ -882,20 +929,62 @@ cfb_error cfb_inverse_host(cfb_codec *cd, int n, const void *const *h_coded, con
                 const int64_t lo = L.band[c][CFB_NUM_LEVELS - 1][0].offset;
                 const cfb_band_layout &last = L.band[c][kk][3];
                 const int64_t hi = last.offset + (int64_t)last.pitch * last.height;
-                CFB_CUDA(cudaMemcpyAsync((unsigned char *)dpy[i] + lo, (const unsigned char *)h_coded[i] + lo, (size_t)(hi - lo),
-                                         cudaMemcpyHostToDevice, ctx->stream));
+                CFB_CUDA(cudaMemcpyAsync((unsigned char *)dpy + lo, (const unsigned char *)h_in[i] + lo, (size_t)(hi - lo),
+                                         cudaMemcpyHostToDevice, s));
                 ctx->h2d_bytes += (uint64_t)(hi - lo);
             }
         }
     }
-    cfb_error err = cfb_inverse_device(cd, n, dpy, quant, out_format, dfr, dpitch);
-    if (err) return err;
-    for (int i = 0; i < n; i++) {
-        CFB_CUDA(cudaMemcpy2DAsync(h_frames[i], frame_pitch, dfr[i], dpitch, rowbytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->d2h_bytes += (uint64_t)rowbytes * rows;
-    }
-    CFB_CUDA(stream_wait(ctx));
     return CFB_OK;
 }
 
-}  // extern "C"
+cfb_error stage_inv_compute(cfb_codec *cd, int n, const cfb_quant *quant, int out_format, bool sparse)
+{
+    if (!cd || !quant) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (n < 1 || n > cd->max_batch) { set_error("batch %d exceeds codec max_batch %d", n, cd->max_batch); return CFB_ERROR_INVALID_ARGUMENT; }
+    int rows, rowbytes, dpitch;
+    cfb_error err = inv_output_geometry(cd, out_format, &rows, &rowbytes, &dpitch);
+    if (err) return err;
+    if (sparse) { err = sparse_expand_device(cd, n); if (err) return err; }
+    void *dpy[kMaxBatch], *dfr[kMaxBatch];
+    for (int i = 0; i < n; i++) { dpy[i] = cfb_codec_device_pyramid(cd, i); dfr[i] = cfb_codec_device_frame(cd, i); }
+    return cfb_inverse_device(cd, n, dpy, quant, out_format, dfr, dpitch);
+}
+
+cfb_error stage_inv_download(cfb_codec *cd, int n, void *const *h_frames, int frame_pitch, int out_format, cudaStream_t s)
+{
+    if (!cd || !h_frames) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (n < 1 || n > cd->max_batch) { set_error("batch %d exceeds codec max_batch %d", n, cd->max_batch); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_context *ctx = cd->ctx;
+    int rows, rowbytes, dpitch;
+    cfb_error err = inv_output_geometry(cd, out_format, &rows, &rowbytes, &dpitch);
+    if (err) return err;
+    if (frame_pitch < rowbytes) { set_error("output pitch %d smaller than a row (%d bytes)", frame_pitch, rowbytes); return CFB_ERROR_INVALID_ARGUMENT; }
+    CFB_CUDA(cudaSetDevice(ctx->device));
+    for (int i = 0; i < n; i++) {
+        if (!h_frames[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
+        if (frame_pitch == rowbytes && dpitch == rowbytes)
+            CFB_CUDA(cudaMemcpyAsync(h_frames[i], cfb_codec_device_frame(cd, i), (size_t)rowbytes * rows, cudaMemcpyDeviceToHost, s));
+        else
+            CFB_CUDA(cudaMemcpy2DAsync(h_frames[i], frame_pitch, cfb_codec_device_frame(cd, i), dpitch, rowbytes, rows, cudaMemcpyDeviceToHost, s));
+        ctx->d2h_bytes += (uint64_t)rowbytes * rows;
+    }
+    return CFB_OK;
+}
+
+cfb_error stage_fwd_download(cfb_codec *cd, int n, void *const *h_out, bool sparse, unsigned guess, cudaStream_t s)
+{
+    if (!cd || !h_out) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (n < 1 || n > cd->max_batch) { set_error("batch %d exceeds codec max_batch %d", n, cd->max_batch); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_context *ctx = cd->ctx;
+    CFB_CUDA(cudaSetDevice(ctx->device));
+    if (sparse) return sparse_download(cd, n, h_out, guess, s);
+    for (int i = 0; i < n; i++) {
+        if (!h_out[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
+        CFB_CUDA(cudaMemcpyAsync(h_out[i], cfb_codec_device_pyramid(cd, i), (size_t)cd->layout.coded_bytes, cudaMemcpyDeviceToHost, s));
+        ctx->d2h_bytes += (uint64_t)cd->layout.coded_bytes;
+    }
+    return CFB_OK;
+}
+
+}  // namespace cfb

@@ -37,6 +37,28 @@ cudaError_t launch_fwd_422_fields(const FwdParams &p, cudaStream_t stream);
 cudaError_t launch_fwd_yu64(const FwdParams &p, cudaStream_t stream);
 cudaError_t launch_fwd_v210(const FwdParams &p, cudaStream_t stream);
 
+// The host forms of the transform as three stages, each on a stream of the caller's choice, so that the frame pool can
+// run uploads, kernels and downloads of different jobs on separate streams (copy engines + SMs all busy).  The compute
+// stage always runs on cfb_context_stream(); the caller orders the stages with events.  Slots [0, n) of the codec's
+// device staging are used.  The synchronous C-ABI calls are these three stages on one stream + a wait.
+cfb_error stage_fwd_upload(cfb_codec *cd, int n, const void *const *h_frames, int frame_pitch, cudaStream_t s);
+cfb_error stage_fwd_compute(cfb_codec *cd, int n, const cfb_quant *quant, bool sparse);
+// sparse: copies header + bitmap + `guess` values of every frame (speculative single pass); dense: the coded region
+cfb_error stage_fwd_download(cfb_codec *cd, int n, void *const *h_out, bool sparse, unsigned guess, cudaStream_t s);
+// sparse only, after the download has completed: fetches the values beyond `guess` (if any frame has more), reports sizes
+cfb_error stage_fwd_tail(cfb_codec *cd, int n, void *const *h_sparse, unsigned guess, cudaStream_t s, size_t *sizes,
+                         unsigned *max_values, bool *more);
+cfb_error stage_inv_upload(cfb_codec *cd, int n, const void *const *h_in, bool sparse, cudaStream_t s);
+cfb_error stage_inv_compute(cfb_codec *cd, int n, const cfb_quant *quant, int out_format, bool sparse);
+cfb_error stage_inv_download(cfb_codec *cd, int n, void *const *h_frames, int frame_pitch, int out_format, cudaStream_t s);
+unsigned sparse_initial_guess(const cfb_codec *cd);
+unsigned sparse_next_guess(const cfb_codec *cd, unsigned max_values);
+// GPU compaction / expansion between the pyramids and the sparse staging buffers of slots [0, n) (kernels only)
+cfb_error sparse_upload(cfb_codec *cd, int n, const void *const *h_sparse, cudaStream_t s);
+cfb_error sparse_download(cfb_codec *cd, int n, void *const *h_sparse, unsigned guess, cudaStream_t s);
+cfb_error sparse_compact_device(cfb_codec *cd, int n);
+cfb_error sparse_expand_device(cfb_codec *cd, int n);
+
 }  // namespace cfb
 
 struct cfb_context {

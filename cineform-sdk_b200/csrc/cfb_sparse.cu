@@ -215,6 +215,96 @@ static cfb_error sparse_prepare(cfb_codec *cd, SparseParams &p, int n)
     return CFB_OK;
 }
 
+namespace cfb {
+
+unsigned sparse_initial_guess(const cfb_codec *cd) { return (unsigned)(cd->layout.coded_bytes / 2) / 8; }
+
+unsigned sparse_next_guess(const cfb_codec *cd, unsigned max_values)
+{
+    const unsigned nwords = (unsigned)(cd->layout.coded_bytes / 2);
+    unsigned g = (max_values + max_values / 8 + 4096 + 63u) & ~63u;
+    if (g > nwords) g = nwords;           // clamp AFTER the rounding: the copy must stay inside cfb_sparse_max_bytes
+    return g;
+}
+
+cfb_error sparse_compact_device(cfb_codec *cd, int n)
+{
+    SparseParams sp;
+    cfb_error err = sparse_prepare(cd, sp, n);
+    if (err) return err;
+    CFB_CUDA(launch_sparse_compact(sp, cd->ctx->stream));
+    cd->ctx->kernel_launches += 3;
+    return CFB_OK;
+}
+
+cfb_error sparse_expand_device(cfb_codec *cd, int n)
+{
+    SparseParams sp;
+    cfb_error err = sparse_prepare(cd, sp, n);
+    if (err) return err;
+    CFB_CUDA(launch_sparse_expand(sp, cd->ctx->stream));
+    cd->ctx->kernel_launches += 3;
+    return CFB_OK;
+}
+
+cfb_error sparse_download(cfb_codec *cd, int n, void *const *h_sparse, unsigned guess, cudaStream_t s)
+{
+    SparseParams sp;
+    cfb_error err = sparse_prepare(cd, sp, n);
+    if (err) return err;
+    if (guess > sp.nwords) guess = sp.nwords;       // never more than the caller's buffer holds (cfb_sparse_max_bytes)
+    for (int i = 0; i < n; i++) {
+        if (!h_sparse[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
+        const size_t bytes = (size_t)sp.values_off + (size_t)guess * 2;
+        CFB_CUDA(cudaMemcpyAsync(h_sparse[i], sp.sparse[i], bytes, cudaMemcpyDeviceToHost, s));
+        cd->ctx->d2h_bytes += (uint64_t)bytes;
+    }
+    return CFB_OK;
+}
+
+cfb_error stage_fwd_tail(cfb_codec *cd, int n, void *const *h_sparse, unsigned guess, cudaStream_t s, size_t *sizes,
+                         unsigned *max_values, bool *more)
+{
+    SparseParams sp;
+    cfb_error err = sparse_prepare(cd, sp, n);
+    if (err) return err;
+    if (guess > sp.nwords) guess = sp.nwords;
+    unsigned maxv = 0;
+    *more = false;
+    for (int i = 0; i < n; i++) {
+        const unsigned nv = ((const unsigned *)h_sparse[i])[2];
+        if (nv > sp.nwords) { set_error("sparse header %d corrupt", i); return CFB_ERROR_UNEXPECTED; }
+        if (nv > maxv) maxv = nv;
+        if (nv > guess) {
+            const size_t off = (size_t)sp.values_off + (size_t)guess * 2, rest = (size_t)(nv - guess) * 2;
+            CFB_CUDA(cudaMemcpyAsync((unsigned char *)h_sparse[i] + off, sp.sparse[i] + off, rest, cudaMemcpyDeviceToHost, s));
+            cd->ctx->d2h_bytes += (uint64_t)rest;
+            *more = true;
+        }
+        if (sizes) sizes[i] = (size_t)sp.values_off + (size_t)nv * 2;
+    }
+    if (max_values) *max_values = maxv;
+    return CFB_OK;
+}
+
+cfb_error sparse_upload(cfb_codec *cd, int n, const void *const *h_sparse, cudaStream_t s)
+{
+    SparseParams sp;
+    cfb_error err = sparse_prepare(cd, sp, n);
+    if (err) return err;
+    for (int i = 0; i < n; i++) {
+        if (!h_sparse[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
+        const unsigned *h = (const unsigned *)h_sparse[i];
+        if (h[0] != 0x50534643u || h[1] != sp.nwords || h[2] > sp.nwords) { set_error("sparse buffer %d: bad header", i); return CFB_ERROR_BADFORMAT; }
+        const size_t bytes = (size_t)sp.values_off + (size_t)h[2] * 2;
+        CFB_CUDA(cudaMemcpyAsync(sp.sparse[i], h_sparse[i], bytes, cudaMemcpyHostToDevice, s));
+        cd->ctx->h2d_bytes += (uint64_t)bytes;
+    }
+    return CFB_OK;
+}
+
+}  // namespace cfb
+
 extern "C" {
 
 size_t cfb_sparse_max_bytes(const cfb_layout *L)
@@ -238,56 +328,24 @@ cfb_error cfb_forward_host_sparse(cfb_codec *cd, int n, const void *const *h_fra
     if (!cd || !h_frames || !quant || !h_sparse) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
     if (n < 1 || n > cd->max_batch) { set_error("batch %d exceeds codec max_batch %d", n, cd->max_batch); return CFB_ERROR_INVALID_ARGUMENT; }
     cfb_context *ctx = cd->ctx;
-    const cfb_layout &L = cd->layout;
-    CFB_CUDA(cudaSetDevice(ctx->device));
-    SparseParams sp;
-    cfb_error err = sparse_prepare(cd, sp, n);
+    for (int i = 0; i < n; i++) if (!h_sparse[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_error err = stage_fwd_upload(cd, n, h_frames, frame_pitch, ctx->stream);
+    if (!err) err = stage_fwd_compute(cd, n, quant, true);
     if (err) return err;
-    const int rows = (int)(L.frame_bytes / L.frame_pitch);
-    const void *dfr[kMaxBatch];
-    void *dpy[kMaxBatch];
-    for (int i = 0; i < n; i++) {
-        if (!h_frames[i] || !h_sparse[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
-        dfr[i] = cfb_codec_device_frame(cd, i);
-        dpy[i] = cfb_codec_device_pyramid(cd, i);
-        CFB_CUDA(cudaMemcpy2DAsync((void *)dfr[i], L.frame_pitch, h_frames[i], frame_pitch, L.frame_pitch, rows,
-                                   cudaMemcpyHostToDevice, ctx->stream));
-        ctx->h2d_bytes += (uint64_t)L.frame_bytes;
-    }
-    err = cfb_forward_device(cd, n, dfr, L.frame_pitch, quant, dpy);
-    if (err) return err;
-    CFB_CUDA(launch_sparse_compact(sp, ctx->stream));
-    ctx->kernel_launches += 3;
     // Speculative single-pass D2H: copy header + bitmap + as many values as recent frames needed (+12 %) right behind the
     // kernels, without a host round trip; only if a frame turns out to hold more values is the remainder fetched.
-    // (never more than the caller's buffer holds: cfb_sparse_max_bytes = values_off + nwords * 2)
-    unsigned guess = cd->value_guess ? cd->value_guess : sp.nwords / 8;
-    if (guess > sp.nwords) guess = sp.nwords;
-    for (int i = 0; i < n; i++) {
-        const size_t bytes = (size_t)sp.values_off + (size_t)guess * 2;
-        CFB_CUDA(cudaMemcpyAsync(h_sparse[i], sp.sparse[i], bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->d2h_bytes += (uint64_t)bytes;
-    }
+    const unsigned guess = cd->value_guess ? cd->value_guess : sparse_initial_guess(cd);
+    err = stage_fwd_download(cd, n, h_sparse, true, guess, ctx->stream);
+    if (err) return err;
     CFB_CUDA(stream_wait(ctx));
     unsigned maxv = 0;
     bool more = false;
-    for (int i = 0; i < n; i++) {
-        const unsigned nv = ((const unsigned *)h_sparse[i])[2];
-        if (nv > maxv) maxv = nv;
-        if (nv > guess) {
-            const size_t off = (size_t)sp.values_off + (size_t)guess * 2, rest = (size_t)(nv - guess) * 2;
-            CFB_CUDA(cudaMemcpyAsync((unsigned char *)h_sparse[i] + off, sp.sparse[i] + off, rest, cudaMemcpyDeviceToHost, ctx->stream));
-            ctx->d2h_bytes += (uint64_t)rest;
-            more = true;
-        }
-        if (sparse_bytes) sparse_bytes[i] = (size_t)sp.values_off + (size_t)nv * 2;
-    }
+    size_t sizes[kMaxBatch];
+    err = stage_fwd_tail(cd, n, h_sparse, guess, ctx->stream, sizes, &maxv, &more);
+    if (err) return err;
     if (more) CFB_CUDA(stream_wait(ctx));
-    {
-        unsigned g = (maxv + maxv / 8 + 4096 + 63u) & ~63u;
-        if (g > sp.nwords) g = sp.nwords;           // clamp AFTER the rounding: the copy must stay inside cfb_sparse_max_bytes
-        cd->value_guess = g;
-    }
+    if (sparse_bytes) for (int i = 0; i < n; i++) sparse_bytes[i] = sizes[i];
+    cd->value_guess = sparse_next_guess(cd, maxv);
     return CFB_OK;
 }
 
@@ -295,35 +353,12 @@ cfb_error cfb_inverse_host_sparse(cfb_codec *cd, int n, const void *const *h_spa
                                   int out_format, void *const *h_frames, int frame_pitch)
 {
     if (!cd || !h_sparse || !quant || !h_frames) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
-    if (n < 1 || n > cd->max_batch) { set_error("batch %d exceeds codec max_batch %d", n, cd->max_batch); return CFB_ERROR_INVALID_ARGUMENT; }
     if (out_format != CFB_PIXEL_YUYV && out_format != CFB_PIXEL_UYVY) { set_error("sparse inverse supports packed 4:2:2 output"); return CFB_ERROR_UNSUPPORTED; }
     cfb_context *ctx = cd->ctx;
-    CFB_CUDA(cudaSetDevice(ctx->device));
-    SparseParams sp;
-    cfb_error err = sparse_prepare(cd, sp, n);
+    cfb_error err = stage_inv_upload(cd, n, h_sparse, true, ctx->stream);
+    if (!err) err = stage_inv_compute(cd, n, quant, out_format, true);
+    if (!err) err = stage_inv_download(cd, n, h_frames, frame_pitch, out_format, ctx->stream);
     if (err) return err;
-    void *dpy[kMaxBatch], *dfr[kMaxBatch];
-    for (int i = 0; i < n; i++) {
-        if (!h_sparse[i] || !h_frames[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
-        const unsigned *h = (const unsigned *)h_sparse[i];
-        if (h[0] != 0x50534643u || h[1] != sp.nwords || h[2] > sp.nwords) { set_error("sparse buffer %d: bad header", i); return CFB_ERROR_BADFORMAT; }
-        const size_t bytes = (size_t)sp.values_off + (size_t)h[2] * 2;
-        dpy[i] = cfb_codec_device_pyramid(cd, i);
-        dfr[i] = cfb_codec_device_frame(cd, i);
-        CFB_CUDA(cudaMemcpyAsync(sp.sparse[i], h_sparse[i], bytes, cudaMemcpyHostToDevice, ctx->stream));
-        ctx->h2d_bytes += (uint64_t)bytes;
-    }
-    CFB_CUDA(launch_sparse_expand(sp, ctx->stream));
-    ctx->kernel_launches += 3;
-    int out_w = 0, out_h = 0;
-    cfb_codec_decoded_size(cd, &out_w, &out_h);     // reduced-resolution decodes return the LL1 / LL2 picture
-    const int rowbytes = out_w * 2, dpitch = (rowbytes + 15) & ~15;
-    err = cfb_inverse_device(cd, n, dpy, quant, out_format, dfr, dpitch);
-    if (err) return err;
-    for (int i = 0; i < n; i++) {
-        CFB_CUDA(cudaMemcpy2DAsync(h_frames[i], frame_pitch, dfr[i], dpitch, rowbytes, out_h, cudaMemcpyDeviceToHost, ctx->stream));
-        ctx->d2h_bytes += (uint64_t)rowbytes * out_h;
-    }
     CFB_CUDA(stream_wait(ctx));
     return CFB_OK;
 }

@@ -6,6 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
 pkg = importlib.import_module("cineform-sdk_b200")
 W, H = 3840, 2160
+pkg.bind_thread_to_device(0)        # as bench.py: pinned buffers on the GPU's own NUMA node
 desc = pkg.FrameDesc(W, H, pkg.PIXEL_YUYV); quant = pkg.quant_for_quality(desc, 4)
 frames = bench.synthetic_frames(16, W, H)
 slots, batch = int(sys.argv[1]), int(sys.argv[2])
