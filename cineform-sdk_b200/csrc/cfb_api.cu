@@ -773,9 +773,18 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
     const bool is422 = (fmt == CFB_PIXEL_YUYV || fmt == CFB_PIXEL_UYVY || fmt == CFB_PIXEL_YU64 || fmt == CFB_PIXEL_V210);
     int out_w = 0, out_h = 0;
     cfb_codec_decoded_size(cd, &out_w, &out_h);
+    const bool is444 = (fmt == CFB_PIXEL_RG48 || fmt == CFB_PIXEL_PLANAR16 || (fmt >= CFB_PIXEL_RG30 && fmt <= CFB_PIXEL_DPX0));
     if (out_format == CFB_PIXEL_YUYV || out_format == CFB_PIXEL_UYVY) {
         if (!is422) { set_error("8-bit 4:2:2 output needs a 4:2:2 codec"); return CFB_ERROR_BADFORMAT; }
         if (frame_pitch < out_w * 2 || (frame_pitch & 15)) { set_error("bad output pitch %d", frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
+    } else if (out_format == CFB_PIXEL_YU64 || out_format == CFB_PIXEL_RG48) {
+        // 16-bit packed outputs of the final level (the reference's ...ToRow16u family): full resolution, progressive
+        if (out_format == CFB_PIXEL_YU64 ? !is422 : !is444) { set_error("YU64 output needs a 4:2:2 codec, RG48 output a 4:4:4 codec"); return CFB_ERROR_BADFORMAT; }
+        if (cd->decode_res != CFB_RESOLUTION_FULL || cd->interlaced) { set_error("16-bit packed output: full-resolution progressive decode only"); return CFB_ERROR_UNSUPPORTED; }
+        const int bpp = (out_format == CFB_PIXEL_YU64) ? 4 : 6;
+        if (frame_pitch < out_w * bpp || (frame_pitch & 15)) { set_error("bad output pitch %d", frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
+        for (int c = 0; c < L.num_channels; c++)
+            if (L.band[c][0][0].width < 16) { set_error("16-bit packed output needs level-1 bands at least 16 coefficients wide"); return CFB_ERROR_UNSUPPORTED; }
     } else if (out_format == CFB_PIXEL_PLANAR16) {
         if (frame_pitch < out_w * 2 || (frame_pitch & 15)) { set_error("bad output pitch %d", frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
     } else { set_error("output format %d not implemented", out_format); return CFB_ERROR_UNSUPPORTED; }
@@ -864,7 +873,20 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
         for (int c = 0; c < 3; c++) { p.ch[c].out_off = 0; p.ch[c].out_pitch = frame_pitch; }
         p.shift = L.precision - 8; p.uyvy = (out_format == CFB_PIXEL_UYVY);
         p.th = pick_th((p.ch[0].width + kInvStrip - 1) / kInvStrip, p.ch[0].height, n, ctx->sm_count);
-        CFB_CUDA(launch_inv_422(p, ctx->stream));
+        if (out_format == CFB_PIXEL_YU64 || out_format == CFB_PIXEL_RG48) {
+            p.up_shift = 16 - L.precision;
+            p.hi_simd = ((1 << L.precision) - 1) << p.up_shift;
+            for (int c = 0; c < 3; c++) {
+                // InvertHorizontalStrip16s.c:16589-16594: the 8-column loop ends at post_column = width - width % 8 - 16; one more
+                // group of 7 columns is produced with the SIMD rule, everything right of it by the scalar code
+                const int w = p.ch[c].width;
+                p.tail_col[c] = (w - (w % 8) - 16) + 7;
+            }
+            if (out_format == CFB_PIXEL_RG48) CFB_CUDA(launch_inv_444_rg48(p, ctx->stream));
+            else CFB_CUDA(launch_inv_422(p, true, ctx->stream));
+        } else {
+            CFB_CUDA(launch_inv_422(p, false, ctx->stream));
+        }
     }
     ctx->kernel_launches++;
     ctx->frames_inverse += n;
@@ -895,7 +917,11 @@ static cfb_error inv_output_geometry(const cfb_codec *cd, int out_format, int *r
     int out_w = 0, out_h = 0;
     cfb_codec_decoded_size(cd, &out_w, &out_h);
     const int kk = cd->decode_res - 1;          // lowest level that is inverted (0 = all three)
-    *rowbytes = out_w * 2; *dpitch = (out_w * 2 + 15) & ~15;
+    const int bpp = (out_format == CFB_PIXEL_YU64) ? 4 : (out_format == CFB_PIXEL_RG48) ? 6 : 2;
+    *rowbytes = out_w * bpp; *dpitch = (out_w * bpp + 15) & ~15;
+    if ((out_format == CFB_PIXEL_YU64 || out_format == CFB_PIXEL_RG48) && (size_t)*dpitch * out_h > cd->frame_stride) {
+        set_error("16-bit packed output does not fit the codec's frame staging"); return CFB_ERROR_UNSUPPORTED;
+    }
     if (out_format == CFB_PIXEL_PLANAR16) {
         *rows = 0;
         for (int c = 0; c < L.num_channels; c++) *rows += kk ? L.band[c][kk - 1][0].height : L.band[c][0][0].height * 2;

@@ -75,6 +75,12 @@ struct InvParams {
     InvGeom ch[kMaxChannels];
     const unsigned char *in_base[kMaxBatch];
     unsigned char *out_base[kMaxBatch];
+    // 16-bit unsigned outputs (YU64, RG48): v = max(t >> 1, 0) << up_shift, limited to hi_simd in the columns the
+    // reference's 8-column SSE2 loop produces and to 65535 from band column tail_col[c] on (scalar tail + right border:
+    // InvertHorizontalStrip16s.c:16571 InvertHorizontalStrip16sToRow16u, `protection` clamp vs SATURATE_16U)
+    int up_shift;       // 16 - precision
+    int hi_simd;        // ((1 << precision) - 1) << up_shift
+    int tail_col[kMaxChannels];
 };
 
 // interlaced (field) inverse: per (frame, channel, band row, strip) carry-in of the difference-coded HL band

@@ -389,7 +389,15 @@ __device__ __forceinline__ unsigned pack_u8x4(int a, int b, int c, int d) {
     return r;
 }
 
-template <bool SMALLDQ>
+// 16-bit unsigned output sample of the final level: see InvParams::up_shift (the reference's ...ToRow16u rule)
+__device__ __forceinline__ unsigned row16u(int t, int up_shift, int hi) {
+    return (unsigned)min(max(t >> 1, 0) << up_shift, hi);
+}
+
+// OUT16 = false: packed 8-bit YUYV / UYVY.  OUT16 = true: packed 16-bit Y0 C1 Y1 C3 (YU64; C1 = channel 1, C3 = channel 2,
+// as the YU64 encoder input assigns them), the reference's 16-bit row output (decoder.c:26351-26366 ->
+// TransformInverseSpatialUniversalThreadedToRow16u -> InvertHorizontalStrip16s.c:17462 / :16571) -- no dither, bit-exact.
+template <bool SMALLDQ, bool OUT16>
 __global__ void __launch_bounds__(128) k_inv_422(const __grid_constant__ InvParams p)
 {
     const int lane = threadIdx.x;
@@ -409,11 +417,32 @@ __global__ void __launch_bounds__(128) k_inv_422(const __grid_constant__ InvPara
     const bool has_border = (strip == 0) || ((strip + 1) * kInvStrip + 4 >= gy.width);
     const unsigned ycol = (unsigned)(col0 * 2), ccol = (unsigned)col0;      // byte offsets (chroma: 2 columns of 2 bytes)
     const unsigned char *in = p.in_base[f];
-    unsigned char *out = p.out_base[f] + gy.out_off + (long long)col0 * 4;     // 2 bytes per luma sample, 2 samples per column
+    unsigned char *out = p.out_base[f] + gy.out_off + (long long)col0 * (OUT16 ? 8 : 4);     // 2 (4) bytes per luma sample, 2 samples per column
 
     const int sh = p.shift + 1;     // final >>1 of the filter merged with the >> (precision-8) reduction
     auto emit = [&](int r, const int *ye, const int *yo, const int *ue, const int *uo, const int *ve, const int *vo) {
         unsigned char *o = out + (long long)(2 * r) * gy.out_pitch;
+        if (OUT16) {
+            const int us = p.up_shift;
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const int *yy = rr ? yo : ye, *uu = rr ? uo : ue, *vv = rr ? vo : ve;
+                unsigned w[8];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    // luma band column col0 + k -> samples 2k, 2k + 1; chroma band column col0 / 2 + (k >> 1) -> sample k
+                    const int hy = (col0 + k >= p.tail_col[0]) ? 65535 : p.hi_simd;
+                    const int hc1 = ((col0 >> 1) + (k >> 1) >= p.tail_col[1]) ? 65535 : p.hi_simd;
+                    const int hc2 = ((col0 >> 1) + (k >> 1) >= p.tail_col[2]) ? 65535 : p.hi_simd;
+                    // pixel pair k: words (Y0, C1) (Y1, C3); C1 = channel 1 (the v arrays), C3 = channel 2 (the u arrays)
+                    w[2 * k] = row16u(yy[2 * k], us, hy) | (row16u(vv[k], us, hc1) << 16);
+                    w[2 * k + 1] = row16u(yy[2 * k + 1], us, hy) | (row16u(uu[k], us, hc2) << 16);
+                }
+                unsigned char *q = o + (rr ? gy.out_pitch : 0);
+                *reinterpret_cast<uint4 *>(q) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4 *>(q + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+        } else {
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {
             const int *yy = rr ? yo : ye, *uu = rr ? uo : ue, *vv = rr ? vo : ve;
@@ -428,6 +457,7 @@ __global__ void __launch_bounds__(128) k_inv_422(const __grid_constant__ InvPara
                 w[k] = p.uyvy ? pack_u8x4(cu, ya, cv, yb) : pack_u8x4(ya, cu, yb, cv);
             }
             *reinterpret_cast<uint4 *>(o + (rr ? gy.out_pitch : 0)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
         }
     };
 
@@ -461,6 +491,82 @@ __global__ void __launch_bounds__(128) k_inv_422(const __grid_constant__ InvPara
         inv_step<2, SMALLDQ>(su, gu, in, r, y1, H, ccol, active, has_border, left_border, right_border, ue, uo);
         inv_step<2, SMALLDQ>(sv, gv, in, r, y1, H, ccol, active, has_border, left_border, right_border, ve, vo);
         if (writer) emit(r, ye, yo, ue, uo, ve, vo);
+    }
+}
+
+// ----------------------------------------------------------------------------
+// final level of a 4:4:4 frame (channels G, R, B): 12 bands -> packed 16-bit R,G,B (RG48).
+// Reference: Codec/decoder.c:26886 -> wavelet.c:4947 TransformInverseRGB444ToRGB48: InvertSpatial{Top,Middle,Bottom}Row16sToYUV16
+// per channel (horizontal stage InvertHorizontalStrip16s.c:16571 ...ToRow16u: max(t >> 1, 0) << (16 - precision), limited
+// as InvParams::hi_simd / tail_col describe), then ConvertPlanarRGB16uToPackedRGB48 (plane 1 -> R, 0 -> G, 2 -> B).
+// One warp reconstructs all three channels of its strip, so every lane owns 8 whole pixels = 48 contiguous bytes.
+template <bool SMALLDQ>
+__global__ void __launch_bounds__(128) k_inv_444_rg48(const __grid_constant__ InvParams p)
+{
+    const int lane = threadIdx.x;
+    const int f = blockIdx.z;
+    const InvGeom &gg = p.ch[0];
+    const InvGeom &gr = p.ch[1];
+    const InvGeom &gb = p.ch[2];
+    const int strip = blockIdx.x;
+    if (strip * kInvStrip >= gg.width) return;
+    const int H = gg.height;
+    const int col0 = strip * kInvStrip - 4 + lane * 4;
+    const bool active = (col0 >= 0) && (col0 < gg.width);
+    const bool writer = active && lane >= 1 && lane <= 30;
+    const bool left_border = (col0 == 0);
+    const bool right_border = (col0 + 4 == gg.width);
+    const bool has_border = (strip == 0) || ((strip + 1) * kInvStrip + 4 >= gg.width);
+    const unsigned cb = (unsigned)(col0 * 2);
+    const unsigned char *in = p.in_base[f];
+    unsigned char *out = p.out_base[f] + gg.out_off + (long long)col0 * 12;        // 2 pixels per band column, 6 bytes per pixel
+    const int us = p.up_shift;
+
+    auto emit = [&](int r, const int *ge, const int *go, const int *re, const int *ro, const int *be, const int *bo) {
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const int *G = rr ? go : ge, *R = rr ? ro : re, *B = rr ? bo : be;
+            unsigned short v[24];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int bc = col0 + (i >> 1);
+                v[3 * i + 0] = (unsigned short)row16u(R[i], us, bc >= p.tail_col[1] ? 65535 : p.hi_simd);
+                v[3 * i + 1] = (unsigned short)row16u(G[i], us, bc >= p.tail_col[0] ? 65535 : p.hi_simd);
+                v[3 * i + 2] = (unsigned short)row16u(B[i], us, bc >= p.tail_col[2] ? 65535 : p.hi_simd);
+            }
+            unsigned w[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) w[i] = (unsigned)v[2 * i] | ((unsigned)v[2 * i + 1] << 16);
+            unsigned char *q = out + (long long)(2 * r + rr) * gg.out_pitch;
+            *reinterpret_cast<uint4 *>(q) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4 *>(q + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+            *reinterpret_cast<uint4 *>(q + 32) = make_uint4(w[8], w[9], w[10], w[11]);
+        }
+    };
+
+    if (blockIdx.y == gridDim.y - 1) {          // border warps: band rows 0 and H-1
+        if (threadIdx.y > 1) return;
+        const bool bottom = (threadIdx.y == 1);
+        int ge[8], go[8], re[8], ro[8], be[8], bo[8];
+        inv_border_row<4>(gg, in, bottom, H, cb, active, has_border, left_border, right_border, ge, go);
+        inv_border_row<4>(gr, in, bottom, H, cb, active, has_border, left_border, right_border, re, ro);
+        inv_border_row<4>(gb, in, bottom, H, cb, active, has_border, left_border, right_border, be, bo);
+        if (writer) emit(bottom ? H - 1 : 0, ge, go, re, ro, be, bo);
+        return;
+    }
+    const int y0 = max((int)(blockIdx.y * blockDim.y + threadIdx.y) * p.th, 1);
+    const int y1 = min((int)(blockIdx.y * blockDim.y + threadIdx.y + 1) * p.th, H - 1);
+    if (y0 >= y1) return;
+    InvChan<4> sg, sr, sb;
+    inv_prologue<4, SMALLDQ>(sg, gg, in, y0, H, cb, active);
+    inv_prologue<4, SMALLDQ>(sr, gr, in, y0, H, cb, active);
+    inv_prologue<4, SMALLDQ>(sb, gb, in, y0, H, cb, active);
+    for (int r = y0; r < y1; r++) {
+        int ge[8], go[8], re[8], ro[8], be[8], bo[8];
+        inv_step<4, SMALLDQ>(sg, gg, in, r, y1, H, cb, active, has_border, left_border, right_border, ge, go);
+        inv_step<4, SMALLDQ>(sr, gr, in, r, y1, H, cb, active, has_border, left_border, right_border, re, ro);
+        inv_step<4, SMALLDQ>(sb, gb, in, r, y1, H, cb, active, has_border, left_border, right_border, be, bo);
+        if (writer) emit(r, ge, go, re, ro, be, bo);
     }
 }
 
@@ -677,13 +783,24 @@ cudaError_t launch_inv_plane(const InvParams &p, int descale, cudaStream_t strea
     return cudaGetLastError();
 }
 
-cudaError_t launch_inv_422(const InvParams &p, cudaStream_t stream)
+cudaError_t launch_inv_422(const InvParams &p, bool out16, cudaStream_t stream)
 {
     dim3 block(32, 4);
     dim3 grid(ceil_div_i(p.ch[0].width, kInvStrip), ceil_div_i(ceil_div_i(p.ch[0].height, p.th), (int)block.y) + 1, p.nframes);
     bool small = true;
     for (int c = 0; c < 3; c++) for (int b = 1; b < 4; b++) small = small && (p.ch[c].dq[b] >= 0 && p.ch[c].dq[b] <= 255);
-    if (small) k_inv_422<true><<<grid, block, 0, stream>>>(p); else k_inv_422<false><<<grid, block, 0, stream>>>(p);
+    if (out16) { if (small) k_inv_422<true, true><<<grid, block, 0, stream>>>(p); else k_inv_422<false, true><<<grid, block, 0, stream>>>(p); }
+    else { if (small) k_inv_422<true, false><<<grid, block, 0, stream>>>(p); else k_inv_422<false, false><<<grid, block, 0, stream>>>(p); }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_inv_444_rg48(const InvParams &p, cudaStream_t stream)
+{
+    dim3 block(32, 4);
+    dim3 grid(ceil_div_i(p.ch[0].width, kInvStrip), ceil_div_i(ceil_div_i(p.ch[0].height, p.th), (int)block.y) + 1, p.nframes);
+    bool small = true;
+    for (int c = 0; c < 3; c++) for (int b = 1; b < 4; b++) small = small && (p.ch[c].dq[b] >= 0 && p.ch[c].dq[b] <= 255);
+    if (small) k_inv_444_rg48<true><<<grid, block, 0, stream>>>(p); else k_inv_444_rg48<false><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

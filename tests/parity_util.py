@@ -404,3 +404,64 @@ def rgb30_planes(r, g, b, precision=12):
     """planes the reference transforms: G, R, B at `precision` bits (value << (precision - 10))."""
     sh = precision - 10
     return [(g.astype(np.int32) << sh).astype(np.int16), (r.astype(np.int32) << sh).astype(np.int16), (b.astype(np.int32) << sh).astype(np.int16)]
+
+
+# ---------------------------------------------------------------- 16-bit packed outputs of the final inverse level
+def row16u_tail_col(band_width):
+    """First band column produced by the scalar tail of Codec/InvertHorizontalStrip16s.c:16571 InvertHorizontalStrip16sToRow16u
+    (8-column SSE2 loop up to post_column = width - width % 8 - 16, one more group of 7 columns with the SIMD rule)."""
+    return (band_width - band_width % 8 - 16) + 7
+
+
+def row16u(plane, precision):
+    """The reference's unsigned 16-bit row output of one reconstructed channel: max(v, 0) << (16 - precision), limited to
+    ((1 << precision) - 1) << shift where its SSE2 loop runs (the `protection` clamp) and to 65535 in the scalar tail and
+    at the right border (SATURATE_16U)."""
+    s = 16 - precision
+    v = np.maximum(plane.astype(np.int64), 0) << s
+    hi = np.full(plane.shape[1], ((1 << precision) - 1) << s, np.int64)
+    hi[2 * row16u_tail_col(plane.shape[1] // 2):] = 65535
+    return np.minimum(v, hi[None, :]).astype(np.uint16)
+
+
+def pack_yu64(planes, precision=10):
+    """[Y, ch1, ch2] int16 planes -> packed Y0 C1 Y1 C3 (height x 2*width uint16), Codec/decoder.c:26351-26366."""
+    y, c1, c3 = [row16u(p, precision) for p in planes]
+    h, w = y.shape
+    out = np.zeros((h, 2 * w), np.uint16)
+    out[:, 0::2] = y
+    out[:, 1::4] = c1
+    out[:, 3::4] = c3
+    return out
+
+
+def pack_rg48(planes, precision=12):
+    """[G, R, B] int16 planes -> packed R G B (height x 3*width uint16), Codec/wavelet.c:4947 TransformInverseRGB444ToRGB48."""
+    g, r, b = [row16u(p, precision) for p in planes]
+    h, w = g.shape
+    out = np.zeros((h, 3 * w), np.uint16)
+    out[:, 0::3], out[:, 1::3], out[:, 2::3] = r, g, b
+    return out
+
+
+def ref_decode_sample_raw(ref_lib, sample, width, height, decoded_format, num_channels, pitch):
+    """Codec-level reference decode into an arbitrary DECODED_FORMAT_*; returns (bytes (height x pitch), dequantised bands)."""
+    out = np.zeros((height, pitch), np.uint8)
+    dims = np.zeros(num_channels * 9, np.int32)
+    quant = np.zeros(num_channels * 12, np.int32)
+    cap = width * height * 4 * num_channels
+    b = np.zeros(cap, np.int16)
+    sample = np.ascontiguousarray(sample)
+    rc = ref_lib.ref_decode_sample_bands(sample.ctypes.data_as(C.c_void_p), C.c_int64(sample.size), width, height,
+                                         decoded_format, num_channels, out.ctypes.data_as(C.c_void_p), pitch,
+                                         dims.ctypes.data_as(C.c_void_p), quant.ctypes.data_as(C.c_void_p),
+                                         b.ctypes.data_as(C.c_void_p), C.c_int64(cap))
+    assert rc == 0, f"reference decode failed ({rc})"
+    bands, pos = {}, 0
+    for c in range(num_channels):
+        for k in range(3):
+            w, h = int(dims[(c * 3 + k) * 3]), int(dims[(c * 3 + k) * 3 + 1])
+            for bi in range(4):
+                bands[(c, k + 1, BAND_NAMES[bi])] = b[pos:pos + w * h].reshape(h, w).copy()
+                pos += w * h
+    return out, bands
