@@ -429,7 +429,6 @@ cfb_error cfb_pool_submit_inverse_sparse(cfb_pool *pool, uint32_t frame_number, 
                                          const cfb_quant *quant, int out_format, void *h_frame, int frame_pitch)
 {
     if (!pool || !h_frame || !quant || !h_sparse) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
-    if (out_format != CFB_PIXEL_YUYV && out_format != CFB_PIXEL_UYVY) { set_error("sparse inverse supports packed 4:2:2 output"); return CFB_ERROR_UNSUPPORTED; }
     auto j = std::make_shared<Job>();
     j->frame_number = frame_number; j->inverse = true; j->sparse = true; j->src = h_sparse; j->dst = h_frame; j->pitch = frame_pitch;
     j->out_format = out_format; j->quant = *quant;

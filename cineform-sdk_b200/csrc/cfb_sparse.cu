@@ -353,7 +353,6 @@ cfb_error cfb_inverse_host_sparse(cfb_codec *cd, int n, const void *const *h_spa
                                   int out_format, void *const *h_frames, int frame_pitch)
 {
     if (!cd || !h_sparse || !quant || !h_frames) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
-    if (out_format != CFB_PIXEL_YUYV && out_format != CFB_PIXEL_UYVY) { set_error("sparse inverse supports packed 4:2:2 output"); return CFB_ERROR_UNSUPPORTED; }
     cfb_context *ctx = cd->ctx;
     cfb_error err = stage_inv_upload(cd, n, h_sparse, true, ctx->stream);
     if (!err) err = stage_inv_compute(cd, n, quant, out_format, true);

@@ -487,4 +487,50 @@ int ref_time_transform_422(const uint8_t *frame, int width, int height, int pitc
     return 0;
 }
 
+// CPU baseline for the planar sources (BASELINE configs 4 and 5: RG48 -> RGB 4:4:4, BYR4 -> four Bayer-derived planes):
+// time the reference's own calls for the forward path of one frame on one thread --
+//   Codec/encoder.c:2768 ConvertRGB48ToFrame16s (or :2638 ConvertBYR4ToFrame16s), then per channel
+//   Codec/encoder.c:3193 TransformForwardSpatial (level 1) and :3254 ComputeGroupTransformQuant (levels 2, 3).
+// width / height / pitch as the encoder takes them (BYR4: plane dimensions and the doubled pitch, SampleEncoder.cpp:494).
+// One real EncodeSample runs first (outside the timed loop) to build the ENCODER state.  Returns 0 on success.
+int ref_time_forward_planar(const uint8_t *frame, int width, int height, int pitch, int color_format, int num_channels,
+                            int quality, int iters, double *fwd_seconds)
+{
+    ENCODER *enc = (ENCODER *)calloc(1, sizeof(ENCODER));
+    TRANSFORM *tr[FRAME_MAX_CHANNELS];
+    for (int c = 0; c < FRAME_MAX_CHANNELS; c++) { tr[c] = (TRANSFORM *)calloc(1, sizeof(TRANSFORM)); InitTransform(tr[c]); }
+    ENCODING_PARAMETERS p;
+    memset(&p, 0, sizeof(p));
+    p.version = 1; p.gop_length = 1; p.encoded_width = width; p.encoded_height = height;
+    p.fixed_quality = quality; p.progressive = 1; p.format = color_format;
+    p.frame_sampling = FRAME_SAMPLING_444; p.colorspace_yuv = 2; p.colorspace_rgb = 1;
+    if (!InitializeEncoderWithParameters(NULL, enc, tr, num_channels, &p)) return 1;
+    if (g_probe_bayer_format >= 0) { enc->bayer.format = g_probe_bayer_format; enc->encode_curve_preset = g_probe_bayer_preset; }
+    size_t scratch_size = 0;
+    PIXEL *scratch = CreateEncodingBuffer(NULL, width, height, pitch, color_format, 1, true, &scratch_size);
+    const size_t outcap = (size_t)width * height * 16 + 65536;
+    Aligned out(outcap), fr((size_t)pitch * (height + 16) + 64);
+    memcpy(fr.p, frame, (size_t)pitch * height);
+    BITSTREAM bs;
+    InitBitstreamBuffer(&bs, out.as<uint8_t>(), outcap, BITSTREAM_ACCESS_WRITE);
+    if (!EncodeSample(enc, fr.as<uint8_t>(), width, height, pitch, color_format, tr, num_channels, &bs,
+                      scratch, scratch_size, quality, 0, NULL, 0.0f, NULL)) return 2;
+    FRAME *f = enc->frame;
+    if (!f) return 3;
+    const double t0 = now_s();
+    for (int i = 0; i < iters; i++) {
+        if (color_format == COLOR_FORMAT_BYR4)
+            ConvertBYR4ToFrame16s(enc->bayer.format, enc->encode_curve, enc->encode_curve_preset, fr.as<uint8_t>(), pitch, f, enc->codec.precision);
+        else
+            ConvertRGB48ToFrame16s(fr.as<uint8_t>(), pitch, f, (uint8_t *)scratch, enc->codec.precision, color_format);
+        for (int c = 0; c < num_channels; c++) {
+            IMAGE *wavelet = tr[c]->wavelet[0];
+            TransformForwardSpatial(NULL, f->channel[c], 0, wavelet, 1, scratch, scratch_size, 0, wavelet->quant, 0);
+        }
+        ComputeGroupTransformQuant(enc, tr, num_channels);
+    }
+    *fwd_seconds = now_s() - t0;
+    return 0;
+}
+
 }  // extern "C"

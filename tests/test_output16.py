@@ -123,6 +123,7 @@ def test_gpu_16bit_outputs_vs_reference_decoder(pkg, size):
                                                         ("rg48", _sample_444, DECODED_FORMAT_RG48, 6, "PIXEL_RG48", "PIXEL_RG48")):
         sample, prescale = sampler(ref_lib, w, h, "qbist")
         ref_out, bands = pu.ref_decode_sample_raw(ref_lib, sample, w, h, dfmt, 3, w * bpp)
+        bands = {k: v for k, v in bands.items() if not (k[2] == "LL" and k[1] != 3)}        # the coded region: LL3 + highpass
         desc = pkg.FrameDesc(w, h, getattr(pkg, cfb_src))
         unit = pkg.make_quant(pu.UNIT_DIVISORS, prescale)
         with pkg.Context(0) as ctx, pkg.Codec(ctx, desc, 1) as codec:
