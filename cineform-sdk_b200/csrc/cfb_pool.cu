@@ -5,8 +5,8 @@
 // borrowed buffers), but a "worker" is a GPU, not a CPU thread running the SSE2 transform.  Frames are
 // independent, so GPUs never exchange data (no NCCL).
 //
-// Per GPU: ONE issuing thread and ONE completing thread drive three streams
-//     upload (H2D copy engine)  ->  compute (SMs)  ->  download (D2H copy engine)
+// Per GPU: ONE issuing thread and ONE completing thread drive
+//     upload streams (H2D copy engine)  ->  one compute stream per slot (SMs)  ->  download streams (D2H copy engine)
 // chained by events, over `slots` sets of device staging.  The issuer takes up to `batch` queued jobs of its GPU,
 // enqueues their uploads, the kernels (gated by the upload event) and the downloads (gated by the kernel event)
 // without ever waiting for the GPU, so uploads of job k+1, kernels of job k and downloads of job k-1 overlap and both
@@ -51,6 +51,7 @@ constexpr int kCopyStreams = 2;
 
 struct Slot {
     int lane = 0;                           // which of the device's copy-stream pairs this slot uses
+    cfb_context *ctx = nullptr;             // own compute stream: the kernels of a job wait for THAT job's upload only
     cfb_codec *codec = nullptr;             // device staging for `batch` frames (frames, pyramids, sparse buffers)
     cudaEvent_t ev_up = nullptr, ev_k = nullptr, ev_down = nullptr;
     std::vector<std::shared_ptr<Job>> jobs;
@@ -61,7 +62,6 @@ struct Slot {
 
 struct Device {
     int device = 0, index = 0;
-    cfb_context *ctx = nullptr;             // its stream is the compute stream
     // kCopyStreams streams per direction, slots alternate between them: two copies of one direction in flight keep the
     // link busy across copy boundaries (measured with tools/pcie_pattern.py: 42 -> 45 GB/s per direction)
     cudaStream_t s_up[kCopyStreams] = {}, s_down[kCopyStreams] = {};
@@ -113,7 +113,7 @@ cfb_error cfb_pool::issue(Device &d, Slot &s)
     const void *src[kMaxBatch];
     void *dst[kMaxBatch];
     for (int i = 0; i < n; i++) { src[i] = s.jobs[i]->src; dst[i] = s.jobs[i]->dst; }
-    cudaStream_t compute = d.ctx->stream, s_up = d.s_up[s.lane], s_down = d.s_down[s.lane];
+    cudaStream_t compute = s.ctx->stream, s_up = d.s_up[s.lane], s_down = d.s_down[s.lane];
     cfb_error e;
     if (!j0.inverse) {
         e = stage_fwd_upload(s.codec, n, src, j0.pitch, s_up);
@@ -207,7 +207,7 @@ void cfb_pool::issue_loop(Device &d)
         s.issue_error = issue(d, s);
         if (s.issue_error != CFB_OK) {
             // whatever was enqueued before the failure must drain before the staging is reused
-            cudaStreamSynchronize(d.s_up[s.lane]); cudaStreamSynchronize(d.ctx->stream); cudaStreamSynchronize(d.s_down[s.lane]);
+            cudaStreamSynchronize(d.s_up[s.lane]); cudaStreamSynchronize(s.ctx->stream); cudaStreamSynchronize(d.s_down[s.lane]);
             cudaGetLastError();
         }
         {
@@ -279,6 +279,7 @@ static void destroy_device(Device &d)
     cudaSetDevice(d.device);
     for (auto &s : d.slots) {
         if (s->codec) cfb_codec_destroy(s->codec);
+        if (s->ctx) cfb_context_destroy(s->ctx);
         if (s->ev_up) cudaEventDestroy(s->ev_up);
         if (s->ev_k) cudaEventDestroy(s->ev_k);
         if (s->ev_down) cudaEventDestroy(s->ev_down);
@@ -287,7 +288,6 @@ static void destroy_device(Device &d)
         if (d.s_up[k]) cudaStreamDestroy(d.s_up[k]);
         if (d.s_down[k]) cudaStreamDestroy(d.s_down[k]);
     }
-    if (d.ctx) cfb_context_destroy(d.ctx);
 }
 
 cfb_error cfb_pool_create(const int *devices, int ndevices, const cfb_frame_desc *desc,
@@ -309,9 +309,8 @@ cfb_error cfb_pool_create(const int *devices, int ndevices, const cfb_frame_desc
     for (int di = 0; di < ndevices && !err; di++) {
         std::unique_ptr<Device> d(new Device());
         d->device = devices[di]; d->index = di;
-        err = cfb_context_create(devices[di], &d->ctx);
-        if (!err) {
-            cudaError_t ce = cudaSuccess;
+        {
+            cudaError_t ce = cudaSetDevice(devices[di]);
             for (int k = 0; k < kCopyStreams && ce == cudaSuccess; k++) {
                 ce = cudaStreamCreateWithFlags(&d->s_up[k], cudaStreamNonBlocking);
                 if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&d->s_down[k], cudaStreamNonBlocking);
@@ -321,7 +320,8 @@ cfb_error cfb_pool_create(const int *devices, int ndevices, const cfb_frame_desc
         for (int k = 0; k < slots && !err; k++) {
             std::unique_ptr<Slot> s(new Slot());
             s->lane = k % kCopyStreams;
-            err = cfb_codec_create(d->ctx, desc, batch, &s->codec);
+            err = cfb_context_create(devices[di], &s->ctx);
+            if (!err) err = cfb_codec_create(s->ctx, desc, batch, &s->codec);
             if (!err) {
                 cudaError_t ce = cudaEventCreateWithFlags(&s->ev_up, cudaEventDisableTiming);
                 if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&s->ev_k, cudaEventDisableTiming);
@@ -462,12 +462,13 @@ cfb_error cfb_pool_stats(cfb_pool *pool, cfb_stats *out)
 {
     if (!pool || !out) return CFB_ERROR_INVALID_ARGUMENT;
     memset(out, 0, sizeof(*out));
-    for (auto &d : pool->devs) {
-        cfb_stats t;
-        cfb_context_stats(d->ctx, &t);
-        out->kernel_launches += t.kernel_launches; out->frames_forward += t.frames_forward; out->frames_inverse += t.frames_inverse;
-        out->h2d_bytes += t.h2d_bytes; out->d2h_bytes += t.d2h_bytes;
-    }
+    for (auto &d : pool->devs)
+        for (auto &s : d->slots) {
+            cfb_stats t;
+            cfb_context_stats(s->ctx, &t);
+            out->kernel_launches += t.kernel_launches; out->frames_forward += t.frames_forward; out->frames_inverse += t.frames_inverse;
+            out->h2d_bytes += t.h2d_bytes; out->d2h_bytes += t.d2h_bytes;
+        }
     return CFB_OK;
 }
 

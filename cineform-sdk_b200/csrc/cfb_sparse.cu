@@ -10,23 +10,25 @@
 //     values  : the nvalues non-zero int16 words in raster (word index) order
 //
 // over the flat coded region [0, coded_bytes) exactly as laid out by cfb_layout (pitch padding included, it is
-// zero).  Compaction and expansion run on the GPU (three small kernels each: per-256-word segment count,
-// per-frame exclusive scan, scatter / gather); the host helpers cfb_sparse_expand / cfb_sparse_compact are
+// zero).  Compaction and expansion run on the GPU (three small kernels each: count per CTA of 8192 words,
+// per-frame exclusive scan of the ~2000 CTA counts, scatter / gather with the position inside the CTA recomputed); the host helpers cfb_sparse_expand / cfb_sparse_compact are
 // pure format conversions for callers that want dense bands.
 #include "cfb_host.h"
 
 namespace cfb {
 
 constexpr int kSeg = 256;           // words per segment (one warp, 8 words per lane)
+constexpr int kBlockSegs = 32;      // segments per CTA (32 warps): the unit of the cross-CTA prefix sum
 
 struct SparseParams {
     int nframes;
     unsigned nwords;                // int16 words in the coded region
     unsigned nseg;
+    unsigned nblocks;               // ceil(nseg / kBlockSegs)
     unsigned bitmap_off, values_off;            // byte offsets inside a sparse buffer
     const unsigned char *dense[kMaxBatch];      // pyramids (coded region at offset 0)
     unsigned char *sparse[kMaxBatch];
-    unsigned *counts[kMaxBatch];                // nseg + 1 entries: counts, then exclusive offsets after the scan
+    unsigned *counts[kMaxBatch];                // nblocks + 1 entries: per-CTA counts, then exclusive offsets after the scan
 };
 
 __device__ __forceinline__ unsigned nonzero_mask8(const uint4 &w) {
@@ -38,75 +40,91 @@ __device__ __forceinline__ unsigned nonzero_mask8(const uint4 &w) {
     return m;
 }
 
-// A: per segment, bitmap + count
-__global__ void __launch_bounds__(256) k_sparse_count(const __grid_constant__ SparseParams p)
+__device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    return v;
+}
+
+// exclusive offset of this warp's segment inside its CTA + the CTA total (all 32 warps call it; one barrier)
+__device__ __forceinline__ unsigned block_exclusive(unsigned warp_total, int lane, int wid, unsigned *smem32, unsigned *cta_total) {
+    if (lane == 0) smem32[wid] = warp_total;
+    __syncthreads();
+    const unsigned mine = smem32[lane];
+    const unsigned incl = warp_incl_scan(mine, lane);
+    if (cta_total) *cta_total = __shfl_sync(0xffffffffu, incl, 31);
+    return __shfl_sync(0xffffffffu, incl - mine, wid);
+}
+
+// A: per segment the bitmap words, per CTA (32 segments) the number of non-zero words
+__global__ void __launch_bounds__(1024) k_sparse_count(const __grid_constant__ SparseParams p)
 {
-    const int lane = threadIdx.x & 31;
-    const unsigned seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ unsigned wtot[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned seg = blockIdx.x * kBlockSegs + wid;
     const int f = blockIdx.y;
-    if (seg >= p.nseg) return;
     const unsigned w0 = seg * kSeg + lane * 8;
     uint4 w = make_uint4(0, 0, 0, 0);
-    if (w0 < p.nwords) w = __ldg(reinterpret_cast<const uint4 *>(p.dense[f] + (size_t)w0 * 2));
+    if (seg < p.nseg && w0 < p.nwords) w = __ldg(reinterpret_cast<const uint4 *>(p.dense[f] + (size_t)w0 * 2));
     const unsigned m8 = nonzero_mask8(w);
     unsigned m = m8 << ((lane & 3) * 8);
     m |= __shfl_xor_sync(0xffffffffu, m, 1);
     m |= __shfl_xor_sync(0xffffffffu, m, 2);
-    if ((lane & 3) == 0 && w0 < p.nwords)
+    if ((lane & 3) == 0 && seg < p.nseg && w0 < p.nwords)
         reinterpret_cast<unsigned *>(p.sparse[f] + p.bitmap_off)[seg * 8 + (lane >> 2)] = m;
     unsigned c = __popc(m8);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) p.counts[f][seg] = c;
+    unsigned total;
+    block_exclusive(c, lane, wid, wtot, &total);
+    if (threadIdx.x == 0) p.counts[f][blockIdx.x] = total;
 }
 
-// A': counts from an uploaded bitmap
+// A': per-CTA counts from an uploaded bitmap (32 segments = 256 bitmap words per CTA)
 __global__ void __launch_bounds__(256) k_sparse_count_bitmap(const __grid_constant__ SparseParams p)
 {
-    const unsigned seg = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ unsigned wtot[8];
     const int f = blockIdx.y;
-    if (seg >= p.nseg) return;
-    const uint4 *b = reinterpret_cast<const uint4 *>(p.sparse[f] + p.bitmap_off) + seg * 2;
-    const uint4 a = __ldg(b), c = __ldg(b + 1);
-    p.counts[f][seg] = __popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(c.x) + __popc(c.y) + __popc(c.z) + __popc(c.w);
+    const unsigned word = blockIdx.x * (kBlockSegs * 8) + threadIdx.x;          // index of a 32-bit bitmap word
+    unsigned c = 0;
+    if (word < p.nwords / 32) c = __popc(__ldg(reinterpret_cast<const unsigned *>(p.sparse[f] + p.bitmap_off) + word));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) wtot[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t += wtot[i];
+        p.counts[f][blockIdx.x] = t;
+    }
 }
 
-// B: per-frame exclusive scan of the segment counts (one CTA per frame); writes the total into the header
+// B: per-frame exclusive scan of the per-CTA counts (one CTA per frame; a 4K 4:2:2 frame has 2026 of them);
+// writes the total into the header
 __global__ void __launch_bounds__(1024) k_sparse_scan(const __grid_constant__ SparseParams p, int write_header)
 {
     __shared__ unsigned wsum[32];
-    __shared__ unsigned chunk_total;
     const int f = blockIdx.x;
     unsigned *cnt = p.counts[f];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     unsigned carry = 0;
-    for (unsigned base = 0; base < p.nseg; base += 1024 * 4) {
+    for (unsigned base = 0; base < p.nblocks; base += 1024 * 4) {
         unsigned v[4], s = 0;
         const unsigned i0 = base + tid * 4;
 #pragma unroll
-        for (int k = 0; k < 4; k++) { v[k] = (i0 + k < p.nseg) ? cnt[i0 + k] : 0u; s += v[k]; }
-        unsigned incl = s;
+        for (int k = 0; k < 4; k++) { v[k] = (i0 + k < p.nblocks) ? cnt[i0 + k] : 0u; s += v[k]; }
+        const unsigned incl = warp_incl_scan(s, lane);
+        unsigned chunk_total;
+        const unsigned wexcl = block_exclusive(__shfl_sync(0xffffffffu, incl, 31), lane, wid, wsum, &chunk_total);
+        unsigned excl = carry + wexcl + (incl - s);
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) wsum[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            const unsigned x = wsum[lane];
-            unsigned xi = x;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
-            wsum[lane] = xi - x;
-            if (lane == 31) chunk_total = xi;
-        }
-        __syncthreads();
-        unsigned excl = carry + wsum[wid] + (incl - s);
-#pragma unroll
-        for (int k = 0; k < 4; k++) { if (i0 + k < p.nseg) cnt[i0 + k] = excl; excl += v[k]; }
+        for (int k = 0; k < 4; k++) { if (i0 + k < p.nblocks) cnt[i0 + k] = excl; excl += v[k]; }
         carry += chunk_total;
         __syncthreads();
     }
     if (tid == 0) {
-        cnt[p.nseg] = carry;
+        cnt[p.nblocks] = carry;
         if (write_header) {
             unsigned *h = reinterpret_cast<unsigned *>(p.sparse[f]);
             h[0] = 0x50534643u; h[1] = p.nwords; h[2] = carry; h[3] = 0;
@@ -114,22 +132,21 @@ __global__ void __launch_bounds__(1024) k_sparse_scan(const __grid_constant__ Sp
     }
 }
 
-// C: scatter the non-zero words in raster order
-__global__ void __launch_bounds__(256) k_sparse_scatter(const __grid_constant__ SparseParams p)
+// C: scatter the non-zero words in raster order (the position inside the CTA is recomputed from the data)
+__global__ void __launch_bounds__(1024) k_sparse_scatter(const __grid_constant__ SparseParams p)
 {
-    const int lane = threadIdx.x & 31;
-    const unsigned seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ unsigned wtot[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned seg = blockIdx.x * kBlockSegs + wid;
     const int f = blockIdx.y;
-    if (seg >= p.nseg) return;
     const unsigned w0 = seg * kSeg + lane * 8;
     uint4 w = make_uint4(0, 0, 0, 0);
-    if (w0 < p.nwords) w = __ldg(reinterpret_cast<const uint4 *>(p.dense[f] + (size_t)w0 * 2));
+    if (seg < p.nseg && w0 < p.nwords) w = __ldg(reinterpret_cast<const uint4 *>(p.dense[f] + (size_t)w0 * 2));
     const unsigned m8 = nonzero_mask8(w);
     const unsigned c = __popc(m8);
-    unsigned incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    unsigned pos = p.counts[f][seg] + incl - c;
+    const unsigned incl = warp_incl_scan(c, lane);
+    const unsigned wexcl = block_exclusive(__shfl_sync(0xffffffffu, incl, 31), lane, wid, wtot, nullptr);
+    unsigned pos = p.counts[f][blockIdx.x] + wexcl + incl - c;
     unsigned short *vals = reinterpret_cast<unsigned short *>(p.sparse[f] + p.values_off);
     const unsigned ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
@@ -140,21 +157,24 @@ __global__ void __launch_bounds__(256) k_sparse_scatter(const __grid_constant__ 
 }
 
 // C': gather back into the dense coded region
-__global__ void __launch_bounds__(256) k_sparse_gather(const __grid_constant__ SparseParams p)
+__global__ void __launch_bounds__(1024) k_sparse_gather(const __grid_constant__ SparseParams p)
 {
-    const int lane = threadIdx.x & 31;
-    const unsigned seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ unsigned wtot[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned seg = blockIdx.x * kBlockSegs + wid;
     const int f = blockIdx.y;
-    if (seg >= p.nseg) return;
     const unsigned w0 = seg * kSeg + lane * 8;
-    if (w0 >= p.nwords) return;         // nwords is a multiple of 8 (bands are 64-byte aligned)
-    const unsigned bw = __ldg(reinterpret_cast<const unsigned *>(p.sparse[f] + p.bitmap_off) + seg * 8 + (lane >> 2));
-    const unsigned m8 = (bw >> ((lane & 3) * 8)) & 0xffu;
+    const bool on = (seg < p.nseg) && (w0 < p.nwords);          // nwords is a multiple of 8 (bands are 64-byte aligned)
+    unsigned m8 = 0;
+    if (on) {
+        const unsigned bw = __ldg(reinterpret_cast<const unsigned *>(p.sparse[f] + p.bitmap_off) + seg * 8 + (lane >> 2));
+        m8 = (bw >> ((lane & 3) * 8)) & 0xffu;
+    }
     const unsigned c = __popc(m8);
-    unsigned incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    unsigned pos = p.counts[f][seg] + incl - c;
+    const unsigned incl = warp_incl_scan(c, lane);
+    const unsigned wexcl = block_exclusive(__shfl_sync(0xffffffffu, incl, 31), lane, wid, wtot, nullptr);
+    if (!on) return;
+    unsigned pos = p.counts[f][blockIdx.x] + wexcl + incl - c;
     const unsigned short *vals = reinterpret_cast<const unsigned short *>(p.sparse[f] + p.values_off);
     unsigned out[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -169,19 +189,19 @@ __global__ void __launch_bounds__(256) k_sparse_gather(const __grid_constant__ S
 
 cudaError_t launch_sparse_compact(const SparseParams &p, cudaStream_t stream)
 {
-    dim3 grid((p.nseg + 7) / 8, p.nframes);
-    k_sparse_count<<<grid, 256, 0, stream>>>(p);
+    dim3 grid(p.nblocks, p.nframes);
+    k_sparse_count<<<grid, 1024, 0, stream>>>(p);
     k_sparse_scan<<<p.nframes, 1024, 0, stream>>>(p, 1);
-    k_sparse_scatter<<<grid, 256, 0, stream>>>(p);
+    k_sparse_scatter<<<grid, 1024, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_sparse_expand(const SparseParams &p, cudaStream_t stream)
 {
-    dim3 g1((p.nseg + 255) / 256, p.nframes), grid((p.nseg + 7) / 8, p.nframes);
-    k_sparse_count_bitmap<<<g1, 256, 0, stream>>>(p);
+    dim3 grid(p.nblocks, p.nframes);
+    k_sparse_count_bitmap<<<grid, 256, 0, stream>>>(p);
     k_sparse_scan<<<p.nframes, 1024, 0, stream>>>(p, 0);
-    k_sparse_gather<<<grid, 256, 0, stream>>>(p);
+    k_sparse_gather<<<grid, 1024, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -200,17 +220,18 @@ static cfb_error sparse_prepare(cfb_codec *cd, SparseParams &p, int n)
     p.nframes = n;
     p.nwords = (unsigned)(L.coded_bytes / 2);
     p.nseg = (p.nwords + kSeg - 1) / kSeg;
+    p.nblocks = (p.nseg + kBlockSegs - 1) / kBlockSegs;
     p.bitmap_off = sp_bitmap_off();
     p.values_off = sp_values_off(p.nwords);
     // each staging buffer under its own check: a failed allocation leaves the others usable for the retry
     cd->sparse_stride = (cfb_sparse_max_bytes(&L) + 255) & ~(size_t)255;
     if (!cd->d_sparse) CFB_CUDA(cudaMalloc((void **)&cd->d_sparse, cd->sparse_stride * cd->max_batch));
-    if (!cd->d_counts) CFB_CUDA(cudaMalloc((void **)&cd->d_counts, sizeof(unsigned) * (size_t)(p.nseg + 1) * cd->max_batch));
+    if (!cd->d_counts) CFB_CUDA(cudaMalloc((void **)&cd->d_counts, sizeof(unsigned) * (size_t)(p.nblocks + 1) * cd->max_batch));
     if (!cd->h_headers) CFB_CUDA(cudaHostAlloc((void **)&cd->h_headers, 16 * (size_t)cd->max_batch, cudaHostAllocPortable));
     for (int i = 0; i < n; i++) {
         p.dense[i] = cd->d_pyramids + cd->pyramid_stride * i;
         p.sparse[i] = cd->d_sparse + cd->sparse_stride * i;
-        p.counts[i] = cd->d_counts + (size_t)(p.nseg + 1) * i;
+        p.counts[i] = cd->d_counts + (size_t)(p.nblocks + 1) * i;
     }
     return CFB_OK;
 }
