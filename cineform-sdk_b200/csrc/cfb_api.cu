@@ -627,19 +627,28 @@ cfb_error cfb_forward_device(cfb_codec *cd, int n, const void *const *d_frames, 
         CFB_CUDA(launch_fwd_plane(p, quant->prescale[0], ctx->stream));
         ctx->kernel_launches++;
     } else if (fmt == CFB_PIXEL_RG48) {
-        // channel order of the reference: plane 0 = G, 1 = R, 2 = B (Codec/frame.c:6155-6157); one launch per channel
-        static const int sel_of_channel[3] = {1, 0, 2};
+        // channel order of the reference: plane 0 = G, 1 = R, 2 = B (Codec/frame.c:6155-6157); all three channels come out
+        // of one pass over the 48-bit pixel groups (k_fwd_tma<SrcRG48>)
         for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_frames[i]; p.out_base[i] = (unsigned char *)d_pyramids[i]; }
         p.shift = 16 - L.precision;
         for (int c = 0; c < 3; c++) {
-            FwdParams q = p;
-            q.nchan = 1;
-            fill_level_geom(cd, quant, c, 0, q.ch[0]);
-            q.ch[0].in_off = 0; q.ch[0].in_pitch = frame_pitch;
-            q.ch[0].quant_ll = quant->divisor[c][0][0] > 1;
-            q.th = pick_th((q.ch[0].width + kStripIn - 1) / kStripIn, q.ch[0].height / 2, n, ctx->sm_count);
-            CFB_CUDA(launch_fwd_rg48(q, sel_of_channel[c], ctx->stream));
-            ctx->kernel_launches++;
+            fill_level_geom(cd, quant, c, 0, p.ch[c]);
+            p.ch[c].in_off = 0; p.ch[c].in_pitch = frame_pitch;
+            p.ch[c].quant_ll = quant->divisor[c][0][0] > 1;
+        }
+        p.th = pick_th((p.ch[0].width + kStripIn - 1) / kStripIn, p.ch[0].height / 2, n * 3, ctx->sm_count);
+        if (getenv("CFB_FWDPLANE") && !strcmp(getenv("CFB_FWDPLANE"), "r1")) {
+            static const int sel_of_channel[3] = {1, 0, 2};
+            for (int c = 0; c < 3; c++) {
+                FwdParams q = p;
+                q.nchan = 1; q.ch[0] = p.ch[c];
+                q.th = pick_th((q.ch[0].width + kStripIn - 1) / kStripIn, q.ch[0].height / 2, n, ctx->sm_count);
+                CFB_CUDA(launch_fwd_rg48(q, sel_of_channel[c], ctx->stream));
+                ctx->kernel_launches++;
+            }
+        } else {
+            CFB_CUDA(launch_fwd_rg48_all(p, ctx->stream));
+            ctx->kernel_launches += 4;
         }
     } else if (fmt >= CFB_PIXEL_RG30 && fmt <= CFB_PIXEL_DPX0) {
         // planes G, R, B; field position of each inside the (possibly byte-swapped) word: spatial.c:2118-2268

@@ -503,6 +503,55 @@ __device__ __forceinline__ void byr4_extract(const RawBYR4Row &r, int shift, int
     o.halo = (unsigned)byr4_sample<LUT>(r.ha.x, r.hb.x, shift, fmt, chan, lut) | ((unsigned)byr4_sample<LUT>(r.ha.y, r.hb.y, shift, fmt, chan, lut) << 16);
 }
 
+// The same plane samples with the channel known at compile time and the Bayer phase folded into byte-permute selectors
+// (warp-uniform registers): g1 always sits on the first line of a quad and g2 on the second, red / blue on either.
+//   selg1 / selg2: halfword of the line word holding g1 / g2;  selx: halfword holding the channel's colour sample,
+//   xline: 0 = first line, 1 = second line
+struct BayerSel { unsigned selg1, selg2, selx; int xline; };
+
+__device__ __forceinline__ BayerSel bayer_sel(int fmt, int chan)
+{
+    // quad layout (line 1: q0 q1, line 2: q2 q3): 0 RED_GRN r g / g b, 1 GRN_RED g r / b g, 2 GRN_BLU g b / r g, 3 BLU_GRN b g / g r
+    const unsigned lo = 0x4410u, hi = 0x4432u;      // PRMT selectors: low / high halfword, upper half zero (second operand = 0)
+    BayerSel s;
+    const bool g_second = (fmt == 0) || (fmt == 3);
+    s.selg1 = g_second ? hi : lo;
+    s.selg2 = g_second ? lo : hi;
+    const int rpos = (fmt == 0) ? 0 : (fmt == 1) ? 1 : (fmt == 2) ? 2 : 3;
+    const int bpos = 3 - rpos;
+    const int xpos = (chan == 1) ? rpos : bpos;
+    s.selx = (xpos & 1) ? hi : lo;
+    s.xline = xpos >> 1;
+    return s;
+}
+
+template <bool LUT, int CHAN>
+__device__ __forceinline__ int byr4_sample_c(unsigned w1, unsigned w2, int shift, const BayerSel &s, const unsigned short *lut)
+{
+    unsigned g1 = __byte_perm(w1, 0u, s.selg1), g2 = __byte_perm(w2, 0u, s.selg2);
+    if (LUT) { g1 = __ldg(lut + (g1 >> 2)); g2 = __ldg(lut + (g2 >> 2)); } else { g1 >>= shift; g2 >>= shift; }
+    if (CHAN == 3) return (int)(g1 - g2 + 4096u) >> 1;
+    const unsigned gg = (g1 + g2) >> 1;
+    if (CHAN == 0) return (int)gg;
+    unsigned x = __byte_perm(s.xline ? w2 : w1, 0u, s.selx);
+    if (LUT) x = __ldg(lut + (x >> 2)); else x >>= shift;
+    return (int)(x - gg + 4096u) >> 1;
+}
+
+template <bool LUT, int CHAN>
+__device__ __forceinline__ void byr4_extract_c(const RawBYR4Row &r, int shift, const BayerSel &s, const unsigned short *lut, RawPlaneRow &o)
+{
+    const unsigned l1[8] = {r.a0.x, r.a0.y, r.a0.z, r.a0.w, r.a1.x, r.a1.y, r.a1.z, r.a1.w};
+    const unsigned l2[8] = {r.b0.x, r.b0.y, r.b0.z, r.b0.w, r.b1.x, r.b1.y, r.b1.z, r.b1.w};
+    unsigned out[4];
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+        out[m] = pack_lo(byr4_sample_c<LUT, CHAN>(l1[2 * m], l2[2 * m], shift, s, lut),
+                         byr4_sample_c<LUT, CHAN>(l1[2 * m + 1], l2[2 * m + 1], shift, s, lut));
+    o.v = make_uint4(out[0], out[1], out[2], out[3]);
+    o.halo = pack_lo(byr4_sample_c<LUT, CHAN>(r.ha.x, r.hb.x, shift, s, lut), byr4_sample_c<LUT, CHAN>(r.ha.y, r.hb.y, shift, s, lut));
+}
+
 template <bool LUT>
 __global__ void __launch_bounds__(128) k_fwd_byr4(const __grid_constant__ FwdParams p)
 {
@@ -1313,22 +1362,79 @@ __global__ void __launch_bounds__(128) k_fwd_422_src(const __grid_constant__ Fwd
 // host-side launchers (called from cfb_api.cu).  gridDim.y = row blocks + 1 border CTA row.
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// A/B switch (profiles/r02_ab_fwdplane.txt): CFB_FWDPLANE = r1 forces the round-1 kernels (direct LDG into registers)
+// everywhere, = tma the TMA-fed kernel everywhere.  Default: TMA where several channels share one read of the source
+// (RG48: 294 -> 174 us per 8 4K frames, BYR4), round-1 kernels for single planes (levels 2 and 3: 66.5 / 22.1 us against
+// 74.0 / 28.9 us with the TMA ring, whose start-up is not amortised over the 8-16 row pairs of a CTA).
+static int fwdplane_variant()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CFB_FWDPLANE"); v = !e ? 0 : !strcmp(e, "r1") ? 1 : !strcmp(e, "tma") ? 2 : 0; }
+    return v;
+}
+
 cudaError_t launch_fwd_plane(const FwdParams &p, int prescale, cudaStream_t stream)
 {
     int maxw = 0, maxoh = 0;
-    bool ragged = false;
+    bool ragged = false, tma_ok = (fwdplane_variant() == 2) && (p.nframes * p.nchan <= kMaxBatch * kMaxChannels);
     for (int c = 0; c < p.nchan; c++) {
         maxw = max(maxw, p.ch[c].width); maxoh = max(maxoh, p.ch[c].height / 2);
         ragged = ragged || (p.ch[c].width & 7);
+        tma_ok = tma_ok && !(p.ch[c].in_pitch & 15) && !(p.ch[c].in_off & 15);
     }
+    for (int i = 0; i < p.nframes; i++) tma_ok = tma_ok && !((uintptr_t)p.in_base[i] & 15);
     if (ragged) {       // the 1-3 output columns right of the last full lane (they include the right border)
         dim3 eblock(128), egrid(ceil_div(maxoh, 128), 3, p.nframes * p.nchan);
         if (prescale) k_fwd_plane_edge<2><<<egrid, eblock, 0, stream>>>(p); else k_fwd_plane_edge<0><<<egrid, eblock, 0, stream>>>(p);
     }
     dim3 block(32, 4);
-    dim3 grid(ceil_div(maxw, kStripIn), ceil_div(ceil_div(maxoh, p.th), (int)block.y) + 1, p.nframes * p.nchan);
-    if (prescale) k_fwd_plane<2><<<grid, block, 0, stream>>>(p);
-    else k_fwd_plane<0><<<grid, block, 0, stream>>>(p);
+    if (!tma_ok) {      // round-1 path (also: plane pointers / pitches that are not 16-byte aligned cannot be described to the TMA)
+        dim3 grid(ceil_div(maxw, kStripIn), ceil_div(ceil_div(maxoh, p.th), (int)block.y) + 1, p.nframes * p.nchan);
+        if (prescale) k_fwd_plane<2><<<grid, block, 0, stream>>>(p);
+        else k_fwd_plane<0><<<grid, block, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
+    FwdTmaPlaneMaps tm;
+    for (int i = 0; i < p.nframes; i++)
+        for (int c = 0; c < p.nchan; c++) {
+            const PlaneGeom &g = p.ch[c];
+            cudaError_t e = tmap_encode_2d(&tm.in_map[i * p.nchan + c], p.in_base[i] + g.in_off, (uint64_t)g.width * 2, (uint64_t)g.height,
+                                           (uint64_t)g.in_pitch, SrcPlane16<0>::kRowBytes, 2);
+            if (e != cudaSuccess) return e;
+        }
+    dim3 tgrid(ceil_div(maxw, kStripIn), ceil_div(maxoh, p.th), p.nframes * p.nchan), tblock(32, 1);
+    const size_t smem = kTmaStages * SrcPlane16<0>::kStageBytes + 2 * kTmaStages * 8;
+    if (prescale) k_fwd_tma<SrcPlane16<2>, 8><<<tgrid, tblock, smem, stream>>>(p, tm);
+    else k_fwd_tma<SrcPlane16<0>, 8><<<tgrid, tblock, smem, stream>>>(p, tm);
+    // first / last HL,HH row: the border CTA row of the round-1 kernel, alone
+    dim3 bgrid(ceil_div(maxw, kStripIn), 1, p.nframes * p.nchan);
+    if (prescale) k_fwd_plane<2><<<bgrid, block, 0, stream>>>(p);
+    else k_fwd_plane<0><<<bgrid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// all three channels of packed RG48 frames from ONE read of the pixel groups: p.ch[0..2] = G, R, B
+cudaError_t launch_fwd_rg48_all(const FwdParams &p, cudaStream_t stream)
+{
+    FwdTmaPlaneMaps tm;
+    const PlaneGeom &g = p.ch[0];
+    for (int i = 0; i < p.nframes; i++) {
+        cudaError_t e = tmap_encode_2d(&tm.in_map[i], p.in_base[i] + g.in_off, (uint64_t)g.width * 6, (uint64_t)g.height, (uint64_t)g.in_pitch,
+                                       SrcRG48::kRowBytes, 2, 8);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 tgrid(ceil_div(g.width, kStripIn), ceil_div(g.height / 2, p.th), p.nframes), tblock(32, 3);
+    k_fwd_tma<SrcRG48, 5><<<tgrid, tblock, kTmaStages * SrcRG48::kStageBytes + 2 * kTmaStages * 8, stream>>>(p, tm);
+    // border rows per channel (round-1 kernel on its border CTA row): p.ch[0] must describe the channel
+    static const int sel_of_channel[3] = {1, 0, 2};
+    dim3 block(32, 4), bgrid(ceil_div(g.width, kStripIn), 1, p.nframes);
+    for (int c = 0; c < 3; c++) {
+        FwdParams q = p;
+        q.nchan = 1; q.ch[0] = p.ch[c];
+        if (sel_of_channel[c] == 0) k_fwd_rg48<0><<<bgrid, block, 0, stream>>>(q);
+        else if (sel_of_channel[c] == 1) k_fwd_rg48<1><<<bgrid, block, 0, stream>>>(q);
+        else k_fwd_rg48<2><<<bgrid, block, 0, stream>>>(q);
+    }
     return cudaGetLastError();
 }
 
@@ -1351,12 +1457,30 @@ cudaError_t launch_fwd_rgb30(const FwdParams &p, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-// all four Bayer-derived channels in one launch (blockIdx.x = strip * 4 + channel); p.uyvy carries the Bayer phase
+// all four Bayer-derived channels; p.uyvy carries the Bayer phase
 cudaError_t launch_fwd_byr4(const FwdParams &p, cudaStream_t stream)
 {
     dim3 block(32, 4);
-    dim3 grid(ceil_div(p.ch[0].width, kStripIn) * 4, ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y) + 1, p.nframes);
-    if (p.lut) k_fwd_byr4<true><<<grid, block, 0, stream>>>(p); else k_fwd_byr4<false><<<grid, block, 0, stream>>>(p);
+    const PlaneGeom &g = p.ch[0];
+    const bool tma_ok = (fwdplane_variant() != 1) && !(g.in_pitch & 15);
+    if (!tma_ok) {
+        dim3 grid(ceil_div(g.width, kStripIn) * 4, ceil_div(ceil_div(g.height / 2, p.th), (int)block.y) + 1, p.nframes);
+        if (p.lut) k_fwd_byr4<true><<<grid, block, 0, stream>>>(p); else k_fwd_byr4<false><<<grid, block, 0, stream>>>(p);
+        return cudaGetLastError();
+    }
+    // one read of the Bayer lines feeds the four channel warps of a CTA (plane width = half the Bayer width)
+    FwdTmaPlaneMaps tm;
+    for (int i = 0; i < p.nframes; i++) {
+        cudaError_t e = tmap_encode_2d(&tm.in_map[i], p.in_base[i], (uint64_t)g.width * 4, (uint64_t)g.height * 2, (uint64_t)g.in_pitch,
+                                       SrcBYR4<false>::kRowBytes, 4, 8);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 tgrid(ceil_div(g.width, kStripIn), ceil_div(g.height / 2, p.th), p.nframes), tblock(32, 4);
+    const size_t smem = kTmaStages * SrcBYR4<false>::kStageBytes + 2 * kTmaStages * 8;
+    if (p.lut) k_fwd_tma<SrcBYR4<true>, 3><<<tgrid, tblock, smem, stream>>>(p, tm);
+    else k_fwd_tma<SrcBYR4<false>, 3><<<tgrid, tblock, smem, stream>>>(p, tm);
+    dim3 bgrid(ceil_div(g.width, kStripIn) * 4, 1, p.nframes);
+    if (p.lut) k_fwd_byr4<true><<<bgrid, block, 0, stream>>>(p); else k_fwd_byr4<false><<<bgrid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

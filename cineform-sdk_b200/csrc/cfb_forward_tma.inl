@@ -17,6 +17,9 @@ constexpr int kTmaWarpBytes = kTmaStages * kTmaStageBytes;
 struct alignas(64) FwdTmaMaps {
     CUtensorMap in_map[kMaxBatch];
 };
+struct alignas(64) FwdTmaPlaneMaps {            // planar sources: one map per (frame, channel)
+    CUtensorMap in_map[kMaxBatch * kMaxChannels];
+};
 
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_fwd_422_tma(const __grid_constant__ FwdParams p, const __grid_constant__ FwdTmaMaps tm)
@@ -145,4 +148,159 @@ __global__ void __launch_bounds__(128, MINB) k_fwd_422_tma(const __grid_constant
         }
     };
     if (L.has_border) run(std::true_type{}); else run(std::false_type{});
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Generic TMA-fed forward level for sources whose channels are separated while loading:
+//   SrcPlane16<PRESCALE>  one int16 plane per channel (levels 2 and 3 of every format, PLANAR16 level 1, cfb_level_*)
+//   SrcRG48               packed 16-bit R,G,B -> planes G, R, B: ONE read of the 48-byte pixel groups feeds all three
+//                         channel warps of the CTA (round 1 launched one kernel per channel: 3 x the input traffic)
+//   SrcBYR4<LUT>          16-bit Bayer quads -> planes G, R-G, B-G, dG: the two Bayer lines of a plane row are loaded
+//                         once for the four channel warps
+// A CTA = SRC::kWarps warps, all on the same strip and the same row block, one channel each.  Warp 0 / lane 0 keeps a
+// CTA-wide ring of kTmaStages stages full (cp.async.bulk.tensor.2d, one box of SRC::kBoxRows rows per row pair); a stage
+// is handed back through an "empty" mbarrier on which every channel warp arrives once it has pulled its samples into
+// registers.  The first / last HL,HH row (6-tap border filters) is left to the round-1 kernels launched on their border
+// CTA row alone (gridDim.y = 1), so this kernel has no border-row code.
+template <int PRESCALE>
+struct SrcPlane16 {
+    static constexpr int kWarps = 1, kBoxRows = 2, kRowBytes = 544, kElem = 4, kPrescale = PRESCALE, kQll = 1;
+    static constexpr int kStageBytes = 1152;
+    static __device__ __forceinline__ int x0(int strip) { return strip * (kStripIn * 2 / 4) - 4; }
+    static __device__ __forceinline__ int map_index(int f, int c, int nchan) { return f * nchan + c; }
+    static __device__ __forceinline__ void extract(unsigned sb, int row, int lane, int, const LaneInfo &L, const FwdParams &, RawPlaneRow &r) {
+        const unsigned a = sb + row * kRowBytes + 16u + (unsigned)lane * 16u;
+        r.v = lds128(a);
+        r.halo = 0u;
+        if (L.use_lh | L.use_rh) r.halo = lds32(a + (L.use_lh ? -4 : 16));
+    }
+};
+
+struct SrcRG48 {
+    static constexpr int kWarps = 3, kBoxRows = 2, kRowBytes = 1568, kElem = 8, kPrescale = 0, kQll = 1;
+    static constexpr int kStageBytes = 3200;        // 2 x 1568 rounded up to a multiple of 128
+    static __device__ __forceinline__ int x0(int strip) { return strip * (kStripIn * 6 / 8) - 2; }
+    static __device__ __forceinline__ int map_index(int f, int, int) { return f; }
+    // channel 0 = G (word 1 of a pixel), 1 = R (word 0), 2 = B (word 2): Codec/frame.c:6155-6157
+    static __device__ __forceinline__ void extract(unsigned sb, int row, int lane, int chan, const LaneInfo &L, const FwdParams &p, RawPlaneRow &r) {
+        const unsigned a = sb + row * kRowBytes + 16u + (unsigned)lane * 48u;
+        RawRG48Row q;
+        q.a = lds128(a); q.b = lds128(a + 16); q.c = lds128(a + 32);
+        q.halo = 0u;
+        const int sel = (chan == 0) ? 1 : (chan == 1 ? 0 : 2);
+        if (L.use_lh | L.use_rh) {
+            const unsigned h = a + (L.use_lh ? -12 : 48) + 2 * sel;
+            q.halo = lds_u16(h) | (lds_u16(h + 6) << 16);
+        }
+        if (sel == 0) rg48_extract<0>(q, p.shift, r); else if (sel == 1) rg48_extract<1>(q, p.shift, r); else rg48_extract<2>(q, p.shift, r);
+    }
+};
+
+template <bool LUT>
+struct SrcBYR4 {
+    static constexpr int kWarps = 4, kBoxRows = 4, kRowBytes = 1056, kElem = 8, kPrescale = 0, kQll = 1;
+    static constexpr int kStageBytes = 4224;        // 4 Bayer lines x 1056
+    static __device__ __forceinline__ int x0(int strip) { return strip * (kStripIn * 4 / 8) - 2; }
+    static __device__ __forceinline__ int map_index(int f, int, int) { return f; }
+    static __device__ __forceinline__ void extract(unsigned sb, int row, int lane, int chan, const LaneInfo &L, const FwdParams &p, RawPlaneRow &r) {
+        const unsigned a = sb + (2 * row) * kRowBytes + 16u + (unsigned)lane * 32u;     // first Bayer line of the plane row
+        RawBYR4Row q;
+        q.a0 = lds128(a); q.a1 = lds128(a + 16);
+        q.b0 = lds128(a + kRowBytes); q.b1 = lds128(a + kRowBytes + 16);
+        q.ha = make_uint2(0u, 0u); q.hb = make_uint2(0u, 0u);
+        if (L.use_lh | L.use_rh) {
+            const unsigned h = a + (L.use_lh ? -8 : 32);
+            q.ha = lds64(h); q.hb = lds64(h + kRowBytes);
+        }
+        const BayerSel s = bayer_sel(p.uyvy, chan);         // warp-uniform (hoisted out of the row loop by the compiler)
+        if (chan == 0) byr4_extract_c<LUT, 0>(q, p.shift, s, p.lut, r);
+        else if (chan == 1) byr4_extract_c<LUT, 1>(q, p.shift, s, p.lut, r);
+        else if (chan == 2) byr4_extract_c<LUT, 2>(q, p.shift, s, p.lut, r);
+        else byr4_extract_c<LUT, 3>(q, p.shift, s, p.lut, r);
+    }
+};
+
+template <class SRC, int MINB>
+__global__ void __launch_bounds__(32 * SRC::kWarps, MINB) k_fwd_tma(const __grid_constant__ FwdParams p, const __grid_constant__ FwdTmaPlaneMaps tm)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NW = SRC::kWarps;
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    // planar sources: blockIdx.z = frame * nchan + channel; interleaved sources: blockIdx.z = frame, channel = warp
+    const int f = (NW == 1) ? blockIdx.z / p.nchan : blockIdx.z;
+    const int c = (NW == 1) ? blockIdx.z - f * p.nchan : warp;
+    const PlaneGeom &g = p.ch[c];
+    const int strip = blockIdx.x;
+    if (strip * kStripIn >= g.width) return;
+    const int oh = g.height >> 1;
+    LaneInfo L;
+    const bool lane_on = lane_setup(strip, g.width, lane, L);
+    const int y0 = blockIdx.y * p.th;
+    if (y0 >= oh) return;
+    const int y1 = min(y0 + p.th, oh);
+    const int jfirst = max(y0 - 1, 0), jlast = min(y1, oh - 1);
+    const int hlo = max(y0, 1);
+
+    const unsigned ring = smem_u32(smem_raw);
+    const unsigned full = ring + kTmaStages * SRC::kStageBytes, empty = full + kTmaStages * 8;
+    const void *map = &tm.in_map[SRC::map_index(f, c, p.nchan)];
+    const int x0 = SRC::x0(strip);
+    constexpr unsigned kTx = SRC::kBoxRows * SRC::kRowBytes;
+    const bool producer = (warp == 0 && lane == 0);
+    if (producer) {
+#pragma unroll
+        for (int s = 0; s < kTmaStages; s++) { mbar_init(full + 8 * s, 1); mbar_init(empty + 8 * s, NW); }
+        mbar_fence_init();
+    }
+    if (NW > 1) __syncthreads(); else __syncwarp();
+    if (producer) {
+#pragma unroll
+        for (int s = 0; s < kTmaStages; s++)
+            if (jfirst + s <= jlast) {
+                mbar_expect_tx(full + 8 * s, kTx);
+                tma_load_2d(ring + s * SRC::kStageBytes, map, x0, SRC::kBoxRows * (jfirst + s), full + 8 * s);
+            }
+    }
+
+    unsigned char *out = p.out_base[f];
+    const unsigned colbyte = (unsigned)((strip * kStripOut + lane * 4) * 2);
+    RotState<4> st;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { st.t[i] = st.s[i] = 0; }
+    unsigned off = (unsigned)(jfirst * g.out_pitch) + colbyte;
+    int stage = 0;
+    unsigned parity = 0;
+#pragma unroll 1
+    for (int j = jfirst; j <= jlast; j++) {
+        const unsigned sb = ring + stage * SRC::kStageBytes;
+        mbar_wait(full + 8 * stage, parity);
+        RawPlaneRow r0, r1;
+        r0.v = make_uint4(0u, 0u, 0u, 0u); r0.halo = 0u; r1 = r0;
+        if (lane_on) {
+            SRC::extract(sb, 0, lane, c, L, p, r0);
+            SRC::extract(sb, 1, lane, c, L, p, r1);
+        }
+        __syncwarp();
+        if (NW > 1) {
+            // hand the stage back: every channel warp arrives once; the producer refills it when all have
+            if (lane == 0) mbar_arrive(empty + 8 * stage);
+            if (producer && j + kTmaStages <= jlast) {
+                mbar_wait(empty + 8 * stage, parity);
+                mbar_expect_tx(full + 8 * stage, kTx);
+                tma_load_2d(sb, map, x0, SRC::kBoxRows * (j + kTmaStages), full + 8 * stage);
+            }
+        } else if (producer && j + kTmaStages <= jlast) {
+            mbar_expect_tx(full + 8 * stage, kTx);
+            tma_load_2d(sb, map, x0, SRC::kBoxRows * (j + kTmaStages), full + 8 * stage);
+        }
+        if (lane_on) {
+            int a[8], b[8];
+            hfilter_plane<SRC::kPrescale>(r0, L, a);
+            hfilter_plane<SRC::kPrescale>(r1, L, b);
+            vstep_rot<4, SRC::kQll>(st, a, b, g, out, off, j >= y0 && j < y1, j - 1 >= hlo);
+        }
+        off += (unsigned)g.out_pitch;
+        if (++stage == kTmaStages) { stage = 0; parity ^= 1; }
+    }
 }

@@ -26,15 +26,16 @@ static EncodeTiledFn encode_fn()
 }
 
 cudaError_t tmap_encode_2d(CUtensorMap *out, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch_bytes,
-                           uint32_t box_bytes, uint32_t box_rows)
+                           uint32_t box_bytes, uint32_t box_rows, int elem_bytes)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return cudaErrorNotSupported;
-    const cuuint64_t dims[2] = {row_bytes / 4, rows};
+    if (elem_bytes != 4 && elem_bytes != 8) return cudaErrorInvalidValue;
+    const cuuint64_t dims[2] = {row_bytes / elem_bytes, rows};
     const cuuint64_t strides[1] = {pitch_bytes};
-    const cuuint32_t box[2] = {box_bytes / 4, box_rows};
+    const cuuint32_t box[2] = {box_bytes / elem_bytes, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+    const CUresult r = fn(out, elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void *>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;

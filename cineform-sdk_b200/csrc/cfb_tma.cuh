@@ -19,6 +19,9 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
     unsigned ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -65,6 +68,11 @@ __device__ __forceinline__ unsigned lds32(unsigned addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ unsigned lds_u16(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void sts64(unsigned addr, unsigned a, unsigned b) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(addr), "r"(a), "r"(b) : "memory");
 }
@@ -76,10 +84,11 @@ __device__ __forceinline__ void sts128(unsigned addr, uint4 v) {
 }
 
 // ---- host ----------------------------------------------------------------------------------------------------------
-// 2-D (or 3-D) tiled tensor map over 32-bit elements.  row_bytes / pitch / box_bytes in BYTES (multiples of 4 / 16 / 16).
+// 2-D (or 3-D) tiled tensor map over 32-bit (or, elem_bytes = 8, 64-bit: boxes up to 2 KB wide) elements.  row_bytes /
+// pitch / box_bytes in BYTES (multiples of elem_bytes / 16 / 16).
 // The driver entry point is resolved through the runtime (cudart is linked statically; libcuda is never linked).
 cudaError_t tmap_encode_2d(CUtensorMap *out, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch_bytes,
-                           uint32_t box_bytes, uint32_t box_rows);
+                           uint32_t box_bytes, uint32_t box_rows, int elem_bytes = 4);
 cudaError_t tmap_encode_3d(CUtensorMap *out, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch_bytes,
                            uint64_t planes, uint64_t plane_bytes, uint32_t box_bytes, uint32_t box_rows, uint32_t box_planes);
 
