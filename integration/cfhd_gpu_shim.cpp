@@ -45,12 +45,13 @@ extern "C" int g_midpoint_prequant;     // Codec/quantize.c:183
 namespace {
 
 std::atomic<long> g_fwd_frames{0}, g_inv_frames{0}, g_fwd_ref{0}, g_inv_ref{0};
+std::atomic<long> g_cuda_errors{0};
 
 struct StatsAtExit {
     ~StatsAtExit() {
         if (getenv("CFHD_B200_STATS"))
-            fprintf(stderr, "cfhd_gpu_shim: forward frames on GPU %ld (reference CPU %ld), inverse frames on GPU %ld (reference CPU %ld)\n",
-                    g_fwd_frames.load(), g_fwd_ref.load(), g_inv_frames.load(), g_inv_ref.load());
+            fprintf(stderr, "cfhd_gpu_shim: forward frames on GPU %ld (reference CPU %ld), inverse frames on GPU %ld (reference CPU %ld), CUDA errors %ld\n",
+                    g_fwd_frames.load(), g_fwd_ref.load(), g_inv_frames.load(), g_inv_ref.load(), g_cuda_errors.load());
     }
 } g_stats_at_exit;
 
@@ -107,6 +108,8 @@ Plan *get_plan(int width, int height, int pixel_format, int interlaced = CFB_PRO
 }
 
 thread_local TRANSFORM *t_pyramid_done_for = nullptr;    // encoder: levels 2,3 already produced for this transform[0]
+thread_local bool t_cuda_failed = false;                 // encoder: the CUDA pyramid of the current frame failed (no CPU fallback)
+enum Took { NOT_COVERED, DONE, FAILED };
 
 bool spatial3(TRANSFORM *t)
 {
@@ -118,19 +121,24 @@ bool spatial3(TRANSFORM *t)
 extern "C" {
 
 // ------------------------------------------------------------------------------------------------ encoder
-// The whole 3-level pyramid of one packed 4:2:2 frame on the GPU (level 1 = spatial or field transform); false = not
-// taken (geometry / options outside the CUDA path, or a CUDA error): the caller then runs the reference's own function.
-static bool forward_pyramid_on_gpu(uint8_t *input, int input_pitch, FRAME_INFO *frame, TRANSFORM *transform[], int frame_index,
+// The whole 3-level pyramid of one packed 4:2:2 frame on the GPU (level 1 = spatial or field transform).
+//   NOT_COVERED  geometry / options outside the CUDA path: the caller runs the reference's own function (the reference
+//                running its own code for a format we do not claim -- counted in g_fwd_ref);
+//   FAILED       the frame IS covered but a CUDA call failed: there is NO CPU fallback on the transform path -- the bands
+//                are zero-filled, ComputeGroupTransformQuant reports CODEC_ERROR through encoder->error, the error is
+//                printed, and CFHD_B200_ABORT_ON_ERROR=1 turns it into an abort().
+static Took forward_pyramid_on_gpu(uint8_t *input, int input_pitch, FRAME_INFO *frame, TRANSFORM *transform[], int frame_index,
                                    int num_channels, int precision, int limit_yuv, int conv_601_709, int interlaced)
 {
     t_pyramid_done_for = nullptr;
+    t_cuda_failed = false;
     const bool fmt_ok = frame && (frame->format == COLOR_FORMAT_YUYV || frame->format == COLOR_FORMAT_UYVY);
     Plan *plan = nullptr;
     if (gpu_enabled() && fmt_ok && frame_index == 0 && num_channels == 3 && precision == 10 && !limit_yuv && !conv_601_709 &&
         input_pitch > 0 && (input_pitch & 15) == 0 && ((uintptr_t)input & 15) == 0 &&
         spatial3(transform[0]) && spatial3(transform[1]) && spatial3(transform[2]))
         plan = get_plan(frame->width, frame->height, frame->format == COLOR_FORMAT_YUYV ? CFB_PIXEL_YUYV : CFB_PIXEL_UYVY, interlaced);
-    if (!plan) return false;
+    if (!plan) return NOT_COVERED;
 
     cfb_quant q;
     memset(&q, 0, sizeof(q));
@@ -146,7 +154,15 @@ static bool forward_pyramid_on_gpu(uint8_t *input, int input_pitch, FRAME_INFO *
         }
     const void *frames[1] = {input};
     void *coded[1] = {plan->coded};
-    if (!ok || cfb_forward_host(plan->codec, 1, frames, input_pitch, &q, coded) != CFB_OK) return false;
+    if (!ok) return NOT_COVERED;                  // the encoder's wavelet geometry is not the one the plan was built for
+    const bool failed = cfb_forward_host(plan->codec, 1, frames, input_pitch, &q, coded) != CFB_OK;
+    if (failed) {
+        fprintf(stderr, "cfhd_gpu_shim: CUDA forward transform failed (%s); no CPU fallback on the transform path\n", cfb_last_error_string());
+        g_cuda_errors++;
+        if (getenv("CFHD_B200_ABORT_ON_ERROR")) abort();
+        memset(plan->coded, 0, (size_t)plan->layout.coded_bytes);
+        t_cuda_failed = true;
+    }
     // hand the bands to the host entropy coder exactly where it expects them
     for (int c = 0; c < 3; c++)
         for (int k = 0; k < 3; k++) {
@@ -158,8 +174,9 @@ static bool forward_pyramid_on_gpu(uint8_t *input, int input_pitch, FRAME_INFO *
             for (int bnd = 0; bnd < 4; bnd++) { w->pixel_type[bnd] = PIXEL_TYPE_16S; w->quantization[bnd] = w->quant[bnd]; }
         }
     t_pyramid_done_for = transform[0];
+    if (failed) return FAILED;
     g_fwd_frames++;
-    return true;
+    return DONE;
 }
 
 void TransformForwardSpatialYUV(uint8_t *input, int input_pitch, FRAME_INFO *frame, TRANSFORM *transform[], int frame_index,
@@ -168,7 +185,7 @@ void TransformForwardSpatialYUV(uint8_t *input, int input_pitch, FRAME_INFO *fra
 {
     typedef void (*fn_t)(uint8_t *, int, FRAME_INFO *, TRANSFORM *[], int, int, PIXEL *, size_t, int, int, int, int, int);
     static fn_t ref = next_symbol<fn_t>("TransformForwardSpatialYUV");
-    if (forward_pyramid_on_gpu(input, input_pitch, frame, transform, frame_index, num_channels, precision, limit_yuv, conv_601_709, CFB_PROGRESSIVE)) return;
+    if (forward_pyramid_on_gpu(input, input_pitch, frame, transform, frame_index, num_channels, precision, limit_yuv, conv_601_709, CFB_PROGRESSIVE) != NOT_COVERED) return;
     g_fwd_ref++;
     ref(input, input_pitch, frame, transform, frame_index, num_channels, buffer, buffer_size, chroma_offset, IFrame, precision, limit_yuv, conv_601_709);
 }
@@ -180,7 +197,7 @@ void TransformForwardFrameYUV(uint8_t *input, int input_pitch, FRAME_INFO *frame
 {
     typedef void (*fn_t)(uint8_t *, int, FRAME_INFO *, TRANSFORM *[], int, int, char *, size_t, int, int, int, int);
     static fn_t ref = next_symbol<fn_t>("TransformForwardFrameYUV");
-    if (forward_pyramid_on_gpu(input, input_pitch, frame, transform, frame_index, num_channels, precision, limit_yuv, conv_601_709, CFB_INTERLACED)) return;
+    if (forward_pyramid_on_gpu(input, input_pitch, frame, transform, frame_index, num_channels, precision, limit_yuv, conv_601_709, CFB_INTERLACED) != NOT_COVERED) return;
     g_fwd_ref++;
     ref(input, input_pitch, frame, transform, frame_index, num_channels, buffer, buffer_size, chroma_offset, precision, limit_yuv, conv_601_709);
 }
@@ -192,6 +209,7 @@ void ComputeGroupTransformQuant(ENCODER *encoder, TRANSFORM *transform[], int nu
     if (t_pyramid_done_for && t_pyramid_done_for == transform[0]) {
         // levels 2 and 3 came out of the same GPU pass as level 1: only the bookkeeping of encoder.c:8366-8420 / :8688-8790 remains
         t_pyramid_done_for = nullptr;
+        if (t_cuda_failed) { encoder->error = CODEC_ERROR_UNEXPECTED; t_cuda_failed = false; }
         for (int c = 0; c < num_transforms; c++) {
             transform[c]->num_frames = encoder->gop_length;
             transform[c]->num_spatial = encoder->num_spatial;
@@ -294,6 +312,8 @@ void ReconstructSampleFrameToBuffer(DECODER *decoder, int frame, uint8_t *output
     }
     if (err != CFB_OK) {
         fprintf(stderr, "cfhd_gpu_shim: CUDA inverse failed: %s\n", cfb_last_error_string());
+        g_cuda_errors++;
+        if (getenv("CFHD_B200_ABORT_ON_ERROR")) abort();
         decoder->error = CODEC_ERROR_BAD_FRAME;
     }
     g_inv_frames++;

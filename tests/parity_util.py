@@ -445,7 +445,22 @@ def pack_rg48(planes, precision=12):
 
 
 def ref_decode_sample_raw(ref_lib, sample, width, height, decoded_format, num_channels, pitch):
-    """Codec-level reference decode into an arbitrary DECODED_FORMAT_*; returns (bytes (height x pitch), dequantised bands)."""
+    """Codec-level reference decode into an arbitrary DECODED_FORMAT_*; returns (bytes (height x pitch), dequantised bands).
+
+    The reference's threaded decoder races when the host is oversubscribed (its output conversion can overtake a
+    transform worker: a whole channel of the returned frame then disagrees with the bands the decoder holds; seen about
+    once in 40 decodes under `pytest -n 8`, never on an idle host).  That is the reference's defect, not part of the
+    transform under test, so the decode is repeated until two consecutive runs return the same frame and bands."""
+    prev = None
+    for _ in range(8):
+        cur = _ref_decode_sample_raw_once(ref_lib, sample, width, height, decoded_format, num_channels, pitch)
+        if prev is not None and np.array_equal(prev[0], cur[0]) and all(np.array_equal(prev[1][k], cur[1][k]) for k in cur[1]):
+            return cur
+        prev = cur
+    return prev
+
+
+def _ref_decode_sample_raw_once(ref_lib, sample, width, height, decoded_format, num_channels, pitch):
     out = np.zeros((height, pitch), np.uint8)
     dims = np.zeros(num_channels * 9, np.int32)
     quant = np.zeros(num_channels * 12, np.int32)
