@@ -24,7 +24,7 @@ BAND_NAMES = ("LL", "LH", "HL", "HH")
 
 OK = 0
 ERROR_NAMES = {0: "OK", 1: "INVALID_ARGUMENT", 2: "OUTOFMEMORY", 3: "BADFORMAT", 10: "UNEXPECTED", 13: "NOT_FINISHED",
-               100: "NO_DEVICE", 101: "CUDA", 102: "UNSUPPORTED"}
+               100: "NO_DEVICE", 101: "CUDA", 102: "UNSUPPORTED", 103: "RANGE"}
 
 
 class CfbError(RuntimeError):
@@ -126,6 +126,7 @@ def lib():
     L.cfb_gop2_quant_for_quality.argtypes = [C.POINTER(FrameDesc), i, i, C.POINTER(Gop2Quant)]
     L.cfb_gop2_forward_host.argtypes = [vp, vp, vp, i, C.POINTER(Gop2Quant), vp]
     L.cfb_gop2_inverse_host.argtypes = [vp, vp, C.POINTER(Gop2Quant), i, vp, vp, i]
+    L.cfb_context_range_status.argtypes = [vp, C.POINTER(C.c_int)]
     L.cfb_level_forward_device.argtypes = [vp, C.POINTER(LevelDesc), vp, C.POINTER(vp)]
     L.cfb_level_inverse_device.argtypes = [vp, C.POINTER(LevelDesc), C.POINTER(vp), vp]
     L.cfb_level_forward_host.argtypes = [vp, C.POINTER(LevelDesc), vp, C.POINTER(vp)]
@@ -150,6 +151,10 @@ def lib():
     L.cfb_inverse_host_sparse.argtypes = [vp, i, C.POINTER(vp), C.POINTER(Quant), i, C.POINTER(vp), i]
     L.cfb_sparse_expand.argtypes = [C.POINTER(Layout), vp, vp]
     L.cfb_sparse_compact.argtypes = [C.POINTER(Layout), vp, vp, C.POINTER(C.c_size_t)]
+    L.cfb_sparse_vlc_band.argtypes = [C.POINTER(Layout), vp, i, i, i, C.POINTER(VlcCodebook), C.POINTER(BitWriter)]
+    L.cfb_dense_vlc_band.argtypes = [vp, i, i, i, C.POINTER(VlcCodebook), C.POINTER(BitWriter)]
+    L.cfb_sparse_band_nonzeros.argtypes = [C.POINTER(Layout), vp, i, i, i, C.POINTER(C.c_uint32)]
+    L.cfb_sparse_expand_band.argtypes = [C.POINTER(Layout), vp, i, i, i, vp, i]
     L.cfb_pool_submit_forward_sparse.argtypes = [vp, C.c_uint32, vp, i, C.POINTER(Quant), vp]
     L.cfb_pool_submit_inverse_sparse.argtypes = [vp, C.c_uint32, vp, C.POINTER(Quant), i, vp, i]
     L.cfb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -217,6 +222,63 @@ def sparse_compact(layout, dense):
     n = C.c_size_t()
     _check(lib().cfb_sparse_compact(C.byref(layout), dense.ctypes.data, out.ctypes.data, C.byref(n)))
     return out[:n.value]
+
+
+class VlcCodebook(C.Structure):
+    """cfb_vlc_codebook: the host entropy coder's run-length and value tables as plain arrays."""
+    _fields_ = [("run_length", C.c_int32), ("value_length", C.c_int32), ("run_bits", C.c_void_p), ("run_size", C.c_void_p),
+                ("run_count", C.c_void_p), ("value_bits", C.c_void_p), ("value_size", C.c_void_p)]
+
+    @classmethod
+    def from_arrays(cls, run_bits, run_size, run_count, value_bits, value_size):
+        self = cls()
+        self._keep = [np.ascontiguousarray(run_bits, np.uint32), np.ascontiguousarray(run_size, np.uint8),
+                      np.ascontiguousarray(run_count, np.uint32), np.ascontiguousarray(value_bits, np.uint32),
+                      np.ascontiguousarray(value_size, np.uint8)]
+        self.run_length, self.value_length = len(self._keep[0]), len(self._keep[3])
+        self.run_bits, self.run_size, self.run_count, self.value_bits, self.value_size = [a.ctypes.data for a in self._keep]
+        return self
+
+
+class BitWriter(C.Structure):
+    """cfb_bitwriter: the BITSTREAM fields the reference's coder reads and leaves behind."""
+    _fields_ = [("cur", C.c_void_p), ("end", C.c_void_p), ("buffer", C.c_uint32), ("bits_free", C.c_int32), ("bytes", C.c_int64)]
+
+
+def _bitwriter(buf, lead_bits):
+    bw = BitWriter()
+    bw.cur, bw.end = buf.ctypes.data, buf.ctypes.data + buf.size
+    bw.buffer, bw.bits_free, bw.bytes = (1 << lead_bits) - 1, 32 - lead_bits, 0
+    return bw
+
+
+def sparse_vlc_band(layout, sparse, channel, level, band, book, capacity, lead_bits=0):
+    """Run-length / VLC codes of one band straight from a sparse buffer -> (whole words written, pending buffer, bits free)."""
+    out = np.zeros(capacity, np.uint8)
+    bw = _bitwriter(out, lead_bits)
+    _check(lib().cfb_sparse_vlc_band(C.byref(layout), sparse.ctypes.data, channel, level, band, C.byref(book), C.byref(bw)))
+    return out[:bw.bytes].copy(), int(bw.buffer), int(bw.bits_free)
+
+
+def dense_vlc_band(band, pitch_bytes, width, book, capacity, lead_bits=0):
+    out = np.zeros(capacity, np.uint8)
+    bw = _bitwriter(out, lead_bits)
+    band = np.ascontiguousarray(band)
+    _check(lib().cfb_dense_vlc_band(band.ctypes.data, width, band.shape[0], pitch_bytes, C.byref(book), C.byref(bw)))
+    return out[:bw.bytes].copy(), int(bw.buffer), int(bw.bits_free)
+
+
+def sparse_band_nonzeros(layout, sparse, channel, level, band):
+    n = C.c_uint32()
+    _check(lib().cfb_sparse_band_nonzeros(C.byref(layout), sparse.ctypes.data, channel, level, band, C.byref(n)))
+    return int(n.value)
+
+
+def sparse_expand_band(layout, sparse, channel, level, band):
+    bl = layout.band[channel][level][band]
+    out = np.zeros((bl.height, bl.width), np.int16)
+    _check(lib().cfb_sparse_expand_band(C.byref(layout), sparse.ctypes.data, channel, level, band, out.ctypes.data, bl.width * 2))
+    return out
 
 
 def gop2_quant_for_quality(desc, quality, interlaced=False):
@@ -304,6 +366,12 @@ class Context:
         d = self._level_desc(2 * w2, 2 * h2, plane.strides[0], bands[0].strides[0], prescale, divisor, 2)
         _check(lib().cfb_level_inverse_host(self.h, C.byref(d), _ptr_array([b.ctypes.data for b in bands]), plane.ctypes.data))
         return plane
+
+    def range_status(self):
+        """Flags of the range audit since the last call (waits for the stream); 0 = every audited plane was in range."""
+        f = C.c_int()
+        _check(lib().cfb_context_range_status(self.h, C.byref(f)))
+        return int(f.value)
 
     def level_forward_device(self, w, h, plane_pitch, band_pitch, prescale, divisor, midpoint, d_plane, d_bands):
         d = self._level_desc(w, h, plane_pitch, band_pitch, prescale, divisor, midpoint)
@@ -488,6 +556,23 @@ class Codec:
         for (c, lvl, name), arr in bands.items():
             self.band_view(buf, c, lvl - 1, BAND_NAMES.index(name))[:] = arr
         return buf
+
+
+def band_view(layout, buf, c, k, b):
+    """View of band (channel c, level index k, band b) inside a coefficient buffer (uint8 array); host only."""
+    bl = layout.band[c][k][b]
+    flat = buf[bl.offset: bl.offset + bl.pitch * bl.height].view(np.int16)
+    return flat.reshape(bl.height, bl.pitch // 2)[:, :bl.width]
+
+
+def pack_coded(layout, bands):
+    """{(c, level 1..3, band name): array} -> dense coded region as cfb_layout describes it; host only."""
+    buf = np.zeros(layout.coded_bytes, np.uint8)
+    for (c, lvl, name), arr in bands.items():
+        if name == "LL" and lvl != NUM_LEVELS:
+            continue
+        band_view(layout, buf, c, lvl - 1, BAND_NAMES.index(name))[:] = arr
+    return buf
 
 
 def pinned_empty(shape, dtype=np.uint8):

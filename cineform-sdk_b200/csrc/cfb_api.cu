@@ -394,6 +394,8 @@ void cfb_context_destroy(cfb_context *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->done) cudaEventDestroy(ctx->done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->d_range) cudaFree(ctx->d_range);
+    if (ctx->h_range) cudaFreeHost(ctx->h_range);
     delete ctx;
 }
 
@@ -458,7 +460,7 @@ void cfb_codec_destroy(cfb_codec *cd)
     if (cd->d_gop) cudaFree(cd->d_gop);
     if (cd->d_curve) cudaFree(cd->d_curve);
     if (cd->d_sparse) cudaFree(cd->d_sparse);
-    if (cd->d_counts) cudaFree(cd->d_counts);
+    if (cd->d_status) cudaFree(cd->d_status);
     if (cd->h_headers) cudaFreeHost(cd->h_headers);
     delete cd;
 }

@@ -161,12 +161,21 @@ cfb_error cfb_gop2_forward_host(cfb_codec *cd, const void *frame_a, const void *
         }
         p.in_base[0] = cd->d_gop; p.out_base[0] = cd->d_gop;
         p.th = pick_rows_per_warp((maxw + kStripIn - 1) / kStripIn, maxoh, nc, ctx->sm_count);
+        // wavelet 3 reads the temporal HIGHPASS: the only signed plane of the pyramid (+-4080 by range), audited
+        if (k == 3) { e = audit_level_input(ctx, p, q->prescale[k]); if (e) return e; }
         CFB_CUDA(launch_fwd_plane(p, q->prescale[k], ctx->stream));
         ctx->kernel_launches++;
     }
     CFB_CUDA(cudaMemcpyAsync(h_coded, cd->d_gop, (size_t)G.coded_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->d2h_bytes += (uint64_t)G.coded_bytes;
     CFB_CUDA(stream_wait(ctx));
+    int range_flags = 0;
+    e = range_status(ctx, &range_flags);
+    if (e) return e;
+    if (range_flags) {
+        set_error("temporal highpass outside the exact-arithmetic range (flags %d): the reference's saturating chains would differ", range_flags);
+        return CFB_ERROR_RANGE;
+    }
     ctx->frames_forward += 2;
     return CFB_OK;
 }

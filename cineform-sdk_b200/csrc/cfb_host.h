@@ -37,6 +37,9 @@ cudaError_t launch_lowpass_422(const InvParams &p, cudaStream_t stream);
 cudaError_t launch_inv_fields(const InvParams &p, const FieldsAux &a, bool planar, cudaStream_t stream);
 cudaError_t launch_fwd_422_fields(const FwdParams &p, cudaStream_t stream);
 cudaError_t launch_fwd_yu64(const FwdParams &p, cudaStream_t stream);
+// range audit of the planes a forward level is about to read (cfb_audit.cu): ORs violation bits into ctx->d_range
+cfb_error audit_level_input(cfb_context *ctx, const FwdParams &p, int prescale);
+cfb_error range_status(cfb_context *ctx, int *flags);
 cudaError_t launch_fwd_v210(const FwdParams &p, cudaStream_t stream);
 
 // The host forms of the transform as three stages, each on a stream of the caller's choice, so that the frame pool can
@@ -45,16 +48,16 @@ cudaError_t launch_fwd_v210(const FwdParams &p, cudaStream_t stream);
 // device staging are used.  The synchronous C-ABI calls are these three stages on one stream + a wait.
 cfb_error stage_fwd_upload(cfb_codec *cd, int n, const void *const *h_frames, int frame_pitch, cudaStream_t s);
 cfb_error stage_fwd_compute(cfb_codec *cd, int n, const cfb_quant *quant, bool sparse);
-// sparse: copies header + bitmap + `guess` values of every frame (speculative single pass); dense: the coded region
+// sparse: copies the first `guess` bytes of every frame's sparse buffer (speculative single pass); dense: the coded region
 cfb_error stage_fwd_download(cfb_codec *cd, int n, void *const *h_out, bool sparse, unsigned guess, cudaStream_t s);
-// sparse only, after the download has completed: fetches the values beyond `guess` (if any frame has more), reports sizes
+// sparse only, after the download has completed: fetches the bytes beyond `guess` (if any frame has more), reports sizes
 cfb_error stage_fwd_tail(cfb_codec *cd, int n, void *const *h_sparse, unsigned guess, cudaStream_t s, size_t *sizes,
-                         unsigned *max_values, bool *more);
+                         unsigned *max_bytes, bool *more);
 cfb_error stage_inv_upload(cfb_codec *cd, int n, const void *const *h_in, bool sparse, cudaStream_t s);
 cfb_error stage_inv_compute(cfb_codec *cd, int n, const cfb_quant *quant, int out_format, bool sparse);
 cfb_error stage_inv_download(cfb_codec *cd, int n, void *const *h_frames, int frame_pitch, int out_format, cudaStream_t s);
 unsigned sparse_initial_guess(const cfb_codec *cd);
-unsigned sparse_next_guess(const cfb_codec *cd, unsigned max_values);
+unsigned sparse_next_guess(const cfb_codec *cd, unsigned max_bytes);
 // GPU compaction / expansion between the pyramids and the sparse staging buffers of slots [0, n) (kernels only)
 cfb_error sparse_upload(cfb_codec *cd, int n, const void *const *h_sparse, cudaStream_t s);
 cfb_error sparse_download(cfb_codec *cd, int n, void *const *h_sparse, unsigned guess, cudaStream_t s);
@@ -68,6 +71,8 @@ struct cfb_context {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;             // blocking-sync event: host threads sleep instead of spinning
     int sm_count = 0;
+    int *d_range = nullptr;                 // device flag word of the range audit (cfb_audit.cu), allocated on first use
+    int *h_range = nullptr;                 // pinned copy
     std::atomic<uint64_t> kernel_launches{0}, frames_forward{0}, frames_inverse{0}, h2d_bytes{0}, d2h_bytes{0};
 };
 
@@ -90,8 +95,8 @@ struct cfb_codec {
     int decode_res = 1;                     // CFB_RESOLUTION_*: 1 full, 2 half (LL1), 3 quarter (LL2)
     // sparse transfer format staging (allocated on first use)
     unsigned char *d_sparse = nullptr;      // max_batch sparse buffers
-    unsigned *d_counts = nullptr;           // max_batch * (nseg + 1)
+    unsigned long long *d_status = nullptr; // max_batch * (nblocks + 1): look-back state of the one-pass packer
     unsigned *h_headers = nullptr;          // pinned, 4 u32 per slot
     size_t sparse_stride = 0;
-    unsigned value_guess = 0;               // running estimate of non-zero words per frame (speculative single-pass D2H)
+    unsigned value_guess = 0;               // running estimate of a frame's sparse size in bytes (speculative single-pass D2H)
 };

@@ -14,6 +14,11 @@
 // stage and writes 8 output samples per row with one 128-bit store.  Lanes 0 and 31 of a warp are
 // halo lanes (their columns belong to the neighbouring strips), so a strip covers 120 band columns.
 #include "cfb_common.cuh"
+#include "cfb_tma.cuh"
+
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
 
 namespace cfb {
 
@@ -394,11 +399,59 @@ __device__ __forceinline__ unsigned row16u(int t, int up_shift, int hi) {
     return (unsigned)min(max(t >> 1, 0) << up_shift, hi);
 }
 
+// One band row r of the final 4:2:2 level -> output rows 2r and 2r + 1 of the lane's 8 luma samples (+ 4 + 4 chroma).
+// `out` already points at the lane's first sample of row 0.  t values arrive BEFORE the filter's final >> 1.
+template <bool OUT16>
+__device__ __forceinline__ void emit_422(const InvParams &p, unsigned char *out, int col0, int r, const int *ye, const int *yo,
+                                         const int *ue, const int *uo, const int *ve, const int *vo)
+{
+    const InvGeom &gy = p.ch[0];
+    const int sh = p.shift + 1;     // final >>1 of the filter merged with the >> (precision-8) reduction
+    unsigned char *o = out + (long long)(2 * r) * gy.out_pitch;
+    if (OUT16) {
+        const int us = p.up_shift;
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const int *yy = rr ? yo : ye, *uu = rr ? uo : ue, *vv = rr ? vo : ve;
+            unsigned w[8];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                // luma band column col0 + k -> samples 2k, 2k + 1; chroma band column col0 / 2 + (k >> 1) -> sample k
+                const int hy = (col0 + k >= p.tail_col[0]) ? 65535 : p.hi_simd;
+                const int hc1 = ((col0 >> 1) + (k >> 1) >= p.tail_col[1]) ? 65535 : p.hi_simd;
+                const int hc2 = ((col0 >> 1) + (k >> 1) >= p.tail_col[2]) ? 65535 : p.hi_simd;
+                // pixel pair k: words (Y0, C1) (Y1, C3); C1 = channel 1 (the v arrays), C3 = channel 2 (the u arrays)
+                w[2 * k] = row16u(yy[2 * k], us, hy) | (row16u(vv[k], us, hc1) << 16);
+                w[2 * k + 1] = row16u(yy[2 * k + 1], us, hy) | (row16u(uu[k], us, hc2) << 16);
+            }
+            unsigned char *q = o + (rr ? gy.out_pitch : 0);
+            *reinterpret_cast<uint4 *>(q) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4 *>(q + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    } else {
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        const int *yy = rr ? yo : ye, *uu = rr ? uo : ue, *vv = rr ? vo : ve;
+        // ordered dither d = (x ^ y) & 1 on the sample's own column index, scaled to the merged shift;
+        // band row r -> output rows 2r (even) and 2r+1 (odd)
+        const int d0 = (rr ? 1 : 0) << (sh - 2), d1 = (rr ? 0 : 1) << (sh - 2);
+        unsigned w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int ya = (yy[2 * k] + d0) >> sh, yb = (yy[2 * k + 1] + d1) >> sh;
+            const int cu = (uu[k] + ((k & 1) ? d1 : d0)) >> sh, cv = (vv[k] + ((k & 1) ? d1 : d0)) >> sh;
+            w[k] = p.uyvy ? pack_u8x4(cu, ya, cv, yb) : pack_u8x4(ya, cu, yb, cv);
+        }
+        *reinterpret_cast<uint4 *>(o + (rr ? gy.out_pitch : 0)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    }
+}
+
 // OUT16 = false: packed 8-bit YUYV / UYVY.  OUT16 = true: packed 16-bit Y0 C1 Y1 C3 (YU64; C1 = channel 1, C3 = channel 2,
 // as the YU64 encoder input assigns them), the reference's 16-bit row output (decoder.c:26351-26366 ->
 // TransformInverseSpatialUniversalThreadedToRow16u -> InvertHorizontalStrip16s.c:17462 / :16571) -- no dither, bit-exact.
-template <bool SMALLDQ, bool OUT16>
-__global__ void __launch_bounds__(128) k_inv_422(const __grid_constant__ InvParams p)
+template <bool SMALLDQ, bool OUT16, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_inv_422(const __grid_constant__ InvParams p)
 {
     const int lane = threadIdx.x;
     const int f = blockIdx.z;
@@ -419,46 +472,8 @@ __global__ void __launch_bounds__(128) k_inv_422(const __grid_constant__ InvPara
     const unsigned char *in = p.in_base[f];
     unsigned char *out = p.out_base[f] + gy.out_off + (long long)col0 * (OUT16 ? 8 : 4);     // 2 (4) bytes per luma sample, 2 samples per column
 
-    const int sh = p.shift + 1;     // final >>1 of the filter merged with the >> (precision-8) reduction
     auto emit = [&](int r, const int *ye, const int *yo, const int *ue, const int *uo, const int *ve, const int *vo) {
-        unsigned char *o = out + (long long)(2 * r) * gy.out_pitch;
-        if (OUT16) {
-            const int us = p.up_shift;
-#pragma unroll
-            for (int rr = 0; rr < 2; rr++) {
-                const int *yy = rr ? yo : ye, *uu = rr ? uo : ue, *vv = rr ? vo : ve;
-                unsigned w[8];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    // luma band column col0 + k -> samples 2k, 2k + 1; chroma band column col0 / 2 + (k >> 1) -> sample k
-                    const int hy = (col0 + k >= p.tail_col[0]) ? 65535 : p.hi_simd;
-                    const int hc1 = ((col0 >> 1) + (k >> 1) >= p.tail_col[1]) ? 65535 : p.hi_simd;
-                    const int hc2 = ((col0 >> 1) + (k >> 1) >= p.tail_col[2]) ? 65535 : p.hi_simd;
-                    // pixel pair k: words (Y0, C1) (Y1, C3); C1 = channel 1 (the v arrays), C3 = channel 2 (the u arrays)
-                    w[2 * k] = row16u(yy[2 * k], us, hy) | (row16u(vv[k], us, hc1) << 16);
-                    w[2 * k + 1] = row16u(yy[2 * k + 1], us, hy) | (row16u(uu[k], us, hc2) << 16);
-                }
-                unsigned char *q = o + (rr ? gy.out_pitch : 0);
-                *reinterpret_cast<uint4 *>(q) = make_uint4(w[0], w[1], w[2], w[3]);
-                *reinterpret_cast<uint4 *>(q + 16) = make_uint4(w[4], w[5], w[6], w[7]);
-            }
-        } else {
-#pragma unroll
-        for (int rr = 0; rr < 2; rr++) {
-            const int *yy = rr ? yo : ye, *uu = rr ? uo : ue, *vv = rr ? vo : ve;
-            // ordered dither d = (x ^ y) & 1 on the sample's own column index, scaled to the merged shift;
-            // band row r -> output rows 2r (even) and 2r+1 (odd)
-            const int d0 = (rr ? 1 : 0) << (sh - 2), d1 = (rr ? 0 : 1) << (sh - 2);
-            unsigned w[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int ya = (yy[2 * k] + d0) >> sh, yb = (yy[2 * k + 1] + d1) >> sh;
-                const int cu = (uu[k] + ((k & 1) ? d1 : d0)) >> sh, cv = (vv[k] + ((k & 1) ? d1 : d0)) >> sh;
-                w[k] = p.uyvy ? pack_u8x4(cu, ya, cv, yb) : pack_u8x4(ya, cu, yb, cv);
-            }
-            *reinterpret_cast<uint4 *>(o + (rr ? gy.out_pitch : 0)) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        }
+        emit_422<OUT16>(p, out, col0, r, ye, yo, ue, uo, ve, vo);
     };
 
     if (blockIdx.y == gridDim.y - 1) {          // border warps: band rows 0 and H-1
@@ -493,6 +508,8 @@ __global__ void __launch_bounds__(128) k_inv_422(const __grid_constant__ InvPara
         if (writer) emit(r, ye, yo, ue, uo, ve, vo);
     }
 }
+
+#include "cfb_inverse_tma.inl"
 
 // ----------------------------------------------------------------------------
 // final level of a 4:4:4 frame (channels G, R, B): 12 bands -> packed 16-bit R,G,B (RG48).
@@ -783,14 +800,92 @@ cudaError_t launch_inv_plane(const InvParams &p, int descale, cudaStream_t strea
     return cudaGetLastError();
 }
 
+// CFB_INV422 selects the variant of the final 4:2:2 level (A/B evidence in profiles/r02_ab_inv422.txt):
+//   r1 (default)  global loads straight into registers, 4 CTAs per SM; r1b5: the same capped at 102 registers (5 CTAs per SM)
+//   tma<R><NS>    TMA ring with R band rows per stage and NS stages per warp -- measured SLOWER than r1 (183 vs 171 us per
+//                 16 4K frames at best): twelve bands per row mean six copy instructions per stage, each wrapped in an
+//                 elect / uniform-register sequence, i.e. as many issue slots as the loads they replace, and the rings
+//                 cost occupancy
+static int inv422_variant()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CFB_INV422");
+        v = 0;
+        if (e && !strcmp(e, "r1b5")) v = 5;
+        else if (e && !strncmp(e, "tma", 3) && strlen(e) == 5) v = atoi(e + 3);
+    }
+    return v;
+}
+
+template <bool SMALLDQ, bool OUT16, int R, int NS>
+static cudaError_t launch_inv_422_tma_t(const InvParams &p, const InvTmaMaps &tm, dim3 grid, dim3 block, cudaStream_t stream)
+{
+    constexpr int smem = 4 * NS * InvStage<R>::kBytes + 4 * NS * 8;
+    constexpr int minb = (smem <= 56 * 1024) ? 4 : (smem <= 75 * 1024 ? 3 : (smem <= 113 * 1024 ? 2 : 1));
+    static_assert(smem <= 227 * 1024, "ring does not fit the shared memory of an SM");
+    auto kern = k_inv_422_tma<SMALLDQ, OUT16, R, NS, minb>;
+    static bool attr_set = false;       // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    kern<<<grid, block, smem, stream>>>(p, tm);
+    return cudaGetLastError();
+}
+
+template <bool SMALLDQ, bool OUT16>
+static cudaError_t launch_inv_422_tma(const InvParams &p, const InvTmaMaps &tm, dim3 grid, dim3 block, int variant, cudaStream_t stream)
+{
+    switch (variant) {
+    case 16: return launch_inv_422_tma_t<SMALLDQ, OUT16, 1, 6>(p, tm, grid, block, stream);
+    case 18: return launch_inv_422_tma_t<SMALLDQ, OUT16, 1, 8>(p, tm, grid, block, stream);
+    case 23: return launch_inv_422_tma_t<SMALLDQ, OUT16, 2, 3>(p, tm, grid, block, stream);
+    case 44: return launch_inv_422_tma_t<SMALLDQ, OUT16, 4, 4>(p, tm, grid, block, stream);
+    case 43: return launch_inv_422_tma_t<SMALLDQ, OUT16, 4, 3>(p, tm, grid, block, stream);
+    case 42: return launch_inv_422_tma_t<SMALLDQ, OUT16, 4, 2>(p, tm, grid, block, stream);
+    case 22: return launch_inv_422_tma_t<SMALLDQ, OUT16, 2, 2>(p, tm, grid, block, stream);
+    default: return launch_inv_422_tma_t<SMALLDQ, OUT16, 2, 4>(p, tm, grid, block, stream);
+    }
+}
+
 cudaError_t launch_inv_422(const InvParams &p, bool out16, cudaStream_t stream)
 {
     dim3 block(32, 4);
     dim3 grid(ceil_div_i(p.ch[0].width, kInvStrip), ceil_div_i(ceil_div_i(p.ch[0].height, p.th), (int)block.y) + 1, p.nframes);
     bool small = true;
     for (int c = 0; c < 3; c++) for (int b = 1; b < 4; b++) small = small && (p.ch[c].dq[b] >= 0 && p.ch[c].dq[b] <= 255);
-    if (out16) { if (small) k_inv_422<true, true><<<grid, block, 0, stream>>>(p); else k_inv_422<false, true><<<grid, block, 0, stream>>>(p); }
-    else { if (small) k_inv_422<true, false><<<grid, block, 0, stream>>>(p); else k_inv_422<false, false><<<grid, block, 0, stream>>>(p); }
+    // The TMA path needs 16-byte aligned band starts and pitches (cfb_layout_compute guarantees both for pyramids it laid
+    // out), whole 32-bit elements per band row, and LH / HL / HH of a channel equally spaced
+    const int variant = inv422_variant();
+    bool tma_ok = variant >= 10;
+    for (int c = 0; c < 3 && tma_ok; c++) {
+        const InvGeom &g = p.ch[c];
+        const long long d1 = g.band_off[2] - g.band_off[1], d2 = g.band_off[3] - g.band_off[2];
+        tma_ok = !(g.width & 1) && !(g.pitch & 15) && d1 == d2 && d1 > 0 && !(d1 & 15) && !(g.band_off[0] & 15) && !(g.band_off[1] & 15);
+    }
+    for (int i = 0; i < p.nframes && tma_ok; i++) tma_ok = !((uintptr_t)p.in_base[i] & 15);
+    if (tma_ok) {
+        InvTmaMaps tm;
+        for (int i = 0; i < p.nframes; i++)
+            for (int c = 0; c < 3; c++) {
+                const InvGeom &g = p.ch[c];
+                const uint32_t box = (c == 0) ? kInvBoxY : kInvBoxC;
+                const int R = variant / 10;
+                cudaError_t e = tmap_encode_2d(&tm.m[i][2 * c], p.in_base[i] + g.band_off[0], (uint64_t)g.width * 2, (uint64_t)g.height,
+                                               (uint64_t)g.pitch, box, R);
+                if (e == cudaSuccess)
+                    e = tmap_encode_3d(&tm.m[i][2 * c + 1], p.in_base[i] + g.band_off[1], (uint64_t)g.width * 2, (uint64_t)g.height,
+                                       (uint64_t)g.pitch, 3, (uint64_t)(g.band_off[2] - g.band_off[1]), box, R, 3);
+                if (e != cudaSuccess) return e;
+            }
+        if (out16) return small ? launch_inv_422_tma<true, true>(p, tm, grid, block, variant, stream) : launch_inv_422_tma<false, true>(p, tm, grid, block, variant, stream);
+        return small ? launch_inv_422_tma<true, false>(p, tm, grid, block, variant, stream) : launch_inv_422_tma<false, false>(p, tm, grid, block, variant, stream);
+    }
+    if (out16) { if (small) k_inv_422<true, true, 3><<<grid, block, 0, stream>>>(p); else k_inv_422<false, true, 3><<<grid, block, 0, stream>>>(p); }
+    else if (variant == 5) { if (small) k_inv_422<true, false, 5><<<grid, block, 0, stream>>>(p); else k_inv_422<false, false, 5><<<grid, block, 0, stream>>>(p); }
+    else { if (small) k_inv_422<true, false, 4><<<grid, block, 0, stream>>>(p); else k_inv_422<false, false, 4><<<grid, block, 0, stream>>>(p); }
     return cudaGetLastError();
 }
 

@@ -56,6 +56,8 @@ cfb_error cfb_level_forward_device(cfb_context *ctx, const cfb_level_desc *d, co
     p.in_base[0] = (const unsigned char *)d_plane;
     p.out_base[0] = (unsigned char *)d_bands[0];
     p.th = pick_rows_per_warp((d->width + kStripIn - 1) / kStripIn, d->height / 2, 1, ctx->sm_count);
+    e = audit_level_input(ctx, p, d->prescale);        // a free-standing plane may be signed: see "Value range" in the header
+    if (e) return e;
     CFB_CUDA(launch_fwd_plane(p, d->prescale, ctx->stream));
     ctx->kernel_launches++;
     return CFB_OK;
@@ -118,6 +120,14 @@ static cfb_error level_host(cfb_context *ctx, bool forward, const cfb_level_desc
     cudaFreeAsync(dev, ctx->stream);
     if (ce == cudaSuccess) ce = stream_wait(ctx);
     if (ce != cudaSuccess) return cuda_fail(ce, "single-level transform (host form)");
+    if (!err && forward) {
+        int flags = 0;
+        err = range_status(ctx, &flags);
+        if (!err && flags) {
+            set_error("plane outside the exact-arithmetic range (flags %d: 1 = input, 2 = horizontal output beyond +-8190): the reference's saturating chains would differ", flags);
+            err = CFB_ERROR_RANGE;
+        }
+    }
     return err;
 }
 
@@ -129,6 +139,12 @@ cfb_error cfb_level_forward_host(cfb_context *ctx, const cfb_level_desc *d, cons
 cfb_error cfb_level_inverse_host(cfb_context *ctx, const cfb_level_desc *d, const void *const *bands, void *plane)
 {
     return level_host(ctx, false, d, plane, (void *const *)bands);
+}
+
+cfb_error cfb_context_range_status(cfb_context *ctx, int *flags)
+{
+    if (!ctx || !flags) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    return range_status(ctx, flags);
 }
 
 }  // extern "C"

@@ -55,7 +55,7 @@ struct Slot {
     cfb_codec *codec = nullptr;             // device staging for `batch` frames (frames, pyramids, sparse buffers)
     cudaEvent_t ev_up = nullptr, ev_k = nullptr, ev_down = nullptr;
     std::vector<std::shared_ptr<Job>> jobs;
-    unsigned guess = 0;                     // values copied speculatively for the sparse results of this batch
+    unsigned guess = 0;                     // bytes copied speculatively for the sparse results of this batch
     uint64_t up_bytes = 0, down_bytes = 0;  // PCIe bytes of this batch in either direction (estimates, for the issue balance)
     cfb_error issue_error = CFB_OK;
 };
@@ -69,7 +69,7 @@ struct Device {
     std::deque<int> free_slots;             // guarded by cfb_pool::mu
     std::deque<int> in_flight;              // issue order, guarded by cfb_pool::mu
     std::condition_variable cv_flight;
-    unsigned value_guess = 0;               // running estimate of non-zero words per frame (all slots of this GPU)
+    unsigned value_guess = 0;               // running estimate of a frame's sparse size in bytes (all slots of this GPU)
     uint64_t up_pending = 0, down_pending = 0;  // bytes issued and not yet delivered, per PCIe direction (guarded by mu)
     bool issuer_done = false;               // guarded by cfb_pool::mu: nothing more will enter in_flight
     std::thread issuer, completer;
@@ -99,8 +99,7 @@ struct cfb_pool {
 // PCIe bytes a job moves in either direction (the sparse size is the device's running estimate)
 void cfb_pool::job_bytes(const Device &d, const Job &j, uint64_t *up, uint64_t *down) const
 {
-    const uint64_t nwords = (uint64_t)layout.coded_bytes / 2;
-    const uint64_t coded = j.sparse ? 16 + nwords / 8 + 2 * (uint64_t)(d.value_guess ? d.value_guess : nwords / 8) : (uint64_t)layout.coded_bytes;
+    const uint64_t coded = j.sparse ? (uint64_t)(d.value_guess ? d.value_guess : layout.coded_bytes / 8) : (uint64_t)layout.coded_bytes;
     const uint64_t frame = (uint64_t)layout.frame_bytes;
     if (!j.inverse) { *up = frame; *down = coded; } else { *up = coded; *down = frame; }
 }

@@ -1,34 +1,39 @@
-// cfb_sparse.cu -- lossless sparse transfer format for the coded region.
+// cfb_sparse.cu -- lossless sparse transfer format for the coded region, version 2 ('CFS2').
 //
-// After quantisation ~90 % of the highpass coefficients are zero, and the dense int16 bands (33 MB per
-// 4K 4:2:2 frame) are what limits the host<->device path (PCIe), not the kernels.  The host entropy coder
-// only ever needs (zero run, value) sequences (Codec/encoder.c:5386-5847 EncodeQuantLongRuns walks the band
-// counting zeros, incl. the pitch gap :5811), so the natural wire format is
+// After quantisation ~90 % of the highpass coefficients are zero and ~99 % of the rest fit a byte, and the dense int16
+// bands (33 MB per 4K 4:2:2 frame) are what limits the host<->device path (PCIe), not the kernels.  The host entropy
+// coder only ever needs (zero run, value) sequences (Codec/encoder.c:5386-5700 EncodeQuantLongRuns walks the band
+// counting zeros, incl. the pitch gap :5653), so the wire format keeps exactly that information, in blocks that both
+// the GPU and the host can address independently:
 //
-//     header  : u32 magic 'CFSP', u32 nwords, u32 nvalues, u32 reserved
-//     bitmap  : nwords bits, bit i set <=> int16 word i of the coded region is non-zero (LSB-first in u32s)
-//     values  : the nvalues non-zero int16 words in raster (word index) order
+//   header   32 B : u32 'CFS2', u32 nwords, u32 total_bytes, u32 nblocks, 4 x u32 0
+//   table    nblocks x 16 B : { u32 chunk offset (bytes from the buffer start), u32 groups, u32 values, u32 escapes }
+//   chunks   one per block of 8192 int16 words of the flat coded region [0, coded_bytes) (pitch padding included, it
+//            is zero), 16-byte aligned, EMPTY (0 bytes) when the whole block is zero:
+//              l1     32 B  : bit g set <=> group g (32 consecutive words) of the block holds a non-zero word
+//              masks  4 B per non-empty group, in order: bit i <=> word i of the group is non-zero
+//              bytes  1 B per non-zero word, in raster order: the value if -127 <= v <= 127, else -128 (escape)
+//              wide   2 B per escape, in order: the int16 value            (each array padded with zeros to 4 B)
 //
-// over the flat coded region [0, coded_bytes) exactly as laid out by cfb_layout (pitch padding included, it is
-// zero).  Compaction and expansion run on the GPU (three small kernels each: count per CTA of 8192 words,
-// per-frame exclusive scan of the ~2000 CTA counts, scatter / gather with the position inside the CTA recomputed); the host helpers cfb_sparse_expand / cfb_sparse_compact are
-// pure format conversions for callers that want dense bands.
+// A 4K 4:2:2 frame at FILMSCAN1 (1.5 M non-zero words) is 2.3 MB instead of 33.2 MB dense (round 1's flat bitmap +
+// int16 values: 5.1 MB).  Packing is ONE kernel that reads the dense region once: every CTA builds its chunk in shared
+// memory, publishes the chunk size, obtains its byte offset by decoupled look-back over the preceding CTAs of the frame
+// and copies the chunk out with 16-byte stores.  Unpacking is one kernel as well: the table gives every CTA its chunk.
+// The host helpers cfb_sparse_expand / cfb_sparse_compact are pure format conversions (cfb_sparse_compact produces
+// byte for byte what the GPU produces); cfb_vlc.cu walks the chunks to emit the run-length / VLC stream directly.
 #include "cfb_host.h"
+#include "cfb_sparse_format.h"
 
 namespace cfb {
 
-constexpr int kSeg = 256;           // words per segment (one warp, 8 words per lane)
-constexpr int kBlockSegs = 32;      // segments per CTA (32 warps): the unit of the cross-CTA prefix sum
-
 struct SparseParams {
     int nframes;
-    unsigned nwords;                // int16 words in the coded region
-    unsigned nseg;
-    unsigned nblocks;               // ceil(nseg / kBlockSegs)
-    unsigned bitmap_off, values_off;            // byte offsets inside a sparse buffer
+    unsigned nwords;                // int16 words in the coded region (a multiple of 32)
+    unsigned nblocks;
+    unsigned chunks_off;            // byte offset of the first chunk
     const unsigned char *dense[kMaxBatch];      // pyramids (coded region at offset 0)
     unsigned char *sparse[kMaxBatch];
-    unsigned *counts[kMaxBatch];                // nblocks + 1 entries: per-CTA counts, then exclusive offsets after the scan
+    unsigned long long *status[kMaxBatch];      // look-back state: nblocks entries + 1 ticket counter per frame
 };
 
 __device__ __forceinline__ unsigned nonzero_mask8(const uint4 &w) {
@@ -46,7 +51,7 @@ __device__ __forceinline__ unsigned warp_incl_scan(unsigned v, int lane) {
     return v;
 }
 
-// exclusive offset of this warp's segment inside its CTA + the CTA total (all 32 warps call it; one barrier)
+// exclusive offset of this warp inside its CTA + the CTA total (all 32 warps call it; one barrier)
 __device__ __forceinline__ unsigned block_exclusive(unsigned warp_total, int lane, int wid, unsigned *smem32, unsigned *cta_total) {
     if (lane == 0) smem32[wid] = warp_total;
     __syncthreads();
@@ -56,152 +61,195 @@ __device__ __forceinline__ unsigned block_exclusive(unsigned warp_total, int lan
     return __shfl_sync(0xffffffffu, incl - mine, wid);
 }
 
-// A: per segment the bitmap words, per CTA (32 segments) the number of non-zero words
-__global__ void __launch_bounds__(1024) k_sparse_count(const __grid_constant__ SparseParams p)
+constexpr unsigned long long kFlagAggregate = 1ull << 62, kFlagPrefix = 2ull << 62, kFlagMask = 3ull << 62;
+
+// ---------------------------------------------------------------------------------------------------------------
+// dense -> sparse, one pass.  CTA = 1024 threads = one block of 8192 words (thread t: words 8t .. 8t + 7; four
+// consecutive lanes = one group).  Blocks take their index from a per-frame ticket, so a CTA only ever waits for
+// CTAs that already run.
+__global__ void __launch_bounds__(1024) k_sparse_pack(const __grid_constant__ SparseParams p)
 {
-    __shared__ unsigned wtot[32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned seg = blockIdx.x * kBlockSegs + wid;
+    __shared__ __align__(16) unsigned char chunk[kSparseMaxChunk];
+    __shared__ unsigned s_scan[32], s_gscan[32], s_ticket, s_base;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int f = blockIdx.y;
-    const unsigned w0 = seg * kSeg + lane * 8;
+    unsigned long long *status = p.status[f];
+    if (tid == 0) s_ticket = (unsigned)atomicAdd(&status[p.nblocks], 1ull);
+    __syncthreads();
+    const unsigned blk = s_ticket;
+    const unsigned w0 = blk * kSparseBlockWords + tid * 8;
     uint4 w = make_uint4(0, 0, 0, 0);
-    if (seg < p.nseg && w0 < p.nwords) w = __ldg(reinterpret_cast<const uint4 *>(p.dense[f] + (size_t)w0 * 2));
+    if (w0 < p.nwords) w = __ldg(reinterpret_cast<const uint4 *>(p.dense[f] + (size_t)w0 * 2));
     const unsigned m8 = nonzero_mask8(w);
     unsigned m = m8 << ((lane & 3) * 8);
     m |= __shfl_xor_sync(0xffffffffu, m, 1);
-    m |= __shfl_xor_sync(0xffffffffu, m, 2);
-    if ((lane & 3) == 0 && seg < p.nseg && w0 < p.nwords)
-        reinterpret_cast<unsigned *>(p.sparse[f] + p.bitmap_off)[seg * 8 + (lane >> 2)] = m;
-    unsigned c = __popc(m8);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    unsigned total;
-    block_exclusive(c, lane, wid, wtot, &total);
-    if (threadIdx.x == 0) p.counts[f][blockIdx.x] = total;
-}
-
-// A': per-CTA counts from an uploaded bitmap (32 segments = 256 bitmap words per CTA)
-__global__ void __launch_bounds__(256) k_sparse_count_bitmap(const __grid_constant__ SparseParams p)
-{
-    __shared__ unsigned wtot[8];
-    const int f = blockIdx.y;
-    const unsigned word = blockIdx.x * (kBlockSegs * 8) + threadIdx.x;          // index of a 32-bit bitmap word
-    unsigned c = 0;
-    if (word < p.nwords / 32) c = __popc(__ldg(reinterpret_cast<const unsigned *>(p.sparse[f] + p.bitmap_off) + word));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0) wtot[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned t = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) t += wtot[i];
-        p.counts[f][blockIdx.x] = t;
-    }
-}
-
-// B: per-frame exclusive scan of the per-CTA counts (one CTA per frame; a 4K 4:2:2 frame has 2026 of them);
-// writes the total into the header
-__global__ void __launch_bounds__(1024) k_sparse_scan(const __grid_constant__ SparseParams p, int write_header)
-{
-    __shared__ unsigned wsum[32];
-    const int f = blockIdx.x;
-    unsigned *cnt = p.counts[f];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    unsigned carry = 0;
-    for (unsigned base = 0; base < p.nblocks; base += 1024 * 4) {
-        unsigned v[4], s = 0;
-        const unsigned i0 = base + tid * 4;
-#pragma unroll
-        for (int k = 0; k < 4; k++) { v[k] = (i0 + k < p.nblocks) ? cnt[i0 + k] : 0u; s += v[k]; }
-        const unsigned incl = warp_incl_scan(s, lane);
-        unsigned chunk_total;
-        const unsigned wexcl = block_exclusive(__shfl_sync(0xffffffffu, incl, 31), lane, wid, wsum, &chunk_total);
-        unsigned excl = carry + wexcl + (incl - s);
-#pragma unroll
-        for (int k = 0; k < 4; k++) { if (i0 + k < p.nblocks) cnt[i0 + k] = excl; excl += v[k]; }
-        carry += chunk_total;
-        __syncthreads();
-    }
-    if (tid == 0) {
-        cnt[p.nblocks] = carry;
-        if (write_header) {
-            unsigned *h = reinterpret_cast<unsigned *>(p.sparse[f]);
-            h[0] = 0x50534643u; h[1] = p.nwords; h[2] = carry; h[3] = 0;
-        }
-    }
-}
-
-// C: scatter the non-zero words in raster order (the position inside the CTA is recomputed from the data)
-__global__ void __launch_bounds__(1024) k_sparse_scatter(const __grid_constant__ SparseParams p)
-{
-    __shared__ unsigned wtot[32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned seg = blockIdx.x * kBlockSegs + wid;
-    const int f = blockIdx.y;
-    const unsigned w0 = seg * kSeg + lane * 8;
-    uint4 w = make_uint4(0, 0, 0, 0);
-    if (seg < p.nseg && w0 < p.nwords) w = __ldg(reinterpret_cast<const uint4 *>(p.dense[f] + (size_t)w0 * 2));
-    const unsigned m8 = nonzero_mask8(w);
-    const unsigned c = __popc(m8);
-    const unsigned incl = warp_incl_scan(c, lane);
-    const unsigned wexcl = block_exclusive(__shfl_sync(0xffffffffu, incl, 31), lane, wid, wtot, nullptr);
-    unsigned pos = p.counts[f][blockIdx.x] + wexcl + incl - c;
-    unsigned short *vals = reinterpret_cast<unsigned short *>(p.sparse[f] + p.values_off);
+    m |= __shfl_xor_sync(0xffffffffu, m, 2);                // all four lanes of a group hold its 32-bit mask
     const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+    int vals[8];
+    unsigned nesc = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const unsigned short x = (unsigned short)((k & 1) ? (ws[k >> 1] >> 16) : (ws[k >> 1] & 0xffffu));
-        if (x) vals[pos++] = x;
+        vals[k] = (k & 1) ? ((int)ws[k >> 1] >> 16) : (int)(short)(ws[k >> 1] & 0xffffu);
+        nesc += (vals[k] < -127 || vals[k] > 127) ? 1u : 0u;
+    }
+    const unsigned nval = __popc(m8);
+    // ---- positions inside the block: values | escapes packed in one scan, groups by ballot ----
+    const unsigned packed = nval | (nesc << 16);
+    const unsigned incl = warp_incl_scan(packed, lane);
+    const bool gleader = ((lane & 3) == 0) && (m != 0);
+    const unsigned gb = __ballot_sync(0xffffffffu, gleader);
+    unsigned tot, gtot;
+    const unsigned wexcl = block_exclusive(__shfl_sync(0xffffffffu, incl, 31), lane, wid, s_scan, &tot);
+    const unsigned gexcl = block_exclusive(__popc(gb), lane, wid, s_gscan, &gtot);
+    const unsigned V = tot & 0xffffu, E = tot >> 16, G = gtot;
+    const unsigned bytes = sparse_chunk_bytes(G, V, E);
+    // ---- publish the chunk size, look back for the offset (warp 0), meanwhile everyone fills the chunk ----
+    if (wid == 0) {
+        const unsigned units = bytes >> 4;
+        unsigned excl = 0;
+        if (blk == 0) {
+            if (lane == 0) atomicExch(&status[0], kFlagPrefix | units);
+        } else {
+            if (lane == 0) atomicExch(&status[blk], kFlagAggregate | units);
+            int look = (int)blk - 1;
+            while (true) {
+                const int idx = look - lane;
+                unsigned long long st = kFlagPrefix;        // before block 0: an empty prefix
+                if (idx >= 0) {
+                    const volatile unsigned long long *sp = status + idx;
+                    do { st = *sp; } while ((st & kFlagMask) == 0);
+                }
+                const unsigned pm = __ballot_sync(0xffffffffu, (st & kFlagMask) == kFlagPrefix);
+                const int first = pm ? (__ffs(pm) - 1) : 31;
+                unsigned c = (lane <= first) ? (unsigned)(st & 0xffffffffull) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                excl += c;
+                if (pm) break;
+                look -= 32;
+            }
+            if (lane == 0) atomicExch(&status[blk], kFlagPrefix | (unsigned long long)(excl + units));
+        }
+        if (lane == 0) {
+            s_base = excl;
+            const unsigned off = p.chunks_off + (excl << 4);
+            reinterpret_cast<uint4 *>(p.sparse[f] + kSparseHeaderBytes)[blk] = make_uint4(off, G, V, E);
+            if (blk == p.nblocks - 1) {
+                uint4 *h = reinterpret_cast<uint4 *>(p.sparse[f]);
+                h[0] = make_uint4(kSparseMagic, p.nwords, off + bytes, p.nblocks);
+                h[1] = make_uint4(0, 0, 0, 0);
+            }
+        }
+    }
+    if (G) {
+        const unsigned masks_off = kSparseL1Bytes, bytes_off = masks_off + 4 * G, wide_off = bytes_off + ((V + 3) & ~3u);
+        if (lane == 0) {                // l1: 8 groups per warp = one byte
+            unsigned b = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) b |= ((gb >> (4 * k)) & 1u) << k;
+            chunk[wid] = (unsigned char)b;
+        }
+        if (gleader) *reinterpret_cast<unsigned *>(chunk + masks_off + 4 * (gexcl + __popc(gb & ((1u << lane) - 1u)))) = m;
+        unsigned vpos = bytes_off + (wexcl & 0xffffu) + ((incl - packed) & 0xffffu);
+        unsigned epos = wide_off + 2 * ((wexcl >> 16) + ((incl - packed) >> 16));
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (m8 & (1u << k)) {
+                const bool esc = (vals[k] < -127 || vals[k] > 127);
+                chunk[vpos++] = (unsigned char)(esc ? 0x80 : (vals[k] & 0xff));
+                if (esc) { *reinterpret_cast<short *>(chunk + epos) = (short)vals[k]; epos += 2; }
+            }
+        }
+        // zero padding: bytes [V, align4(V)), wide [2E, align4(2E)) and the tail up to the 16-byte boundary
+        if (tid < 3 && bytes_off + V + tid < wide_off) chunk[bytes_off + V + tid] = 0;
+        if (tid >= 32 && tid < 48) { const unsigned q = wide_off + 2 * E + (tid - 32); if (q < bytes) chunk[q] = 0; }
+    }
+    __syncthreads();
+    if (G) {
+        unsigned char *dst = p.sparse[f] + p.chunks_off + ((size_t)s_base << 4);
+        for (unsigned i = tid * 16; i < bytes; i += 1024 * 16)
+            *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(chunk + i);
     }
 }
 
-// C': gather back into the dense coded region
-__global__ void __launch_bounds__(1024) k_sparse_gather(const __grid_constant__ SparseParams p)
+// ---------------------------------------------------------------------------------------------------------------
+// sparse -> dense: one CTA per block, the table entry gives the chunk
+__global__ void __launch_bounds__(1024) k_sparse_unpack(const __grid_constant__ SparseParams p)
 {
-    __shared__ unsigned wtot[32];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned seg = blockIdx.x * kBlockSegs + wid;
+    __shared__ __align__(16) unsigned char chunk[kSparseMaxChunk];
+    __shared__ unsigned s_scan[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int f = blockIdx.y;
-    const unsigned w0 = seg * kSeg + lane * 8;
-    const bool on = (seg < p.nseg) && (w0 < p.nwords);          // nwords is a multiple of 8 (bands are 64-byte aligned)
-    unsigned m8 = 0;
-    if (on) {
-        const unsigned bw = __ldg(reinterpret_cast<const unsigned *>(p.sparse[f] + p.bitmap_off) + seg * 8 + (lane >> 2));
-        m8 = (bw >> ((lane & 3) * 8)) & 0xffu;
+    const unsigned blk = blockIdx.x;
+    const unsigned w0 = blk * kSparseBlockWords + tid * 8;
+    const uint4 ent = __ldg(reinterpret_cast<const uint4 *>(p.sparse[f] + kSparseHeaderBytes) + blk);
+    const unsigned G = min(ent.y, (unsigned)kSparseBlockGroups), V = min(ent.z, (unsigned)kSparseBlockWords), E = min(ent.w, V);
+    unsigned char *out = const_cast<unsigned char *>(p.dense[f]) + (size_t)w0 * 2;
+    if (G == 0) {
+        if (w0 < p.nwords) *reinterpret_cast<uint4 *>(out) = make_uint4(0, 0, 0, 0);
+        return;
     }
-    const unsigned c = __popc(m8);
-    const unsigned incl = warp_incl_scan(c, lane);
-    const unsigned wexcl = block_exclusive(__shfl_sync(0xffffffffu, incl, 31), lane, wid, wtot, nullptr);
-    if (!on) return;
-    unsigned pos = p.counts[f][blockIdx.x] + wexcl + incl - c;
-    const unsigned short *vals = reinterpret_cast<const unsigned short *>(p.sparse[f] + p.values_off);
-    unsigned out[4] = {0, 0, 0, 0};
+    const unsigned bytes = sparse_chunk_bytes(G, V, E);
+    const unsigned char *src = p.sparse[f] + ent.x;
+    for (unsigned i = tid * 16; i < bytes; i += 1024 * 16)
+        *reinterpret_cast<uint4 *>(chunk + i) = __ldg(reinterpret_cast<const uint4 *>(src + i));
+    __syncthreads();
+    const unsigned masks_off = kSparseL1Bytes, bytes_off = masks_off + 4 * G, wide_off = bytes_off + ((V + 3) & ~3u);
+    // group rank: l1 byte k belongs to warp k
+    const unsigned pc = __popc((unsigned)chunk[lane]);
+    const unsigned gincl = warp_incl_scan(pc, lane);
+    const unsigned gbase = __shfl_sync(0xffffffffu, gincl - pc, wid);
+    const unsigned l1b = chunk[wid];
+    const int gi = lane >> 2;
+    unsigned m = 0;
+    if ((l1b >> gi) & 1u) {
+        const unsigned grank = min(gbase + __popc(l1b & ((1u << gi) - 1u)), G - 1);
+        m = *reinterpret_cast<const unsigned *>(chunk + masks_off + 4 * grank);
+    }
+    const unsigned m8 = (m >> ((lane & 3) * 8)) & 0xffu;
+    const unsigned nval = __popc(m8);
+    const unsigned incl = warp_incl_scan(nval, lane);
+    const unsigned wexcl = block_exclusive(__shfl_sync(0xffffffffu, incl, 31), lane, wid, s_scan, nullptr);
+    unsigned vpos = wexcl + incl - nval;
+    int vals[8];
+    unsigned nesc = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
+        vals[k] = 0;
         if (m8 & (1u << k)) {
-            const unsigned x = vals[pos++];
-            out[k >> 1] |= (k & 1) ? (x << 16) : x;
+            vals[k] = (int)(signed char)chunk[bytes_off + min(vpos, V - 1)];
+            vpos++;
+            nesc += (vals[k] == -128) ? 1u : 0u;
         }
     }
-    *reinterpret_cast<uint4 *>(const_cast<unsigned char *>(p.dense[f]) + (size_t)w0 * 2) = make_uint4(out[0], out[1], out[2], out[3]);
+    const unsigned eincl = warp_incl_scan(nesc, lane);
+    __syncthreads();                    // s_scan is reused
+    const unsigned eexcl = block_exclusive(__shfl_sync(0xffffffffu, eincl, 31), lane, wid, s_scan, nullptr);
+    unsigned epos = eexcl + eincl - nesc;
+    if (nesc) {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (vals[k] == -128 && (m8 & (1u << k))) { vals[k] = *reinterpret_cast<const short *>(chunk + wide_off + 2 * min(epos, E ? E - 1 : 0)); epos++; }
+    }
+    if (w0 < p.nwords)
+        *reinterpret_cast<uint4 *>(out) = make_uint4(pack_lo(vals[0], vals[1]), pack_lo(vals[2], vals[3]), pack_lo(vals[4], vals[5]), pack_lo(vals[6], vals[7]));
 }
 
 cudaError_t launch_sparse_compact(const SparseParams &p, cudaStream_t stream)
 {
+    for (int i = 0; i < p.nframes; i++) {
+        cudaError_t e = cudaMemsetAsync(p.status[i], 0, sizeof(unsigned long long) * (p.nblocks + 1), stream);
+        if (e != cudaSuccess) return e;
+    }
     dim3 grid(p.nblocks, p.nframes);
-    k_sparse_count<<<grid, 1024, 0, stream>>>(p);
-    k_sparse_scan<<<p.nframes, 1024, 0, stream>>>(p, 1);
-    k_sparse_scatter<<<grid, 1024, 0, stream>>>(p);
+    k_sparse_pack<<<grid, 1024, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_sparse_expand(const SparseParams &p, cudaStream_t stream)
 {
     dim3 grid(p.nblocks, p.nframes);
-    k_sparse_count_bitmap<<<grid, 256, 0, stream>>>(p);
-    k_sparse_scan<<<p.nframes, 1024, 0, stream>>>(p, 0);
-    k_sparse_gather<<<grid, 1024, 0, stream>>>(p);
+    k_sparse_unpack<<<grid, 1024, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -211,41 +259,51 @@ cudaError_t launch_sparse_expand(const SparseParams &p, cudaStream_t stream)
 // C ABI
 using namespace cfb;
 
-static inline unsigned sp_bitmap_off() { return 16u; }
-static inline unsigned sp_values_off(unsigned nwords) { return (16u + nwords / 8u + 15u) & ~15u; }
-
 static cfb_error sparse_prepare(cfb_codec *cd, SparseParams &p, int n)
 {
     const cfb_layout &L = cd->layout;
     p.nframes = n;
     p.nwords = (unsigned)(L.coded_bytes / 2);
-    p.nseg = (p.nwords + kSeg - 1) / kSeg;
-    p.nblocks = (p.nseg + kBlockSegs - 1) / kBlockSegs;
-    p.bitmap_off = sp_bitmap_off();
-    p.values_off = sp_values_off(p.nwords);
+    p.nblocks = sparse_nblocks(p.nwords);
+    p.chunks_off = sparse_chunks_off(p.nblocks);
     // each staging buffer under its own check: a failed allocation leaves the others usable for the retry
     cd->sparse_stride = (cfb_sparse_max_bytes(&L) + 255) & ~(size_t)255;
     if (!cd->d_sparse) CFB_CUDA(cudaMalloc((void **)&cd->d_sparse, cd->sparse_stride * cd->max_batch));
-    if (!cd->d_counts) CFB_CUDA(cudaMalloc((void **)&cd->d_counts, sizeof(unsigned) * (size_t)(p.nblocks + 1) * cd->max_batch));
+    if (!cd->d_status) CFB_CUDA(cudaMalloc((void **)&cd->d_status, sizeof(unsigned long long) * (size_t)(p.nblocks + 1) * cd->max_batch));
     if (!cd->h_headers) CFB_CUDA(cudaHostAlloc((void **)&cd->h_headers, 16 * (size_t)cd->max_batch, cudaHostAllocPortable));
     for (int i = 0; i < n; i++) {
         p.dense[i] = cd->d_pyramids + cd->pyramid_stride * i;
         p.sparse[i] = cd->d_sparse + cd->sparse_stride * i;
-        p.counts[i] = cd->d_counts + (size_t)(p.nblocks + 1) * i;
+        p.status[i] = cd->d_status + (size_t)(p.nblocks + 1) * i;
     }
     return CFB_OK;
 }
 
+// what the fixed part (header + table) of a sparse buffer says about its size; 0 = not a sparse buffer of this layout
+static size_t sparse_checked_bytes(const void *sparse, unsigned nwords)
+{
+    const unsigned *h = (const unsigned *)sparse;
+    const unsigned nblocks = sparse_nblocks(nwords);
+    const size_t lo = sparse_chunks_off(nblocks), hi = lo + (size_t)nblocks * kSparseMaxChunk;
+    if (h[0] != kSparseMagic || h[1] != nwords || h[3] != nblocks || h[2] < lo || h[2] > hi || (h[2] & 15)) return 0;
+    return h[2];
+}
+
 namespace cfb {
 
-unsigned sparse_initial_guess(const cfb_codec *cd) { return (unsigned)(cd->layout.coded_bytes / 2) / 8; }
-
-unsigned sparse_next_guess(const cfb_codec *cd, unsigned max_values)
+// sizes are in BYTES of the whole sparse buffer
+unsigned sparse_initial_guess(const cfb_codec *cd)
 {
     const unsigned nwords = (unsigned)(cd->layout.coded_bytes / 2);
-    unsigned g = (max_values + max_values / 8 + 4096 + 63u) & ~63u;
-    if (g > nwords) g = nwords;           // clamp AFTER the rounding: the copy must stay inside cfb_sparse_max_bytes
-    return g;
+    return sparse_chunks_off(sparse_nblocks(nwords)) + nwords / 4;         // 1/8 of the words non-zero
+}
+
+unsigned sparse_next_guess(const cfb_codec *cd, unsigned max_bytes)
+{
+    const size_t cap = cfb_sparse_max_bytes(&cd->layout);
+    size_t g = ((size_t)max_bytes + max_bytes / 8 + 65536 + 255u) & ~(size_t)255;
+    if (g > cap) g = cap;               // clamp AFTER the rounding: the copy must stay inside cfb_sparse_max_bytes
+    return (unsigned)g;
 }
 
 cfb_error sparse_compact_device(cfb_codec *cd, int n)
@@ -254,7 +312,7 @@ cfb_error sparse_compact_device(cfb_codec *cd, int n)
     cfb_error err = sparse_prepare(cd, sp, n);
     if (err) return err;
     CFB_CUDA(launch_sparse_compact(sp, cd->ctx->stream));
-    cd->ctx->kernel_launches += 3;
+    cd->ctx->kernel_launches += 1;
     return CFB_OK;
 }
 
@@ -264,7 +322,7 @@ cfb_error sparse_expand_device(cfb_codec *cd, int n)
     cfb_error err = sparse_prepare(cd, sp, n);
     if (err) return err;
     CFB_CUDA(launch_sparse_expand(sp, cd->ctx->stream));
-    cd->ctx->kernel_launches += 3;
+    cd->ctx->kernel_launches += 1;
     return CFB_OK;
 }
 
@@ -273,10 +331,12 @@ cfb_error sparse_download(cfb_codec *cd, int n, void *const *h_sparse, unsigned 
     SparseParams sp;
     cfb_error err = sparse_prepare(cd, sp, n);
     if (err) return err;
-    if (guess > sp.nwords) guess = sp.nwords;       // never more than the caller's buffer holds (cfb_sparse_max_bytes)
+    const size_t cap = cfb_sparse_max_bytes(&cd->layout);
+    size_t bytes = guess;
+    if (bytes > cap) bytes = cap;       // never more than the caller's buffer holds (cfb_sparse_max_bytes)
+    if (bytes < sp.chunks_off) bytes = sp.chunks_off;
     for (int i = 0; i < n; i++) {
         if (!h_sparse[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
-        const size_t bytes = (size_t)sp.values_off + (size_t)guess * 2;
         CFB_CUDA(cudaMemcpyAsync(h_sparse[i], sp.sparse[i], bytes, cudaMemcpyDeviceToHost, s));
         cd->ctx->d2h_bytes += (uint64_t)bytes;
     }
@@ -284,27 +344,29 @@ cfb_error sparse_download(cfb_codec *cd, int n, void *const *h_sparse, unsigned 
 }
 
 cfb_error stage_fwd_tail(cfb_codec *cd, int n, void *const *h_sparse, unsigned guess, cudaStream_t s, size_t *sizes,
-                         unsigned *max_values, bool *more)
+                         unsigned *max_bytes, bool *more)
 {
     SparseParams sp;
     cfb_error err = sparse_prepare(cd, sp, n);
     if (err) return err;
-    if (guess > sp.nwords) guess = sp.nwords;
-    unsigned maxv = 0;
+    const size_t cap = cfb_sparse_max_bytes(&cd->layout);
+    size_t have = guess;
+    if (have > cap) have = cap;
+    if (have < sp.chunks_off) have = sp.chunks_off;
+    unsigned maxb = 0;
     *more = false;
     for (int i = 0; i < n; i++) {
-        const unsigned nv = ((const unsigned *)h_sparse[i])[2];
-        if (nv > sp.nwords) { set_error("sparse header %d corrupt", i); return CFB_ERROR_UNEXPECTED; }
-        if (nv > maxv) maxv = nv;
-        if (nv > guess) {
-            const size_t off = (size_t)sp.values_off + (size_t)guess * 2, rest = (size_t)(nv - guess) * 2;
-            CFB_CUDA(cudaMemcpyAsync((unsigned char *)h_sparse[i] + off, sp.sparse[i] + off, rest, cudaMemcpyDeviceToHost, s));
-            cd->ctx->d2h_bytes += (uint64_t)rest;
+        const size_t total = sparse_checked_bytes(h_sparse[i], sp.nwords);
+        if (!total) { set_error("sparse header %d corrupt", i); return CFB_ERROR_UNEXPECTED; }
+        if (total > maxb) maxb = (unsigned)total;
+        if (total > have) {
+            CFB_CUDA(cudaMemcpyAsync((unsigned char *)h_sparse[i] + have, sp.sparse[i] + have, total - have, cudaMemcpyDeviceToHost, s));
+            cd->ctx->d2h_bytes += (uint64_t)(total - have);
             *more = true;
         }
-        if (sizes) sizes[i] = (size_t)sp.values_off + (size_t)nv * 2;
+        if (sizes) sizes[i] = total;
     }
-    if (max_values) *max_values = maxv;
+    if (max_bytes) *max_bytes = maxb;
     return CFB_OK;
 }
 
@@ -315,9 +377,18 @@ cfb_error sparse_upload(cfb_codec *cd, int n, const void *const *h_sparse, cudaS
     if (err) return err;
     for (int i = 0; i < n; i++) {
         if (!h_sparse[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
-        const unsigned *h = (const unsigned *)h_sparse[i];
-        if (h[0] != 0x50534643u || h[1] != sp.nwords || h[2] > sp.nwords) { set_error("sparse buffer %d: bad header", i); return CFB_ERROR_BADFORMAT; }
-        const size_t bytes = (size_t)sp.values_off + (size_t)h[2] * 2;
+        const size_t bytes = sparse_checked_bytes(h_sparse[i], sp.nwords);
+        if (!bytes) { set_error("sparse buffer %d: bad header", i); return CFB_ERROR_BADFORMAT; }
+        // the table is the only part the kernel trusts for addressing: every chunk must lie inside the buffer
+        const unsigned *tab = (const unsigned *)((const unsigned char *)h_sparse[i] + kSparseHeaderBytes);
+        for (unsigned b = 0; b < sp.nblocks; b++) {
+            const unsigned off = tab[4 * b], G = tab[4 * b + 1], V = tab[4 * b + 2], E = tab[4 * b + 3];
+            if (G > kSparseBlockGroups || V > kSparseBlockWords || E > V || (G == 0) != (V == 0) || (off & 15) || off < sp.chunks_off ||
+                (size_t)off + sparse_chunk_bytes(G, V, E) > bytes) {
+                set_error("sparse buffer %d: block %u out of bounds", i, b);
+                return CFB_ERROR_BADFORMAT;
+            }
+        }
         CFB_CUDA(cudaMemcpyAsync(sp.sparse[i], h_sparse[i], bytes, cudaMemcpyHostToDevice, s));
         cd->ctx->h2d_bytes += (uint64_t)bytes;
     }
@@ -331,16 +402,16 @@ extern "C" {
 size_t cfb_sparse_max_bytes(const cfb_layout *L)
 {
     if (!L) return 0;
-    const unsigned nwords = (unsigned)(L->coded_bytes / 2);
-    return (size_t)sp_values_off(nwords) + (size_t)nwords * 2;
+    const unsigned nblocks = sparse_nblocks((unsigned)(L->coded_bytes / 2));
+    return (size_t)sparse_chunks_off(nblocks) + (size_t)nblocks * kSparseMaxChunk;
 }
 
 size_t cfb_sparse_bytes(const void *sparse)
 {
     if (!sparse) return 0;
     const unsigned *h = (const unsigned *)sparse;
-    if (h[0] != 0x50534643u) return 0;
-    return (size_t)sp_values_off(h[1]) + (size_t)h[2] * 2;
+    if (h[0] != kSparseMagic) return 0;
+    return sparse_checked_bytes(sparse, h[1]);
 }
 
 cfb_error cfb_forward_host_sparse(cfb_codec *cd, int n, const void *const *h_frames, int frame_pitch,
@@ -353,20 +424,20 @@ cfb_error cfb_forward_host_sparse(cfb_codec *cd, int n, const void *const *h_fra
     cfb_error err = stage_fwd_upload(cd, n, h_frames, frame_pitch, ctx->stream);
     if (!err) err = stage_fwd_compute(cd, n, quant, true);
     if (err) return err;
-    // Speculative single-pass D2H: copy header + bitmap + as many values as recent frames needed (+12 %) right behind the
-    // kernels, without a host round trip; only if a frame turns out to hold more values is the remainder fetched.
+    // Speculative single-pass D2H: copy as many bytes as recent frames needed (+12 %) right behind the kernels, without
+    // a host round trip; only if a frame turns out to be larger is the remainder fetched.
     const unsigned guess = cd->value_guess ? cd->value_guess : sparse_initial_guess(cd);
     err = stage_fwd_download(cd, n, h_sparse, true, guess, ctx->stream);
     if (err) return err;
     CFB_CUDA(stream_wait(ctx));
-    unsigned maxv = 0;
+    unsigned maxb = 0;
     bool more = false;
     size_t sizes[kMaxBatch];
-    err = stage_fwd_tail(cd, n, h_sparse, guess, ctx->stream, sizes, &maxv, &more);
+    err = stage_fwd_tail(cd, n, h_sparse, guess, ctx->stream, sizes, &maxb, &more);
     if (err) return err;
     if (more) CFB_CUDA(stream_wait(ctx));
     if (sparse_bytes) for (int i = 0; i < n; i++) sparse_bytes[i] = sizes[i];
-    cd->value_guess = sparse_next_guess(cd, maxv);
+    cd->value_guess = sparse_next_guess(cd, maxb);
     return CFB_OK;
 }
 
@@ -386,23 +457,35 @@ cfb_error cfb_inverse_host_sparse(cfb_codec *cd, int n, const void *const *h_spa
 cfb_error cfb_sparse_expand(const cfb_layout *L, const void *sparse, void *dense_coded)
 {
     if (!L || !sparse || !dense_coded) return CFB_ERROR_INVALID_ARGUMENT;
-    const unsigned *h = (const unsigned *)sparse;
     const unsigned nwords = (unsigned)(L->coded_bytes / 2);
-    if (h[0] != 0x50534643u || h[1] != nwords) { set_error("bad sparse header"); return CFB_ERROR_BADFORMAT; }
-    const unsigned *bm = (const unsigned *)((const unsigned char *)sparse + sp_bitmap_off());
-    const int16_t *vals = (const int16_t *)((const unsigned char *)sparse + sp_values_off(nwords));
+    const size_t total = sparse_checked_bytes(sparse, nwords);
+    if (!total) { set_error("bad sparse header"); return CFB_ERROR_BADFORMAT; }
+    const unsigned nblocks = sparse_nblocks(nwords);
     int16_t *out = (int16_t *)dense_coded;
-    size_t pos = 0;
-    for (unsigned w = 0; w < nwords; w += 32) {
-        unsigned m = bm[w >> 5];
-        for (int k = 0; k < 32 && w + k < nwords; k++) {
-            if ((m >> k) & 1u) {
-                if (pos >= h[2]) { set_error("sparse bitmap has more set bits than the header's value count"); return CFB_ERROR_BADFORMAT; }
-                out[w + k] = vals[pos++];
-            } else out[w + k] = 0;
+    memset(out, 0, (size_t)nwords * 2);
+    for (unsigned b = 0; b < nblocks; b++) {
+        SparseChunk c;
+        if (!sparse_chunk_open(sparse, total, b, &c)) { set_error("sparse block %u out of bounds", b); return CFB_ERROR_BADFORMAT; }
+        unsigned gi = 0, vi = 0, ei = 0;
+        for (unsigned g = 0; g < kSparseBlockGroups && c.groups; g++) {
+            if (!((c.l1[g >> 3] >> (g & 7)) & 1u)) continue;
+            if (gi >= c.groups) { set_error("sparse block %u: more groups than the table says", b); return CFB_ERROR_BADFORMAT; }
+            unsigned m = c.masks[gi++];
+            const size_t w = (size_t)b * kSparseBlockWords + (size_t)g * kSparseGroupWords;
+            while (m) {
+                const int k = __builtin_ctz(m);
+                m &= m - 1;
+                if (vi >= c.values || w + k >= nwords) { set_error("sparse block %u: value overrun", b); return CFB_ERROR_BADFORMAT; }
+                int v = c.bytes[vi++];
+                if (v == -128) {
+                    if (ei >= c.escapes) { set_error("sparse block %u: escape overrun", b); return CFB_ERROR_BADFORMAT; }
+                    v = c.wide[ei++];
+                }
+                out[w + k] = (int16_t)v;
+            }
         }
+        if (gi != c.groups || vi != c.values || ei != c.escapes) { set_error("sparse block %u: count mismatch", b); return CFB_ERROR_BADFORMAT; }
     }
-    if (pos != h[2]) { set_error("sparse value count mismatch"); return CFB_ERROR_BADFORMAT; }
     return CFB_OK;
 }
 
@@ -410,18 +493,44 @@ cfb_error cfb_sparse_compact(const cfb_layout *L, const void *dense_coded, void 
 {
     if (!L || !sparse || !dense_coded) return CFB_ERROR_INVALID_ARGUMENT;
     const unsigned nwords = (unsigned)(L->coded_bytes / 2);
+    const unsigned nblocks = sparse_nblocks(nwords);
     unsigned *h = (unsigned *)sparse;
-    unsigned *bm = (unsigned *)((unsigned char *)sparse + sp_bitmap_off());
-    int16_t *vals = (int16_t *)((unsigned char *)sparse + sp_values_off(nwords));
+    unsigned *tab = (unsigned *)((unsigned char *)sparse + kSparseHeaderBytes);
     const int16_t *in = (const int16_t *)dense_coded;
-    size_t pos = 0;
-    for (unsigned w = 0; w < nwords; w += 32) {
-        unsigned m = 0;
-        for (int k = 0; k < 32 && w + k < nwords; k++) if (in[w + k]) { m |= 1u << k; vals[pos++] = in[w + k]; }
-        bm[w >> 5] = m;
+    size_t off = sparse_chunks_off(nblocks);
+    memset((unsigned char *)sparse + kSparseHeaderBytes + (size_t)nblocks * kSparseTableEntry, 0, off - kSparseHeaderBytes - (size_t)nblocks * kSparseTableEntry);
+    for (unsigned b = 0; b < nblocks; b++) {
+        unsigned char *chunk = (unsigned char *)sparse + off;
+        unsigned char l1[kSparseL1Bytes] = {0};
+        unsigned masks[kSparseBlockGroups];
+        signed char vb[kSparseBlockWords];
+        int16_t wide[kSparseBlockWords];
+        unsigned G = 0, V = 0, E = 0;
+        for (unsigned g = 0; g < kSparseBlockGroups; g++) {
+            const size_t w = (size_t)b * kSparseBlockWords + (size_t)g * kSparseGroupWords;
+            if (w >= nwords) break;
+            unsigned m = 0;
+            for (unsigned k = 0; k < kSparseGroupWords && w + k < nwords; k++) {
+                const int v = in[w + k];
+                if (!v) continue;
+                m |= 1u << k;
+                if (v < -127 || v > 127) { vb[V++] = -128; wide[E++] = (int16_t)v; } else vb[V++] = (signed char)v;
+            }
+            if (m) { l1[g >> 3] |= (unsigned char)(1u << (g & 7)); masks[G++] = m; }
+        }
+        const unsigned cb = sparse_chunk_bytes(G, V, E);
+        tab[4 * b] = (unsigned)off; tab[4 * b + 1] = G; tab[4 * b + 2] = V; tab[4 * b + 3] = E;
+        if (G) {
+            memset(chunk, 0, cb);
+            memcpy(chunk, l1, kSparseL1Bytes);
+            memcpy(chunk + kSparseL1Bytes, masks, 4 * (size_t)G);
+            memcpy(chunk + kSparseL1Bytes + 4 * (size_t)G, vb, V);
+            memcpy(chunk + kSparseL1Bytes + 4 * (size_t)G + ((V + 3) & ~3u), wide, 2 * (size_t)E);
+        }
+        off += cb;
     }
-    h[0] = 0x50534643u; h[1] = nwords; h[2] = (unsigned)pos; h[3] = 0;
-    if (bytes) *bytes = (size_t)sp_values_off(nwords) + pos * 2;
+    h[0] = kSparseMagic; h[1] = nwords; h[2] = (unsigned)off; h[3] = nblocks; h[4] = h[5] = h[6] = h[7] = 0;
+    if (bytes) *bytes = off;
     return CFB_OK;
 }
 

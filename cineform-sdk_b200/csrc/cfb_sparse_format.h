@@ -1,0 +1,61 @@
+// cfb_sparse_format.h -- constants and accessors of the 'CFS2' sparse transfer format (see cfb_sparse.cu for the
+// description).  Shared by the device kernels, the host-side conversions and the host VLC walker (cfb_vlc.cu).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __CUDACC__
+#define CFB_HD __host__ __device__ __forceinline__
+#else
+#define CFB_HD inline
+#endif
+
+namespace cfb {
+
+constexpr unsigned kSparseMagic = 0x32534643u;      // 'CFS2'
+constexpr unsigned kSparseHeaderBytes = 32;
+constexpr unsigned kSparseTableEntry = 16;          // {u32 chunk offset, u32 groups, u32 values, u32 escapes}
+constexpr unsigned kSparseBlockWords = 8192;        // int16 words per block (one CTA of 1024 threads x 8 words)
+constexpr unsigned kSparseGroupWords = 32;
+constexpr unsigned kSparseBlockGroups = kSparseBlockWords / kSparseGroupWords;      // 256
+constexpr unsigned kSparseL1Bytes = kSparseBlockGroups / 8;                         // 32
+// worst case: every word non-zero and outside [-127, 127]
+constexpr unsigned kSparseMaxChunk = kSparseL1Bytes + 4 * kSparseBlockGroups + kSparseBlockWords + 2 * kSparseBlockWords;     // 25632
+
+CFB_HD unsigned sparse_nblocks(unsigned nwords) { return (nwords + kSparseBlockWords - 1) / kSparseBlockWords; }
+CFB_HD unsigned sparse_chunks_off(unsigned nblocks) { return (kSparseHeaderBytes + kSparseTableEntry * nblocks + 15u) & ~15u; }
+// bytes of a block's chunk (a multiple of 16; 0 for an all-zero block)
+CFB_HD unsigned sparse_chunk_bytes(unsigned groups, unsigned values, unsigned escapes)
+{
+    if (!groups) return 0;
+    return (kSparseL1Bytes + 4 * groups + ((values + 3u) & ~3u) + ((2 * escapes + 3u) & ~3u) + 15u) & ~15u;
+}
+
+// host view of one block
+struct SparseChunk {
+    unsigned groups, values, escapes;
+    const unsigned char *l1;        // 32 bytes (null when the block is empty)
+    const unsigned *masks;
+    const signed char *bytes;
+    const int16_t *wide;
+};
+
+// bounds-checked against `total` (the buffer's size from its header); false = damaged table
+inline bool sparse_chunk_open(const void *sparse, size_t total, unsigned block, SparseChunk *c)
+{
+    const unsigned char *base = (const unsigned char *)sparse;
+    const unsigned *e = (const unsigned *)(base + kSparseHeaderBytes + (size_t)block * kSparseTableEntry);
+    c->groups = e[1]; c->values = e[2]; c->escapes = e[3];
+    c->l1 = nullptr; c->masks = nullptr; c->bytes = nullptr; c->wide = nullptr;
+    if (c->groups > kSparseBlockGroups || c->values > kSparseBlockWords || c->escapes > c->values || (c->groups == 0) != (c->values == 0)) return false;
+    if (!c->groups) return true;
+    const size_t off = e[0];
+    if ((off & 15) || off + sparse_chunk_bytes(c->groups, c->values, c->escapes) > total) return false;
+    c->l1 = base + off;
+    c->masks = (const unsigned *)(base + off + kSparseL1Bytes);
+    c->bytes = (const signed char *)(base + off + kSparseL1Bytes + 4 * (size_t)c->groups);
+    c->wide = (const int16_t *)(base + off + kSparseL1Bytes + 4 * (size_t)c->groups + ((c->values + 3u) & ~3u));
+    return true;
+}
+
+}  // namespace cfb

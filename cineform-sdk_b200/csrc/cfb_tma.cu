@@ -2,7 +2,9 @@
 // statically and libcuda is never linked; cuTensorMapEncodeTiled is resolved with cudaGetDriverEntryPoint).
 #include "cfb_tma.cuh"
 
+#include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 namespace cfb {
 
@@ -25,7 +27,65 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 
+static cudaError_t tmap_encode_2d_uncached(CUtensorMap *out, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch_bytes,
+                                           uint32_t box_bytes, uint32_t box_rows, int elem_bytes);
+static cudaError_t tmap_encode_3d_uncached(CUtensorMap *out, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch_bytes,
+                                           uint64_t planes, uint64_t plane_bytes, uint32_t box_bytes, uint32_t box_rows, uint32_t box_planes);
+
+// Encoded maps are memoised per host thread: a codec presents the same (base, geometry, box) tuples launch after launch
+// (its device staging never moves), and one cuTensorMapEncodeTiled costs about a microsecond of host time -- the final
+// inverse level alone needs six maps per frame of a batch.
+namespace {
+struct MapKey {
+    uint64_t v[9];
+    bool operator==(const MapKey &o) const { return !memcmp(v, o.v, sizeof(v)); }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey &k) const {
+        uint64_t h = 1469598103934665603ull;
+        for (uint64_t x : k.v) { h ^= x; h *= 1099511628211ull; h ^= h >> 29; }
+        return (size_t)h;
+    }
+};
+typedef std::unordered_map<MapKey, CUtensorMap, MapKeyHash> MapCache;
+MapCache &map_cache() { static thread_local MapCache c; return c; }
+bool cache_get(const MapKey &k, CUtensorMap *out)
+{
+    MapCache &c = map_cache();
+    auto it = c.find(k);
+    if (it == c.end()) return false;
+    *out = it->second;
+    return true;
+}
+void cache_put(const MapKey &k, const CUtensorMap &m)
+{
+    MapCache &c = map_cache();
+    if (c.size() >= 8192) c.clear();
+    c.emplace(k, m);
+}
+}  // namespace
+
 cudaError_t tmap_encode_2d(CUtensorMap *out, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch_bytes,
+                           uint32_t box_bytes, uint32_t box_rows, int elem_bytes)
+{
+    const MapKey key = {{(uint64_t)(uintptr_t)base, row_bytes, rows, pitch_bytes, 1, 0, box_bytes, ((uint64_t)box_rows << 32) | 1u, (uint64_t)elem_bytes}};
+    if (cache_get(key, out)) return cudaSuccess;
+    const cudaError_t e = tmap_encode_2d_uncached(out, base, row_bytes, rows, pitch_bytes, box_bytes, box_rows, elem_bytes);
+    if (e == cudaSuccess) cache_put(key, *out);
+    return e;
+}
+
+cudaError_t tmap_encode_3d(CUtensorMap *out, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch_bytes,
+                           uint64_t planes, uint64_t plane_bytes, uint32_t box_bytes, uint32_t box_rows, uint32_t box_planes)
+{
+    const MapKey key = {{(uint64_t)(uintptr_t)base, row_bytes, rows, pitch_bytes, planes, plane_bytes, box_bytes, ((uint64_t)box_rows << 32) | box_planes, 4}};
+    if (cache_get(key, out)) return cudaSuccess;
+    const cudaError_t e = tmap_encode_3d_uncached(out, base, row_bytes, rows, pitch_bytes, planes, plane_bytes, box_bytes, box_rows, box_planes);
+    if (e == cudaSuccess) cache_put(key, *out);
+    return e;
+}
+
+static cudaError_t tmap_encode_2d_uncached(CUtensorMap *out, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch_bytes,
                            uint32_t box_bytes, uint32_t box_rows, int elem_bytes)
 {
     EncodeTiledFn fn = encode_fn();
@@ -41,7 +101,7 @@ cudaError_t tmap_encode_2d(CUtensorMap *out, const void *base, uint64_t row_byte
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-cudaError_t tmap_encode_3d(CUtensorMap *out, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch_bytes,
+static cudaError_t tmap_encode_3d_uncached(CUtensorMap *out, const void *base, uint64_t row_bytes, uint64_t rows, uint64_t pitch_bytes,
                            uint64_t planes, uint64_t plane_bytes, uint32_t box_bytes, uint32_t box_rows, uint32_t box_planes)
 {
     EncodeTiledFn fn = encode_fn();

@@ -36,6 +36,10 @@ __device__ __forceinline__ void tma_load_2d(unsigned dst, const void *tmap, int 
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  :: "r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const void *tmap, int x, int y, int z, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(dst), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
 // shared -> global (tensor map); completion tracked by bulk async-groups
 __device__ __forceinline__ void tma_store_2d(const void *tmap, int x, int y, unsigned src) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"

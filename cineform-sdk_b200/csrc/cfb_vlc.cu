@@ -1,0 +1,238 @@
+// cfb_vlc.cu -- host side of SURVEY 8f rank 1: the run-length / VLC stream of a band straight from the sparse
+// transfer format (no CUDA in this file; it is a .cu only so that the one-line build picks it up).
+//
+// Replaces the walk of the reference's coder over a DENSE band:
+//   Codec/encoder.c:5386-5700 EncodeQuantLongRuns   rows of `width` coefficients, zero runs carried across the pitch
+//                                                   gap (:5653) and across rows, pending run flushed at the end (:5671)
+//   Codec/vlc.c:366 PutZeroRun (inlined :5493-5545) greedy split of a run: entry min(count, length - 1), count -= entry.count
+//   Codec/vlc.c:188 PutVlcByte (inlined :5553-5568) value clamped to +-(VALUE_TABLE_LENGTH / 2 - 1), negative values index
+//                                                   from the top of the table
+//   Codec/bitstream.c:819 PutBits (inlined)         32-bit buffer, flushed big-endian only when a code does NOT fit
+// The sparse format already holds the positions of the non-zero coefficients (two-level bitmaps) and their values, so
+// a zero run is the distance between consecutive set bits of the flat coded region -- the pitch gap and the 64-byte band
+// alignment are zero words of that region -- and the host reads ~2 MB per 4K frame instead of 33 MB.
+#include <stdint.h>
+#include <string.h>
+
+#include "cfb_host.h"
+#include "cfb_sparse_format.h"
+
+using namespace cfb;
+
+namespace {
+
+// the reference's bit buffer, widened: `acc` holds `n` pending bits (n <= 32 between codes).  A word is stored only when
+// a code does not fit any more (n + size > 32), exactly as PutBits does, so the state left behind is the reference's.
+struct Bits {
+    uint64_t acc;
+    int n;
+    uint8_t *cur, *end;
+    int64_t bytes;
+    bool overflow;
+    explicit Bits(const cfb_bitwriter &bw) : acc(bw.bits_free >= 32 ? 0 : (bw.buffer & (0xffffffffu >> bw.bits_free))), n(32 - bw.bits_free),
+                                             cur(bw.cur), end(bw.end), bytes(bw.bytes), overflow(false) {}
+    inline void put(uint32_t bits, int size)
+    {
+        acc = (acc << size) | (bits & (0xffffffffu >> (32 - size)));
+        n += size;
+        if (n > 32) {
+            const uint32_t word = (uint32_t)(acc >> (n - 32));
+            if (cur + 4 > end) { overflow = true; n -= 32; return; }
+            cur[0] = (uint8_t)(word >> 24); cur[1] = (uint8_t)(word >> 16); cur[2] = (uint8_t)(word >> 8); cur[3] = (uint8_t)word;
+            cur += 4; bytes += 4;
+            n -= 32;
+        }
+    }
+    void store(cfb_bitwriter *bw) const
+    {
+        bw->cur = cur; bw->bytes = bytes;
+        bw->bits_free = 32 - n;
+        bw->buffer = n ? (uint32_t)(acc & (0xffffffffull >> (32 - n))) : 0u;
+    }
+};
+
+struct Coder {
+    const cfb_vlc_codebook &b;
+    Bits &out;
+    const int half;
+    Coder(const cfb_vlc_codebook &book, Bits &o) : b(book), out(o), half(book.value_length >> 1) {}
+    inline void run(uint64_t count)
+    {
+        const uint64_t last = (uint64_t)b.run_length - 1;
+        while (count > 0) {
+            const uint64_t i = count < last ? count : last;
+            out.put(b.run_bits[i], b.run_size[i]);
+            count -= b.run_count[i];
+        }
+    }
+    inline void value(int v)
+    {
+        int idx;
+        if (v < 0) { if (v <= -half) v = -(half - 1); idx = b.value_length + v; }
+        else { if (v >= half) v = half - 1; idx = v; }
+        out.put(b.value_bits[idx], b.value_size[idx]);
+    }
+};
+
+bool book_ok(const cfb_vlc_codebook *b)
+{
+    if (!b || b->run_length < 2 || b->value_length < 4 || (b->value_length & 1) || !b->run_bits || !b->run_size || !b->run_count ||
+        !b->value_bits || !b->value_size) return false;
+    // entry i must not cover more zeros than the run it is chosen for (the reference's loop would run past zero otherwise)
+    for (int i = 1; i < b->run_length; i++)
+        if (b->run_count[i] < 1 || b->run_count[i] > (uint32_t)i || b->run_size[i] < 1 || b->run_size[i] > 31) return false;
+    return true;
+}
+
+bool writer_ok(const cfb_bitwriter *bw) { return bw && bw->cur && bw->end && bw->cur <= bw->end && bw->bits_free >= 0 && bw->bits_free <= 32; }
+
+// flat word range of a band inside the coded region
+cfb_error band_range(const cfb_layout *L, int channel, int level, int band, size_t *w0, size_t *w1, const cfb_band_layout **bl)
+{
+    if (!L || channel < 0 || channel >= L->num_channels || level < 0 || level >= CFB_NUM_LEVELS || band < 0 || band >= CFB_NUM_BANDS) {
+        set_error("bad band (%d, %d, %d)", channel, level, band);
+        return CFB_ERROR_INVALID_ARGUMENT;
+    }
+    if (band == 0 && level != CFB_NUM_LEVELS - 1) { set_error("LL of level %d is not in the coded region", level + 1); return CFB_ERROR_INVALID_ARGUMENT; }
+    const cfb_band_layout &b = L->band[channel][level][band];
+    *w0 = (size_t)b.offset / 2;
+    *w1 = *w0 + (size_t)(b.pitch / 2) * b.height;
+    if (bl) *bl = &b;
+    return CFB_OK;
+}
+
+// Calls f(pos, value) for every non-zero word of the flat range [w0, w1) in raster order.  w0 is a multiple of 32.
+template <class F>
+cfb_error walk(const cfb_layout *L, const void *sparse, size_t w0, size_t w1, F &&f)
+{
+    const unsigned nwords = (unsigned)(L->coded_bytes / 2);
+    const unsigned *h = (const unsigned *)sparse;
+    const unsigned nblocks = sparse_nblocks(nwords);
+    if (!sparse || h[0] != kSparseMagic || h[1] != nwords || h[3] != nblocks || h[2] < sparse_chunks_off(nblocks)) {
+        set_error("bad sparse header");
+        return CFB_ERROR_BADFORMAT;
+    }
+    const size_t total = h[2];
+    for (size_t b = w0 / kSparseBlockWords; b * kSparseBlockWords < w1; b++) {
+        SparseChunk c;
+        if (!sparse_chunk_open(sparse, total, (unsigned)b, &c)) { set_error("sparse block %u out of bounds", (unsigned)b); return CFB_ERROR_BADFORMAT; }
+        if (!c.groups) continue;
+        const size_t base = b * kSparseBlockWords;
+        const unsigned g_lo = w0 > base ? (unsigned)((w0 - base) / kSparseGroupWords) : 0u;
+        unsigned gi = 0, vi = 0, ei = 0;
+        if (g_lo) {         // the band starts inside this block: skip the groups, values and escapes before it
+            for (unsigned g = 0; g < g_lo; g++) gi += (c.l1[g >> 3] >> (g & 7)) & 1u;
+            if (gi > c.groups) { set_error("sparse block %u: damaged group bitmap", (unsigned)b); return CFB_ERROR_BADFORMAT; }
+            for (unsigned k = 0; k < gi; k++) vi += (unsigned)__builtin_popcount(c.masks[k]);
+            if (vi > c.values) { set_error("sparse block %u: damaged masks", (unsigned)b); return CFB_ERROR_BADFORMAT; }
+            for (unsigned k = 0; k < vi; k++) ei += (c.bytes[k] == -128);
+        }
+        const uint64_t *l1w = (const uint64_t *)c.l1;       // chunks are 16-byte aligned
+        for (unsigned q = g_lo >> 6; q < 4; q++) {
+            uint64_t bits = l1w[q];
+            if (q == (g_lo >> 6)) bits &= ~0ull << (g_lo & 63);
+            while (bits) {
+                const unsigned g = q * 64 + (unsigned)__builtin_ctzll(bits);
+                bits &= bits - 1;
+                const size_t wbase = base + (size_t)g * kSparseGroupWords;
+                if (wbase >= w1) return CFB_OK;
+                if (gi >= c.groups) { set_error("sparse block %u: more groups than the table says", (unsigned)b); return CFB_ERROR_BADFORMAT; }
+                unsigned m = c.masks[gi++];
+                while (m) {
+                    const size_t pos = wbase + (unsigned)__builtin_ctz(m);
+                    m &= m - 1;
+                    if (vi >= c.values) { set_error("sparse block %u: value overrun", (unsigned)b); return CFB_ERROR_BADFORMAT; }
+                    int v = c.bytes[vi++];
+                    if (v == -128) {
+                        if (ei >= c.escapes) { set_error("sparse block %u: escape overrun", (unsigned)b); return CFB_ERROR_BADFORMAT; }
+                        v = c.wide[ei++];
+                    }
+                    if (pos >= w1) return CFB_OK;
+                    f(pos, v);
+                }
+            }
+        }
+    }
+    return CFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+cfb_error cfb_sparse_vlc_band(const cfb_layout *L, const void *sparse, int channel, int level, int band,
+                              const cfb_vlc_codebook *book, cfb_bitwriter *bw)
+{
+    size_t w0, w1;
+    cfb_error e = band_range(L, channel, level, band, &w0, &w1, nullptr);
+    if (e) return e;
+    if (!book_ok(book)) { set_error("bad code book"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (!writer_ok(bw)) { set_error("bad bit writer"); return CFB_ERROR_INVALID_ARGUMENT; }
+    Bits bits(*bw);
+    Coder coder(*book, bits);
+    size_t next = w0;               // first word not yet accounted for
+    e = walk(L, sparse, w0, w1, [&](size_t pos, int v) {
+        coder.run(pos - next);
+        coder.value(v);
+        next = pos + 1;
+    });
+    if (e) return e;
+    coder.run(w1 - next);           // pending run, incl. the last row's pitch gap (encoder.c:5671)
+    if (bits.overflow) { set_error("bit writer out of space"); return CFB_ERROR_OUTOFMEMORY; }
+    bits.store(bw);
+    return CFB_OK;
+}
+
+cfb_error cfb_dense_vlc_band(const int16_t *image, int width, int height, int pitch_bytes, const cfb_vlc_codebook *book, cfb_bitwriter *bw)
+{
+    if (!image || width <= 0 || height <= 0 || pitch_bytes < 2 * width || (pitch_bytes & 1)) { set_error("bad band geometry"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (!book_ok(book)) { set_error("bad code book"); return CFB_ERROR_INVALID_ARGUMENT; }
+    if (!writer_ok(bw)) { set_error("bad bit writer"); return CFB_ERROR_INVALID_ARGUMENT; }
+    Bits bits(*bw);
+    Coder coder(*book, bits);
+    const int pitch = pitch_bytes / 2, gap = pitch - width;
+    uint64_t count = 0;
+    for (int r = 0; r < height; r++) {
+        const int16_t *row = image + (size_t)r * pitch;
+        for (int x = 0; x < width; x++) {
+            if (row[x] == 0) { count++; continue; }
+            coder.run(count);
+            count = 0;
+            coder.value(row[x]);
+        }
+        count += (uint64_t)gap;
+    }
+    coder.run(count);
+    if (bits.overflow) { set_error("bit writer out of space"); return CFB_ERROR_OUTOFMEMORY; }
+    bits.store(bw);
+    return CFB_OK;
+}
+
+cfb_error cfb_sparse_band_nonzeros(const cfb_layout *L, const void *sparse, int channel, int level, int band, uint32_t *count)
+{
+    size_t w0, w1;
+    cfb_error e = band_range(L, channel, level, band, &w0, &w1, nullptr);
+    if (e) return e;
+    if (!count) return CFB_ERROR_INVALID_ARGUMENT;
+    uint32_t n = 0;
+    e = walk(L, sparse, w0, w1, [&](size_t, int) { n++; });
+    *count = n;
+    return e;
+}
+
+cfb_error cfb_sparse_expand_band(const cfb_layout *L, const void *sparse, int channel, int level, int band, int16_t *out, int pitch_bytes)
+{
+    size_t w0, w1;
+    const cfb_band_layout *bl = nullptr;
+    cfb_error e = band_range(L, channel, level, band, &w0, &w1, &bl);
+    if (e) return e;
+    if (!out || pitch_bytes < 2 * bl->width || (pitch_bytes & 1)) { set_error("bad output pitch"); return CFB_ERROR_INVALID_ARGUMENT; }
+    for (int r = 0; r < bl->height; r++) memset((unsigned char *)out + (size_t)r * pitch_bytes, 0, (size_t)bl->width * 2);
+    const size_t pitch = (size_t)bl->pitch / 2;
+    return walk(L, sparse, w0, w1, [&](size_t pos, int v) {
+        const size_t r = (pos - w0) / pitch, x = (pos - w0) % pitch;
+        if (x < (size_t)bl->width) *(int16_t *)((unsigned char *)out + r * (size_t)pitch_bytes + 2 * x) = (int16_t)v;
+    });
+}
+
+}  // extern "C"

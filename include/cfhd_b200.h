@@ -53,7 +53,8 @@ typedef enum cfb_error {
     CFB_ERROR_NOT_FINISHED = 13,
     CFB_ERROR_NO_DEVICE = 100,      /* no CUDA device / not sm_100 */
     CFB_ERROR_CUDA = 101,           /* a CUDA call failed; see cfb_last_error_string() */
-    CFB_ERROR_UNSUPPORTED = 102     /* geometry the kernels do not cover (see cfb_frame_desc) */
+    CFB_ERROR_UNSUPPORTED = 102,    /* geometry the kernels do not cover (see cfb_frame_desc) */
+    CFB_ERROR_RANGE = 103           /* a signed plane outside the range in which exact and saturating arithmetic agree */
 } cfb_error;
 
 /* Input / output pixel layouts of level 1 (the reference's COLOR_FORMAT_* subset used by the
@@ -268,6 +269,15 @@ typedef struct cfb_level_desc {
     int32_t midpoint_prequant;      /* quantiser midpoint rule, as cfb_quant */
     int32_t divisor[4];
 } cfb_level_desc;
+/* Value range.  The kernels compute in exact 32-bit arithmetic; the reference's SSE2 loops use saturating 16-bit chains
+ * (spatial.c:290-413, :10290-10413).  The two agree whenever no chain input exceeds 8190 in magnitude (4 * 8190 + 4 is
+ * the largest partial sum).  Every source format of the codec objects satisfies this by its declared precision
+ * (DESIGN.md 4); a free-standing SIGNED plane (the temporal highpass of a two-frame GOP, +-4080 by range) need not.
+ * The forward level therefore audits its input on the device -- |x| and both horizontal outputs of every pair against
+ * the bound, one extra read of the plane -- and a violation is REPORTED, never silently computed differently from the
+ * reference: the host forms return CFB_ERROR_RANGE, the asynchronous device form records it for
+ * cfb_context_range_status (which waits for the stream, returns the flags and clears them; 0 = in range). */
+CFB_API cfb_error cfb_context_range_status(cfb_context *ctx, int *flags);
 CFB_API cfb_error cfb_level_forward_device(cfb_context *ctx, const cfb_level_desc *desc, const void *d_plane, void *const *d_bands);
 CFB_API cfb_error cfb_level_inverse_device(cfb_context *ctx, const cfb_level_desc *desc, const void *const *d_bands, void *d_plane);
 CFB_API cfb_error cfb_level_forward_host(cfb_context *ctx, const cfb_level_desc *desc, const void *plane, void *const *bands);
@@ -305,10 +315,12 @@ CFB_API cfb_error cfb_gop2_inverse_host(cfb_codec *codec, const void *coded, con
                                         void *frame_a, void *frame_b, int frame_pitch);
 
 /* ---- sparse transfer format of the coded region (lossless) ---- */
-/* Layout of a sparse buffer:  16-byte header {u32 'CFSP', u32 nwords, u32 nvalues, u32 0};
- * bitmap (nwords bits, bit i <=> int16 word i of the coded region [0, coded_bytes) is non-zero);
- * 16-byte aligned array of the nvalues non-zero int16 words in raster order.  Zero runs (incl. the pitch gap
- * the reference's run-length coder walks, encoder.c:5811) are implicit in the bitmap. */
+/* Layout of a sparse buffer ('CFS2', cineform-sdk_b200/csrc/cfb_sparse_format.h):
+ *   header 32 B {u32 'CFS2', u32 nwords, u32 total_bytes, u32 nblocks, 0...}; table nblocks x {u32 chunk offset, u32 groups,
+ *   u32 values, u32 escapes}; one 16-byte aligned chunk per block of 8192 int16 words of the coded region [0, coded_bytes)
+ *   (empty when the block is all zero): 32-byte bitmap of the block's non-empty 32-word groups, one 32-bit mask per
+ *   non-empty group, one byte per non-zero word (-128 = escape), one int16 per escape.  Zero runs (incl. the pitch gap
+ *   the reference's run-length coder walks, encoder.c:5653) are implicit in the bitmaps. */
 CFB_API size_t cfb_sparse_max_bytes(const cfb_layout *layout);          /* worst case (no zero at all) */
 CFB_API size_t cfb_sparse_bytes(const void *sparse);                    /* actual size, from the header */
 /* forward + GPU compaction; sparse_bytes[i] receives the size written to h_sparse[i] */
@@ -320,6 +332,50 @@ CFB_API cfb_error cfb_inverse_host_sparse(cfb_codec *codec, int n, const void *c
 /* host-side format conversion (no transform arithmetic): sparse <-> dense coded region */
 CFB_API cfb_error cfb_sparse_expand(const cfb_layout *layout, const void *sparse, void *dense_coded);
 CFB_API cfb_error cfb_sparse_compact(const cfb_layout *layout, const void *dense_coded, void *sparse, size_t *bytes);
+
+/* ---- host run-length / VLC packing straight from the sparse format (host side) ----
+ * Replaces the walk of the reference's run-length coder over a DENSE band:
+ *   Codec/encoder.c:5386-5700 EncodeQuantLongRuns (zero runs incl. the pitch gap :5653, greedy run-code split :5493-5545
+ *   = Codec/vlc.c:366 PutZeroRun, value code with the +-(length/2 - 1) clamp :5553-5568 = vlc.c:188 PutVlcByte,
+ *   32-bit big-endian bit buffer = bitstream.c:819 PutBits)
+ * by a walk over the bitmap + values of the sparse format: zero runs are distances between set bits (the pitch gap is
+ * part of the flat coded region and is zero), so the host never touches the 33 MB of dense int16 per 4K frame.  The
+ * output is bit-for-bit what EncodeQuantLongRuns writes for the same band, incl. the state it leaves in the bit buffer.
+ * The code tables belong to the host entropy coder (Codec/codebooks.c, out of scope): the caller passes them as plain
+ * arrays (INTEGRATION.md shows how the shim fills them from encoder->codebook_runbook / encoder->valuebook). */
+typedef struct cfb_vlc_codebook {
+    int32_t run_length;             /* entries in run_* (RLCBOOK::length); entry i is used for runs >= i, i < length - 1 */
+    int32_t value_length;           /* VALUE_TABLE_LENGTH: index v for 0 <= v < n/2, n + v for -n/2 < v < 0 */
+    const uint32_t *run_bits;       /* code word, right justified */
+    const uint8_t *run_size;        /* code size in bits (1..31) */
+    const uint32_t *run_count;      /* zeros covered by the entry (>= 1) */
+    const uint32_t *value_bits;
+    const uint8_t *value_size;
+} cfb_vlc_codebook;
+
+typedef struct cfb_bitwriter {      /* the BITSTREAM fields the coder reads and leaves behind (Codec/bitstream.h) */
+    uint8_t *cur;                   /* lpCurrentWord: the next 32-bit word is stored here, big-endian */
+    uint8_t *end;                   /* first byte the writer may not touch */
+    uint32_t buffer;                /* wBuffer: the low (32 - bits_free) bits are pending */
+    int32_t bits_free;              /* nBitsFree: 32 = empty, 0 = a whole word pending */
+    int64_t bytes;                  /* nWordsUsed */
+} cfb_bitwriter;
+
+/* band (channel, level 0..2 = wavelet level 1..3, band 0..3 = LL, LH, HL, HH) -> run-length / value codes appended to bw.
+ * CFB_ERROR_INVALID_ARGUMENT for a band that is not in the coded region (LL of levels 1, 2), CFB_ERROR_BADFORMAT for a
+ * damaged sparse buffer, CFB_ERROR_OUTOFMEMORY when bw->end would be passed (bw is then unusable). */
+CFB_API cfb_error cfb_sparse_vlc_band(const cfb_layout *layout, const void *sparse, int channel, int level, int band,
+                                      const cfb_vlc_codebook *book, cfb_bitwriter *bw);
+/* number of non-zero coefficients of a band (what the walk above will emit as value codes) */
+CFB_API cfb_error cfb_sparse_band_nonzeros(const cfb_layout *layout, const void *sparse, int channel, int level, int band,
+                                           uint32_t *count);
+/* one band of a sparse buffer -> dense int16 rows (pitch_bytes per row); the lowpass band LL3 is entropy coded by a
+ * different routine that wants it dense (encoder.c:4251 EncodeLowPassBand) */
+CFB_API cfb_error cfb_sparse_expand_band(const cfb_layout *layout, const void *sparse, int channel, int level, int band,
+                                         int16_t *out, int pitch_bytes);
+/* the same coder over a dense band (what the reference does); for A/B timing and for bands that never went sparse */
+CFB_API cfb_error cfb_dense_vlc_band(const int16_t *band, int width, int height, int pitch_bytes,
+                                     const cfb_vlc_codebook *book, cfb_bitwriter *bw);
 
 /* ---- statistics record -------------------------------------------------------- */
 typedef struct cfb_stats {

@@ -6,7 +6,11 @@
 // call sites of SURVEY 8(b) are served by the CUDA path through ELF symbol interposition:
 //
 //   encoder   TransformForwardSpatialYUV   (Codec/wavelet.c:2823, called at Codec/encoder.c:3121)
+//             TransformForwardSpatialRGB30 (Codec/wavelet.c:3597, called at :3171; RG30 / R210 / DPX0 / AR10 / AB10 sources)
 //             ComputeGroupTransformQuant   (Codec/encoder.c:8366, called at :3254)
+//             EncodeQuantLongRuns          (Codec/encoder.c:5386, called at :6497): the run-length / VLC stream of a band is
+//                                          written straight from the SPARSE transfer format (cfb_sparse_vlc_band), so the
+//                                          dense bands never cross PCIe and the host never scans them
 //   decoder   ReconstructWaveletBand       (Codec/decoder.c:12984, called at :11756/:11765 and by the worker threads)
 //             ReconstructSampleFrameToBuffer (Codec/decoder.c:13387, called at :11836)
 //
@@ -28,6 +32,8 @@
 #include <atomic>
 #include <map>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 extern "C" {
 #include "config.h"
@@ -37,6 +43,8 @@ extern "C" {
 #include "quantize.h"
 #include "codec.h"
 #include "image.h"
+#include "vlc.h"
+#include "bitstream.h"
 }
 #include "cfhd_b200.h"
 
@@ -46,12 +54,15 @@ namespace {
 
 std::atomic<long> g_fwd_frames{0}, g_inv_frames{0}, g_fwd_ref{0}, g_inv_ref{0};
 std::atomic<long> g_cuda_errors{0};
+std::atomic<long> g_vlc_sparse_bands{0}, g_vlc_ref_bands{0};
 
 struct StatsAtExit {
     ~StatsAtExit() {
         if (getenv("CFHD_B200_STATS"))
-            fprintf(stderr, "cfhd_gpu_shim: forward frames on GPU %ld (reference CPU %ld), inverse frames on GPU %ld (reference CPU %ld), CUDA errors %ld\n",
-                    g_fwd_frames.load(), g_fwd_ref.load(), g_inv_frames.load(), g_inv_ref.load(), g_cuda_errors.load());
+            fprintf(stderr, "cfhd_gpu_shim: forward frames on GPU %ld (reference CPU %ld), inverse frames on GPU %ld (reference CPU %ld), CUDA errors %ld, "
+                            "bands coded from the sparse format %ld (dense, by the reference's coder %ld)\n",
+                    g_fwd_frames.load(), g_fwd_ref.load(), g_inv_frames.load(), g_inv_ref.load(), g_cuda_errors.load(),
+                    g_vlc_sparse_bands.load(), g_vlc_ref_bands.load());
     }
 } g_stats_at_exit;
 
@@ -80,6 +91,7 @@ struct Plan {
     cfb_codec *codec = nullptr;
     cfb_layout layout{};
     void *coded = nullptr;          // pinned staging for the coded region
+    void *sparse = nullptr;         // pinned staging for the coded region in the sparse transfer format
     void *frame = nullptr;          // pinned staging for a decoded frame at the ENCODED size (allocated on first use)
     bool tried = false;
 };
@@ -104,12 +116,64 @@ Plan *get_plan(int width, int height, int pixel_format, int interlaced = CFB_PRO
         cfb_codec_destroy(p.codec); p.codec = nullptr; cfb_context_destroy(p.ctx); p.ctx = nullptr; return nullptr;
     }
     if (cfb_host_alloc((size_t)p.layout.coded_bytes, &p.coded) != CFB_OK) { cfb_codec_destroy(p.codec); p.codec = nullptr; return nullptr; }
+    if (cfb_host_alloc(cfb_sparse_max_bytes(&p.layout), &p.sparse) != CFB_OK) p.sparse = nullptr;      // dense transfers then
     return &p;
 }
 
 thread_local TRANSFORM *t_pyramid_done_for = nullptr;    // encoder: levels 2,3 already produced for this transform[0]
 thread_local bool t_cuda_failed = false;                 // encoder: the CUDA pyramid of the current frame failed (no CPU fallback)
 enum Took { NOT_COVERED, DONE, FAILED };
+
+// Sparse hand-over of the current frame of this thread: the highpass bands were NOT copied to the encoder's band buffers;
+// EncodeQuantLongRuns recognises a band by its buffer address and codes it from plan->sparse.  The token (encoder,
+// frame_count) is taken in ComputeGroupTransformQuant and ends with the frame (encoder.c:3274 advances frame_count after
+// the entropy coder has run), so a later frame that the reference transforms itself into the same buffers is never
+// mistaken for this one.
+struct SparseFrame {
+    Plan *plan = nullptr;
+    const void *band[3][3][4] = {};
+    const ENCODER *encoder = nullptr;
+    uint32_t frame_count = 0;
+    bool armed = false;             // bands recorded, token not taken yet
+    bool valid = false;
+};
+thread_local SparseFrame t_sparse;
+
+bool sparse_enabled()
+{
+    static int state = -1;
+    if (state < 0) { const char *e = getenv("CFHD_B200_DENSE"); state = (e && *e == '1') ? 0 : 1; }
+    return state == 1;
+}
+
+// The reference's code tables as the plain arrays the C ABI takes (built once per code set)
+struct Book {
+    std::vector<uint32_t> run_bits, run_count, value_bits;
+    std::vector<uint8_t> run_size, value_size;
+    cfb_vlc_codebook c{};
+};
+const cfb_vlc_codebook *codebook_for(ENCODER *encoder, int active_codebook)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, const void *>, Book *> books;
+    if (active_codebook < 0 || active_codebook >= CODEC_NUM_CODESETS) return nullptr;
+    RLCBOOK *rb = encoder->codebook_runbook[active_codebook];
+    VALBOOK *vb = encoder->valuebook[active_codebook];
+    if (!rb || !vb) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    Book *&b = books[{rb, vb}];
+    if (!b) {
+        b = new Book;
+        const RLC *rlc = (const RLC *)((const char *)rb + sizeof(RLCBOOK));         // vlc.h:105-131
+        for (int i = 0; i < rb->length; i++) { b->run_bits.push_back(rlc[i].bits); b->run_size.push_back((uint8_t)rlc[i].size); b->run_count.push_back((uint32_t)rlc[i].count); }
+        const VLE *tab = (const VLE *)((const char *)vb + sizeof(VALBOOK));         // vlc.h:67-73
+        for (int i = 0; i < VALUE_TABLE_LENGTH; i++) { b->value_bits.push_back(tab[i].entry & VLE_CODEWORD_MASK); b->value_size.push_back((uint8_t)(tab[i].entry >> VLE_CODESIZE_SHIFT)); }
+        b->c.run_length = rb->length; b->c.value_length = VALUE_TABLE_LENGTH;
+        b->c.run_bits = b->run_bits.data(); b->c.run_size = b->run_size.data(); b->c.run_count = b->run_count.data();
+        b->c.value_bits = b->value_bits.data(); b->c.value_size = b->value_size.data();
+    }
+    return &b->c;
+}
 
 bool spatial3(TRANSFORM *t)
 {
@@ -128,17 +192,17 @@ extern "C" {
 //                are zero-filled, ComputeGroupTransformQuant reports CODEC_ERROR through encoder->error, the error is
 //                printed, and CFHD_B200_ABORT_ON_ERROR=1 turns it into an abort().
 static Took forward_pyramid_on_gpu(uint8_t *input, int input_pitch, FRAME_INFO *frame, TRANSFORM *transform[], int frame_index,
-                                   int num_channels, int precision, int limit_yuv, int conv_601_709, int interlaced)
+                                   int num_channels, int precision, int limit_yuv, int conv_601_709, int interlaced, int cfb_format)
 {
     t_pyramid_done_for = nullptr;
     t_cuda_failed = false;
-    const bool fmt_ok = frame && (frame->format == COLOR_FORMAT_YUYV || frame->format == COLOR_FORMAT_UYVY);
+    t_sparse.valid = t_sparse.armed = false;
     Plan *plan = nullptr;
-    if (gpu_enabled() && fmt_ok && frame_index == 0 && num_channels == 3 && precision == 10 && !limit_yuv && !conv_601_709 &&
+    if (gpu_enabled() && frame && cfb_format >= 0 && frame_index == 0 && num_channels == 3 && !limit_yuv && !conv_601_709 &&
         input_pitch > 0 && (input_pitch & 15) == 0 && ((uintptr_t)input & 15) == 0 &&
         spatial3(transform[0]) && spatial3(transform[1]) && spatial3(transform[2]))
-        plan = get_plan(frame->width, frame->height, frame->format == COLOR_FORMAT_YUYV ? CFB_PIXEL_YUYV : CFB_PIXEL_UYVY, interlaced);
-    if (!plan) return NOT_COVERED;
+        plan = get_plan(frame->width, frame->height, cfb_format, interlaced);
+    if (!plan || precision != plan->layout.precision) return NOT_COVERED;
 
     cfb_quant q;
     memset(&q, 0, sizeof(q));
@@ -153,9 +217,18 @@ static Took forward_pyramid_on_gpu(uint8_t *input, int input_pitch, FRAME_INFO *
             for (int bnd = 0; bnd < 4; bnd++) q.divisor[c][k][bnd] = w->quant[bnd];
         }
     const void *frames[1] = {input};
-    void *coded[1] = {plan->coded};
     if (!ok) return NOT_COVERED;                  // the encoder's wavelet geometry is not the one the plan was built for
-    const bool failed = cfb_forward_host(plan->codec, 1, frames, input_pitch, &q, coded) != CFB_OK;
+    // Progressive frames cross PCIe in the sparse format and are entropy coded from it (EncodeQuantLongRuns below); the
+    // interlaced level-1 HL band is coded by EncodeQuantLongRunsPlusPeaks (encoder.c:6458), which wants it dense.
+    const bool sparse = sparse_enabled() && plan->sparse && interlaced == CFB_PROGRESSIVE;
+    bool failed;
+    if (sparse) {
+        void *out[1] = {plan->sparse};
+        failed = cfb_forward_host_sparse(plan->codec, 1, frames, input_pitch, &q, out, nullptr) != CFB_OK;
+    } else {
+        void *coded[1] = {plan->coded};
+        failed = cfb_forward_host(plan->codec, 1, frames, input_pitch, &q, coded) != CFB_OK;
+    }
     if (failed) {
         fprintf(stderr, "cfhd_gpu_shim: CUDA forward transform failed (%s); no CPU fallback on the transform path\n", cfb_last_error_string());
         g_cuda_errors++;
@@ -169,14 +242,28 @@ static Took forward_pyramid_on_gpu(uint8_t *input, int input_pitch, FRAME_INFO *
             IMAGE *w = transform[c]->wavelet[k];
             for (int bnd = (k == 2 ? 0 : 1); bnd < 4; bnd++) {
                 const cfb_band_layout &b = plan->layout.band[c][k][bnd];
-                memcpy(w->band[bnd], (const char *)plan->coded + b.offset, (size_t)b.pitch * b.height);
+                if (!sparse || failed) memcpy(w->band[bnd], (const char *)plan->coded + b.offset, (size_t)b.pitch * b.height);
+                else if (bnd == 0) {
+                    // the lowpass band LL3 is coded by EncodeLowPassBand (encoder.c:4251) from the dense band: 1/64 of the frame
+                    if (cfb_sparse_expand_band(&plan->layout, plan->sparse, c, k, 0, (int16_t *)w->band[0], w->pitch) != CFB_OK) {
+                        fprintf(stderr, "cfhd_gpu_shim: damaged sparse buffer (%s)\n", cfb_last_error_string());
+                        g_cuda_errors++; t_cuda_failed = true; failed = true;
+                    }
+                } else t_sparse.band[c][k][bnd] = w->band[bnd];
             }
             for (int bnd = 0; bnd < 4; bnd++) { w->pixel_type[bnd] = PIXEL_TYPE_16S; w->quantization[bnd] = w->quant[bnd]; }
         }
+    if (sparse && !failed) { t_sparse.plan = plan; t_sparse.armed = true; }
     t_pyramid_done_for = transform[0];
     if (failed) return FAILED;
     g_fwd_frames++;
     return DONE;
+}
+
+static int cfb_format_of_422(const FRAME_INFO *frame)
+{
+    if (!frame) return -1;
+    return frame->format == COLOR_FORMAT_YUYV ? CFB_PIXEL_YUYV : (frame->format == COLOR_FORMAT_UYVY ? CFB_PIXEL_UYVY : -1);
 }
 
 void TransformForwardSpatialYUV(uint8_t *input, int input_pitch, FRAME_INFO *frame, TRANSFORM *transform[], int frame_index,
@@ -185,7 +272,7 @@ void TransformForwardSpatialYUV(uint8_t *input, int input_pitch, FRAME_INFO *fra
 {
     typedef void (*fn_t)(uint8_t *, int, FRAME_INFO *, TRANSFORM *[], int, int, PIXEL *, size_t, int, int, int, int, int);
     static fn_t ref = next_symbol<fn_t>("TransformForwardSpatialYUV");
-    if (forward_pyramid_on_gpu(input, input_pitch, frame, transform, frame_index, num_channels, precision, limit_yuv, conv_601_709, CFB_PROGRESSIVE) != NOT_COVERED) return;
+    if (forward_pyramid_on_gpu(input, input_pitch, frame, transform, frame_index, num_channels, precision, limit_yuv, conv_601_709, CFB_PROGRESSIVE, cfb_format_of_422(frame)) != NOT_COVERED) return;
     g_fwd_ref++;
     ref(input, input_pitch, frame, transform, frame_index, num_channels, buffer, buffer_size, chroma_offset, IFrame, precision, limit_yuv, conv_601_709);
 }
@@ -197,9 +284,73 @@ void TransformForwardFrameYUV(uint8_t *input, int input_pitch, FRAME_INFO *frame
 {
     typedef void (*fn_t)(uint8_t *, int, FRAME_INFO *, TRANSFORM *[], int, int, char *, size_t, int, int, int, int);
     static fn_t ref = next_symbol<fn_t>("TransformForwardFrameYUV");
-    if (forward_pyramid_on_gpu(input, input_pitch, frame, transform, frame_index, num_channels, precision, limit_yuv, conv_601_709, CFB_INTERLACED) != NOT_COVERED) return;
+    if (forward_pyramid_on_gpu(input, input_pitch, frame, transform, frame_index, num_channels, precision, limit_yuv, conv_601_709, CFB_INTERLACED, cfb_format_of_422(frame)) != NOT_COVERED) return;
     g_fwd_ref++;
     ref(input, input_pitch, frame, transform, frame_index, num_channels, buffer, buffer_size, chroma_offset, precision, limit_yuv, conv_601_709);
+}
+
+// 10-bit packed RGB sources: Codec/encoder.c:3158-3176 -> Codec/wavelet.c:3597 (planes G, R, B; fields filtered after << 2)
+void TransformForwardSpatialRGB30(uint8_t *input, int input_pitch, FRAME_INFO *frame, TRANSFORM *transform[], int frame_index,
+                                  int num_channels, PIXEL *buffer, size_t buffer_size, int chroma_offset, int IFrame,
+                                  int display_height, int precision, int format)
+{
+    typedef void (*fn_t)(uint8_t *, int, FRAME_INFO *, TRANSFORM *[], int, int, PIXEL *, size_t, int, int, int, int, int);
+    static fn_t ref = next_symbol<fn_t>("TransformForwardSpatialRGB30");
+    int fmt = -1;
+    switch (format) {
+    case COLOR_FORMAT_RG30: fmt = CFB_PIXEL_RG30; break;
+    case COLOR_FORMAT_AB10: fmt = CFB_PIXEL_AB10; break;
+    case COLOR_FORMAT_AR10: fmt = CFB_PIXEL_AR10; break;
+    case COLOR_FORMAT_R210: fmt = CFB_PIXEL_R210; break;
+    case COLOR_FORMAT_DPX0: fmt = CFB_PIXEL_DPX0; break;
+    }
+    // the reference leaves the last two rows of a frame whose display height equals its coded height to a special
+    // path (wavelet.c:3642 last_row); only frames padded by the encoder (display_height < height) take the plain one
+    if (frame && display_height != frame->height &&
+        forward_pyramid_on_gpu(input, input_pitch, frame, transform, frame_index, num_channels, precision, 0, 0, CFB_PROGRESSIVE, fmt) != NOT_COVERED) return;
+    t_sparse.valid = t_sparse.armed = false;
+    g_fwd_ref++;
+    ref(input, input_pitch, frame, transform, frame_index, num_channels, buffer, buffer_size, chroma_offset, IFrame, display_height, precision, format);
+}
+
+// Run-length / VLC coding of one highpass band (Codec/encoder.c:5386).  Bands of the frame this thread has just
+// transformed on the GPU are coded straight from the sparse transfer format; everything else is the reference's.
+void EncodeQuantLongRuns(ENCODER *encoder, BITSTREAM *stream, PIXEL *image, int width, int height, int pitch, int divisor, int active_codebook)
+{
+    typedef void (*fn_t)(ENCODER *, BITSTREAM *, PIXEL *, int, int, int, int, int);
+    static fn_t ref = next_symbol<fn_t>("EncodeQuantLongRuns");
+    SparseFrame &sf = t_sparse;
+    if (sf.valid && sf.encoder == encoder && sf.frame_count == (uint32_t)encoder->frame_count) {
+        for (int c = 0; c < 3; c++)
+            for (int k = 0; k < 3; k++)
+                for (int b = 1; b < 4; b++) {
+                    if (sf.band[c][k][b] != (const void *)image) continue;
+                    const cfb_band_layout &bl = sf.plan->layout.band[c][k][b];
+                    const cfb_vlc_codebook *book = codebook_for(encoder, active_codebook);
+                    if (!book || bl.width != width || bl.height != height || bl.pitch != pitch) break;
+                    cfb_bitwriter bw;
+                    bw.cur = stream->lpCurrentWord;
+                    bw.end = stream->lpCurrentBuffer + stream->dwBlockLength;
+                    bw.buffer = stream->wBuffer; bw.bits_free = stream->nBitsFree; bw.bytes = stream->nWordsUsed;
+                    if (cfb_sparse_vlc_band(&sf.plan->layout, sf.plan->sparse, c, k, b, book, &bw) != CFB_OK) {
+                        fprintf(stderr, "cfhd_gpu_shim: coding band (%d, %d, %d) from the sparse format failed: %s\n", c, k, b, cfb_last_error_string());
+                        if (getenv("CFHD_B200_ABORT_ON_ERROR")) abort();
+                        encoder->error = CODEC_ERROR_UNEXPECTED;
+                        stream->error = BITSTREAM_ERROR_OVERFLOW;
+                        return;
+                    }
+                    stream->lpCurrentWord = bw.cur; stream->wBuffer = bw.buffer; stream->nBitsFree = bw.bits_free; stream->nWordsUsed = (int)bw.bytes;
+                    g_vlc_sparse_bands++;
+                    return;
+                }
+        // a band of this frame that we do not hold sparse must not exist: its buffer was never filled
+        fprintf(stderr, "cfhd_gpu_shim: EncodeQuantLongRuns on an unknown band of a sparse frame\n");
+        if (getenv("CFHD_B200_ABORT_ON_ERROR")) abort();
+        encoder->error = CODEC_ERROR_UNEXPECTED;
+        return;
+    }
+    g_vlc_ref_bands++;
+    ref(encoder, stream, image, width, height, pitch, divisor, active_codebook);
 }
 
 void ComputeGroupTransformQuant(ENCODER *encoder, TRANSFORM *transform[], int num_transforms)
@@ -210,6 +361,7 @@ void ComputeGroupTransformQuant(ENCODER *encoder, TRANSFORM *transform[], int nu
         // levels 2 and 3 came out of the same GPU pass as level 1: only the bookkeeping of encoder.c:8366-8420 / :8688-8790 remains
         t_pyramid_done_for = nullptr;
         if (t_cuda_failed) { encoder->error = CODEC_ERROR_UNEXPECTED; t_cuda_failed = false; }
+        if (t_sparse.armed) { t_sparse.encoder = encoder; t_sparse.frame_count = (uint32_t)encoder->frame_count; t_sparse.valid = true; t_sparse.armed = false; }
         for (int c = 0; c < num_transforms; c++) {
             transform[c]->num_frames = encoder->gop_length;
             transform[c]->num_spatial = encoder->num_spatial;
@@ -218,6 +370,7 @@ void ComputeGroupTransformQuant(ENCODER *encoder, TRANSFORM *transform[], int nu
         }
         return;
     }
+    t_sparse.valid = t_sparse.armed = false;
     ref(encoder, transform, num_transforms);
 }
 

@@ -5,7 +5,9 @@
 // reference, so the same program times both and their outputs can be compared.
 //
 //   sdk_roundtrip <width> <height> <frames> [pool_threads [queue]]
-// prints one JSON line: sync encode/decode ms, sample bytes, luma PSNR, FNV-1a hash of the decoded frames, pool fps.
+// prints one JSON line: sync encode/decode ms, sample bytes, FNV-1a digests of the encoded samples (sync loop and pool;
+// from byte 512 on: the sample header carries the wall-clock time of the encode as metadata, bytes 155-180 at 640x96),
+// luma PSNR, digest of the decoded frames, pool fps.
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -58,7 +60,7 @@ int main(int argc, char **argv)
     memset(out + (size_t)pitch * h, 0xA5, guard_bytes);
     double enc_s = 0, dec_s = 0, mse_sum = 0;
     size_t bytes = 0;
-    uint64_t hash = 1469598103934665603ull;
+    uint64_t hash = 1469598103934665603ull, sample_hash = 1469598103934665603ull, pool_hash = 1469598103934665603ull;
     bool prepared = false;
     for (int i = -1; i < nframes; i++) {          // i == -1: untimed warm-up (lazy allocations, CUDA context)
         uint8_t *f = frames[(i + distinct) % distinct];
@@ -68,7 +70,14 @@ int main(int argc, char **argv)
         if (e) { fprintf(stderr, "CFHD_EncodeSample failed: %d\n", (int)e); return 2; }
         void *sample = nullptr; size_t size = 0;
         CFHD_GetSampleData(enc, &sample, &size);
-        if (i >= 0) bytes += size;
+        if (i == 0 && getenv("CFHD_DUMP_SAMPLE")) {      // development aid: the first timed sample, for byte-level comparison of two builds
+            FILE *fp = fopen(getenv("CFHD_DUMP_SAMPLE"), "wb");
+            if (fp) { fwrite(sample, 1, size, fp); fclose(fp); }
+        }
+        if (i >= 0) {
+            bytes += size;
+            for (size_t k = 512; k < size; k++) { sample_hash ^= ((const uint8_t *)sample)[k]; sample_hash *= 1099511628211ull; }
+        }
         if (!prepared) {
             int aw, ah; CFHD_PixelFormat af;
             e = CFHD_PrepareToDecode(dec, w, h, fmt, CFHD_DECODED_RESOLUTION_FULL, CFHD_DECODING_FLAGS_NONE, sample, size, &aw, &ah, &af);
@@ -111,6 +120,11 @@ int main(int argc, char **argv)
             e = CFHD_WaitForSample(pool, &frameNumber, &sb);
             if (e) { fprintf(stderr, "CFHD_WaitForSample failed: %d\n", (int)e); return 7; }
             if ((int)frameNumber != received) { fprintf(stderr, "out-of-order delivery %u != %d\n", frameNumber, received); return 8; }
+            if (received < 8) {         // entropy-coded bytes of the first pool samples (all distinct source frames)
+                void *data = nullptr; size_t size = 0;
+                if (CFHD_GetEncodedSample(sb, &data, &size) == CFHD_ERROR_OKAY)
+                    for (size_t k = 512; k < size; k++) { pool_hash ^= ((const uint8_t *)data)[k]; pool_hash *= 1099511628211ull; }
+            }
             CFHD_ReleaseSampleBuffer(pool, sb);
             received++;
         }
@@ -119,8 +133,10 @@ int main(int argc, char **argv)
         CFHD_ReleaseEncoderPool(pool);
     }
     printf("{\"width\": %d, \"height\": %d, \"frames\": %d, \"enc_ms\": %.3f, \"dec_ms\": %.3f, \"sample_bytes\": %zu, "
+           "\"sample_digest\": \"%016llx\", \"pool_sample_digest\": \"%016llx\", "
            "\"luma_psnr_db\": %.3f, \"decoded_digest\": \"%016llx\", \"pool_threads\": %d, \"pool_fps\": %.1f, \"interlaced\": %d, \"guard_ok\": %d}\n",
-           w, h, nframes, 1e3 * enc_s / nframes, 1e3 * dec_s / nframes, bytes / nframes, psnr, (unsigned long long)hash,
+           w, h, nframes, 1e3 * enc_s / nframes, 1e3 * dec_s / nframes, bytes / nframes, (unsigned long long)sample_hash, (unsigned long long)pool_hash,
+           psnr, (unsigned long long)hash,
            pool_threads, pool_fps, interlaced ? 1 : 0, guard_ok ? 1 : 0);
     CFHD_CloseEncoder(enc);
     CFHD_CloseDecoder(dec);

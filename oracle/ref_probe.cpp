@@ -282,6 +282,73 @@ int ref_encode_frame_bands(const uint8_t *frame, int width, int height, int pitc
 }
 
 // ---------------------------------------------------------------------------------------------
+// Run-length / VLC stage: the reference's own code tables and its own EncodeQuantLongRuns, so that
+// tests can require cfb_sparse_vlc_band's output to be bit-identical.  The tables are read from an encoder the
+// reference initialised itself (InitializeEncoderWithParameters -> InitCodebooks, Codec/codebooks.c:202).
+extern "C" void EncodeQuantLongRuns(ENCODER *encoder, BITSTREAM *stream, PIXEL *image, int width, int height, int pitch,
+                                    int divisor, int active_codebook);
+static ENCODER *probe_vlc_encoder(void)
+{
+    static ENCODER *enc = nullptr;
+    if (enc) return enc;
+    enc = (ENCODER *)calloc(1, sizeof(ENCODER));
+    static TRANSFORM *tr[FRAME_MAX_CHANNELS];
+    for (int c = 0; c < FRAME_MAX_CHANNELS; c++) { tr[c] = (TRANSFORM *)calloc(1, sizeof(TRANSFORM)); InitTransform(tr[c]); }
+    ENCODING_PARAMETERS p;
+    memset(&p, 0, sizeof(p));
+    p.version = 1; p.gop_length = 1; p.encoded_width = 256; p.encoded_height = 64;
+    p.fixed_quality = 4; p.progressive = 1; p.format = COLOR_FORMAT_YUYV;
+    p.frame_sampling = FRAME_SAMPLING_422; p.colorspace_yuv = 2; p.colorspace_rgb = 1;
+    if (!InitializeEncoderWithParameters(NULL, enc, tr, 3, &p)) { free(enc); enc = nullptr; }
+    return enc;
+}
+
+// lengths of the run table and the value table of code set `codebook` (0 on failure)
+int ref_vlc_table_lengths(int codebook, int32_t *run_length, int32_t *value_length)
+{
+    ENCODER *enc = probe_vlc_encoder();
+    if (!enc || codebook < 0 || codebook >= CODEC_NUM_CODESETS || !enc->codebook_runbook[codebook] || !enc->valuebook[codebook]) return 0;
+    *run_length = enc->codebook_runbook[codebook]->length;
+    *value_length = VALUE_TABLE_LENGTH;
+    return 1;
+}
+
+int ref_vlc_tables(int codebook, uint32_t *run_bits, uint8_t *run_size, uint32_t *run_count, uint32_t *value_bits, uint8_t *value_size)
+{
+    ENCODER *enc = probe_vlc_encoder();
+    if (!enc || codebook < 0 || codebook >= CODEC_NUM_CODESETS) return 0;
+    RLCBOOK *rb = enc->codebook_runbook[codebook];
+    VALBOOK *vb = enc->valuebook[codebook];
+    if (!rb || !vb) return 0;
+    const RLC *rlc = (const RLC *)((const char *)rb + sizeof(RLCBOOK));
+    for (int i = 0; i < rb->length; i++) { run_bits[i] = rlc[i].bits; run_size[i] = (uint8_t)rlc[i].size; run_count[i] = (uint32_t)rlc[i].count; }
+    const VLE *tab = (const VLE *)((const char *)vb + sizeof(VALBOOK));
+    for (int i = 0; i < VALUE_TABLE_LENGTH; i++) { value_bits[i] = tab[i].entry & VLE_CODEWORD_MASK; value_size[i] = (uint8_t)(tab[i].entry >> VLE_CODESIZE_SHIFT); }
+    return 1;
+}
+
+// The reference's coder on one dense band (rows of `width` int16, `pitch` bytes apart).  The bit stream is primed with
+// `lead_bits` one-bits so that the band starts in the middle of a word.  Returns the bytes written so far (whole words),
+// and the state the coder left in the buffer through buffer_out / bits_free_out.
+int64_t ref_vlc_encode_band(const int16_t *band, int width, int height, int pitch, int codebook, int lead_bits,
+                            uint8_t *out, int64_t capacity, uint32_t *buffer_out, int32_t *bits_free_out)
+{
+    ENCODER *enc = probe_vlc_encoder();
+    if (!enc) return -1;
+    Aligned img((size_t)pitch * height + 64), buf((size_t)capacity + 64);
+    memcpy(img.p, band, (size_t)pitch * height);
+    BITSTREAM bs;
+    InitBitstreamBuffer(&bs, buf.as<uint8_t>(), (size_t)capacity, BITSTREAM_ACCESS_WRITE);
+    for (int i = 0; i < lead_bits; i++) PutBits(&bs, 1, 1);
+    EncodeQuantLongRuns(enc, &bs, img.as<PIXEL>(), width, height, pitch, 1, codebook);
+    *buffer_out = bs.wBuffer; *bits_free_out = bs.nBitsFree;
+    const int64_t n = bs.nWordsUsed;
+    if (n > capacity) return -1;
+    memcpy(out, buf.p, (size_t)n);
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Two-frame GOP (CFHD_ENCODING_FLAGS_YUV_2FRAME_GOP -> parameters.gop_length = 2, EncoderSDK/SampleEncoder.cpp:211):
 // run the reference's EncodeSample on frame A then frame B and copy out all six wavelets of every channel of the
 // FIELDPLUS transform (Codec/encoder.c:8431 FinishFieldPlusTransformQuant): wavelet 0/1 = level 1 of frame A/B,

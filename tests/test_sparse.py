@@ -25,11 +25,15 @@ def test_host_compact_expand_roundtrip(pkg, density):
     sp = pkg.sparse_compact(lay, dense_u8)
     assert pkg.sparse_bytes(sp) == sp.size
     hdr = sp[:16].view(np.uint32)
-    assert hdr[0] == 0x50534643 and hdr[1] == words and hdr[2] == int((dense != 0).sum())
+    nblocks = (words + 8191) // 8192
+    assert hdr[0] == 0x32534643 and hdr[1] == words and hdr[2] == sp.size and hdr[3] == nblocks        # 'CFS2'
+    table = sp[32:32 + 16 * nblocks].view(np.uint32).reshape(nblocks, 4)
+    assert int(table[:, 2].sum()) == int((dense != 0).sum())
+    assert int(table[:, 3].sum()) == int((np.abs(dense.astype(np.int32)) > 127).sum())
     back = pkg.sparse_expand(lay, sp)
     assert np.array_equal(back, dense_u8)
     if density == 0.0:
-        assert sp.size < lay.coded_bytes // 15          # bitmap only
+        assert sp.size < lay.coded_bytes // 500         # header + block table only
     bad = sp.copy(); bad[0] ^= 1
     with pytest.raises(pkg.CfbError):
         pkg.sparse_expand(lay, bad)

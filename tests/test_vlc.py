@@ -1,0 +1,143 @@
+"""Host run-length / VLC packing straight from the sparse transfer format (host side).
+
+The product entry point cfb_sparse_vlc_band must write, bit for bit, what the reference's EncodeQuantLongRuns
+(Codec/encoder.c:5386) writes for the same band with the same code tables -- including the state it leaves in the 32-bit
+bit buffer -- while reading only the sparse format.  The reference's coder and its tables come from oracle/_ref
+(ref_probe.cpp ref_vlc_*); nothing here needs a GPU."""
+import ctypes as C
+import importlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import parity_util as pu
+
+needs_ref = pytest.mark.skipif(not ol.ref_available(), reason="oracle/_ref not built (reference absent)")
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    return importlib.import_module("cineform-sdk_b200")
+
+
+def ref_tables(ref_lib, codebook):
+    rl, vl = C.c_int32(), C.c_int32()
+    assert ref_lib.ref_vlc_table_lengths(codebook, C.byref(rl), C.byref(vl)) == 1
+    rb, rs, rc = np.zeros(rl.value, np.uint32), np.zeros(rl.value, np.uint8), np.zeros(rl.value, np.uint32)
+    vb, vs = np.zeros(vl.value, np.uint32), np.zeros(vl.value, np.uint8)
+    assert ref_lib.ref_vlc_tables(codebook, rb.ctypes.data_as(C.c_void_p), rs.ctypes.data_as(C.c_void_p), rc.ctypes.data_as(C.c_void_p),
+                                  vb.ctypes.data_as(C.c_void_p), vs.ctypes.data_as(C.c_void_p)) == 1
+    return rb, rs, rc, vb, vs
+
+
+def ref_encode_band(ref_lib, band_padded, width, codebook, lead_bits):
+    """The reference's EncodeQuantLongRuns on a (height x pitch/2) int16 array whose first `width` columns are the band."""
+    h, pitch = band_padded.shape[0], band_padded.strides[0]
+    cap = 4 * band_padded.size + 4096
+    out = np.zeros(cap, np.uint8)
+    buf, free = C.c_uint32(), C.c_int32()
+    fn = ref_lib.ref_vlc_encode_band
+    fn.restype = C.c_int64
+    n = fn(band_padded.ctypes.data_as(C.c_void_p), width, h, pitch, codebook, lead_bits, out.ctypes.data_as(C.c_void_p),
+           C.c_int64(cap), C.byref(buf), C.byref(free))
+    assert n >= 0
+    return out[:n].copy(), int(buf.value), int(free.value)
+
+
+def all_bands(lay):
+    for c in range(lay.num_channels):
+        for k in (2, 1, 0):
+            for b in range(4):
+                if b == 0 and k != 2:
+                    continue
+                yield c, k, b
+
+
+def check_frame(pkg, ref_lib, lay, coded, book, codebook, lead_bits):
+    sparse = pkg.sparse_compact(lay, coded)
+    assert np.array_equal(pkg.sparse_expand(lay, sparse), coded)
+    total_bits = 0
+    for c, k, b in all_bands(lay):
+        bl = lay.band[c][k][b]
+        padded = coded[bl.offset: bl.offset + bl.pitch * bl.height].view(np.int16).reshape(bl.height, bl.pitch // 2)
+        want = ref_encode_band(ref_lib, padded, bl.width, codebook, lead_bits)
+        cap = want[0].size + 64
+        got = pkg.sparse_vlc_band(lay, sparse, c, k, b, book, cap, lead_bits)
+        assert np.array_equal(got[0], want[0]), f"band ({c},{k},{b}): stream differs"
+        assert got[1:] == want[1:], f"band ({c},{k},{b}): bit-buffer state differs {got[1:]} vs {want[1:]}"
+        dense = pkg.dense_vlc_band(padded, bl.pitch, bl.width, book, cap, lead_bits)
+        assert np.array_equal(dense[0], want[0]) and dense[1:] == want[1:]
+        assert pkg.sparse_band_nonzeros(lay, sparse, c, k, b) == int(np.count_nonzero(padded[:, :bl.width]))
+        assert np.array_equal(pkg.sparse_expand_band(lay, sparse, c, k, b), padded[:, :bl.width])
+        total_bits += want[0].size * 8
+    return total_bits, sparse.size
+
+
+@needs_ref
+@pytest.mark.parametrize("size,lead", [((256, 64), 0), ((704, 96), 5), ((720, 480), 31), ((1920, 1080), 13)])
+def test_vlc_from_sparse_matches_reference_coder_on_qbist(pkg, size, lead):
+    """TestCFHD's Qbist frames through the reference's real encoder; every coded band of every channel."""
+    w, h = size
+    ref_lib = ol.load_ref()
+    frame = pu.qbist_yuy2(ref_lib, w, h, 3)
+    bands, _, _, sample = pu.ref_encode_frame(ref_lib, frame, w, h, pu.COLOR_FORMAT_YUYV, 0, 3, 4)
+    lay = pkg.layout_for(pkg.FrameDesc(w, h, pkg.PIXEL_YUYV))
+    coded = pkg.pack_coded(lay, bands)
+    book = pkg.VlcCodebook.from_arrays(*ref_tables(ref_lib, 1))
+    bits, sparse_bytes = check_frame(pkg, ref_lib, lay, coded, book, 1, lead)
+    # the highpass payload is the bulk of the reference's sample: the per-band streams add up to (almost) its size
+    assert 0.5 * sample.size < bits / 8 < 1.5 * sample.size
+    if w >= 1920:
+        assert sparse_bytes < lay.coded_bytes // 8
+
+
+@needs_ref
+@pytest.mark.parametrize("codebook", [0, 1, 2])
+@pytest.mark.parametrize("kind", ["dense-small", "sparse-large", "extreme", "empty", "single"])
+def test_vlc_from_sparse_matches_reference_coder_adversarial(pkg, codebook, kind):
+    """Every code set; values beyond the table (clamp), beyond a byte (escapes), runs longer than any run code and across
+    block / band boundaries, an all-zero frame, a single coefficient at the very end."""
+    ref_lib = ol.load_ref()
+    lay = pkg.layout_for(pkg.FrameDesc(704, 96, pkg.PIXEL_YUYV))
+    rng = np.random.default_rng(len(kind) + codebook)
+    words = lay.coded_bytes // 2
+    dense = np.zeros(words, np.int16)
+    if kind == "dense-small":
+        dense[:] = rng.integers(-3, 4, words)
+    elif kind == "sparse-large":
+        nz = rng.random(words) < 0.01
+        dense[nz] = rng.integers(-2000, 2000, int(nz.sum()))
+    elif kind == "extreme":
+        nz = rng.random(words) < 0.2
+        dense[nz] = rng.choice(np.array([-32768, -32767, -1025, -1024, -1023, -512, -129, -128, -127, -1, 1, 127, 128, 129, 511, 512, 1023, 1024, 32767], np.int16), int(nz.sum()))
+    elif kind == "single":
+        dense[-1] = -5
+    coded = dense.view(np.uint8).copy()
+    # the pitch gap and the band alignment are zero in a real coded region
+    clean = np.zeros_like(coded)
+    for c, k, b in all_bands(lay):
+        pkg.band_view(lay, clean, c, k, b)[:] = pkg.band_view(lay, coded, c, k, b)
+    book = pkg.VlcCodebook.from_arrays(*ref_tables(ref_lib, codebook))
+    check_frame(pkg, ref_lib, lay, clean, book, codebook, 7)
+
+
+def test_vlc_rejects_bad_arguments(pkg):
+    lay = pkg.layout_for(pkg.FrameDesc(256, 64, pkg.PIXEL_YUYV))
+    sparse = pkg.sparse_compact(lay, np.zeros(lay.coded_bytes, np.uint8))
+    book = pkg.VlcCodebook.from_arrays(np.array([0, 1, 2], np.uint32), np.array([1, 2, 3], np.uint8), np.array([1, 1, 2], np.uint32),
+                                       np.arange(8, dtype=np.uint32), np.full(8, 4, np.uint8))
+    with pytest.raises(pkg.CfbError):
+        pkg.sparse_vlc_band(lay, sparse, 0, 0, 0, book, 4096)          # LL1 is not in the coded region
+    with pytest.raises(pkg.CfbError):
+        pkg.sparse_vlc_band(lay, sparse, 3, 2, 1, book, 4096)          # no such channel
+    with pytest.raises(pkg.CfbError):
+        pkg.sparse_vlc_band(lay, sparse, 0, 0, 1, book, 0)             # no room: all-zero band still needs run codes
+    bad = sparse.copy(); bad[0] ^= 1
+    with pytest.raises(pkg.CfbError):
+        pkg.sparse_vlc_band(lay, bad, 0, 0, 1, book, 4096)
+    # a run table whose entry covers more zeros than the run it is chosen for would never terminate in the reference
+    worse = pkg.VlcCodebook.from_arrays(np.array([0, 1, 2], np.uint32), np.array([1, 2, 3], np.uint8), np.array([1, 2, 2], np.uint32),
+                                        np.arange(8, dtype=np.uint32), np.full(8, 4, np.uint8))
+    with pytest.raises(pkg.CfbError):
+        pkg.sparse_vlc_band(lay, sparse, 0, 0, 1, worse, 4096)

@@ -73,7 +73,7 @@ def main():
     ms = e0.elapsed_time(e1) / a.iters
     # algorithmic bytes of this level: level 1 = input frame + 2P, level k = 2P / 4^(k-1) read+write ... all channels
     P = sum(lay.band[c][0][0].width * lay.band[c][0][0].height * 4 for c in range(lay.num_channels))     # samples of all channels
-    algo = (lay.frame_bytes + 2 * P) if a.level == 1 else (P // (4 ** (a.level - 1)))
+    algo = (lay.frame_bytes + 2 * P) if a.level == 1 else (4 * P // (4 ** (a.level - 1)))
     gbs = algo * n / (ms * 1e-3) / 1e9
     env = {k: v for k, v in os.environ.items() if k.startswith("CFB_")}
     print(f"{a.tag or a.dir + str(a.level)} {a.format} {env}: {ms * 1000:.1f} us per {n}-frame launch, {gbs:.0f} GB/s algorithmic "

@@ -1,5 +1,8 @@
 #!/bin/bash
+# round 2: full GPU suite (sparse v2, VLC hand-over in the SDK shim), inverse occupancy A/B, bench
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_output16.py tests/test_sparse.py tests/test_pool_gpu.py tests/test_config_sizes_gpu.py -m gpu -x -q 2>&1 | tail -4
-timeout 300 python tools/e2e_trace.py 8 1 2>&1 | tee gpurun_out/r02_e2e_trace.txt
-for cfg in "8 1" "12 1" "8 2"; do set -- $cfg; timeout 200 python tools/e2e_probe.py $1 $2; done 2>&1 | tee gpurun_out/r02_e2e_sweep4.txt
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/r02_tests_b.log; tail -15 gpurun_out/r02_tests_b.log
+for v in r1 r1b5; do
+  CFB_INV422=$v timeout 120 python tools/kernel_ab.py --level 1 --dir inv 2>&1 | tail -1 | tee -a gpurun_out/r02_ab_inv422.txt
+done
+timeout 600 python bench.py > gpurun_out/r02_bench_b.json 2> gpurun_out/r02_bench_b.err; tail -c 1500 gpurun_out/r02_bench_b.json; tail -3 gpurun_out/r02_bench_b.err
