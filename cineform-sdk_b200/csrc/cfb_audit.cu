@@ -2,7 +2,7 @@
 //
 // The level kernels compute in exact int32; the reference's SSE2 loops run saturating 16-bit chains
 // (Codec/spatial.c:290-413 horizontal, :10290-10413 vertical: 0 -s x0 -s x1 +s x4 +s x5 +s 4, >> 3, +s (x2 -s x3)) and its
-// scalar tails clamp or wrap once (oracle/cfhd_oracle.c restates both).  All of them equal exact arithmetic when every
+// scalar tails clamp or wrap once (SURVEY.md appendix A1 / A2 restate both).  All of them equal exact arithmetic when every
 // chain input is at most 8190 in magnitude: the largest partial sum is then 4 * 8190 + 4 = 32764.  The horizontal
 // chains read the plane (through the prescale taps (x + 3) >> 2 when prescale = 2), the vertical chains read the
 // horizontal outputs, so the audit checks
