@@ -151,6 +151,7 @@ def lib():
     L.cfb_inverse_host_sparse.argtypes = [vp, i, C.POINTER(vp), C.POINTER(Quant), i, C.POINTER(vp), i]
     L.cfb_sparse_expand.argtypes = [C.POINTER(Layout), vp, vp]
     L.cfb_sparse_compact.argtypes = [C.POINTER(Layout), vp, vp, C.POINTER(C.c_size_t)]
+    L.cfb_sparse_compact_bands.argtypes = [C.POINTER(Layout), C.POINTER(vp), C.POINTER(C.c_int32), vp, C.POINTER(C.c_size_t)]
     L.cfb_sparse_vlc_band.argtypes = [C.POINTER(Layout), vp, i, i, i, C.POINTER(VlcCodebook), C.POINTER(BitWriter)]
     L.cfb_dense_vlc_band.argtypes = [vp, i, i, i, C.POINTER(VlcCodebook), C.POINTER(BitWriter)]
     L.cfb_sparse_band_nonzeros.argtypes = [C.POINTER(Layout), vp, i, i, i, C.POINTER(C.c_uint32)]
@@ -222,6 +223,19 @@ def sparse_compact(layout, dense):
     n = C.c_size_t()
     _check(lib().cfb_sparse_compact(C.byref(layout), dense.ctypes.data, out.ctypes.data, C.byref(n)))
     return out[:n.value]
+
+
+def sparse_compact_bands(layout, bands):
+    """{(c, level 1..3, band name): 2-D int16 array (any row stride)} -> sparse buffer, as cfb_sparse_compact_bands."""
+    n = MAX_CHANNELS * NUM_LEVELS * NUM_BANDS
+    ptrs, pitches = (C.c_void_p * n)(), (C.c_int32 * n)()
+    for (c, lvl, name), arr in bands.items():
+        idx = (c * NUM_LEVELS + (lvl - 1)) * NUM_BANDS + BAND_NAMES.index(name)
+        ptrs[idx], pitches[idx] = arr.ctypes.data, arr.strides[0]
+    out = np.zeros(sparse_max_bytes(layout), np.uint8)
+    nbytes = C.c_size_t()
+    _check(lib().cfb_sparse_compact_bands(C.byref(layout), ptrs, pitches, out.ctypes.data, C.byref(nbytes)))
+    return out[:nbytes.value]
 
 
 class VlcCodebook(C.Structure):

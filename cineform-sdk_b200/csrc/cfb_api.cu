@@ -696,6 +696,9 @@ cfb_error cfb_forward_device(cfb_codec *cd, int n, const void *const *d_frames, 
         int maxw = 0, maxoh = 0;
         for (int c = 0; c < L.num_channels; c++) { if (p.ch[c].width > maxw) maxw = p.ch[c].width; if (p.ch[c].height / 2 > maxoh) maxoh = p.ch[c].height / 2; }
         p.th = pick_th((maxw + kStripIn - 1) / kStripIn, maxoh, n * L.num_channels, ctx->sm_count);
+        // the LL bands of every unsigned source format are non-negative (<= 4 * 4095): the prescaled level may use its
+        // packed non-negative taps; caller-supplied planes (CFB_PIXEL_PLANAR16) carry no such promise
+        p.pad = (fmt != CFB_PIXEL_PLANAR16) ? 1 : 0;
         CFB_CUDA(launch_fwd_plane(p, quant->prescale[k], ctx->stream));
         ctx->kernel_launches++;
     }

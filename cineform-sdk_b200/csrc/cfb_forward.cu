@@ -195,6 +195,19 @@ __device__ __forceinline__ int tap(int x) { return PRESCALE ? ((x + 3) >> 2) : x
 
 // horizontal 2-6 for the lane's 4 output columns: o[0..3] = low, o[4..7] = high
 // (Codec/spatial.c:253 FilterHorizontalRow16s / :3669 FilterHorizontalRow10bit16s)
+// dp2a with unsigned 16-bit halves (a) and signed byte coefficients (b): lo16(a) * b0 + hi16(a) * b1 + c
+__device__ __forceinline__ int dp2a_lo_us(unsigned a, unsigned b, int c) {
+    int d;
+    asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// PRESCALE = 3: the prescaled filter (PRESCALE = 2 arithmetic) for planes known to be NON-NEGATIVE, which every level-2 / 3
+// input of the codec pyramid is (an LL band of an unsigned source).  Both taps of a packed pair are then prescaled in the
+// packed word -- (w + 0x00030003) >> 2, masked -- and tap sum, tap difference and the lowpass (x0 + x1 + 3) >> 2 are one
+// dp2a each: 7 instructions per pair against 10 (the prescaled level is issue-bound: profiles/r02_prof_fwdplane_summary.csv)
+constexpr unsigned kOnes2 = 0x0101u, kPlusMinus2 = 0xff01u;       // dp2a byte coefficients (+1, +1) and (+1, -1)
+__device__ __forceinline__ unsigned prescale_pair_nonneg(unsigned w) { return ((w + 0x00030003u) >> 2) & 0x3fff3fffu; }
+
 template <int PRESCALE>
 __device__ __forceinline__ void hfilter_plane(const RawPlaneRow &r, const LaneInfo &L, int *o)
 {
@@ -202,15 +215,23 @@ __device__ __forceinline__ void hfilter_plane(const RawPlaneRow &r, const LaneIn
     int S[4], d[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int x0 = lo16(w[k]), x1 = hi16(w[k]);
-        const int t0 = tap<PRESCALE>(x0), t1 = tap<PRESCALE>(x1);
-        S[k] = t0 + t1;
-        d[k] = t0 - t1;
-        o[k] = PRESCALE ? ((x0 + x1 + 3) >> 2) : S[k];
+        if (PRESCALE == 3) {
+            const unsigned t = prescale_pair_nonneg(w[k]);
+            S[k] = dp2a_lo_us(t, kOnes2, 0);
+            d[k] = dp2a_lo_us(t, kPlusMinus2, 0);
+            o[k] = dp2a_lo_us(w[k], kOnes2, 3) >> 2;
+        } else {
+            const int x0 = lo16(w[k]), x1 = hi16(w[k]);
+            const int t0 = tap<PRESCALE>(x0), t1 = tap<PRESCALE>(x1);
+            S[k] = t0 + t1;
+            d[k] = t0 - t1;
+            o[k] = PRESCALE ? ((x0 + x1 + 3) >> 2) : S[k];
+        }
     }
     int Sp = __shfl_up_sync(L.amask, S[3], 1);
     int Sn = __shfl_down_sync(L.amask, S[0], 1);
-    const int hs = tap<PRESCALE>(lo16(r.halo)) + tap<PRESCALE>(hi16(r.halo));
+    const int hs = (PRESCALE == 3) ? dp2a_lo_us(prescale_pair_nonneg(r.halo), kOnes2, 0)
+                                   : tap<PRESCALE>(lo16(r.halo)) + tap<PRESCALE>(hi16(r.halo));
     Sp = L.use_lh ? hs : Sp;
     Sn = L.use_rh ? hs : Sn;
     o[4] = ((S[1] - Sp + 4) >> 3) + d[0];
@@ -1388,9 +1409,14 @@ cudaError_t launch_fwd_plane(const FwdParams &p, int prescale, cudaStream_t stre
         if (prescale) k_fwd_plane_edge<2><<<egrid, eblock, 0, stream>>>(p); else k_fwd_plane_edge<0><<<egrid, eblock, 0, stream>>>(p);
     }
     dim3 block(32, 4);
+    // p.pad != 0: the caller vouches that the planes are non-negative (LL bands of an unsigned source); CFB_FWDPLANE_NN=0
+    // keeps the generic prescaled kernel for the A/B
+    static const bool nn_on = !(getenv("CFB_FWDPLANE_NN") && !strcmp(getenv("CFB_FWDPLANE_NN"), "0"));
+    const bool nonneg = prescale && p.pad && nn_on;
     if (!tma_ok) {      // round-1 path (also: plane pointers / pitches that are not 16-byte aligned cannot be described to the TMA)
         dim3 grid(ceil_div(maxw, kStripIn), ceil_div(ceil_div(maxoh, p.th), (int)block.y) + 1, p.nframes * p.nchan);
-        if (prescale) k_fwd_plane<2><<<grid, block, 0, stream>>>(p);
+        if (nonneg) k_fwd_plane<3><<<grid, block, 0, stream>>>(p);
+        else if (prescale) k_fwd_plane<2><<<grid, block, 0, stream>>>(p);
         else k_fwd_plane<0><<<grid, block, 0, stream>>>(p);
         return cudaGetLastError();
     }

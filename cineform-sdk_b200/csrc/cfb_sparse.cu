@@ -62,45 +62,68 @@ __device__ __forceinline__ unsigned block_exclusive(unsigned warp_total, int lan
 }
 
 constexpr unsigned long long kFlagAggregate = 1ull << 62, kFlagPrefix = 2ull << 62, kFlagMask = 3ull << 62;
+constexpr int kSpThreads = 256, kSpWarps = kSpThreads / 32, kSpPieces = kSparseBlockWords / (8 * kSpThreads);     // 4 pieces of 8 words per thread
 
 // ---------------------------------------------------------------------------------------------------------------
-// dense -> sparse, one pass.  CTA = 1024 threads = one block of 8192 words (thread t: words 8t .. 8t + 7; four
-// consecutive lanes = one group).  Blocks take their index from a per-frame ticket, so a CTA only ever waits for
-// CTAs that already run.
-__global__ void __launch_bounds__(1024) k_sparse_pack(const __grid_constant__ SparseParams p)
+// dense -> sparse, one pass.  CTA = 256 threads = one block of 8192 words; thread t owns words 8 (256 j + t) ... + 7 for
+// j = 0..3, so every load is a coalesced 16-byte access, all four are in flight together, and four consecutive lanes
+// hold one 32-word group of piece j.  A 1024-thread CTA with one piece per thread (the first version) capped the SM at
+// two resident CTAs = 32 KB in flight and ran at 0.95 TB/s; eight resident CTAs of this shape keep 128 KB in flight.
+// Blocks take their index from a per-frame ticket, so a CTA only ever waits for CTAs that already run.
+__global__ void __launch_bounds__(kSpThreads, 4) k_sparse_pack(const __grid_constant__ SparseParams p)
 {
     __shared__ __align__(16) unsigned char chunk[kSparseMaxChunk];
-    __shared__ unsigned s_scan[32], s_gscan[32], s_ticket, s_base;
+    __shared__ unsigned s_cnt[kSpPieces][kSpWarps], s_grp[kSpPieces][kSpWarps], s_ticket, s_base;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int f = blockIdx.y;
     unsigned long long *status = p.status[f];
     if (tid == 0) s_ticket = (unsigned)atomicAdd(&status[p.nblocks], 1ull);
     __syncthreads();
     const unsigned blk = s_ticket;
-    const unsigned w0 = blk * kSparseBlockWords + tid * 8;
-    uint4 w = make_uint4(0, 0, 0, 0);
-    if (w0 < p.nwords) w = __ldg(reinterpret_cast<const uint4 *>(p.dense[f] + (size_t)w0 * 2));
-    const unsigned m8 = nonzero_mask8(w);
-    unsigned m = m8 << ((lane & 3) * 8);
-    m |= __shfl_xor_sync(0xffffffffu, m, 1);
-    m |= __shfl_xor_sync(0xffffffffu, m, 2);                // all four lanes of a group hold its 32-bit mask
-    const unsigned ws[4] = {w.x, w.y, w.z, w.w};
-    int vals[8];
-    unsigned nesc = 0;
+    const unsigned char *src = p.dense[f] + ((size_t)blk * kSparseBlockWords + (size_t)tid * 8) * 2;
+    const unsigned wfirst = blk * kSparseBlockWords + tid * 8;
+    // ---- phase 1: counts only (the words are read again in phase 2, from L2 / L1: keeping them would cost 16 registers
+    //      and halve the resident CTAs) ----
+    unsigned packed[kSpPieces], incl[kSpPieces], gb[kSpPieces];
+    {
+        uint4 w[kSpPieces];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        vals[k] = (k & 1) ? ((int)ws[k >> 1] >> 16) : (int)(short)(ws[k >> 1] & 0xffffu);
-        nesc += (vals[k] < -127 || vals[k] > 127) ? 1u : 0u;
+        for (int j = 0; j < kSpPieces; j++)
+            w[j] = (wfirst + j * kSpThreads * 8 < p.nwords) ? __ldg(reinterpret_cast<const uint4 *>(src + (size_t)j * kSpThreads * 16)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < kSpPieces; j++) {
+            // most 256-word warp pieces of a quantised frame are all zero: one OR + one ballot settles those
+            const unsigned any = __ballot_sync(0xffffffffu, (w[j].x | w[j].y | w[j].z | w[j].w) != 0);
+            packed[j] = 0; incl[j] = 0; gb[j] = 0;
+            if (any) {
+                const unsigned m8 = nonzero_mask8(w[j]);
+                const unsigned ws[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
+                unsigned nesc = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int v = (k & 1) ? ((int)ws[k >> 1] >> 16) : (int)(short)(ws[k >> 1] & 0xffffu);
+                    nesc += ((unsigned)(v + 127) > 254u) ? 1u : 0u;
+                }
+                packed[j] = __popc(m8) | (nesc << 16);      // values | escapes in one scan (<= 256 each per warp)
+                incl[j] = warp_incl_scan(packed[j], lane);
+                // bit 4g of gb <=> group g of this (piece, warp) is non-empty: OR of its four lanes, kept at the leader's position
+                gb[j] = (any | (any >> 1) | (any >> 2) | (any >> 3)) & 0x11111111u;
+            }
+            if (lane == 31) s_cnt[j][wid] = incl[j];
+            if (lane == 0) s_grp[j][wid] = __popc(gb[j]);
+        }
     }
-    const unsigned nval = __popc(m8);
-    // ---- positions inside the block: values | escapes packed in one scan, groups by ballot ----
-    const unsigned packed = nval | (nesc << 16);
-    const unsigned incl = warp_incl_scan(packed, lane);
-    const bool gleader = ((lane & 3) == 0) && (m != 0);
-    const unsigned gb = __ballot_sync(0xffffffffu, gleader);
-    unsigned tot, gtot;
-    const unsigned wexcl = block_exclusive(__shfl_sync(0xffffffffu, incl, 31), lane, wid, s_scan, &tot);
-    const unsigned gexcl = block_exclusive(__popc(gb), lane, wid, s_gscan, &gtot);
+    __syncthreads();
+    // raster order = piece-major: offsets of (piece j, warp wid) and the block totals
+    unsigned vbase[kSpPieces], gbase[kSpPieces], tot = 0, gtot = 0;
+#pragma unroll
+    for (int j = 0; j < kSpPieces; j++) {
+#pragma unroll
+        for (int q = 0; q < kSpWarps; q++) {
+            if (q == wid) { vbase[j] = tot; gbase[j] = gtot; }
+            tot += s_cnt[j][q]; gtot += s_grp[j][q];
+        }
+    }
     const unsigned V = tot & 0xffffu, E = tot >> 16, G = gtot;
     const unsigned bytes = sparse_chunk_bytes(G, V, E);
     // ---- publish the chunk size, look back for the offset (warp 0), meanwhile everyone fills the chunk ----
@@ -141,23 +164,36 @@ __global__ void __launch_bounds__(1024) k_sparse_pack(const __grid_constant__ Sp
             }
         }
     }
+    // ---- phase 2: fill the chunk ----
     if (G) {
         const unsigned masks_off = kSparseL1Bytes, bytes_off = masks_off + 4 * G, wide_off = bytes_off + ((V + 3) & ~3u);
-        if (lane == 0) {                // l1: 8 groups per warp = one byte
-            unsigned b = 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) b |= ((gb >> (4 * k)) & 1u) << k;
-            chunk[wid] = (unsigned char)b;
-        }
-        if (gleader) *reinterpret_cast<unsigned *>(chunk + masks_off + 4 * (gexcl + __popc(gb & ((1u << lane) - 1u)))) = m;
-        unsigned vpos = bytes_off + (wexcl & 0xffffu) + ((incl - packed) & 0xffffu);
-        unsigned epos = wide_off + 2 * ((wexcl >> 16) + ((incl - packed) >> 16));
+        for (int j = 0; j < kSpPieces; j++) {
+            if (lane == 0) {            // l1: the 8 groups of (piece j, warp wid) are groups 64 j + 8 wid ... + 7 of the block = one byte
+                unsigned b = 0;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (m8 & (1u << k)) {
-                const bool esc = (vals[k] < -127 || vals[k] > 127);
-                chunk[vpos++] = (unsigned char)(esc ? 0x80 : (vals[k] & 0xff));
-                if (esc) { *reinterpret_cast<short *>(chunk + epos) = (short)vals[k]; epos += 2; }
+                for (int k = 0; k < 8; k++) b |= ((gb[j] >> (4 * k)) & 1u) << k;
+                chunk[j * kSpWarps + wid] = (unsigned char)b;
+            }
+            if (!gb[j]) continue;       // nothing in this warp's 256 words (warp-uniform)
+            const uint4 w = (wfirst + j * kSpThreads * 8 < p.nwords) ? __ldg(reinterpret_cast<const uint4 *>(src + (size_t)j * kSpThreads * 16)) : make_uint4(0, 0, 0, 0);
+            const unsigned m8 = nonzero_mask8(w);
+            unsigned mm = m8 << ((lane & 3) * 8);
+            mm |= __shfl_xor_sync(0xffffffffu, mm, 1);
+            mm |= __shfl_xor_sync(0xffffffffu, mm, 2);      // all four lanes of a group hold its 32-bit mask
+            if (((lane & 3) == 0) && mm)
+                *reinterpret_cast<unsigned *>(chunk + masks_off + 4 * (gbase[j] + __popc(gb[j] & ((1u << lane) - 1u)))) = mm;
+            unsigned vpos = bytes_off + (vbase[j] & 0xffffu) + ((incl[j] - packed[j]) & 0xffffu);
+            unsigned epos = wide_off + 2 * ((vbase[j] >> 16) + ((incl[j] - packed[j]) >> 16));
+            const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (m8 & (1u << k)) {
+                    const int v = (k & 1) ? ((int)ws[k >> 1] >> 16) : (int)(short)(ws[k >> 1] & 0xffffu);
+                    const bool esc = (v < -127 || v > 127);
+                    chunk[vpos++] = (unsigned char)(esc ? 0x80 : (v & 0xff));
+                    if (esc) { *reinterpret_cast<short *>(chunk + epos) = (short)v; epos += 2; }
+                }
             }
         }
         // zero padding: bytes [V, align4(V)), wide [2E, align4(2E)) and the tail up to the 16-byte boundary
@@ -167,72 +203,113 @@ __global__ void __launch_bounds__(1024) k_sparse_pack(const __grid_constant__ Sp
     __syncthreads();
     if (G) {
         unsigned char *dst = p.sparse[f] + p.chunks_off + ((size_t)s_base << 4);
-        for (unsigned i = tid * 16; i < bytes; i += 1024 * 16)
+        for (unsigned i = tid * 16; i < bytes; i += kSpThreads * 16)
             *reinterpret_cast<uint4 *>(dst + i) = *reinterpret_cast<const uint4 *>(chunk + i);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// sparse -> dense: one CTA per block, the table entry gives the chunk
-__global__ void __launch_bounds__(1024) k_sparse_unpack(const __grid_constant__ SparseParams p)
+// sparse -> dense: one CTA per block (same thread-to-word mapping as the packer), the table entry gives the chunk
+__global__ void __launch_bounds__(kSpThreads, 4) k_sparse_unpack(const __grid_constant__ SparseParams p)
 {
     __shared__ __align__(16) unsigned char chunk[kSparseMaxChunk];
-    __shared__ unsigned s_scan[32];
+    __shared__ unsigned s_cnt[kSpPieces][kSpWarps];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int f = blockIdx.y;
     const unsigned blk = blockIdx.x;
-    const unsigned w0 = blk * kSparseBlockWords + tid * 8;
     const uint4 ent = __ldg(reinterpret_cast<const uint4 *>(p.sparse[f] + kSparseHeaderBytes) + blk);
     const unsigned G = min(ent.y, (unsigned)kSparseBlockGroups), V = min(ent.z, (unsigned)kSparseBlockWords), E = min(ent.w, V);
-    unsigned char *out = const_cast<unsigned char *>(p.dense[f]) + (size_t)w0 * 2;
+    unsigned char *out = const_cast<unsigned char *>(p.dense[f]) + ((size_t)blk * kSparseBlockWords + (size_t)tid * 8) * 2;
+    const unsigned wfirst = blk * kSparseBlockWords + tid * 8;
     if (G == 0) {
-        if (w0 < p.nwords) *reinterpret_cast<uint4 *>(out) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < kSpPieces; j++)
+            if (wfirst + j * kSpThreads * 8 < p.nwords) *reinterpret_cast<uint4 *>(out + (size_t)j * kSpThreads * 16) = make_uint4(0, 0, 0, 0);
         return;
     }
     const unsigned bytes = sparse_chunk_bytes(G, V, E);
     const unsigned char *src = p.sparse[f] + ent.x;
-    for (unsigned i = tid * 16; i < bytes; i += 1024 * 16)
+    for (unsigned i = tid * 16; i < bytes; i += kSpThreads * 16)
         *reinterpret_cast<uint4 *>(chunk + i) = __ldg(reinterpret_cast<const uint4 *>(src + i));
     __syncthreads();
     const unsigned masks_off = kSparseL1Bytes, bytes_off = masks_off + 4 * G, wide_off = bytes_off + ((V + 3) & ~3u);
-    // group rank: l1 byte k belongs to warp k
+    // group rank: l1 byte (j * 8 + w) belongs to (piece j, warp w); every warp scans the 32 bytes itself
     const unsigned pc = __popc((unsigned)chunk[lane]);
     const unsigned gincl = warp_incl_scan(pc, lane);
-    const unsigned gbase = __shfl_sync(0xffffffffu, gincl - pc, wid);
-    const unsigned l1b = chunk[wid];
-    const int gi = lane >> 2;
-    unsigned m = 0;
-    if ((l1b >> gi) & 1u) {
-        const unsigned grank = min(gbase + __popc(l1b & ((1u << gi) - 1u)), G - 1);
-        m = *reinterpret_cast<const unsigned *>(chunk + masks_off + 4 * grank);
-    }
-    const unsigned m8 = (m >> ((lane & 3) * 8)) & 0xffu;
-    const unsigned nval = __popc(m8);
-    const unsigned incl = warp_incl_scan(nval, lane);
-    const unsigned wexcl = block_exclusive(__shfl_sync(0xffffffffu, incl, 31), lane, wid, s_scan, nullptr);
-    unsigned vpos = wexcl + incl - nval;
-    int vals[8];
-    unsigned nesc = 0;
+    unsigned m8all = 0, vexcl[kSpPieces];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        vals[k] = 0;
-        if (m8 & (1u << k)) {
-            vals[k] = (int)(signed char)chunk[bytes_off + min(vpos, V - 1)];
-            vpos++;
-            nesc += (vals[k] == -128) ? 1u : 0u;
+    for (int j = 0; j < kSpPieces; j++) {
+        const unsigned gbase = __shfl_sync(0xffffffffu, gincl - pc, j * kSpWarps + wid);
+        const unsigned l1b = chunk[j * kSpWarps + wid];
+        const int gi = lane >> 2;
+        unsigned m = 0;
+        if ((l1b >> gi) & 1u) {
+            const unsigned grank = min(gbase + __popc(l1b & ((1u << gi) - 1u)), G - 1);
+            m = *reinterpret_cast<const unsigned *>(chunk + masks_off + 4 * grank);
+        }
+        const unsigned m8 = (m >> ((lane & 3) * 8)) & 0xffu;
+        m8all |= m8 << (8 * j);
+        const unsigned nval = __popc(m8);
+        const unsigned incl = warp_incl_scan(nval, lane);
+        if (lane == 31) s_cnt[j][wid] = incl;
+        vexcl[j] = incl - nval;                             // exclusive inside the warp
+    }
+    __syncthreads();
+    // value positions; escapes among this thread's values (the bytes are read again below: keeping them would cost 32 registers)
+    unsigned vpos[kSpPieces], nesc[kSpPieces], eexcl[kSpPieces];
+    {
+        unsigned tot = 0;
+#pragma unroll
+        for (int j = 0; j < kSpPieces; j++) {
+            unsigned vbase = 0;
+#pragma unroll
+            for (int q = 0; q < kSpWarps; q++) { if (q == wid) vbase = tot; tot += s_cnt[j][q]; }
+            vpos[j] = vbase + vexcl[j];
+            unsigned e = 0;
+            if (E && chunk[j * kSpWarps + wid]) {           // warp-uniform: blocks without escapes / empty warp pieces skip the byte scan
+                const unsigned n = __popc((m8all >> (8 * j)) & 0xffu);
+                for (unsigned k = 0; k < n; k++) e += ((signed char)chunk[bytes_off + min(vpos[j] + k, V - 1)] == -128) ? 1u : 0u;
+            }
+            nesc[j] = e;
         }
     }
-    const unsigned eincl = warp_incl_scan(nesc, lane);
-    __syncthreads();                    // s_scan is reused
-    const unsigned eexcl = block_exclusive(__shfl_sync(0xffffffffu, eincl, 31), lane, wid, s_scan, nullptr);
-    unsigned epos = eexcl + eincl - nesc;
-    if (nesc) {
+    __syncthreads();                    // s_cnt is reused for the escape counts
 #pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (vals[k] == -128 && (m8 & (1u << k))) { vals[k] = *reinterpret_cast<const short *>(chunk + wide_off + 2 * min(epos, E ? E - 1 : 0)); epos++; }
+    for (int j = 0; j < kSpPieces; j++) {
+        const unsigned incl = warp_incl_scan(nesc[j], lane);
+        if (lane == 31) s_cnt[j][wid] = incl;
+        eexcl[j] = incl - nesc[j];
     }
-    if (w0 < p.nwords)
-        *reinterpret_cast<uint4 *>(out) = make_uint4(pack_lo(vals[0], vals[1]), pack_lo(vals[2], vals[3]), pack_lo(vals[4], vals[5]), pack_lo(vals[6], vals[7]));
+    __syncthreads();
+    {
+        unsigned tot = 0;
+#pragma unroll
+        for (int j = 0; j < kSpPieces; j++) {
+            unsigned ebase = 0;
+#pragma unroll
+            for (int q = 0; q < kSpWarps; q++) { if (q == wid) ebase = tot; tot += s_cnt[j][q]; }
+            unsigned epos = ebase + eexcl[j], vp = vpos[j];
+            const unsigned m8 = (m8all >> (8 * j)) & 0xffu;
+            if (!chunk[j * kSpWarps + wid]) {               // warp-uniform: the whole 256-word piece is zero
+                if (wfirst + j * kSpThreads * 8 < p.nwords) *reinterpret_cast<uint4 *>(out + (size_t)j * kSpThreads * 16) = make_uint4(0, 0, 0, 0);
+                continue;
+            }
+            int vals[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                vals[k] = 0;
+                if (m8 & (1u << k)) {
+                    int v = (int)(signed char)chunk[bytes_off + min(vp, V - 1)];
+                    vp++;
+                    if (v == -128) { v = *reinterpret_cast<const short *>(chunk + wide_off + 2 * min(epos, E ? E - 1 : 0)); epos++; }
+                    vals[k] = v;
+                }
+            }
+            if (wfirst + j * kSpThreads * 8 < p.nwords)
+                *reinterpret_cast<uint4 *>(out + (size_t)j * kSpThreads * 16) = make_uint4(pack_lo(vals[0], vals[1]), pack_lo(vals[2], vals[3]),
+                                                                                      pack_lo(vals[4], vals[5]), pack_lo(vals[6], vals[7]));
+        }
+    }
 }
 
 cudaError_t launch_sparse_compact(const SparseParams &p, cudaStream_t stream)
@@ -242,14 +319,14 @@ cudaError_t launch_sparse_compact(const SparseParams &p, cudaStream_t stream)
         if (e != cudaSuccess) return e;
     }
     dim3 grid(p.nblocks, p.nframes);
-    k_sparse_pack<<<grid, 1024, 0, stream>>>(p);
+    k_sparse_pack<<<grid, kSpThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_sparse_expand(const SparseParams &p, cudaStream_t stream)
 {
     dim3 grid(p.nblocks, p.nframes);
-    k_sparse_unpack<<<grid, 1024, 0, stream>>>(p);
+    k_sparse_unpack<<<grid, kSpThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -397,6 +474,66 @@ cfb_error sparse_upload(cfb_codec *cd, int n, const void *const *h_sparse, cudaS
 
 }  // namespace cfb
 
+// One block of 8192 words -> its chunk at `chunk`; returns the chunk size and the table entry's counts
+static unsigned compact_block(const int16_t *in, unsigned nvalid, unsigned char *chunk, unsigned *G_out, unsigned *V_out, unsigned *E_out)
+{
+    unsigned char l1[kSparseL1Bytes] = {0};
+    unsigned masks[kSparseBlockGroups];
+    signed char vb[kSparseBlockWords];
+    int16_t wide[kSparseBlockWords];
+    unsigned G = 0, V = 0, E = 0;
+    for (unsigned g = 0; g * kSparseGroupWords < nvalid; g++) {
+        const int16_t *grp = in + (size_t)g * kSparseGroupWords;
+        const unsigned n = nvalid - g * kSparseGroupWords < kSparseGroupWords ? nvalid - g * kSparseGroupWords : kSparseGroupWords;
+        if (n == kSparseGroupWords) {           // most groups are empty: eight 64-bit tests
+            uint64_t any = 0, q[8];
+            memcpy(q, grp, sizeof(q));
+            for (int k = 0; k < 8; k++) any |= q[k];
+            if (!any) continue;
+        }
+        unsigned m = 0;
+        for (unsigned k = 0; k < n; k++) {
+            const int v = grp[k];
+            if (!v) continue;
+            m |= 1u << k;
+            if (v < -127 || v > 127) { vb[V++] = -128; wide[E++] = (int16_t)v; } else vb[V++] = (signed char)v;
+        }
+        if (m) { l1[g >> 3] |= (unsigned char)(1u << (g & 7)); masks[G++] = m; }
+    }
+    const unsigned cb = sparse_chunk_bytes(G, V, E);
+    if (G) {
+        memset(chunk, 0, cb);
+        memcpy(chunk, l1, kSparseL1Bytes);
+        memcpy(chunk + kSparseL1Bytes, masks, 4 * (size_t)G);
+        memcpy(chunk + kSparseL1Bytes + 4 * (size_t)G, vb, V);
+        memcpy(chunk + kSparseL1Bytes + 4 * (size_t)G + ((V + 3) & ~3u), wide, 2 * (size_t)E);
+    }
+    *G_out = G; *V_out = V; *E_out = E;
+    return cb;
+}
+
+// fetch(b, buf): returns a pointer to the 8192 words of block b (its own storage, or buf after filling it)
+template <class Fetch>
+static size_t compact_all(unsigned nwords, void *sparse, Fetch &&fetch)
+{
+    const unsigned nblocks = sparse_nblocks(nwords);
+    unsigned *h = (unsigned *)sparse;
+    unsigned *tab = (unsigned *)((unsigned char *)sparse + kSparseHeaderBytes);
+    size_t off = sparse_chunks_off(nblocks);
+    memset((unsigned char *)sparse + kSparseHeaderBytes + (size_t)nblocks * kSparseTableEntry, 0, off - kSparseHeaderBytes - (size_t)nblocks * kSparseTableEntry);
+    alignas(64) int16_t buf[kSparseBlockWords];
+    for (unsigned b = 0; b < nblocks; b++) {
+        const unsigned nvalid = nwords - b * kSparseBlockWords < kSparseBlockWords ? nwords - b * kSparseBlockWords : kSparseBlockWords;
+        const int16_t *in = fetch(b, buf);
+        unsigned G, V, E;
+        const unsigned cb = compact_block(in, nvalid, (unsigned char *)sparse + off, &G, &V, &E);
+        tab[4 * b] = (unsigned)off; tab[4 * b + 1] = G; tab[4 * b + 2] = V; tab[4 * b + 3] = E;
+        off += cb;
+    }
+    h[0] = kSparseMagic; h[1] = nwords; h[2] = (unsigned)off; h[3] = nblocks; h[4] = h[5] = h[6] = h[7] = 0;
+    return off;
+}
+
 extern "C" {
 
 size_t cfb_sparse_max_bytes(const cfb_layout *L)
@@ -493,44 +630,50 @@ cfb_error cfb_sparse_compact(const cfb_layout *L, const void *dense_coded, void 
 {
     if (!L || !sparse || !dense_coded) return CFB_ERROR_INVALID_ARGUMENT;
     const unsigned nwords = (unsigned)(L->coded_bytes / 2);
-    const unsigned nblocks = sparse_nblocks(nwords);
-    unsigned *h = (unsigned *)sparse;
-    unsigned *tab = (unsigned *)((unsigned char *)sparse + kSparseHeaderBytes);
     const int16_t *in = (const int16_t *)dense_coded;
-    size_t off = sparse_chunks_off(nblocks);
-    memset((unsigned char *)sparse + kSparseHeaderBytes + (size_t)nblocks * kSparseTableEntry, 0, off - kSparseHeaderBytes - (size_t)nblocks * kSparseTableEntry);
-    for (unsigned b = 0; b < nblocks; b++) {
-        unsigned char *chunk = (unsigned char *)sparse + off;
-        unsigned char l1[kSparseL1Bytes] = {0};
-        unsigned masks[kSparseBlockGroups];
-        signed char vb[kSparseBlockWords];
-        int16_t wide[kSparseBlockWords];
-        unsigned G = 0, V = 0, E = 0;
-        for (unsigned g = 0; g < kSparseBlockGroups; g++) {
-            const size_t w = (size_t)b * kSparseBlockWords + (size_t)g * kSparseGroupWords;
-            if (w >= nwords) break;
-            unsigned m = 0;
-            for (unsigned k = 0; k < kSparseGroupWords && w + k < nwords; k++) {
-                const int v = in[w + k];
-                if (!v) continue;
-                m |= 1u << k;
-                if (v < -127 || v > 127) { vb[V++] = -128; wide[E++] = (int16_t)v; } else vb[V++] = (signed char)v;
+    const size_t total = compact_all(nwords, sparse, [&](unsigned b, int16_t *) { return in + (size_t)b * kSparseBlockWords; });
+    if (bytes) *bytes = total;
+    return CFB_OK;
+}
+
+// The coded region as the entropy DEcoder leaves it: one buffer per band (pitch bytes per row; whatever lies between
+// `width` and the pitch is ignored), e.g. the reference decoder's wavelet->band[] after Codec/decoder.c:19534-19808.
+// Produces byte for byte what cfb_sparse_compact gives for the equivalent dense region -- the host-side half of
+// "FSM output -> sparse upload" (SURVEY 8f rank 1): the host reads the bands once and uploads ~1/8 of them.
+cfb_error cfb_sparse_compact_bands(const cfb_layout *L, const void *const *bands, const int32_t *pitches, void *sparse, size_t *bytes)
+{
+    if (!L || !bands || !pitches || !sparse) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    struct Seg { size_t w0, w1; const unsigned char *src; int pitch, width, lpitch; };
+    Seg segs[CFB_MAX_CHANNELS * CFB_NUM_LEVELS * CFB_NUM_BANDS];
+    int ns = 0;
+    for (int c = 0; c < L->num_channels; c++)
+        for (int k = CFB_NUM_LEVELS - 1; k >= 0; k--)
+            for (int b = (k == CFB_NUM_LEVELS - 1 ? 0 : 1); b < CFB_NUM_BANDS; b++) {       // the coded region's order (cfb_layout_compute)
+                const int idx = (c * CFB_NUM_LEVELS + k) * CFB_NUM_BANDS + b;
+                const cfb_band_layout &bl = L->band[c][k][b];
+                if (!bands[idx] || pitches[idx] < bl.width * 2) { set_error("band (%d, %d, %d): null or pitch too small", c, k, b); return CFB_ERROR_INVALID_ARGUMENT; }
+                segs[ns++] = {(size_t)bl.offset / 2, (size_t)bl.offset / 2 + (size_t)(bl.pitch / 2) * bl.height, (const unsigned char *)bands[idx], pitches[idx], bl.width, bl.pitch / 2};
             }
-            if (m) { l1[g >> 3] |= (unsigned char)(1u << (g & 7)); masks[G++] = m; }
+    const unsigned nwords = (unsigned)(L->coded_bytes / 2);
+    int cur = 0;
+    const size_t total = compact_all(nwords, sparse, [&](unsigned b, int16_t *buf) {
+        const size_t lo = (size_t)b * kSparseBlockWords, hi = lo + kSparseBlockWords;
+        memset(buf, 0, kSparseBlockWords * sizeof(int16_t));
+        while (cur < ns && segs[cur].w1 <= lo) cur++;
+        for (int s = cur; s < ns && segs[s].w0 < hi; s++) {
+            const Seg &g = segs[s];
+            const size_t a = g.w0 > lo ? g.w0 : lo, z = g.w1 < hi ? g.w1 : hi;
+            for (size_t row = (a - g.w0) / g.lpitch; row * g.lpitch + g.w0 < z; row++) {
+                const size_t r0 = g.w0 + row * g.lpitch;                    // flat position of the row's first coefficient
+                const size_t x0 = a > r0 ? a - r0 : 0;
+                size_t x1 = (size_t)g.width;
+                if (r0 + x1 > z) x1 = z - r0;
+                if (x0 < x1) memcpy(buf + (r0 + x0 - lo), g.src + row * (size_t)g.pitch + 2 * x0, 2 * (x1 - x0));
+            }
         }
-        const unsigned cb = sparse_chunk_bytes(G, V, E);
-        tab[4 * b] = (unsigned)off; tab[4 * b + 1] = G; tab[4 * b + 2] = V; tab[4 * b + 3] = E;
-        if (G) {
-            memset(chunk, 0, cb);
-            memcpy(chunk, l1, kSparseL1Bytes);
-            memcpy(chunk + kSparseL1Bytes, masks, 4 * (size_t)G);
-            memcpy(chunk + kSparseL1Bytes + 4 * (size_t)G, vb, V);
-            memcpy(chunk + kSparseL1Bytes + 4 * (size_t)G + ((V + 3) & ~3u), wide, 2 * (size_t)E);
-        }
-        off += cb;
-    }
-    h[0] = kSparseMagic; h[1] = nwords; h[2] = (unsigned)off; h[3] = nblocks; h[4] = h[5] = h[6] = h[7] = 0;
-    if (bytes) *bytes = off;
+        return (const int16_t *)buf;
+    });
+    if (bytes) *bytes = total;
     return CFB_OK;
 }
 

@@ -332,6 +332,12 @@ CFB_API cfb_error cfb_inverse_host_sparse(cfb_codec *codec, int n, const void *c
 /* host-side format conversion (no transform arithmetic): sparse <-> dense coded region */
 CFB_API cfb_error cfb_sparse_expand(const cfb_layout *layout, const void *sparse, void *dense_coded);
 CFB_API cfb_error cfb_sparse_compact(const cfb_layout *layout, const void *dense_coded, void *sparse, size_t *bytes);
+/* the same from one buffer per band, as an entropy decoder leaves them (Codec/decoder.c:19534-19808 writes
+ * wavelet->band[b]): bands[(channel * CFB_NUM_LEVELS + level) * CFB_NUM_BANDS + band] with pitches[] bytes per row; bytes
+ * between the band's width and its pitch are ignored; LL of levels 1, 2 may be null.  Host half of the decoder-side
+ * hand-over: read the bands once, upload ~1/8 of them (cfb_inverse_host_sparse) */
+CFB_API cfb_error cfb_sparse_compact_bands(const cfb_layout *layout, const void *const *bands, const int32_t *pitches,
+                                           void *sparse, size_t *bytes);
 
 /* ---- host run-length / VLC packing straight from the sparse format (host side) ----
  * Replaces the walk of the reference's run-length coder over a DENSE band:

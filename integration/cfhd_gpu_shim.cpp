@@ -46,6 +46,8 @@ extern "C" {
 #include "vlc.h"
 #include "bitstream.h"
 }
+#include <math.h>
+#include "AVIExtendedHeader.h"     // CURVE_LIN2LOG, CURVE_LOG_90: the host builds the Bayer encode curve, as the reference does
 #include "cfhd_b200.h"
 
 extern "C" int g_midpoint_prequant;     // Codec/quantize.c:183
@@ -85,39 +87,67 @@ bool gpu_enabled()
     return state == 1;
 }
 
-// one context + codec per (thread, geometry): encoder pool threads and decoder threads never share a stream
+// Plans = (context + stream, codec, pinned staging) for one geometry.  They live in a process-wide pool and are BORROWED by
+// a thread for the duration of one frame (EncodeSample / one decode): TestCFHD -E creates a new encoder pool -- new threads
+// -- for every row of its format table, and per-thread plans (the first version) re-created sixteen CUDA contexts and
+// re-pinned 1.4 GB of host memory per row.  Two threads never share a plan at the same time, hence never a stream.
 struct Plan {
     cfb_context *ctx = nullptr;
     cfb_codec *codec = nullptr;
     cfb_layout layout{};
-    void *coded = nullptr;          // pinned staging for the coded region
-    void *sparse = nullptr;         // pinned staging for the coded region in the sparse transfer format
+    uint64_t key = 0;
+    void *coded = nullptr;          // pinned staging for the dense coded region (allocated on first use)
+    void *sparse = nullptr;         // pinned staging for the coded region in the sparse transfer format (allocated on first use)
+    int curve_mode = -1;            // Bayer: encode curve the codec currently holds (-1 unknown, 0 none = curve applied, 1 = default log 90)
     void *frame = nullptr;          // pinned staging for a decoded frame at the ENCODED size (allocated on first use)
-    bool tried = false;
+    bool ensure_coded() { return coded || cfb_host_alloc((size_t)layout.coded_bytes, &coded) == CFB_OK; }
+    bool ensure_sparse() { return sparse || cfb_host_alloc(cfb_sparse_max_bytes(&layout), &sparse) == CFB_OK; }
 };
+
+std::mutex g_plan_mu;
+std::map<uint64_t, std::vector<Plan *>> g_free_plans;
+std::map<uint64_t, bool> g_uncovered;                   // geometries cfb_layout_compute rejected
+int g_next_device = 0;
+thread_local std::vector<Plan *> t_held;                // plans this thread has borrowed for the frame in progress
+
+void release_plans()
+{
+    if (t_held.empty()) return;
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    for (Plan *p : t_held) g_free_plans[p->key].push_back(p);
+    t_held.clear();
+}
 
 // interlaced: CFB_PROGRESSIVE, CFB_INTERLACED (encoder: coded HL band) or CFB_INTERLACED_HL_INTEGRATED (decoder bands)
 Plan *get_plan(int width, int height, int pixel_format, int interlaced = CFB_PROGRESSIVE)
 {
-    static thread_local std::map<uint64_t, Plan> plans;
-    static std::mutex mu;
-    static int next_device = 0;
     const uint64_t key = ((uint64_t)width << 40) | ((uint64_t)height << 16) | ((uint64_t)interlaced << 8) | (uint64_t)pixel_format;
-    Plan &p = plans[key];
-    if (p.tried) return p.codec ? &p : nullptr;
-    p.tried = true;
-    cfb_frame_desc d = {width, height, pixel_format, 0};
-    if (cfb_layout_compute(&d, &p.layout) != CFB_OK) return nullptr;        // geometry outside the CUDA path
+    for (Plan *p : t_held) if (p->key == key) return p;
     int dev;
-    { std::lock_guard<std::mutex> lk(mu); dev = next_device++ % cfb_device_count(); }      // frames sharded over the GPUs
-    if (cfb_context_create(dev, &p.ctx) != CFB_OK) return nullptr;
-    if (cfb_codec_create(p.ctx, &d, 1, &p.codec) != CFB_OK) { cfb_context_destroy(p.ctx); p.ctx = nullptr; return nullptr; }
-    if (interlaced && cfb_codec_set_interlaced(p.codec, interlaced) != CFB_OK) {
-        cfb_codec_destroy(p.codec); p.codec = nullptr; cfb_context_destroy(p.ctx); p.ctx = nullptr; return nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_plan_mu);
+        if (g_uncovered.count(key)) return nullptr;
+        std::vector<Plan *> &fl = g_free_plans[key];
+        if (!fl.empty()) { Plan *p = fl.back(); fl.pop_back(); t_held.push_back(p); return p; }
+        dev = g_next_device++ % cfb_device_count();     // frames sharded over the GPUs
     }
-    if (cfb_host_alloc((size_t)p.layout.coded_bytes, &p.coded) != CFB_OK) { cfb_codec_destroy(p.codec); p.codec = nullptr; return nullptr; }
-    if (cfb_host_alloc(cfb_sparse_max_bytes(&p.layout), &p.sparse) != CFB_OK) p.sparse = nullptr;      // dense transfers then
-    return &p;
+    Plan *p = new Plan;
+    p->key = key;
+    cfb_frame_desc d = {width, height, pixel_format, 0};
+    bool ok = cfb_layout_compute(&d, &p->layout) == CFB_OK;                 // else: geometry outside the CUDA path
+    ok = ok && cfb_context_create(dev, &p->ctx) == CFB_OK;
+    ok = ok && cfb_codec_create(p->ctx, &d, 1, &p->codec) == CFB_OK;
+    ok = ok && (!interlaced || cfb_codec_set_interlaced(p->codec, interlaced) == CFB_OK);
+    if (!ok) {
+        if (p->codec) cfb_codec_destroy(p->codec);
+        if (p->ctx) cfb_context_destroy(p->ctx);
+        delete p;
+        std::lock_guard<std::mutex> lk(g_plan_mu);
+        g_uncovered[key] = true;
+        return nullptr;
+    }
+    t_held.push_back(p);
+    return p;
 }
 
 thread_local TRANSFORM *t_pyramid_done_for = nullptr;    // encoder: levels 2,3 already produced for this transform[0]
@@ -131,7 +161,7 @@ enum Took { NOT_COVERED, DONE, FAILED };
 // mistaken for this one.
 struct SparseFrame {
     Plan *plan = nullptr;
-    const void *band[3][3][4] = {};
+    const void *band[CFB_MAX_CHANNELS][3][4] = {};
     const ENCODER *encoder = nullptr;
     uint32_t frame_count = 0;
     bool armed = false;             // bands recorded, token not taken yet
@@ -175,12 +205,60 @@ const cfb_vlc_codebook *codebook_for(ENCODER *encoder, int active_codebook)
     return &b->c;
 }
 
+// Sources the reference first converts to planes on the CPU (encoder.c:2518-2776: ConvertV210ToFrame16s,
+// ConvertYU64ToFrame16s, ConvertRGB48ToFrame16s, ConvertBYR4ToFrame16s) and then transforms plane by plane
+// (TransformForwardSpatial, encoder.c:3180-3193).  The CUDA kernels read the PACKED frame, so the converter hook only
+// records where it is -- the conversion itself and the per-plane level-1 calls are skipped -- and
+// ComputeGroupTransformQuant runs the whole pyramid in one pass.  The hooks only engage inside EncodeSample of an
+// intra-frame, progressive, compressed encode whose geometry the plan covers (checked in the converter hook, while the
+// reference's own path is still intact).
+struct PendingSource {
+    Plan *plan = nullptr;
+    uint8_t *data = nullptr;
+    int pitch = 0;
+    int bayer_phase = -1;
+    int curve_mode = 0;             // Bayer: 0 = the frame carries its curve, 1 = the encoder's default curve (log base 90)
+    FRAME *frame = nullptr;
+};
+thread_local ENCODER *t_enc = nullptr;
+thread_local TRANSFORM **t_transform = nullptr;
+thread_local int t_num_transforms = 0;
+thread_local PendingSource t_pending;
+
 bool spatial3(TRANSFORM *t)
 {
     return t && t->type == TRANSFORM_TYPE_SPATIAL && t->wavelet[0] && t->wavelet[1] && t->wavelet[2];
 }
 
 }  // namespace
+
+extern "C" {
+static Plan *covered_plan(const uint8_t *input, int input_pitch, int width, int height, TRANSFORM *transform[], int num_channels,
+                          int precision, int interlaced, int cfb_format);
+}
+
+// converter hooks: true = the packed source was recorded for the GPU pass (the caller skips the CPU conversion)
+static bool record_source(int cfb_format, uint8_t *data, int pitch, FRAME *frame, int width, int height, int precision, int bayer_phase,
+                          int curve_mode = 0)
+{
+    t_pending = PendingSource();
+    ENCODER *e = t_enc;
+    static const bool debug = getenv("CFHD_B200_DEBUG") != nullptr;
+    if (debug) fprintf(stderr, "cfhd_gpu_shim: record_source fmt %d enc %p gop %d progressive %d uncompressed %d num_spatial %d frame channels %d transforms %d %dx%d pitch %d\n",
+                       cfb_format, (void *)e, e ? e->gop_length : -1, e ? (int)e->progressive : -1, e ? (int)e->uncompressed : -1, e ? e->num_spatial : -1,
+                       frame ? frame->num_channels : -1, t_num_transforms, width, height, pitch);
+    if (!e || !frame || e->gop_length != 1 || !e->progressive || e->uncompressed || e->num_spatial != 2) return false;     // num_spatial = wavelets above level 1 (encoder.c:8390: num_levels = num_spatial + 1)
+    if (frame->num_channels != t_num_transforms) return false;
+    // a source whose coded height was rounded up (encoder.c:2232; 1080-line Bayer -> 544-row planes) has no rows behind its
+    // display height: the reference's converters replicate the last row into the planes, the packed frame does not hold them
+    if (frame->display_height != frame->height) return false;
+    Plan *plan = covered_plan(data, pitch, width, height, t_transform, t_num_transforms, precision, CFB_PROGRESSIVE, cfb_format);
+    if (debug) fprintf(stderr, "cfhd_gpu_shim: record_source plan %p\n", (void *)plan);
+    if (!plan) return false;
+    t_pending.plan = plan; t_pending.data = data; t_pending.pitch = pitch; t_pending.bayer_phase = bayer_phase; t_pending.frame = frame;
+    t_pending.curve_mode = curve_mode;
+    return true;
+}
 
 extern "C" {
 
@@ -191,6 +269,28 @@ extern "C" {
 //   FAILED       the frame IS covered but a CUDA call failed: there is NO CPU fallback on the transform path -- the bands
 //                are zero-filled, ComputeGroupTransformQuant reports CODEC_ERROR through encoder->error, the error is
 //                printed, and CFHD_B200_ABORT_ON_ERROR=1 turns it into an abort().
+// Is this source covered?  Returns the plan (context + codec of this thread for the geometry) or null.  width / height
+// are what cfb_frame_desc wants (the Bayer mosaic's dimensions for BYR4), input_pitch bytes per row (per Bayer line).
+static Plan *covered_plan(const uint8_t *input, int input_pitch, int width, int height, TRANSFORM *transform[], int num_channels,
+                          int precision, int interlaced, int cfb_format)
+{
+    if (!gpu_enabled() || cfb_format < 0 || !transform || input_pitch <= 0 || (input_pitch & 15) || ((uintptr_t)input & 15)) return nullptr;
+    if (num_channels < 3 || num_channels > CFB_MAX_CHANNELS) return nullptr;
+    for (int c = 0; c < num_channels; c++) if (!spatial3(transform[c])) return nullptr;
+    Plan *plan = get_plan(width, height, cfb_format, interlaced);
+    if (!plan || plan->layout.num_channels != num_channels || precision != plan->layout.precision) return nullptr;
+    if (input_pitch < plan->layout.frame_pitch) return nullptr;      // rows that overlap in memory (TestCFHD -E does that for R210): not a frame layout we read
+    for (int c = 0; c < num_channels; c++)
+        for (int k = 0; k < 3; k++) {
+            IMAGE *w = transform[c]->wavelet[k];
+            const cfb_band_layout &b = plan->layout.band[c][k][1];
+            if (w->width != b.width || w->height != b.height || w->pitch != b.pitch) return nullptr;     // not the geometry the plan was built for
+        }
+    return plan;
+}
+
+static Took run_pyramid(Plan *plan, uint8_t *input, int input_pitch, TRANSFORM *transform[], int interlaced, int bayer_phase, int curve_mode = 0);
+
 static Took forward_pyramid_on_gpu(uint8_t *input, int input_pitch, FRAME_INFO *frame, TRANSFORM *transform[], int frame_index,
                                    int num_channels, int precision, int limit_yuv, int conv_601_709, int interlaced, int cfb_format)
 {
@@ -198,29 +298,49 @@ static Took forward_pyramid_on_gpu(uint8_t *input, int input_pitch, FRAME_INFO *
     t_cuda_failed = false;
     t_sparse.valid = t_sparse.armed = false;
     Plan *plan = nullptr;
-    if (gpu_enabled() && frame && cfb_format >= 0 && frame_index == 0 && num_channels == 3 && !limit_yuv && !conv_601_709 &&
-        input_pitch > 0 && (input_pitch & 15) == 0 && ((uintptr_t)input & 15) == 0 &&
-        spatial3(transform[0]) && spatial3(transform[1]) && spatial3(transform[2]))
-        plan = get_plan(frame->width, frame->height, cfb_format, interlaced);
-    if (!plan || precision != plan->layout.precision) return NOT_COVERED;
+    if (frame && frame_index == 0 && num_channels == 3 && !limit_yuv && !conv_601_709)
+        plan = covered_plan(input, input_pitch, frame->width, frame->height, transform, num_channels, precision, interlaced, cfb_format);
+    if (!plan) return NOT_COVERED;
+    return run_pyramid(plan, input, input_pitch, transform, interlaced, -1);
+}
+
+// The encoder's default Bayer encode curve as the reference builds it inside ConvertBYR4ToFrame16s (frame.c:5208-5222:
+// log base 90 over 1 << 14 input levels, 12-bit output), with the reference's own macro
+static const uint16_t *default_bayer_curve()
+{
+    static uint16_t table[1 << 14];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const int max_value = 1 << 14, precision = 12;
+        table[0] = 0;
+        for (int i = 1; i < max_value; i++) table[i] = (uint16_t)(int)(CURVE_LIN2LOG((float)i / (float)max_value, 90) * (float)((1 << precision) - 1));
+    });
+    return table;
+}
+
+static Took run_pyramid(Plan *plan, uint8_t *input, int input_pitch, TRANSFORM *transform[], int interlaced, int bayer_phase, int curve_mode)
+{
+    const int nc = plan->layout.num_channels;
+    if (bayer_phase >= 0) {
+        if (cfb_codec_set_bayer_phase(plan->codec, bayer_phase) != CFB_OK) return NOT_COVERED;
+        if (plan->curve_mode != curve_mode) {       // the table is uploaded once per codec, not per frame
+            if (cfb_codec_set_bayer_curve(plan->codec, curve_mode ? default_bayer_curve() : nullptr, curve_mode ? 1 << 14 : 0) != CFB_OK) return NOT_COVERED;
+            plan->curve_mode = curve_mode;
+        }
+    }
 
     cfb_quant q;
     memset(&q, 0, sizeof(q));
     q.midpoint_prequant = g_midpoint_prequant;
     for (int k = 0; k < 3; k++) q.prescale[k] = transform[0]->prescale[k];
-    bool ok = true;
-    for (int c = 0; c < 3 && ok; c++)
-        for (int k = 0; k < 3 && ok; k++) {
-            IMAGE *w = transform[c]->wavelet[k];
-            const cfb_band_layout &b = plan->layout.band[c][k][1];
-            ok = (w->width == b.width && w->height == b.height && w->pitch == b.pitch);
-            for (int bnd = 0; bnd < 4; bnd++) q.divisor[c][k][bnd] = w->quant[bnd];
-        }
+    for (int c = 0; c < nc; c++)
+        for (int k = 0; k < 3; k++)
+            for (int bnd = 0; bnd < 4; bnd++) q.divisor[c][k][bnd] = transform[c]->wavelet[k]->quant[bnd];
     const void *frames[1] = {input};
-    if (!ok) return NOT_COVERED;                  // the encoder's wavelet geometry is not the one the plan was built for
     // Progressive frames cross PCIe in the sparse format and are entropy coded from it (EncodeQuantLongRuns below); the
     // interlaced level-1 HL band is coded by EncodeQuantLongRunsPlusPeaks (encoder.c:6458), which wants it dense.
-    const bool sparse = sparse_enabled() && plan->sparse && interlaced == CFB_PROGRESSIVE;
+    const bool sparse = sparse_enabled() && interlaced == CFB_PROGRESSIVE && plan->ensure_sparse();
+    if (!plan->ensure_coded()) return NOT_COVERED;
     bool failed;
     if (sparse) {
         void *out[1] = {plan->sparse};
@@ -237,7 +357,7 @@ static Took forward_pyramid_on_gpu(uint8_t *input, int input_pitch, FRAME_INFO *
         t_cuda_failed = true;
     }
     // hand the bands to the host entropy coder exactly where it expects them
-    for (int c = 0; c < 3; c++)
+    for (int c = 0; c < nc; c++)
         for (int k = 0; k < 3; k++) {
             IMAGE *w = transform[c]->wavelet[k];
             for (int bnd = (k == 2 ? 0 : 1); bnd < 4; bnd++) {
@@ -289,6 +409,85 @@ void TransformForwardFrameYUV(uint8_t *input, int input_pitch, FRAME_INFO *frame
     ref(input, input_pitch, frame, transform, frame_index, num_channels, buffer, buffer_size, chroma_offset, precision, limit_yuv, conv_601_709);
 }
 
+// The codec-level entry of every encode (SampleEncoder.cpp:604 and the pool's worker threads call it): remembers which
+// encoder and transforms the hooks below are working for.
+bool EncodeSample(ENCODER *encoder, uint8_t *data, int width, int height, int pitch, int format, TRANSFORM *transform[], int num_transforms,
+                  BITSTREAM *output, PIXEL *buffer, size_t buffer_size, int fixedquality, int fixedbitrate, uint8_t *pPreviewBuffer,
+                  float framerate, custom_quant *custom)
+{
+    typedef bool (*fn_t)(ENCODER *, uint8_t *, int, int, int, int, TRANSFORM *[], int, BITSTREAM *, PIXEL *, size_t, int, int, uint8_t *, float, custom_quant *);
+    static fn_t ref = next_symbol<fn_t>("EncodeSample");
+    t_enc = encoder; t_transform = transform; t_num_transforms = num_transforms;
+    t_pending = PendingSource();
+    const bool r = ref(encoder, data, width, height, pitch, format, transform, num_transforms, output, buffer, buffer_size, fixedquality,
+                       fixedbitrate, pPreviewBuffer, framerate, custom);
+    t_enc = nullptr; t_transform = nullptr; t_num_transforms = 0;
+    t_pending = PendingSource();
+    t_sparse.valid = t_sparse.armed = false;
+    release_plans();                // the frame is done: its plan goes back to the pool
+    return r;
+}
+
+void ConvertV210ToFrame16s(uint8_t *data, int pitch, FRAME *frame, uint8_t *buffer)          // Codec/frame.c:1431, encoder.c:2532
+{
+    typedef void (*fn_t)(uint8_t *, int, FRAME *, uint8_t *);
+    static fn_t ref = next_symbol<fn_t>("ConvertV210ToFrame16s");
+    if (frame && record_source(CFB_PIXEL_V210, data, pitch, frame, frame->width, frame->height, 10, -1)) return;
+    if (t_enc) g_fwd_ref++;         // this frame's planes and its transform stay with the reference's CPU code
+    ref(data, pitch, frame, buffer);
+}
+
+void ConvertYU64ToFrame16s(uint8_t *data, int pitch, FRAME *frame, uint8_t *buffer)          // Codec/frame.c:1556, encoder.c:2547
+{
+    typedef void (*fn_t)(uint8_t *, int, FRAME *, uint8_t *);
+    static fn_t ref = next_symbol<fn_t>("ConvertYU64ToFrame16s");
+    if (frame && record_source(CFB_PIXEL_YU64, data, pitch, frame, frame->width, frame->height, 10, -1)) return;
+    if (t_enc) g_fwd_ref++;
+    ref(data, pitch, frame, buffer);
+}
+
+void ConvertRGB48ToFrame16s(uint8_t *data, int pitch, FRAME *frame, uint8_t *buffer, int precision, int origformat)   // frame.c:5968, encoder.c:2768
+{
+    typedef void (*fn_t)(uint8_t *, int, FRAME *, uint8_t *, int, int);
+    static fn_t ref = next_symbol<fn_t>("ConvertRGB48ToFrame16s");
+    // only the plain 16-bit RGB layout (the default branch, frame.c:6130-6164: planes G, R, B, samples >> 4)
+    if (frame && origformat == COLOR_FORMAT_RG48 && precision == 12 &&
+        record_source(CFB_PIXEL_RG48, data, pitch, frame, frame->width, frame->height, 12, -1)) return;
+    if (t_enc) g_fwd_ref++;
+    ref(data, pitch, frame, buffer, precision, origformat);
+}
+
+void ConvertBYR4ToFrame16s(int bayer_format, uint32_t encode_curve, uint32_t encode_curve_preset, uint8_t *data, int pitch,
+                           FRAME *frame, int precision)                                       // Codec/frame.c:4993, encoder.c:2638
+{
+    typedef void (*fn_t)(int, uint32_t, uint32_t, uint8_t *, int, FRAME *, int);
+    static fn_t ref = next_symbol<fn_t>("ConvertBYR4ToFrame16s");
+    if (getenv("CFHD_B200_DEBUG")) fprintf(stderr, "cfhd_gpu_shim: ConvertBYR4ToFrame16s bayer %d curve %u preset %u pitch %d precision %d frame %dx%d\n",
+                                           bayer_format, encode_curve, encode_curve_preset, pitch, precision, frame ? frame->width : -1, frame ? frame->height : -1);
+    // frames that already carry their curve (metadata TAG_ENCODE_PRESET = 1: samples >> 4) and frames the encoder maps
+    // through its default curve (no curve metadata: log base 90, the table built above); the other curve families
+    // (frame.c:5224-5330) stay with the reference.  The SDK describes a Bayer frame by its PLANE dimensions and a pitch
+    // of two Bayer lines (SampleEncoder.cpp:268-269, :494).
+    const int curve_mode = encode_curve_preset == 1 ? 0 : ((encode_curve == 0 || encode_curve == CURVE_LOG_90) ? 1 : -1);
+    if (frame && curve_mode >= 0 && precision == 12 && !(pitch & 31) &&
+        record_source(CFB_PIXEL_BYR4, data, pitch / 2, frame, frame->width * 2, frame->height * 2, 12, bayer_format, curve_mode)) return;
+    if (t_enc) g_fwd_ref++;
+    ref(bayer_format, encode_curve, encode_curve_preset, data, pitch, frame, precision);
+}
+
+// level 1 of one plane (Codec/wavelet.c:2420, called per channel at encoder.c:3180-3193): nothing to do for the planes of
+// a frame whose packed source is waiting for the GPU pass
+IMAGE *TransformForwardSpatial(ALLOCATOR *allocator, IMAGE *image, int band, IMAGE *wavelet, int level, PIXEL *buffer, size_t size,
+                               int prescale, int quantization[IMAGE_NUM_BANDS], int difference_LL)
+{
+    typedef IMAGE *(*fn_t)(ALLOCATOR *, IMAGE *, int, IMAGE *, int, PIXEL *, size_t, int, int *, int);
+    static fn_t ref = next_symbol<fn_t>("TransformForwardSpatial");
+    if (t_pending.plan && level == 1 && band == 0)
+        for (int c = 0; c < t_pending.frame->num_channels; c++)
+            if (t_pending.frame->channel[c] == image && t_transform && t_transform[c]->wavelet[0] == wavelet) return wavelet;
+    return ref(allocator, image, band, wavelet, level, buffer, size, prescale, quantization, difference_LL);
+}
+
 // 10-bit packed RGB sources: Codec/encoder.c:3158-3176 -> Codec/wavelet.c:3597 (planes G, R, B; fields filtered after << 2)
 void TransformForwardSpatialRGB30(uint8_t *input, int input_pitch, FRAME_INFO *frame, TRANSFORM *transform[], int frame_index,
                                   int num_channels, PIXEL *buffer, size_t buffer_size, int chroma_offset, int IFrame,
@@ -304,9 +503,10 @@ void TransformForwardSpatialRGB30(uint8_t *input, int input_pitch, FRAME_INFO *f
     case COLOR_FORMAT_R210: fmt = CFB_PIXEL_R210; break;
     case COLOR_FORMAT_DPX0: fmt = CFB_PIXEL_DPX0; break;
     }
-    // the reference leaves the last two rows of a frame whose display height equals its coded height to a special
-    // path (wavelet.c:3642 last_row); only frames padded by the encoder (display_height < height) take the plain one
-    if (frame && display_height != frame->height &&
+    // frames whose coded height is their display height (wavelet.c:3645-3648: the last row pair goes through the border
+    // filters as everywhere else); a frame the encoder padded (display_height < height) is transformed by the reference
+    // from stale filter rows (:4066-4073), which is not a transform we reproduce
+    if (frame && display_height == frame->height &&
         forward_pyramid_on_gpu(input, input_pitch, frame, transform, frame_index, num_channels, precision, 0, 0, CFB_PROGRESSIVE, fmt) != NOT_COVERED) return;
     t_sparse.valid = t_sparse.armed = false;
     g_fwd_ref++;
@@ -321,7 +521,7 @@ void EncodeQuantLongRuns(ENCODER *encoder, BITSTREAM *stream, PIXEL *image, int 
     static fn_t ref = next_symbol<fn_t>("EncodeQuantLongRuns");
     SparseFrame &sf = t_sparse;
     if (sf.valid && sf.encoder == encoder && sf.frame_count == (uint32_t)encoder->frame_count) {
-        for (int c = 0; c < 3; c++)
+        for (int c = 0; c < sf.plan->layout.num_channels; c++)
             for (int k = 0; k < 3; k++)
                 for (int b = 1; b < 4; b++) {
                     if (sf.band[c][k][b] != (const void *)image) continue;
@@ -357,6 +557,17 @@ void ComputeGroupTransformQuant(ENCODER *encoder, TRANSFORM *transform[], int nu
 {
     typedef void (*fn_t)(ENCODER *, TRANSFORM *[], int);
     static fn_t ref = next_symbol<fn_t>("ComputeGroupTransformQuant");
+    if (t_pending.plan && t_transform == transform) {
+        // the frame's packed source has been waiting since the converter hook: the whole pyramid, all channels, one GPU pass
+        PendingSource ps = t_pending;
+        t_pending = PendingSource();
+        t_pyramid_done_for = nullptr; t_cuda_failed = false; t_sparse.valid = t_sparse.armed = false;
+        if (run_pyramid(ps.plan, ps.data, ps.pitch, transform, CFB_PROGRESSIVE, ps.bayer_phase, ps.curve_mode) == NOT_COVERED) {
+            // cannot happen after covered_plan(); if it does the planes were never converted: report, do not guess
+            fprintf(stderr, "cfhd_gpu_shim: recorded source no longer covered\n");
+            g_cuda_errors++; t_cuda_failed = true; t_pyramid_done_for = transform[0];
+        }
+    }
     if (t_pyramid_done_for && t_pyramid_done_for == transform[0]) {
         // levels 2 and 3 came out of the same GPU pass as level 1: only the bookkeeping of encoder.c:8366-8420 / :8688-8790 remains
         t_pyramid_done_for = nullptr;
@@ -426,7 +637,7 @@ void ReconstructSampleFrameToBuffer(DECODER *decoder, int frame, uint8_t *output
             const cfb_band_layout &b = plan->layout.band[c][k][1];
             ok = w && w->width == b.width && w->height == b.height && w->pitch == b.pitch;
         }
-    if (!ok) { g_inv_ref++; ref(decoder, frame, output, pitch); return; }
+    if (!ok) { g_inv_ref++; release_plans(); ref(decoder, frame, output, pitch); return; }
     decoder->gop_frame_num = frame;
     // the FSM entropy decoder already multiplied by the quantiser (decoder.c:20551): divisors = 1 here
     cfb_quant q;
@@ -434,6 +645,27 @@ void ReconstructSampleFrameToBuffer(DECODER *decoder, int frame, uint8_t *output
     q.midpoint_prequant = 2;
     for (int k = 0; k < 3; k++) q.prescale[k] = decoder->transform[0]->prescale[k];
     for (int c = 0; c < 3; c++) for (int k = 0; k < 3; k++) for (int b = 0; b < 4; b++) q.divisor[c][k][b] = 1;
+    // Hand-over of the decoder's bands (the FSM entropy decoder wrote them dense, decoder.c:19534-19808).  Default: staged
+    // copy + dense upload (33 MB per 4K frame; 8.8 ms per 4K decode on the B200 box).  CFHD_B200_DECODE_SPARSE=1: the host
+    // reads the bands once, straight into the sparse transfer format, and ~1/8 of the bytes cross PCIe -- less PCIe and
+    // host-memory traffic when many decoders share a link, but the single-threaded compaction makes one decode slower
+    // (11.9 ms), so it is opt-in.
+    static const bool decode_sparse = getenv("CFHD_B200_DECODE_SPARSE") && *getenv("CFHD_B200_DECODE_SPARSE") == '1';
+    const bool sparse = decode_sparse && sparse_enabled() && plan->ensure_sparse();
+    if (!sparse && !plan->ensure_coded()) { g_inv_ref++; release_plans(); ref(decoder, frame, output, pitch); return; }
+    if (sparse) {
+        const void *ptrs[CFB_MAX_CHANNELS * CFB_NUM_LEVELS * CFB_NUM_BANDS] = {};
+        int32_t pitches[CFB_MAX_CHANNELS * CFB_NUM_LEVELS * CFB_NUM_BANDS] = {};
+        for (int c = 0; c < 3; c++)
+            for (int k = 0; k < 3; k++) {
+                IMAGE *w = decoder->transform[c]->wavelet[k];
+                for (int bnd = (k == 2 ? 0 : 1); bnd < 4; bnd++) {
+                    ptrs[(c * CFB_NUM_LEVELS + k) * CFB_NUM_BANDS + bnd] = w->band[bnd];
+                    pitches[(c * CFB_NUM_LEVELS + k) * CFB_NUM_BANDS + bnd] = w->pitch;
+                }
+            }
+        if (cfb_sparse_compact_bands(&plan->layout, ptrs, pitches, plan->sparse, nullptr) != CFB_OK) { g_inv_ref++; release_plans(); ref(decoder, frame, output, pitch); return; }
+    } else
     for (int c = 0; c < 3; c++)
         for (int k = 0; k < 3; k++) {
             IMAGE *w = decoder->transform[c]->wavelet[k];
@@ -442,7 +674,7 @@ void ReconstructSampleFrameToBuffer(DECODER *decoder, int frame, uint8_t *output
                 memcpy((char *)plan->coded + b.offset, w->band[bnd], (size_t)b.pitch * b.height);
             }
         }
-    const void *coded[1] = {plan->coded};
+    const void *coded[1] = {sparse ? plan->sparse : plan->coded};
     const int fmt = decoder->frame.format == DECODED_FORMAT_YUYV ? CFB_PIXEL_YUYV : CFB_PIXEL_UYVY;
     // The pyramid has the ENCODED size (height rounded up to a multiple of 8, encoder.c:2232: 720x486 is coded as 488
     // rows) while the caller's buffer holds the DISPLAY size (decoder->frame): the reference writes info->height rows of
@@ -450,15 +682,16 @@ void ReconstructSampleFrameToBuffer(DECODER *decoder, int frame, uint8_t *output
     // copied out, so nothing is ever written past the caller's last row.
     const int enc_w = plan->layout.band[0][0][0].width * 2, enc_h = plan->layout.band[0][0][0].height * 2;
     const int out_w = decoder->frame.width, out_h = decoder->frame.height;
-    if (out_w <= 0 || out_h <= 0 || out_w > enc_w || out_h > enc_h || pitch < out_w * 2) { g_inv_ref++; ref(decoder, frame, output, pitch); return; }
+    if (out_w <= 0 || out_h <= 0 || out_w > enc_w || out_h > enc_h || pitch < out_w * 2) { g_inv_ref++; release_plans(); ref(decoder, frame, output, pitch); return; }
     cfb_error err;
     if (out_w == enc_w && out_h == enc_h) {
         void *frames[1] = {output};
-        err = cfb_inverse_host(plan->codec, 1, coded, &q, fmt, frames, pitch);
+        err = sparse ? cfb_inverse_host_sparse(plan->codec, 1, coded, &q, fmt, frames, pitch) : cfb_inverse_host(plan->codec, 1, coded, &q, fmt, frames, pitch);
     } else {
         if (!plan->frame && cfb_host_alloc((size_t)plan->layout.frame_bytes, &plan->frame) != CFB_OK) plan->frame = nullptr;
         void *frames[1] = {plan->frame};
-        err = plan->frame ? cfb_inverse_host(plan->codec, 1, coded, &q, fmt, frames, plan->layout.frame_pitch) : CFB_ERROR_OUTOFMEMORY;
+        err = !plan->frame ? CFB_ERROR_OUTOFMEMORY : sparse ? cfb_inverse_host_sparse(plan->codec, 1, coded, &q, fmt, frames, plan->layout.frame_pitch)
+                                                           : cfb_inverse_host(plan->codec, 1, coded, &q, fmt, frames, plan->layout.frame_pitch);
         if (err == CFB_OK)
             for (int r = 0; r < out_h; r++)
                 memcpy(output + (size_t)r * pitch, (const char *)plan->frame + (size_t)r * plan->layout.frame_pitch, (size_t)out_w * 2);
@@ -470,6 +703,7 @@ void ReconstructSampleFrameToBuffer(DECODER *decoder, int frame, uint8_t *output
         decoder->error = CODEC_ERROR_BAD_FRAME;
     }
     g_inv_frames++;
+    release_plans();
 }
 
 }  // extern "C"

@@ -125,3 +125,24 @@ def test_public_api_interlaced_roundtrip_matches_reference(size):
     # >= : the reference's own threaded decode of interlaced frames occasionally returns unfinished chroma rows (see
     # tests/test_pyramid_cpu.py), which can only lower ITS luma-independent score; ours must not be worse
     assert g["luma_psnr_db"] > r["luma_psnr_db"] - 0.1 and g["luma_psnr_db"] > 45.0
+
+
+@needs_build
+@pytest.mark.parametrize("fmt", ["2vuy", "yu64", "v210", "rg48", "rg30", "r210", "dpx0", "ab10", "ar10", "byr4"])
+def test_public_api_encode_of_every_wired_source_format(fmt):
+    """Every source format whose level-1 kernel exists is served by the GPU under the unmodified SDK: the packed frame is
+    read by the kernels directly (the reference's CPU conversion to planes and its per-plane level-1 calls are skipped),
+    the samples -- sync loop and encoder pool -- are byte-identical to the reference's, and no frame of these formats
+    takes the CPU transform."""
+    # V210 rows are whole 48-pixel groups; Bayer planes (half size) need a height that is a multiple of 8 as well, else the
+    # encoder pads the planes and the frame stays with the reference's converter
+    w, h = {"v210": (1536, 864), "byr4": (2048, 1152)}.get(fmt, (1920, 1080))
+    gpu = run("sdk_roundtrip", w, h, 3, 2, 24, 0, fmt)
+    ref = run("sdk_roundtrip_ref", w, h, 3, 2, 24, 0, fmt)
+    g, r = json.loads(gpu.stdout.strip().splitlines()[-1]), json.loads(ref.stdout.strip().splitlines()[-1])
+    assert g["format"] == fmt
+    assert g["sample_bytes"] == r["sample_bytes"]
+    assert g["sample_digest"] == r["sample_digest"] and g["pool_sample_digest"] == r["pool_sample_digest"]
+    st = shim_stats(gpu.stderr)
+    assert st["fwd_gpu"] >= 4 + 32 and st["fwd_ref"] == 0 and st["cuda_errors"] == 0
+    assert st["sparse_bands"] > 0 and st["dense_bands"] == 0

@@ -39,6 +39,31 @@ def test_host_compact_expand_roundtrip(pkg, density):
         pkg.sparse_expand(lay, bad)
 
 
+@pytest.mark.parametrize("size", [(704, 96), (720, 480), (1920, 1080)])
+def test_host_compact_from_band_buffers(pkg, size):
+    """cfb_sparse_compact_bands: one buffer per band with its own pitch and garbage behind the band's width (what an
+    entropy decoder leaves in wavelet->band[]) gives the bytes cfb_sparse_compact gives for the clean dense region."""
+    w, h = size
+    lay = pkg.layout_for(pkg.FrameDesc(w, h, pkg.PIXEL_YUYV))
+    rng = np.random.default_rng(w)
+    bands, clean = {}, {}
+    for c in range(lay.num_channels):
+        for k in range(3):
+            for b in range(4):
+                if b == 0 and k != 2:
+                    continue
+                bl = lay.band[c][k][b]
+                pitch_words = bl.pitch // 2 + 8 * ((c + k + b) % 3)             # some bands with a wider pitch than the layout's
+                buf = rng.integers(-999, 999, (bl.height, pitch_words)).astype(np.int16)       # garbage everywhere ...
+                data = np.where(rng.random((bl.height, bl.width)) < 0.07, rng.integers(-2000, 2000, (bl.height, bl.width)), 0).astype(np.int16)
+                buf[:, :bl.width] = data                                        # ... except the band itself
+                bands[(c, k + 1, pkg.BAND_NAMES[b])] = buf[:, :bl.width]        # a view: the row stride stays pitch_words
+                clean[(c, k + 1, pkg.BAND_NAMES[b])] = data
+    want = pkg.sparse_compact(lay, pkg.pack_coded(lay, clean))
+    got = pkg.sparse_compact_bands(lay, bands)
+    assert np.array_equal(got, want)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("size,kind", [((704, 96), "natural"), ((704, 96), "random"), ((1920, 1080), "natural"), ((256, 64), "constant")])
 def test_gpu_sparse_matches_dense(pkg, size, kind):

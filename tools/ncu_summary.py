@@ -1,6 +1,6 @@
 """Turn an `ncu --set full` report into the small per-kernel summary committed under profiles/:
     python tools/ncu_summary.py gpurun_out/prof_fwd422.ncu-rep profiles/r01_prof_fwd422_summary.csv
-One line per metric: name,unit,value (first launch in the report), preceded by kernel name / block / grid."""
+One line per metric: name,unit,value, preceded by kernel name / block / grid; one such block per launch in the report."""
 import csv
 import io
 import subprocess
@@ -11,9 +11,12 @@ def main():
     rep, out = sys.argv[1], sys.argv[2]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units = rows[0], rows[1]
     col = {n: i for i, n in enumerate(hdr)}
     with open(out, "w") as f:
+      for vals in rows[2:]:             # one block per launch in the report
+        if len(vals) < len(hdr) // 2:
+            continue
         f.write(f"Kernel Name,,{vals[col['Kernel Name']]}\n")
         f.write(f"Block Size,,{vals[col['Block Size']]}\n")
         f.write(f"Grid Size,,{vals[col['Grid Size']]}\n")

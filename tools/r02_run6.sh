@@ -1,6 +1,12 @@
 #!/bin/bash
+# round 2: non-negative prescale taps at level 2 (A/B), SDK shim byte identity, full GPU suite, benches of configs 3-5
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_byr4.py tests/test_rg48.py tests/test_config_sizes_gpu.py tests/test_forward_gpu.py tests/test_ragged_gpu.py tests/test_gop2.py -m gpu -x -q 2>&1 | tail -3
-( CFB_FWDPLANE=r1 python tools/kernel_ab.py --level 1 --dir fwd --format BYR4 --batch 4 --width 7680 --height 4320
-  python tools/kernel_ab.py --level 1 --dir fwd --format BYR4 --batch 4 --width 7680 --height 4320
-  python tools/kernel_ab.py --level 1 --dir fwd --format RG48 --batch 8 ) 2>&1 | tee gpurun_out/r02_ab_fwdplane2.txt
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -8 > gpurun_out/r02_tests_c.log; tail -8 gpurun_out/r02_tests_c.log
+for nn in 0 1; do
+  CFB_FWDPLANE_NN=$nn timeout 120 python tools/kernel_ab.py --level 2 --dir fwd 2>&1 | tail -1 | tee -a gpurun_out/r02_ab_fwdplane_nn.txt
+  CFB_FWDPLANE_NN=$nn timeout 120 python tools/kernel_ab.py --level 2 --dir fwd --format RG48 --batch 8 2>&1 | tail -1 | tee -a gpurun_out/r02_ab_fwdplane_nn.txt
+  CFB_FWDPLANE_NN=$nn timeout 120 python tools/kernel_ab.py --level 3 --dir fwd --format RG48 --batch 8 2>&1 | tail -1 | tee -a gpurun_out/r02_ab_fwdplane_nn.txt
+done
+for cfg in yuv422 rgb444 bayer8k; do
+  timeout 600 python bench.py --config $cfg > gpurun_out/r02_bench_c_$cfg.json 2> gpurun_out/r02_bench_c_$cfg.err; tail -c 600 gpurun_out/r02_bench_c_$cfg.json; echo
+done
