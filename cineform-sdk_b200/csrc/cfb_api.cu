@@ -517,8 +517,8 @@ cfb_error cfb_codec_set_interlaced(cfb_codec *cd, int interlaced)
 {
     if (!cd) { set_error("null codec"); return CFB_ERROR_INVALID_ARGUMENT; }
     const int fmt = cd->desc.pixel_format;
-    if (interlaced && fmt != CFB_PIXEL_YUYV && fmt != CFB_PIXEL_UYVY) {
-        set_error("the interlaced (field) transform is implemented for packed 8-bit 4:2:2 sources (CFHD_ENCODING_FLAGS_YUV_INTERLACED)");
+    if (interlaced && fmt != CFB_PIXEL_YUYV && fmt != CFB_PIXEL_UYVY && fmt != CFB_PIXEL_YU64 && fmt != CFB_PIXEL_V210) {
+        set_error("the interlaced (field) transform is implemented for 4:2:2 sources (YUYV, UYVY, YU64, V210)");
         return CFB_ERROR_UNSUPPORTED;
     }
     if (interlaced && !cd->d_carry) {
@@ -616,6 +616,15 @@ cfb_error cfb_forward_device(cfb_codec *cd, int n, const void *const *d_frames, 
         for (int i = 0; i < n; i++) { p.in_base[i] = (const unsigned char *)d_frames[i]; p.out_base[i] = (unsigned char *)d_pyramids[i]; }
         p.shift = 16 - L.precision;
         p.th = pick_th((p.ch[0].width + kStripIn - 1) / kStripIn, p.ch[0].height / 2, n, ctx->sm_count);
+        if (cd->interlaced) {
+            // planar field transform (filter.c:273): LH rounded with divisor / 2 (spatial.c:5856), HL as the packed path
+            for (int c = 0; c < 3; c++) {
+                if (quant->divisor[c][0][0] > 1) { set_error("interlaced 16-bit / 10-bit 4:2:2 sources: a quantised level-1 lowpass band is not supported"); return CFB_ERROR_UNSUPPORTED; }
+                p.ch[c].q[1] = make_quant_param(quant->divisor[c][0][1], 2, true);
+                p.ch[c].q[2] = make_quant_param(quant->divisor[c][0][2], quant->midpoint_prequant, true);
+            }
+            CFB_CUDA(launch_fwd_422_fields_src(p, fmt == CFB_PIXEL_V210 ? 1 : 0, ctx->stream));
+        } else
         CFB_CUDA(fmt == CFB_PIXEL_V210 ? launch_fwd_v210(p, ctx->stream) : launch_fwd_yu64(p, ctx->stream));
         ctx->kernel_launches++;
     } else if (fmt == CFB_PIXEL_PLANAR16) {

@@ -1377,6 +1377,93 @@ __global__ void __launch_bounds__(128) k_fwd_422_src(const __grid_constant__ Fwd
     }
 }
 
+// Interlaced (field) level 1 of the packed 16-bit / 10-bit 4:2:2 sources: the reference converts them to planes and runs
+//   Codec/filter.c:273 FilterFrameQuant16s: temporal.c FilterTemporalRow16s (even + odd, odd - even), then
+//   spatial.c:5826 FilterHorizontalRowQuant16s on the temporal lowpass -- LL (quantised only when its divisor > 1) and LH,
+//   both with the midpoint divisor / 2 (filter.c:352 / spatial.c:5856; the packed 8-bit path rounds LH with
+//   divisor / 2 - 1) in the columns its 16-sample SSE2 loop produces and WITHOUT a midpoint in the columns of its scalar
+//   tail and in the last column, which it redoes with the border filter (spatial.c:6192-6266) -- and spatial.c:5327
+//   ...DifferenceFiltered + QuantizeRow16sTo16s on the temporal highpass, as the packed path.  Same structure as
+//   k_fwd_422_fields; SRC supplies the row load and the linear sums.  (LL is quantised by the same routine when its divisor
+//   exceeds 1, which no schedule of the reference produces at level 1: the host side rejects such a table.)
+//   p.ch[1] receives the position-1 chroma, p.ch[2] the position-3 chroma (as k_fwd_422_src).
+// LH of the planar field transform: per column, midpoint divisor / 2 or none (see k_fwd_422_fields_src)
+template <int NC>
+__device__ __forceinline__ void store_quant_lh_planar(unsigned char *ptr, const int *v, const QuantParam &q, int col0, int width_out)
+{
+    // columns >= tail belong to the scalar tail of a (2 * width_out)-sample row; the last column is the border column
+    const int tail = (2 * width_out - (2 * width_out) % 16) / 2;
+    int o[NC];
+#pragma unroll
+    for (int i = 0; i < NC; i++) {
+        const int col = col0 + i;
+        const bool nomid = (col >= tail) || (col == width_out - 1);
+        o[i] = (v[i] * q.m + (v[i] < 0 ? (nomid ? 65535 : q.cneg) : (nomid ? 0 : q.cpos))) >> 16;
+    }
+    store_raw<NC>(ptr, o);
+}
+
+template <class SRC>
+__global__ void __launch_bounds__(128) k_fwd_422_fields_src(const __grid_constant__ FwdParams p)
+{
+    const int lane = threadIdx.x;
+    const int f = blockIdx.z;
+    const PlaneGeom &gy = p.ch[0];
+    const PlaneGeom &g1 = p.ch[1];
+    const PlaneGeom &g3 = p.ch[2];
+    const int strip = blockIdx.x;
+    if (strip * kStripIn >= gy.width) return;
+    const int oh = gy.height >> 1;
+    LaneInfo L;
+    if (!lane_setup(strip, gy.width, lane, L)) return;
+    const unsigned colbyte_y = (unsigned)((strip * kStripOut + lane * 4) * 2);
+    const unsigned colbyte_c = (unsigned)((strip * (kStripOut / 2) + lane * 2) * 2);
+    const int lg = strip * 32 + lane;
+    const unsigned char *in = p.in_base[f] + gy.in_off + SRC::offset(lg);
+    unsigned char *out = p.out_base[f];
+    const int shift = p.shift;
+    const int y0 = (blockIdx.y * blockDim.y + threadIdx.y) * p.th;
+    if (y0 >= oh) return;
+    const int y1 = min(y0 + p.th, oh);
+    const unsigned char *rp = in + (long long)(2 * y0) * gy.in_pitch;
+    typename SRC::Row c0, c1, n0, n1;
+    SRC::load(rp, lg, L, c0);
+    SRC::load(rp + gy.in_pitch, lg, L, c1);
+    n0 = c0; n1 = c1;
+    unsigned offy = (unsigned)(y0 * gy.out_pitch) + colbyte_y;
+    unsigned offc = (unsigned)(y0 * g1.out_pitch) + colbyte_c;
+    for (int j = y0; j < y1; j++) {
+        rp += 2 * gy.in_pitch;
+        if (j + 1 < y1) {
+            SRC::load(rp, lg, L, n0);
+            SRC::load(rp + gy.in_pitch, lg, L, n1);
+        }
+        Lin422 e, o, t;
+        SRC::linear(c0, shift, L, e);
+        SRC::linear(c1, shift, L, o);
+        int ay[8], a1[4], a3[4];
+        lin_combine(e, o, +1, t);               // temporal lowpass: even + odd
+        hfinish_422(t, L, ay, a1, a3);
+        store_raw<4>(out + (gy.band_off[0] + offy), ay);
+        store_quant_lh_planar<4>(out + (gy.band_off[1] + offy), ay + 4, gy.q[1], strip * kStripOut + lane * 4, gy.width >> 1);
+        store_raw<2>(out + (g1.band_off[0] + offc), a1);
+        store_quant_lh_planar<2>(out + (g1.band_off[1] + offc), a1 + 2, g1.q[1], strip * (kStripOut / 2) + lane * 2, g1.width >> 1);
+        store_raw<2>(out + (g3.band_off[0] + offc), a3);
+        store_quant_lh_planar<2>(out + (g3.band_off[1] + offc), a3 + 2, g3.q[1], strip * (kStripOut / 2) + lane * 2, g3.width >> 1);
+        lin_combine(e, o, -1, t);               // temporal highpass: odd - even
+        hfinish_422(t, L, ay, a1, a3);
+        store_diffq<4>(out + (gy.band_off[2] + offy), ay, t.hy, gy.q[2], L);
+        store_quant<4>(out + (gy.band_off[3] + offy), ay + 4, gy.q[3]);
+        store_diffq<2>(out + (g1.band_off[2] + offc), a1, t.hu, g1.q[2], L);
+        store_quant<2>(out + (g1.band_off[3] + offc), a1 + 2, g1.q[3]);
+        store_diffq<2>(out + (g3.band_off[2] + offc), a3, t.hv, g3.q[2], L);
+        store_quant<2>(out + (g3.band_off[3] + offc), a3 + 2, g3.q[3]);
+        offy += (unsigned)gy.out_pitch;
+        offc += (unsigned)g1.out_pitch;
+        c0 = n0; c1 = n1;
+    }
+}
+
 #include "cfb_forward_tma.inl"
 
 // ----------------------------------------------------------------------------
@@ -1547,6 +1634,15 @@ cudaError_t launch_fwd_v210(const FwdParams &p, cudaStream_t stream)
     dim3 block(32, 4);
     dim3 grid(ceil_div(p.ch[0].width, kStripIn), ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y) + 1, p.nframes);
     k_fwd_422_src<SrcV210><<<grid, block, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// sel: 0 = YU64, 1 = V210
+cudaError_t launch_fwd_422_fields_src(const FwdParams &p, int sel, cudaStream_t stream)
+{
+    dim3 block(32, 4);
+    dim3 grid(ceil_div(p.ch[0].width, kStripIn), ceil_div(ceil_div(p.ch[0].height / 2, p.th), (int)block.y), p.nframes);
+    if (sel) k_fwd_422_fields_src<SrcV210><<<grid, block, 0, stream>>>(p); else k_fwd_422_fields_src<SrcYU64><<<grid, block, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

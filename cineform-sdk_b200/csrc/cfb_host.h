@@ -36,6 +36,7 @@ cudaError_t launch_inv_444_rg48(const InvParams &p, cudaStream_t stream);
 cudaError_t launch_lowpass_422(const InvParams &p, cudaStream_t stream);
 cudaError_t launch_inv_fields(const InvParams &p, const FieldsAux &a, bool planar, cudaStream_t stream);
 cudaError_t launch_fwd_422_fields(const FwdParams &p, cudaStream_t stream);
+cudaError_t launch_fwd_422_fields_src(const FwdParams &p, int sel, cudaStream_t stream);
 cudaError_t launch_fwd_yu64(const FwdParams &p, cudaStream_t stream);
 // range audit of the planes a forward level is about to read (cfb_audit.cu): ORs violation bits into ctx->d_range
 cfb_error audit_level_input(cfb_context *ctx, const FwdParams &p, int prescale);

@@ -182,7 +182,9 @@ CFB_API cfb_error cfb_codec_set_bayer_curve(cfb_codec *codec, const uint16_t *cu
  * instead of the spatial transform.  Replaces Codec/encoder.c:2976 TransformForwardFrameYUV (wavelet.c:6076; planar
  * form filter.c:273 FilterFrameQuant16s) and Codec/decoder.c:21493 TransformInverseFrameToYUV / :22027 ...ToRow16u
  * (temporal.c:3741 InvertInterlaced16s) including the HL row integration of decoder.c:20822-20836.
- * Packed 8-bit 4:2:2 codecs only.  Reduced-resolution decodes of an interlaced sample (cfb_codec_set_decode_resolution)
+ * 4:2:2 codecs: packed 8-bit (YUYV, UYVY: the packed routine) and YU64 / V210 (the planar routine filter.c:273, whose LH
+ * band is rounded with divisor / 2 in the columns of its SSE2 loop and without a midpoint in its scalar tail and last column,
+ * spatial.c:5826-6266).  Reduced-resolution decodes of an interlaced sample (cfb_codec_set_decode_resolution)
  * return the lowpass image LL1 / LL2 exactly as the reference does: its half- and quarter-resolution paths
  * (Codec/decoder.c:26078 and :11818) run before / outside the progressive-vs-interlaced split of
  * ReconstructSampleFrameToBuffer, so the level-1 transform type does not enter. */

@@ -46,8 +46,8 @@ extern "C" {
 #include "vlc.h"
 #include "bitstream.h"
 }
-#include <math.h>
-#include "AVIExtendedHeader.h"     // CURVE_LIN2LOG, CURVE_LOG_90: the host builds the Bayer encode curve, as the reference does
+#include "AVIExtendedHeader.h"     // CURVE_LOG_90
+extern "C" void cfhd_shim_default_bayer_curve(uint16_t *table);       // bayer_curve.c (C on purpose, see there)
 #include "cfhd_b200.h"
 
 extern "C" int g_midpoint_prequant;     // Codec/quantize.c:183
@@ -305,16 +305,12 @@ static Took forward_pyramid_on_gpu(uint8_t *input, int input_pitch, FRAME_INFO *
 }
 
 // The encoder's default Bayer encode curve as the reference builds it inside ConvertBYR4ToFrame16s (frame.c:5208-5222:
-// log base 90 over 1 << 14 input levels, 12-bit output), with the reference's own macro
+// log base 90 over 1 << 14 input levels, 12-bit output), with the reference's own macro compiled as C (bayer_curve.c)
 static const uint16_t *default_bayer_curve()
 {
     static uint16_t table[1 << 14];
     static std::once_flag once;
-    std::call_once(once, [] {
-        const int max_value = 1 << 14, precision = 12;
-        table[0] = 0;
-        for (int i = 1; i < max_value; i++) table[i] = (uint16_t)(int)(CURVE_LIN2LOG((float)i / (float)max_value, 90) * (float)((1 << precision) - 1));
-    });
+    std::call_once(once, [] { cfhd_shim_default_bayer_curve(table); });
     return table;
 }
 

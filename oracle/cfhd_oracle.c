@@ -435,6 +435,70 @@ void orc_fwd_fields_422(const uint8_t *frame, int frame_pitch, int width, int he
     free(e); free(o); free(tl); free(th); free(a); free(b); free(tmp);
 }
 
+/* Planar form of the field transform (Codec/filter.c:273 FilterFrameQuant16s, the path of 16-bit / 10-bit 4:2:2 sources
+ * after their conversion to planes): as above on one int16 plane, except that LL and LH come out of
+ * spatial.c:5826 FilterHorizontalRowQuant16s:
+ *   outputs of the 16-column SSE2 loop (i < (width - width % 16) / 2): 16-bit |x|, + divisor / 2 (:5856-5857, no "- 1",
+ *     whatever g is), unsigned mulhi by 65536 / divisor, sign restored (:6082-6140); LL only when its divisor > 1 (:6074);
+ *   outputs of the scalar tail (:6192-6225) and the last output, which is redone with the border filter (:6232-6266):
+ *     highpass sign * ((|x| * (65536 / divisor)) >> 16) -- NO midpoint; lowpass (x * (65536 / divisor)) >> 16. */
+static int16_t fields_quant_half(int32_t v, int d, int simd, int lowpass)
+{
+    if (d <= 1) return wrap16(v);
+    if (!simd) {
+        const int32_t mult = 65536 / d;
+        if (lowpass) return sat16((int32_t)(((int64_t)v * mult) >> 16));
+        return sat16(v < 0 ? -(int32_t)(((int64_t)(-v) * mult) >> 16) : (int32_t)(((int64_t)v * mult) >> 16));
+    }
+    {
+        const int16_t x = wrap16(v);
+        const uint16_t sgn = x < 0 ? 0xFFFFu : 0u;
+        uint16_t a = (uint16_t)(((uint16_t)x ^ sgn) - sgn);
+        a = (uint16_t)(a + (uint16_t)(d / 2));
+        {
+            const uint16_t q = (uint16_t)(((uint32_t)a * (uint32_t)(uint16_t)(65536 / d)) >> 16);
+            return (int16_t)(uint16_t)((uint16_t)(q ^ sgn) - sgn);
+        }
+    }
+}
+
+void orc_fwd_fields_plane(const int16_t *plane, int plane_pitch, int width, int height,
+                          const int quant[4], int midpoint_prequant,
+                          int16_t *ll, int16_t *lh, int16_t *hl, int16_t *hh, int out_pitch)
+{
+    const int m = width / 2, op = out_pitch / 2, pp = plane_pitch / 2;
+    int32_t *tl = (int32_t *)malloc((size_t)width * 4), *th = (int32_t *)malloc((size_t)width * 4);
+    int32_t *a = (int32_t *)malloc((size_t)m * 4), *b = (int32_t *)malloc((size_t)m * 4);
+    int16_t *tmp = (int16_t *)malloc((size_t)m * 2);
+    int r, i;
+    for (r = 0; r < height / 2; r++) {
+        const int16_t *e = plane + (size_t)(2 * r) * pp, *o = plane + (size_t)(2 * r + 1) * pp;
+        for (i = 0; i < width; i++) { tl[i] = (int32_t)e[i] + o[i]; th[i] = (int32_t)o[i] - e[i]; }
+        fields_hrow(tl, width, a, b);
+        for (i = 0; i < m; i++) {
+            const int simd = (2 * i < width - width % 16) && (i != m - 1);
+            ll[(size_t)r * op + i] = fields_quant_half(a[i], quant[0], simd, 1);
+            lh[(size_t)r * op + i] = fields_quant_half(b[i], quant[1], simd, 0);
+        }
+        fields_hrow(th, width, a, b);
+        {
+            const int d = quant[2];
+            const int mid = (d > 1 && midpoint_prequant >= 2 && midpoint_prequant < 9) ? d / midpoint_prequant : 0;
+            const int mult = (d > 1) ? 65536 / d : 0;
+            int32_t prev = 0;
+            for (i = 0; i < m; i++) {
+                int32_t q = a[i];
+                if (d > 1) { const int32_t mag = ((q < 0 ? -q : q) + mid) * mult >> 16; q = q < 0 ? -mag : mag; }
+                hl[(size_t)r * op + i] = wrap16(q - prev);
+                prev = q;
+            }
+        }
+        for (i = 0; i < m; i++) tmp[i] = wrap16(b[i]);
+        orc_quantize_row(tmp, hh + (size_t)r * op, m, quant[3], midpoint_prequant);
+    }
+    free(tl); free(th); free(a); free(b); free(tmp);
+}
+
 static void fields_hinv(const int16_t *l, const int16_t *h, int n, int32_t *out)
 {
     int i;

@@ -95,6 +95,11 @@ void orc_fwd_fields_422(const uint8_t *frame, int frame_pitch, int width, int he
                         int format, int precision, const int quant[4], int midpoint_prequant,
                         int16_t *ll, int16_t *lh, int16_t *hl, int16_t *hh, int out_pitch);
 
+/* planar form (Codec/filter.c:273 FilterFrameQuant16s): one int16 plane; LL / LH quantised by FilterHorizontalRowQuant16s */
+void orc_fwd_fields_plane(const int16_t *plane, int plane_pitch, int width, int height,
+                          const int quant[4], int midpoint_prequant,
+                          int16_t *ll, int16_t *lh, int16_t *hl, int16_t *hh, int out_pitch);
+
 /* Inverse of the above on DECODER-SIDE bands, i.e. dequantised and with HL already integrated along each row
  * (Codec/decoder.c:20822-20836 `line[x] += line[x-1]` after the FSM decode):
  *   t_low = hinv(LL, LH), t_high = hinv(HL, HH)  (Codec/decoder.c:21493 TransformInverseFrameToYUV ->

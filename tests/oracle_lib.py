@@ -115,6 +115,18 @@ class Impl:
         f(frame, pitch, w, h, channel, fmt, precision, q, midpoint, *bands, (w // 2) * 2)
         return bands
 
+    def fwd_fields_plane(self, plane, quant, midpoint=2):
+        """Planar interlaced (field) transform of level 1, oracle only (orc_fwd_fields_plane)."""
+        plane = np.ascontiguousarray(plane, dtype=np.int16)
+        h, w = plane.shape
+        bands = [np.zeros((h // 2, w // 2), np.int16) for _ in range(4)]
+        q = np.asarray(quant, dtype=np.int32)
+        f = self._f("fwd_fields_plane")
+        f.argtypes = [_i16p, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, _i16p, _i16p, _i16p, _i16p, C.c_int]
+        f.restype = None
+        f(plane, w * 2, w, h, q, midpoint, *bands, (w // 2) * 2)
+        return bands
+
     def inv_fields(self, ll, lh, hl, hh):
         """Inverse field transform on decoder-side (dequantised, HL integrated) bands (orc_inv_fields)."""
         bands = [np.ascontiguousarray(b, dtype=np.int16) for b in (ll, lh, hl, hh)]
