@@ -31,6 +31,7 @@
 
 #include <atomic>
 #include <map>
+#include <chrono>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -57,14 +58,17 @@ namespace {
 std::atomic<long> g_fwd_frames{0}, g_inv_frames{0}, g_fwd_ref{0}, g_inv_ref{0};
 std::atomic<long> g_cuda_errors{0};
 std::atomic<long> g_vlc_sparse_bands{0}, g_vlc_ref_bands{0};
+std::atomic<long> g_plans_created{0}, g_plan_create_us{0}, g_gpu_us{0}, g_vlc_us{0};
 
 struct StatsAtExit {
     ~StatsAtExit() {
         if (getenv("CFHD_B200_STATS"))
             fprintf(stderr, "cfhd_gpu_shim: forward frames on GPU %ld (reference CPU %ld), inverse frames on GPU %ld (reference CPU %ld), CUDA errors %ld, "
-                            "bands coded from the sparse format %ld (dense, by the reference's coder %ld)\n",
+                            "bands coded from the sparse format %ld (dense, by the reference's coder %ld); plans created %ld in %.1f ms, "
+                            "forward host calls %.1f ms, sparse VLC walk %.1f ms (summed over threads)\n",
                     g_fwd_frames.load(), g_fwd_ref.load(), g_inv_frames.load(), g_inv_ref.load(), g_cuda_errors.load(),
-                    g_vlc_sparse_bands.load(), g_vlc_ref_bands.load());
+                    g_vlc_sparse_bands.load(), g_vlc_ref_bands.load(), g_plans_created.load(), g_plan_create_us.load() / 1e3,
+                    g_gpu_us.load() / 1e3, g_vlc_us.load() / 1e3);
     }
 } g_stats_at_exit;
 
@@ -131,6 +135,7 @@ Plan *get_plan(int width, int height, int pixel_format, int interlaced = CFB_PRO
         if (!fl.empty()) { Plan *p = fl.back(); fl.pop_back(); t_held.push_back(p); return p; }
         dev = g_next_device++ % cfb_device_count();     // frames sharded over the GPUs
     }
+    const auto t0 = std::chrono::steady_clock::now();
     Plan *p = new Plan;
     p->key = key;
     cfb_frame_desc d = {width, height, pixel_format, 0};
@@ -147,6 +152,8 @@ Plan *get_plan(int width, int height, int pixel_format, int interlaced = CFB_PRO
         return nullptr;
     }
     t_held.push_back(p);
+    g_plans_created++;
+    g_plan_create_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
     return p;
 }
 
@@ -338,6 +345,7 @@ static Took run_pyramid(Plan *plan, uint8_t *input, int input_pitch, TRANSFORM *
     const bool sparse = sparse_enabled() && interlaced == CFB_PROGRESSIVE && plan->ensure_sparse();
     if (!plan->ensure_coded()) return NOT_COVERED;
     bool failed;
+    const auto tg0 = std::chrono::steady_clock::now();
     if (sparse) {
         void *out[1] = {plan->sparse};
         failed = cfb_forward_host_sparse(plan->codec, 1, frames, input_pitch, &q, out, nullptr) != CFB_OK;
@@ -345,6 +353,7 @@ static Took run_pyramid(Plan *plan, uint8_t *input, int input_pitch, TRANSFORM *
         void *coded[1] = {plan->coded};
         failed = cfb_forward_host(plan->codec, 1, frames, input_pitch, &q, coded) != CFB_OK;
     }
+    g_gpu_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - tg0).count();
     if (failed) {
         fprintf(stderr, "cfhd_gpu_shim: CUDA forward transform failed (%s); no CPU fallback on the transform path\n", cfb_last_error_string());
         g_cuda_errors++;
@@ -528,7 +537,10 @@ void EncodeQuantLongRuns(ENCODER *encoder, BITSTREAM *stream, PIXEL *image, int 
                     bw.cur = stream->lpCurrentWord;
                     bw.end = stream->lpCurrentBuffer + stream->dwBlockLength;
                     bw.buffer = stream->wBuffer; bw.bits_free = stream->nBitsFree; bw.bytes = stream->nWordsUsed;
-                    if (cfb_sparse_vlc_band(&sf.plan->layout, sf.plan->sparse, c, k, b, book, &bw) != CFB_OK) {
+                    const auto tv0 = std::chrono::steady_clock::now();
+                    const cfb_error ve = cfb_sparse_vlc_band(&sf.plan->layout, sf.plan->sparse, c, k, b, book, &bw);
+                    g_vlc_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - tv0).count();
+                    if (ve != CFB_OK) {
                         fprintf(stderr, "cfhd_gpu_shim: coding band (%d, %d, %d) from the sparse format failed: %s\n", c, k, b, cfb_last_error_string());
                         if (getenv("CFHD_B200_ABORT_ON_ERROR")) abort();
                         encoder->error = CODEC_ERROR_UNEXPECTED;

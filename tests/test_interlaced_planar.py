@@ -70,7 +70,7 @@ def test_cuda_planar_fields_vs_oracle(fmt, size, kind):
     rng = np.random.default_rng(w * 3 + h + len(kind))
     src, planes, _ = make_source(fmt, w, h, rng, kind)
     desc = pkg.FrameDesc(w, h, pkg.PIXEL_YU64 if fmt == "yu64" else pkg.PIXEL_V210)
-    quant = pkg.quant_for_source(desc, 4, interlaced=True)
+    quant = pkg.quant_for_quality(desc, 4, interlaced=True)
     want = planar_fields_pyramid(orc, planes, quant.table(3), tuple(quant.prescale), quant.midpoint_prequant)
     with pkg.Context(0) as ctx, pkg.Codec(ctx, desc, 2) as codec:
         codec.set_interlaced(True)

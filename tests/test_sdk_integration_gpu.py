@@ -18,7 +18,7 @@ needs_build = pytest.mark.skipif(not have, reason="integration/_build not presen
 def shim_stats(stderr):
     """Counters the shim prints at exit (CFHD_B200_STATS=1)."""
     line = stderr.split("cfhd_gpu_shim: forward frames on GPU")[-1]
-    num = lambda after: int(line.split(after)[1].split()[0].rstrip(",)"))
+    num = lambda after: int("".join(ch for ch in line.split(after)[1].split()[0] if ch.isdigit()))
     return {"fwd_gpu": int(line.split()[0]), "fwd_ref": num("(reference CPU"), "inv_gpu": num("inverse frames on GPU"),
             "cuda_errors": num("CUDA errors"), "sparse_bands": num("bands coded from the sparse format"),
             "dense_bands": num("(dense, by the reference's coder")}
