@@ -11,6 +11,8 @@
 #include <new>
 
 #include "cfb_host.h"
+
+#include <mutex>
 #include <ctype.h>
 #include <sched.h>
 #include <stdio.h>
@@ -370,17 +372,31 @@ cfb_error cfb_context_create(int device, cfb_context **out)
         return CFB_ERROR_NO_DEVICE;
     }
     if (device < 0 || device >= n) { set_error("device %d out of range [0,%d)", device, n); return CFB_ERROR_INVALID_ARGUMENT; }
-    cudaDeviceProp prop;
-    CFB_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
-        set_error("device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+    // three attributes, queried once per device: cudaGetDeviceProperties costs tens of milliseconds and serialises the
+    // sixteen encoder threads of an SDK pool that all create their context at the same moment
+    struct DevInfo { int major = -1, minor = 0, sms = 0; };
+    static DevInfo info[64];
+    static std::mutex info_mu;
+    DevInfo di;
+    {
+        std::lock_guard<std::mutex> lk(info_mu);
+        if (device < 64 && info[device].major >= 0) di = info[device];
+        else {
+            CFB_CUDA(cudaDeviceGetAttribute(&di.major, cudaDevAttrComputeCapabilityMajor, device));
+            CFB_CUDA(cudaDeviceGetAttribute(&di.minor, cudaDevAttrComputeCapabilityMinor, device));
+            CFB_CUDA(cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, device));
+            if (device < 64) info[device] = di;
+        }
+    }
+    if (di.major != 10) {
+        set_error("device %d is sm_%d%d; this library carries sm_100a code only", device, di.major, di.minor);
         return CFB_ERROR_NO_DEVICE;
     }
     CFB_CUDA(cudaSetDevice(device));
     cfb_context *ctx = new (std::nothrow) cfb_context();
     if (!ctx) return CFB_ERROR_OUTOFMEMORY;
     ctx->device = device;
-    ctx->sm_count = prop.multiProcessorCount;
+    ctx->sm_count = di.sms;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->done, cudaEventBlockingSync | cudaEventDisableTiming);
     if (e != cudaSuccess) { if (ctx->stream) cudaStreamDestroy(ctx->stream); delete ctx; return cuda_fail(e, "cudaStreamCreate"); }

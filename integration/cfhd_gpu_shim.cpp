@@ -50,6 +50,8 @@ extern "C" {
 #include "AVIExtendedHeader.h"     // CURVE_LOG_90
 extern "C" void cfhd_shim_default_bayer_curve(uint16_t *table);       // bayer_curve.c (C on purpose, see there)
 #include "cfhd_b200.h"
+#include "CFHDEncoder.h"            // the public SDK entry points whose preparation calls pre-create the plans
+#include <thread>
 
 extern "C" int g_midpoint_prequant;     // Codec/quantize.c:183
 
@@ -712,6 +714,100 @@ void ReconstructSampleFrameToBuffer(DECODER *decoder, int frame, uint8_t *output
     }
     g_inv_frames++;
     release_plans();
+}
+
+// ------------------------------------------------------------------------------------------------ preparation
+// Plans (context, device staging, pinned buffers: tens of milliseconds each, more when sixteen threads create theirs at
+// once) are created when the application PREPARES its encoder / encoder pool, as any allocation of that size would be,
+// not inside its first EncodeSample calls.  Without this, Example/TestCFHD.cpp -E -- a new pool and 500 frames per row --
+// spends most of a row creating plans.
+static int cfb_format_of_pixel_format(CFHD_PixelFormat pf, CFHD_EncodedFormat ef)
+{
+    const bool yuv = (ef == CFHD_ENCODED_FORMAT_YUV_422), rgb = (ef == CFHD_ENCODED_FORMAT_RGB_444);
+    switch (pf) {
+    case CFHD_PIXEL_FORMAT_YUY2: return yuv ? CFB_PIXEL_YUYV : -1;
+    case CFHD_PIXEL_FORMAT_2VUY: return yuv ? CFB_PIXEL_UYVY : -1;
+    case CFHD_PIXEL_FORMAT_YU64: return yuv ? CFB_PIXEL_YU64 : -1;
+    case CFHD_PIXEL_FORMAT_V210: return yuv ? CFB_PIXEL_V210 : -1;
+    case CFHD_PIXEL_FORMAT_RG48: return rgb ? CFB_PIXEL_RG48 : -1;
+    case CFHD_PIXEL_FORMAT_RG30: return rgb ? CFB_PIXEL_RG30 : -1;
+    case CFHD_PIXEL_FORMAT_R210: return rgb ? CFB_PIXEL_R210 : -1;
+    case CFHD_PIXEL_FORMAT_DPX0: return rgb ? CFB_PIXEL_DPX0 : -1;
+    case CFHD_PIXEL_FORMAT_AB10: return rgb ? CFB_PIXEL_AB10 : -1;
+    case CFHD_PIXEL_FORMAT_AR10: return rgb ? CFB_PIXEL_AR10 : -1;
+    case CFHD_PIXEL_FORMAT_BYR4: return (ef == CFHD_ENCODED_FORMAT_BAYER) ? CFB_PIXEL_BYR4 : -1;
+    default: return -1;
+    }
+}
+
+static void prewarm_plans(int count, int width, int height, CFHD_PixelFormat pf, CFHD_EncodedFormat ef, CFHD_EncodingFlags flags)
+{
+    const int fmt = cfb_format_of_pixel_format(pf, ef);
+    if (fmt < 0 || count < 1 || !gpu_enabled() || getenv("CFHD_B200_NO_PREWARM")) return;
+    const int h8 = (height + 7) & ~7;                       // the coded height (encoder.c:2232)
+    const int interlaced = ((flags & CFHD_ENCODING_FLAGS_YUV_INTERLACED) && (fmt == CFB_PIXEL_YUYV || fmt == CFB_PIXEL_UYVY)) ? CFB_INTERLACED : CFB_PROGRESSIVE;
+    std::vector<std::thread> th;
+    for (int i = 0; i < count && i < 64; i++)
+        th.emplace_back([=] {
+            Plan *p = get_plan(width, h8, fmt, interlaced);
+            if (p) {
+                // one transform of a grey frame: loads the kernels, allocates the codec's lazily created device buffers and pins
+                // the host staging this plan will use
+                const bool sparse = sparse_enabled() && interlaced == CFB_PROGRESSIVE && p->ensure_sparse();
+                std::vector<uint8_t> frame((size_t)p->layout.frame_bytes + 64, 0x80);
+                uint8_t *f = (uint8_t *)(((uintptr_t)frame.data() + 63) & ~(uintptr_t)63);
+                cfb_quant q;
+                cfb_frame_desc d = {width, h8, fmt, 0};
+                if (p->ensure_coded() && cfb_quant_for_source(&d, 4, interlaced != CFB_PROGRESSIVE, &q) == CFB_OK) {
+                    const void *frames[1] = {f};
+                    void *out[1] = {sparse ? p->sparse : p->coded};
+                    if (sparse) cfb_forward_host_sparse(p->codec, 1, frames, p->layout.frame_pitch, &q, out, nullptr);
+                    else cfb_forward_host(p->codec, 1, frames, p->layout.frame_pitch, &q, out);
+                }
+            }
+            release_plans();        // back to the pool, ready for whichever encoder thread asks first
+        });
+    for (auto &t : th) t.join();
+}
+
+static std::mutex g_pool_mu;
+static std::map<void *, int> g_pool_threads;                // encoder pool -> its thread count
+
+CFHD_Error CFHD_CreateEncoderPool(CFHD_EncoderPoolRef *encoderPoolRefOut, int encoderThreadCount, int jobQueueLength, CFHD_ALLOCATOR *allocator)
+{
+    typedef CFHD_Error (*fn_t)(CFHD_EncoderPoolRef *, int, int, CFHD_ALLOCATOR *);
+    static fn_t ref = next_symbol<fn_t>("CFHD_CreateEncoderPool");
+    const CFHD_Error e = ref(encoderPoolRefOut, encoderThreadCount, jobQueueLength, allocator);
+    if (e == CFHD_ERROR_OKAY && encoderPoolRefOut && *encoderPoolRefOut) {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        g_pool_threads[(void *)*encoderPoolRefOut] = encoderThreadCount;
+    }
+    return e;
+}
+
+CFHD_Error CFHD_PrepareEncoderPool(CFHD_EncoderPoolRef encoderPoolRef, uint_least16_t frameWidth, uint_least16_t frameHeight,
+                                   CFHD_PixelFormat pixelFormat, CFHD_EncodedFormat encodedFormat, CFHD_EncodingFlags encodingFlags,
+                                   CFHD_EncodingQuality encodingQuality)
+{
+    typedef CFHD_Error (*fn_t)(CFHD_EncoderPoolRef, uint_least16_t, uint_least16_t, CFHD_PixelFormat, CFHD_EncodedFormat, CFHD_EncodingFlags, CFHD_EncodingQuality);
+    static fn_t ref = next_symbol<fn_t>("CFHD_PrepareEncoderPool");
+    const CFHD_Error e = ref(encoderPoolRef, frameWidth, frameHeight, pixelFormat, encodedFormat, encodingFlags, encodingQuality);
+    if (e == CFHD_ERROR_OKAY) {
+        int n = 0;
+        { std::lock_guard<std::mutex> lk(g_pool_mu); auto it = g_pool_threads.find((void *)encoderPoolRef); if (it != g_pool_threads.end()) n = it->second; }
+        prewarm_plans(n, frameWidth, frameHeight, pixelFormat, encodedFormat, encodingFlags);
+    }
+    return e;
+}
+
+CFHD_Error CFHD_PrepareToEncode(CFHD_EncoderRef encoderRef, int frameWidth, int frameHeight, CFHD_PixelFormat pixelFormat,
+                                CFHD_EncodedFormat encodedFormat, CFHD_EncodingFlags encodingFlags, CFHD_EncodingQuality encodingQuality)
+{
+    typedef CFHD_Error (*fn_t)(CFHD_EncoderRef, int, int, CFHD_PixelFormat, CFHD_EncodedFormat, CFHD_EncodingFlags, CFHD_EncodingQuality);
+    static fn_t ref = next_symbol<fn_t>("CFHD_PrepareToEncode");
+    const CFHD_Error e = ref(encoderRef, frameWidth, frameHeight, pixelFormat, encodedFormat, encodingFlags, encodingQuality);
+    if (e == CFHD_ERROR_OKAY) prewarm_plans(1, frameWidth, frameHeight, pixelFormat, encodedFormat, encodingFlags);
+    return e;
 }
 
 }  // extern "C"
