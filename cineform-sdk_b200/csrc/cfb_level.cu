@@ -7,8 +7,8 @@
 //                                                            / spatial.c:12942 FilterSpatialV210Quant16s  (prescale 2)
 //   inverse  = Codec/wavelet.c:5685 TransformInverseSpatialQuantLowpass -> spatial.c:21877 / :22414
 // These entry points expose the level kernels (k_fwd_plane / k_inv_plane) for such compositions; together with
-// cfb_temporal_* they are enough to build the FIELDPLUS pyramid device-resident (tests/test_gop2_gpu.py does, and
-// checks every band against the reference's own two-frame-GOP encode).
+// cfb_temporal_* they are enough to build the FIELDPLUS pyramid device-resident (tests/test_gop2.py::test_cuda_gop2_device_resident
+// does, and checks every band against the reference's own two-frame-GOP encode).
 #include "cfb_host.h"
 
 namespace cfb {
