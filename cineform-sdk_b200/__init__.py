@@ -152,6 +152,19 @@ def lib():
     L.cfb_sparse_expand.argtypes = [C.POINTER(Layout), vp, vp]
     L.cfb_sparse_compact.argtypes = [C.POINTER(Layout), vp, vp, C.POINTER(C.c_size_t)]
     L.cfb_sparse_compact_bands.argtypes = [C.POINTER(Layout), C.POINTER(vp), C.POINTER(C.c_int32), vp, C.POINTER(C.c_size_t)]
+    L.cfb_sparse_writer_create.argtypes = [C.POINTER(Layout), C.POINTER(vp)]
+    L.cfb_sparse_writer_destroy.argtypes = [vp]
+    L.cfb_sparse_writer_destroy.restype = None
+    L.cfb_sparse_writer_begin.argtypes = [vp, vp, C.c_size_t]
+    L.cfb_sparse_writer_band.argtypes = [vp, i, i, i]
+    L.cfb_sparse_writer_run.argtypes = [vp, C.c_uint32]
+    L.cfb_sparse_writer_value.argtypes = [vp, i]
+    L.cfb_sparse_writer_dense_band.argtypes = [vp, i, i, i, vp, i]
+    L.cfb_sparse_writer_end.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.cfb_vlc_decoder_create.argtypes = [C.POINTER(VlcDecodebook), C.POINTER(vp)]
+    L.cfb_vlc_decoder_destroy.argtypes = [vp]
+    L.cfb_vlc_decoder_destroy.restype = None
+    L.cfb_vlc_decode_band.argtypes = [vp, vp, i, i, i, vp, C.c_size_t, i, C.POINTER(C.c_size_t)]
     L.cfb_sparse_vlc_band.argtypes = [C.POINTER(Layout), vp, i, i, i, C.POINTER(VlcCodebook), C.POINTER(BitWriter)]
     L.cfb_dense_vlc_band.argtypes = [vp, i, i, i, C.POINTER(VlcCodebook), C.POINTER(BitWriter)]
     L.cfb_sparse_band_nonzeros.argtypes = [C.POINTER(Layout), vp, i, i, i, C.POINTER(C.c_uint32)]
@@ -252,6 +265,62 @@ class VlcCodebook(C.Structure):
         self.run_length, self.value_length = len(self._keep[0]), len(self._keep[3])
         self.run_bits, self.run_size, self.run_count, self.value_bits, self.value_size = [a.ctypes.data for a in self._keep]
         return self
+
+
+class VlcDecodebook(C.Structure):
+    """cfb_vlc_decodebook: every code word of the band stream once -- kind 0 value, 1 zero run, 2 end of band."""
+    _fields_ = [("count", C.c_int32), ("bits", C.c_void_p), ("size", C.c_void_p), ("kind", C.c_void_p), ("arg", C.c_void_p)]
+
+    @classmethod
+    def from_arrays(cls, bits, size, kind, arg):
+        self = cls()
+        self._keep = [np.ascontiguousarray(bits, np.uint32), np.ascontiguousarray(size, np.uint8),
+                      np.ascontiguousarray(kind, np.uint8), np.ascontiguousarray(arg, np.int32)]
+        self.count = len(self._keep[0])
+        self.bits, self.size, self.kind, self.arg = [a.ctypes.data for a in self._keep]
+        return self
+
+
+class VlcDecoder:
+    """Compiled code set (cfb_vlc_decoder) + a sparse writer: band bit streams -> one 'CFS2' buffer."""
+
+    def __init__(self, layout, book):
+        self.layout, self.book = layout, book
+        self.d, self.w = C.c_void_p(), C.c_void_p()
+        _check(lib().cfb_vlc_decoder_create(C.byref(book), C.byref(self.d)))
+        _check(lib().cfb_sparse_writer_create(C.byref(layout), C.byref(self.w)))
+        self.out = None
+
+    def begin(self):
+        self.out = np.zeros(sparse_max_bytes(self.layout), np.uint8)
+        _check(lib().cfb_sparse_writer_begin(self.w, self.out.ctypes.data, self.out.size))
+
+    def dense_band(self, c, k, b, rows):
+        rows = np.ascontiguousarray(rows, np.int16)
+        _check(lib().cfb_sparse_writer_dense_band(self.w, c, k, b, rows.ctypes.data, rows.strides[0]))
+
+    def band(self, c, k, b, stream, quant):
+        stream = np.ascontiguousarray(stream, np.uint8)
+        used = C.c_size_t()
+        _check(lib().cfb_vlc_decode_band(self.d, self.w, c, k, b, stream.ctypes.data, stream.size, quant, C.byref(used)))
+        return int(used.value)
+
+    def end(self):
+        n = C.c_size_t()
+        _check(lib().cfb_sparse_writer_end(self.w, C.byref(n)))
+        return self.out[:n.value]
+
+    def close(self):
+        if self.d:
+            lib().cfb_vlc_decoder_destroy(self.d); self.d = C.c_void_p()
+        if self.w:
+            lib().cfb_sparse_writer_destroy(self.w); self.w = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class BitWriter(C.Structure):

@@ -3,6 +3,7 @@
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
+#include <string.h>
 
 #ifdef __CUDACC__
 #define CFB_HD __host__ __device__ __forceinline__
@@ -57,5 +58,45 @@ inline bool sparse_chunk_open(const void *sparse, size_t total, unsigned block, 
     c->wide = (const int16_t *)(base + off + kSparseL1Bytes + 4 * (size_t)c->groups + ((c->values + 3u) & ~3u));
     return true;
 }
+
+// ---- host side: compaction of one block (shared by cfb_sparse_compact*, the sparse writer) ----
+// One block of 8192 words -> its chunk at `chunk`; returns the chunk size and the table entry's counts
+inline unsigned sparse_compact_block(const int16_t *in, unsigned nvalid, unsigned char *chunk, unsigned *G_out, unsigned *V_out, unsigned *E_out)
+{
+    unsigned char l1[kSparseL1Bytes] = {0};
+    unsigned masks[kSparseBlockGroups];
+    signed char vb[kSparseBlockWords];
+    int16_t wide[kSparseBlockWords];
+    unsigned G = 0, V = 0, E = 0;
+    for (unsigned g = 0; g * kSparseGroupWords < nvalid; g++) {
+        const int16_t *grp = in + (size_t)g * kSparseGroupWords;
+        const unsigned n = nvalid - g * kSparseGroupWords < kSparseGroupWords ? nvalid - g * kSparseGroupWords : kSparseGroupWords;
+        if (n == kSparseGroupWords) {           // most groups are empty: eight 64-bit tests
+            uint64_t any = 0, q[8];
+            memcpy(q, grp, sizeof(q));
+            for (int k = 0; k < 8; k++) any |= q[k];
+            if (!any) continue;
+        }
+        unsigned m = 0;
+        for (unsigned k = 0; k < n; k++) {
+            const int v = grp[k];
+            if (!v) continue;
+            m |= 1u << k;
+            if (v < -127 || v > 127) { vb[V++] = -128; wide[E++] = (int16_t)v; } else vb[V++] = (signed char)v;
+        }
+        if (m) { l1[g >> 3] |= (unsigned char)(1u << (g & 7)); masks[G++] = m; }
+    }
+    const unsigned cb = sparse_chunk_bytes(G, V, E);
+    if (G) {
+        memset(chunk, 0, cb);
+        memcpy(chunk, l1, kSparseL1Bytes);
+        memcpy(chunk + kSparseL1Bytes, masks, 4 * (size_t)G);
+        memcpy(chunk + kSparseL1Bytes + 4 * (size_t)G, vb, V);
+        memcpy(chunk + kSparseL1Bytes + 4 * (size_t)G + ((V + 3) & ~3u), wide, 2 * (size_t)E);
+    }
+    *G_out = G; *V_out = V; *E_out = E;
+    return cb;
+}
+
 
 }  // namespace cfb

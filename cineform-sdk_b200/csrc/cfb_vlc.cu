@@ -14,6 +14,9 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <new>
+#include <vector>
+
 #include "cfb_host.h"
 #include "cfb_sparse_format.h"
 
@@ -233,6 +236,216 @@ cfb_error cfb_sparse_expand_band(const cfb_layout *L, const void *sparse, int ch
         const size_t r = (pos - w0) / pitch, x = (pos - w0) % pitch;
         if (x < (size_t)bl->width) *(int16_t *)((unsigned char *)out + r * (size_t)pitch_bytes + 2 * x) = (int16_t)v;
     });
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// decoder side: tokens -> sparse
+
+struct cfb_sparse_writer {
+    cfb_layout layout;
+    unsigned nwords = 0, nblocks = 0;
+    unsigned char *out = nullptr;
+    size_t capacity = 0, off = 0;
+    size_t pos = 0;                 // next word of the flat coded region
+    size_t band_end = 0;            // end of the band being written
+    unsigned cur_block = 0;
+    bool dirty = false;             // scratch holds a non-zero word
+    bool open = false;
+    alignas(64) int16_t scratch[kSparseBlockWords];
+};
+
+namespace {
+
+// close every block before `block`: the current one from the scratch, the ones in between are empty
+cfb_error writer_flush_until(cfb_sparse_writer *w, unsigned block)
+{
+    unsigned *tab = (unsigned *)(w->out + kSparseHeaderBytes);
+    while (w->cur_block < block && w->cur_block < w->nblocks) {
+        const unsigned b = w->cur_block;
+        unsigned G = 0, V = 0, E = 0, cb = 0;
+        if (w->dirty) {
+            if (w->off + kSparseMaxChunk > w->capacity) { set_error("sparse writer: output buffer too small"); return CFB_ERROR_OUTOFMEMORY; }
+            const unsigned nvalid = w->nwords - b * kSparseBlockWords < kSparseBlockWords ? w->nwords - b * kSparseBlockWords : kSparseBlockWords;
+            cb = sparse_compact_block(w->scratch, nvalid, w->out + w->off, &G, &V, &E);
+            memset(w->scratch, 0, sizeof(w->scratch));
+            w->dirty = false;
+        }
+        tab[4 * b] = (unsigned)w->off; tab[4 * b + 1] = G; tab[4 * b + 2] = V; tab[4 * b + 3] = E;
+        w->off += cb;
+        w->cur_block++;
+    }
+    return CFB_OK;
+}
+
+inline cfb_error writer_advance(cfb_sparse_writer *w, size_t n)
+{
+    if (w->pos + n > w->band_end) { set_error("sparse writer: tokens run past the end of the band"); return CFB_ERROR_BADFORMAT; }
+    w->pos += n;
+    const unsigned blk = (unsigned)(w->pos / kSparseBlockWords);
+    return blk > w->cur_block ? writer_flush_until(w, blk) : CFB_OK;
+}
+
+}  // namespace
+
+cfb_error cfb_sparse_writer_create(const cfb_layout *L, cfb_sparse_writer **out)
+{
+    if (!L || !out) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_sparse_writer *w = new (std::nothrow) cfb_sparse_writer();
+    if (!w) return CFB_ERROR_OUTOFMEMORY;
+    w->layout = *L;
+    w->nwords = (unsigned)(L->coded_bytes / 2);
+    w->nblocks = sparse_nblocks(w->nwords);
+    *out = w;
+    return CFB_OK;
+}
+
+void cfb_sparse_writer_destroy(cfb_sparse_writer *w) { delete w; }
+
+cfb_error cfb_sparse_writer_begin(cfb_sparse_writer *w, void *sparse, size_t capacity)
+{
+    if (!w || !sparse) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    const size_t chunks = sparse_chunks_off(w->nblocks);
+    if (capacity < chunks) { set_error("sparse writer: output buffer too small"); return CFB_ERROR_OUTOFMEMORY; }
+    w->out = (unsigned char *)sparse; w->capacity = capacity; w->off = chunks;
+    memset(w->out, 0, chunks);
+    memset(w->scratch, 0, sizeof(w->scratch));
+    w->pos = 0; w->band_end = 0; w->cur_block = 0; w->dirty = false; w->open = true;
+    return CFB_OK;
+}
+
+cfb_error cfb_sparse_writer_band(cfb_sparse_writer *w, int channel, int level, int band)
+{
+    if (!w || !w->open) { set_error("sparse writer not begun"); return CFB_ERROR_INVALID_ARGUMENT; }
+    size_t w0, w1;
+    cfb_error e = band_range(&w->layout, channel, level, band, &w0, &w1, nullptr);
+    if (e) return e;
+    if (w0 < w->pos) { set_error("sparse writer: band (%d, %d, %d) is not the next one in the coded region", channel, level, band); return CFB_ERROR_INVALID_ARGUMENT; }
+    w->band_end = w0;
+    e = writer_advance(w, w0 - w->pos);         // whatever lies between two bands is zero
+    w->band_end = w1;
+    return e;
+}
+
+cfb_error cfb_sparse_writer_run(cfb_sparse_writer *w, uint32_t zeros) { return writer_advance(w, zeros); }
+
+cfb_error cfb_sparse_writer_value(cfb_sparse_writer *w, int value)
+{
+    if (w->pos >= w->band_end) { set_error("sparse writer: tokens run past the end of the band"); return CFB_ERROR_BADFORMAT; }
+    const int16_t v = (int16_t)value;
+    if (v) { w->scratch[w->pos % kSparseBlockWords] = v; w->dirty = true; }
+    return writer_advance(w, 1);
+}
+
+cfb_error cfb_sparse_writer_dense_band(cfb_sparse_writer *w, int channel, int level, int band, const int16_t *rows, int pitch_bytes)
+{
+    cfb_error e = cfb_sparse_writer_band(w, channel, level, band);
+    if (e) return e;
+    const cfb_band_layout &bl = w->layout.band[channel][level][band];
+    if (!rows || pitch_bytes < 2 * bl.width) { set_error("bad band rows"); return CFB_ERROR_INVALID_ARGUMENT; }
+    for (int r = 0; r < bl.height && !e; r++) {
+        const int16_t *row = (const int16_t *)((const unsigned char *)rows + (size_t)r * pitch_bytes);
+        for (int x = 0; x < bl.width && !e; x++) e = cfb_sparse_writer_value(w, row[x]);
+        if (!e) e = writer_advance(w, (size_t)(bl.pitch / 2 - bl.width));
+    }
+    return e;
+}
+
+cfb_error cfb_sparse_writer_end(cfb_sparse_writer *w, size_t *bytes)
+{
+    if (!w || !w->open) { set_error("sparse writer not begun"); return CFB_ERROR_INVALID_ARGUMENT; }
+    w->band_end = w->nwords;
+    cfb_error e = writer_flush_until(w, w->nblocks);
+    if (e) return e;
+    unsigned *h = (unsigned *)w->out;
+    h[0] = kSparseMagic; h[1] = w->nwords; h[2] = (unsigned)w->off; h[3] = w->nblocks; h[4] = h[5] = h[6] = h[7] = 0;
+    if (bytes) *bytes = w->off;
+    w->open = false;
+    return CFB_OK;
+}
+
+// ---- table-driven band parser -----------------------------------------------------------------------------------
+struct cfb_vlc_decoder {
+    static constexpr int kPrimaryBits = 11;
+    struct Token { uint8_t kind; int32_t arg; };
+    struct Node { int32_t child[2]; int32_t token; };          // token >= 0: leaf (index into tokens)
+    struct Fast { uint8_t len; int32_t token; int32_t node; };  // len 0: not resolved inside the primary window -> continue at `node`
+    std::vector<Token> tokens;
+    std::vector<Node> nodes;
+    std::vector<Fast> fast;
+};
+
+cfb_error cfb_vlc_decoder_create(const cfb_vlc_decodebook *book, cfb_vlc_decoder **out)
+{
+    if (!book || !out || book->count < 2 || !book->bits || !book->size || !book->kind || !book->arg) { set_error("bad decode book"); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_vlc_decoder *d = new (std::nothrow) cfb_vlc_decoder();
+    if (!d) return CFB_ERROR_OUTOFMEMORY;
+    d->nodes.push_back({{-1, -1}, -1});
+    bool has_end = false;
+    for (int i = 0; i < book->count; i++) {
+        const int n = book->size[i];
+        if (n < 1 || n > 31 || book->kind[i] > 2 || (book->kind[i] == 1 && book->arg[i] < 1)) { delete d; set_error("decode book entry %d malformed", i); return CFB_ERROR_INVALID_ARGUMENT; }
+        has_end = has_end || book->kind[i] == 2;
+        int node = 0;
+        for (int k = n - 1; k >= 0; k--) {
+            if (d->nodes[node].token >= 0) { delete d; set_error("decode book is not prefix free (entry %d)", i); return CFB_ERROR_INVALID_ARGUMENT; }
+            const int bit = (book->bits[i] >> k) & 1;
+            if (d->nodes[node].child[bit] < 0) { d->nodes[node].child[bit] = (int32_t)d->nodes.size(); d->nodes.push_back({{-1, -1}, -1}); }
+            node = d->nodes[node].child[bit];
+        }
+        if (d->nodes[node].token >= 0 || d->nodes[node].child[0] >= 0 || d->nodes[node].child[1] >= 0) {
+            delete d; set_error("decode book is not prefix free (entry %d)", i); return CFB_ERROR_INVALID_ARGUMENT;
+        }
+        d->nodes[node].token = (int32_t)d->tokens.size();
+        d->tokens.push_back({book->kind[i], book->arg[i]});
+    }
+    if (!has_end) { delete d; set_error("decode book has no end-of-band code"); return CFB_ERROR_INVALID_ARGUMENT; }
+    const int P = cfb_vlc_decoder::kPrimaryBits;
+    d->fast.resize((size_t)1 << P);
+    for (unsigned p = 0; p < (1u << P); p++) {
+        int node = 0, len = 0;
+        while (len < P && node >= 0 && d->nodes[node].token < 0) { node = d->nodes[node].child[(p >> (P - 1 - len)) & 1]; len++; }
+        if (node >= 0 && d->nodes[node].token >= 0) d->fast[p] = {(uint8_t)len, d->nodes[node].token, -1};
+        else d->fast[p] = {0, -1, node};          // node < 0: no code starts with these bits
+    }
+    *out = d;
+    return CFB_OK;
+}
+
+void cfb_vlc_decoder_destroy(cfb_vlc_decoder *d) { delete d; }
+
+cfb_error cfb_vlc_decode_band(const cfb_vlc_decoder *d, cfb_sparse_writer *w, int channel, int level, int band,
+                              const uint8_t *stream, size_t stream_bytes, int quant, size_t *consumed)
+{
+    if (!d || !w || !stream) { set_error("null argument"); return CFB_ERROR_INVALID_ARGUMENT; }
+    cfb_error e = cfb_sparse_writer_band(w, channel, level, band);
+    if (e) return e;
+    const int P = cfb_vlc_decoder::kPrimaryBits;
+    uint64_t acc = 0;           // the next `have` bits of the stream, left-aligned at bit 63
+    int have = 0;
+    size_t rd = 0, bitpos = 0;  // bytes fetched, bits consumed
+    auto fill = [&]() { while (have <= 56 && rd < stream_bytes) { acc |= (uint64_t)stream[rd++] << (56 - have); have += 8; } };
+    for (;;) {
+        fill();
+        if (have <= 0) { set_error("band stream ends without an end-of-band code"); return CFB_ERROR_BADFORMAT; }
+        const cfb_vlc_decoder::Fast &f = d->fast[(size_t)(acc >> (64 - P))];
+        int token, len;
+        if (f.len) { token = f.token; len = f.len; }
+        else {
+            int node = f.node;
+            len = P;
+            while (node >= 0 && d->nodes[node].token < 0 && len < 32) { node = d->nodes[node].child[(acc >> (63 - len)) & 1]; len++; }
+            if (node < 0 || d->nodes[node].token < 0) { set_error("band stream: no code word matches at bit %zu", bitpos); return CFB_ERROR_BADFORMAT; }
+            token = d->nodes[node].token;
+        }
+        if (len > have) { set_error("band stream truncated inside a code word"); return CFB_ERROR_BADFORMAT; }
+        acc <<= len; have -= len; bitpos += (size_t)len;
+        const cfb_vlc_decoder::Token &t = d->tokens[token];
+        if (t.kind == 2) break;
+        e = (t.kind == 1) ? cfb_sparse_writer_run(w, (uint32_t)t.arg) : cfb_sparse_writer_value(w, (int)(int16_t)(t.arg * quant));
+        if (e) return e;
+    }
+    if (consumed) *consumed = (bitpos + 7) / 8;
+    return CFB_OK;
 }
 
 }  // extern "C"

@@ -385,6 +385,41 @@ CFB_API cfb_error cfb_sparse_expand_band(const cfb_layout *layout, const void *s
 CFB_API cfb_error cfb_dense_vlc_band(const int16_t *band, int width, int height, int pitch_bytes,
                                      const cfb_vlc_codebook *book, cfb_bitwriter *bw);
 
+/* ---- decoder side of the same row: entropy-decoded tokens -> sparse format (host) ----------------------------------
+ * A decoder that produces (zero run, value) tokens -- which is what the reference's FSM decoder does internally before it
+ * scatters them into a dense band (Codec/decoder.c:19534 DecodeBandFSM16sNoGap) -- can write the 'CFS2' buffer directly and
+ * upload ~1/10 of the bytes (cfb_inverse_host_sparse).  The writer takes the bands in the order of the coded region
+ * (per channel: LL3, then LH, HL, HH of levels 3, 2, 1); inside a band, runs count the pitch gap exactly as the
+ * encoder's runs do (encoder.c:5653), so a token stream decoded from the reference's bit stream maps one to one. */
+typedef struct cfb_sparse_writer cfb_sparse_writer;
+CFB_API cfb_error cfb_sparse_writer_create(const cfb_layout *layout, cfb_sparse_writer **out);
+CFB_API void cfb_sparse_writer_destroy(cfb_sparse_writer *w);
+CFB_API cfb_error cfb_sparse_writer_begin(cfb_sparse_writer *w, void *sparse, size_t capacity);    /* capacity >= cfb_sparse_max_bytes */
+CFB_API cfb_error cfb_sparse_writer_band(cfb_sparse_writer *w, int channel, int level, int band);  /* next band, coded order */
+CFB_API cfb_error cfb_sparse_writer_run(cfb_sparse_writer *w, uint32_t zeros);
+CFB_API cfb_error cfb_sparse_writer_value(cfb_sparse_writer *w, int value);
+/* a band that arrives dense (the lowpass band LL3 is stored as plain 16-bit values, decoder.c DecodeLowPassBand) */
+CFB_API cfb_error cfb_sparse_writer_dense_band(cfb_sparse_writer *w, int channel, int level, int band, const int16_t *rows, int pitch_bytes);
+CFB_API cfb_error cfb_sparse_writer_end(cfb_sparse_writer *w, size_t *bytes);
+
+/* A table-driven parser of the band bit stream for such a decoder.  The code set is the host entropy coder's (out of
+ * scope): the caller lists every code word once -- kind 0 = coefficient with the (already decompanded, signed) value arg,
+ * kind 1 = run of arg zeros, kind 2 = end of band.  Decoded coefficients are multiplied by `quant` and wrapped to int16,
+ * as the reference's FSM tables are (decoder.c:20551 DeQuantFSM).  `consumed` receives the bytes read up to and including
+ * the byte that holds the last bit of the end-of-band code. */
+typedef struct cfb_vlc_decodebook {
+    int32_t count;
+    const uint32_t *bits;           /* code word, right justified */
+    const uint8_t *size;            /* 1..31 bits */
+    const uint8_t *kind;            /* 0 value, 1 zero run, 2 end of band */
+    const int32_t *arg;
+} cfb_vlc_decodebook;
+typedef struct cfb_vlc_decoder cfb_vlc_decoder;
+CFB_API cfb_error cfb_vlc_decoder_create(const cfb_vlc_decodebook *book, cfb_vlc_decoder **out);   /* fails if the set is not prefix free */
+CFB_API void cfb_vlc_decoder_destroy(cfb_vlc_decoder *d);
+CFB_API cfb_error cfb_vlc_decode_band(const cfb_vlc_decoder *d, cfb_sparse_writer *w, int channel, int level, int band,
+                                      const uint8_t *stream, size_t stream_bytes, int quant, size_t *consumed);
+
 /* ---- statistics record -------------------------------------------------------- */
 typedef struct cfb_stats {
     uint64_t kernel_launches;   /* kernels launched by this library on this context */

@@ -348,6 +348,58 @@ int64_t ref_vlc_encode_band(const int16_t *band, int width, int height, int pitc
     return n;
 }
 
+// The same band as it stands in a sample: codes, then the end-of-band code (encoder.c:6503 FinishEncodeBand), padded to a
+// 32-bit boundary.  Returns the bytes written.
+extern "C" void FinishEncodeBand(BITSTREAM *output, unsigned int code, int size);
+int64_t ref_vlc_encode_band_finished(const int16_t *band, int width, int height, int pitch, int codebook, uint8_t *out, int64_t capacity)
+{
+    ENCODER *enc = probe_vlc_encoder();
+    if (!enc) return -1;
+    Aligned img((size_t)pitch * height + 64), buf((size_t)capacity + 64);
+    memcpy(img.p, band, (size_t)pitch * height);
+    BITSTREAM bs;
+    InitBitstreamBuffer(&bs, buf.as<uint8_t>(), (size_t)capacity, BITSTREAM_ACCESS_WRITE);
+    EncodeQuantLongRuns(enc, &bs, img.as<PIXEL>(), width, height, pitch, 1, codebook);
+    FinishEncodeBand(&bs, enc->band_end_code[codebook], enc->band_end_size[codebook]);
+    PadBits(&bs);
+    FlushBitstream(&bs);
+    const int64_t n = bs.nWordsUsed;
+    if (n > capacity) return -1;
+    memcpy(out, buf.p, (size_t)n);
+    return n;
+}
+
+int ref_vlc_band_end(int codebook, uint32_t *bits, int32_t *size)
+{
+    ENCODER *enc = probe_vlc_encoder();
+    if (!enc || codebook < 0 || codebook >= CODEC_NUM_CODESETS) return 0;
+    *bits = enc->band_end_code[codebook]; *size = enc->band_end_size[codebook];
+    return 1;
+}
+
+// The reference's FSM band decoder (Codec/decoder.c:19534 DecodeBandFSM16sNoGap) on such a stream, with its tables scaled by
+// `quant` as the sample decoder does (decoder.c:20551 DeQuantFSM).  out = pitch * height bytes.  Returns 0 on success.
+extern "C" bool DecodeBandFSM16sNoGap(FSM *fsm, BITSTREAM *stream, PIXEL16S *image, int width, int height, int pitch);
+extern "C" void DeQuantFSM(FSM *fsm, int quant);
+int ref_vlc_decode_band(const uint8_t *stream, int64_t nbytes, int width, int height, int pitch, int codebook, int quant, int16_t *out)
+{
+    static DECODER *dec = nullptr;
+    if (!dec) {
+        dec = (DECODER *)calloc(1, DecoderSize());
+        if (!DecodeInit(NULL, dec, 256, 64, DECODED_FORMAT_YUYV, DECODED_RESOLUTION_FULL, NULL)) { free(dec); dec = nullptr; return 1; }
+    }
+    if (codebook < 0 || codebook >= CODEC_NUM_CODESETS) return 2;
+    FSM *fsm = &dec->fsm[codebook];
+    DeQuantFSM(fsm, quant);
+    Aligned smp((size_t)nbytes + 1024), img((size_t)pitch * height + 4096);
+    memcpy(smp.p, stream, (size_t)nbytes);
+    BITSTREAM bs;
+    InitBitstreamBuffer(&bs, smp.as<uint8_t>(), (size_t)nbytes + 512, BITSTREAM_ACCESS_READ);
+    if (!DecodeBandFSM16sNoGap(fsm, &bs, img.as<PIXEL16S>(), width, height, pitch)) return 3;
+    memcpy(out, img.p, (size_t)pitch * height);
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Two-frame GOP (CFHD_ENCODING_FLAGS_YUV_2FRAME_GOP -> parameters.gop_length = 2, EncoderSDK/SampleEncoder.cpp:211):
 // run the reference's EncodeSample on frame A then frame B and copy out all six wavelets of every channel of the

@@ -141,3 +141,108 @@ def test_vlc_rejects_bad_arguments(pkg):
                                         np.arange(8, dtype=np.uint32), np.full(8, 4, np.uint8))
     with pytest.raises(pkg.CfbError):
         pkg.sparse_vlc_band(lay, sparse, 0, 0, 1, worse, 4096)
+
+
+# ---------------------------------------------------------------------------------------------------- decoder side
+def ref_encode_band_finished(ref_lib, band_padded, width, codebook):
+    h, pitch = band_padded.shape[0], band_padded.strides[0]
+    cap = 4 * band_padded.size + 4096
+    out = np.zeros(cap, np.uint8)
+    fn = ref_lib.ref_vlc_encode_band_finished
+    fn.restype = C.c_int64
+    n = fn(band_padded.ctypes.data_as(C.c_void_p), width, h, pitch, codebook, out.ctypes.data_as(C.c_void_p), C.c_int64(cap))
+    assert n > 0
+    return out[:n].copy()
+
+
+def ref_decode_band(ref_lib, stream, width, height, pitch, codebook, quant):
+    out = np.zeros((height, pitch // 2), np.int16)
+    rc = ref_lib.ref_vlc_decode_band(stream.ctypes.data_as(C.c_void_p), C.c_int64(stream.size), width, height, pitch, codebook, quant,
+                                     out.ctypes.data_as(C.c_void_p))
+    assert rc == 0, rc
+    return out
+
+
+def decode_book(pkg, ref_lib, codebook):
+    """Every code word of code set `codebook` once.  Run codes and the end-of-band code come from the encoder's tables; the
+    value a coefficient code DECODES to (the codec compands magnitudes above 27 inside its entropy coder, codebooks.c:932)
+    is learnt from the reference's own FSM decoder: one band holding every table value once, through its coder and back."""
+    rb, rs, rc, vb, vs = ref_tables(ref_lib, codebook)
+    n = vb.size
+    values = np.concatenate([np.arange(1, n // 2), np.arange(-(n // 2) + 1, 0)]).astype(np.int16)
+    width, height, pitch = 64, (values.size + 31) // 32, 128
+    band = np.zeros((height, pitch // 2), np.int16)
+    band[:, 0:64:2].reshape(-1)[:values.size] = values                  # every second column: no two codes adjacent to a run boundary issue
+    decoded = ref_decode_band(ref_lib, ref_encode_band_finished(ref_lib, band, width, codebook), width, height, pitch, codebook, 1)
+    dec_values = decoded[:, 0:64:2].reshape(-1)[:values.size]
+    codes = {}
+    for v, dv in zip(values.tolist(), dec_values.tolist()):
+        idx = v if v >= 0 else n + v
+        key = (int(vb[idx]), int(vs[idx]))
+        assert codes.setdefault(key, (0, dv)) == (0, dv), "one code, two decoded values"
+    # The run table is indexed by run LENGTH: entry i holds the best single PutBits for a run of at least i zeros, and many
+    # entries are concatenations of shorter run codes (codebooks.c ComputeRunLengthCodeTable packs up to 32 bits).  Only the
+    # atomic code words belong in a decode book: a concatenation starts with a code word that is already in the set.
+    as_string = lambda bits, size: format(bits, "b").zfill(size)[-size:]
+    atoms = {as_string(*k) for k in codes}
+    for i in range(1, rb.size):
+        key = (int(rb[i]), int(rs[i]))
+        text = as_string(*key)
+        if key in codes or any(text.startswith(a) for a in atoms if len(a) < len(text)):
+            continue
+        codes[key] = (1, int(rc[i]))
+        atoms.add(text)
+    eb, es = C.c_uint32(), C.c_int32()
+    assert ref_lib.ref_vlc_band_end(codebook, C.byref(eb), C.byref(es)) == 1
+    codes[(int(eb.value), int(es.value))] = (2, 0)
+    keys = list(codes)
+    return pkg.VlcDecodebook.from_arrays([k[0] for k in keys], [k[1] for k in keys], [codes[k][0] for k in keys], [codes[k][1] for k in keys])
+
+
+@needs_ref
+@pytest.mark.parametrize("size", [(256, 64), (704, 96), (720, 480), (1920, 1080)])
+def test_band_streams_to_sparse_match_reference_fsm_decoder(pkg, size):
+    """Decoder side of the hand-over: the band bit streams of a Qbist frame (the reference's coder, end-of-band code and
+    padding included) are parsed straight into the sparse format; expanded, it equals band for band what the reference's
+    FSM decoder (DecodeBandFSM16sNoGap, tables scaled by the band's quantiser) writes into its dense bands."""
+    w, h = size
+    ref_lib = ol.load_ref()
+    frame = pu.qbist_yuy2(ref_lib, w, h, 2)
+    bands, div, _, _ = pu.ref_encode_frame(ref_lib, frame, w, h, pu.COLOR_FORMAT_YUYV, 0, 3, 4)
+    lay = pkg.layout_for(pkg.FrameDesc(w, h, pkg.PIXEL_YUYV))
+    coded = pkg.pack_coded(lay, bands)
+    dec = pkg.VlcDecoder(lay, decode_book(pkg, ref_lib, 1))
+    dec.begin()
+    want = np.zeros(lay.coded_bytes, np.uint8)
+    for c, k, b in all_bands(lay):
+        bl = lay.band[c][k][b]
+        padded = coded[bl.offset: bl.offset + bl.pitch * bl.height].view(np.int16).reshape(bl.height, bl.pitch // 2)
+        if b == 0:                      # LL3 travels as plain 16-bit values
+            dec.dense_band(c, k, b, padded[:, :bl.width])
+            pkg.band_view(lay, want, c, k, b)[:] = padded[:, :bl.width]
+            continue
+        quant = div[c][k][b]
+        stream = ref_encode_band_finished(ref_lib, padded, bl.width, 1)
+        used = dec.band(c, k, b, stream, quant)
+        assert stream.size - 4 <= used <= stream.size
+        pkg.band_view(lay, want, c, k, b)[:] = ref_decode_band(ref_lib, stream, bl.width, bl.height, bl.pitch, 1, quant)[:, :bl.width]
+    sparse = dec.end()
+    assert np.array_equal(pkg.sparse_expand(lay, sparse), want)
+    assert np.array_equal(sparse, pkg.sparse_compact(lay, want))            # and byte for byte the canonical packing
+    dec.close()
+
+
+def test_sparse_writer_rejects_misuse(pkg):
+    lay = pkg.layout_for(pkg.FrameDesc(256, 64, pkg.PIXEL_YUYV))
+    book = pkg.VlcDecodebook.from_arrays([0b0, 0b10, 0b11], [1, 2, 2], [1, 0, 2], [1, 5, 0])
+    dec = pkg.VlcDecoder(lay, book)
+    dec.begin()
+    with pytest.raises(pkg.CfbError):
+        dec.band(0, 0, 1, np.array([0x00, 0x00], np.uint8), 1)            # zero runs only, never an end-of-band code
+    dec.begin()
+    dec.band(0, 2, 1, np.array([0b10110000], np.uint8), 3)                 # value 5 * 3, end of band
+    with pytest.raises(pkg.CfbError):
+        dec.band(0, 2, 1, np.array([0b11000000], np.uint8), 1)             # the same band again: not the next one
+    with pytest.raises(pkg.CfbError):
+        pkg.VlcDecoder(lay, pkg.VlcDecodebook.from_arrays([0b0, 0b01], [1, 2], [1, 2], [1, 0]))      # 0 is a prefix of 01
+    dec.close()
