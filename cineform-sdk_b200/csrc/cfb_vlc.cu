@@ -41,7 +41,8 @@ struct Bits {
         if (n > 32) {
             const uint32_t word = (uint32_t)(acc >> (n - 32));
             if (cur + 4 > end) { overflow = true; n -= 32; return; }
-            cur[0] = (uint8_t)(word >> 24); cur[1] = (uint8_t)(word >> 16); cur[2] = (uint8_t)(word >> 8); cur[3] = (uint8_t)word;
+            const uint32_t be = __builtin_bswap32(word);        // big-endian in the stream (bitstream.c PutLong)
+            memcpy(cur, &be, 4);
             cur += 4; bytes += 4;
             n -= 32;
         }
@@ -54,11 +55,76 @@ struct Bits {
     }
 };
 
+// (short zero run, small value) pairs are most of a band's tokens: their run codes + value code are pre-joined into one
+// code word of at most 32 bits.  Writing the joined word leaves the bit buffer in the same state as writing its parts one
+// after the other (a word is flushed exactly when the pending count passes 32 either way, and two flushes cannot occur
+// within 32 bits).
+constexpr int kFastRuns = 32, kFastValues = 32;
+struct FastPairs {
+    uint64_t key = 0;
+    uint64_t e[kFastRuns][2 * kFastValues + 1];     // (size << 32) | bits, 0 = not available
+};
+
+uint64_t book_key(const cfb_vlc_codebook &b)
+{
+    uint64_t h = 1469598103934665603ull ^ (uint64_t)b.run_length ^ ((uint64_t)b.value_length << 32);
+    auto mix = [&](uint64_t x) { h ^= x; h *= 1099511628211ull; h ^= h >> 31; };
+    for (int i = 1; i < kFastRuns && i < b.run_length; i++) mix(((uint64_t)b.run_bits[i] << 24) ^ ((uint64_t)b.run_size[i] << 16) ^ b.run_count[i]);
+    for (int v = -kFastValues; v <= kFastValues; v++) {
+        const int idx = v < 0 ? b.value_length + v : v;
+        mix(((uint64_t)b.value_bits[idx] << 8) ^ b.value_size[idx]);
+    }
+    return h | 1;
+}
+
+const FastPairs &fast_pairs(const cfb_vlc_codebook &b)
+{
+    static thread_local FastPairs cache[4];
+    static thread_local int next = 0;
+    const uint64_t key = book_key(b);
+    for (FastPairs &f : cache) if (f.key == key) return f;
+    FastPairs &f = cache[next++ & 3];
+    f.key = key;
+    const int half = b.value_length >> 1;
+    for (int r = 0; r < kFastRuns; r++) {
+        // the greedy split of a run of r zeros (vlc.c:366)
+        uint64_t rbits = 0; int rsize = 0; bool ok = true;
+        for (int count = r; count > 0 && ok; ) {
+            const int i = count < b.run_length - 1 ? count : b.run_length - 1;
+            if (rsize + b.run_size[i] > 32) { ok = false; break; }
+            rbits = (rbits << b.run_size[i]) | (b.run_bits[i] & (0xffffffffu >> (32 - b.run_size[i])));
+            rsize += b.run_size[i];
+            count -= (int)b.run_count[i];
+        }
+        for (int v = -kFastValues; v <= kFastValues; v++) {
+            uint64_t &e = f.e[r][v + kFastValues];
+            e = 0;
+            if (!ok || v == 0 || v <= -half || v >= half) continue;
+            const int idx = v < 0 ? b.value_length + v : v;
+            const int size = rsize + b.value_size[idx];
+            if (size > 32) continue;
+            const uint64_t bits = (rbits << b.value_size[idx]) | (b.value_bits[idx] & (0xffffffffu >> (32 - b.value_size[idx])));
+            e = ((uint64_t)size << 32) | bits;
+        }
+    }
+    return f;
+}
+
 struct Coder {
     const cfb_vlc_codebook &b;
     Bits &out;
     const int half;
-    Coder(const cfb_vlc_codebook &book, Bits &o) : b(book), out(o), half(book.value_length >> 1) {}
+    const FastPairs &fast;
+    Coder(const cfb_vlc_codebook &book, Bits &o) : b(book), out(o), half(book.value_length >> 1), fast(fast_pairs(book)) {}
+    inline void token(uint64_t zeros, int v)
+    {
+        if (zeros < (uint64_t)kFastRuns && v >= -kFastValues && v <= kFastValues) {
+            const uint64_t e = fast.e[zeros][v + kFastValues];
+            if (e) { out.put((uint32_t)e, (int)(e >> 32)); return; }
+        }
+        run(zeros);
+        value(v);
+    }
     inline void run(uint64_t count)
     {
         const uint64_t last = (uint64_t)b.run_length - 1;
@@ -175,8 +241,7 @@ cfb_error cfb_sparse_vlc_band(const cfb_layout *L, const void *sparse, int chann
     Coder coder(*book, bits);
     size_t next = w0;               // first word not yet accounted for
     e = walk(L, sparse, w0, w1, [&](size_t pos, int v) {
-        coder.run(pos - next);
-        coder.value(v);
+        coder.token(pos - next, v);
         next = pos + 1;
     });
     if (e) return e;
@@ -199,9 +264,8 @@ cfb_error cfb_dense_vlc_band(const int16_t *image, int width, int height, int pi
         const int16_t *row = image + (size_t)r * pitch;
         for (int x = 0; x < width; x++) {
             if (row[x] == 0) { count++; continue; }
-            coder.run(count);
+            coder.token(count, row[x]);
             count = 0;
-            coder.value(row[x]);
         }
         count += (uint64_t)gap;
     }
