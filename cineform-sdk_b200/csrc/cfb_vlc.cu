@@ -177,7 +177,9 @@ cfb_error walk(const cfb_layout *L, const void *sparse, size_t w0, size_t w1, F 
     const unsigned nwords = (unsigned)(L->coded_bytes / 2);
     const unsigned *h = (const unsigned *)sparse;
     const unsigned nblocks = sparse_nblocks(nwords);
-    if (!sparse || h[0] != kSparseMagic || h[1] != nwords || h[3] != nblocks || h[2] < sparse_chunks_off(nblocks)) {
+    // total_bytes is bounded by the worst case, i.e. by the size every sparse buffer is required to have (cfb_sparse_max_bytes)
+    if (!sparse || h[0] != kSparseMagic || h[1] != nwords || h[3] != nblocks || h[2] < sparse_chunks_off(nblocks) || (h[2] & 15) ||
+        h[2] > sparse_chunks_off(nblocks) + (size_t)nblocks * kSparseMaxChunk) {
         set_error("bad sparse header");
         return CFB_ERROR_BADFORMAT;
     }

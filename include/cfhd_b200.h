@@ -323,7 +323,9 @@ CFB_API cfb_error cfb_gop2_inverse_host(cfb_codec *codec, const void *coded, con
  *   (empty when the block is all zero): 32-byte bitmap of the block's non-empty 32-word groups, one 32-bit mask per
  *   non-empty group, one byte per non-zero word (-128 = escape), one int16 per escape.  Zero runs (incl. the pitch gap
  *   the reference's run-length coder walks, encoder.c:5653) are implicit in the bitmaps. */
-CFB_API size_t cfb_sparse_max_bytes(const cfb_layout *layout);          /* worst case (no zero at all) */
+CFB_API size_t cfb_sparse_max_bytes(const cfb_layout *layout);          /* worst case (no zero at all); every buffer handed to a
+                                                                         * cfb_sparse_* / cfb_*_sparse call must be this large: readers bound a
+                                                                         * damaged header's size field by it */
 CFB_API size_t cfb_sparse_bytes(const void *sparse);                    /* actual size, from the header */
 /* forward + GPU compaction; sparse_bytes[i] receives the size written to h_sparse[i] */
 CFB_API cfb_error cfb_forward_host_sparse(cfb_codec *codec, int n, const void *const *h_frames, int frame_pitch,

@@ -246,3 +246,46 @@ def test_sparse_writer_rejects_misuse(pkg):
     with pytest.raises(pkg.CfbError):
         pkg.VlcDecoder(lay, pkg.VlcDecodebook.from_arrays([0b0, 0b01], [1, 2], [1, 2], [1, 0]))      # 0 is a prefix of 01
     dec.close()
+
+
+# ---------------------------------------------------------------------------------------------------- robustness
+def test_host_parsers_survive_damaged_input(pkg):
+    """Host entry points that take buffers from outside (a sparse buffer from the wire, a band bit stream) must answer a
+    damaged one with an error or with a well-formed result -- never read or write out of bounds (the process would die)."""
+    lay = pkg.layout_for(pkg.FrameDesc(704, 96, pkg.PIXEL_YUYV))
+    rng = np.random.default_rng(11)
+    words = lay.coded_bytes // 2
+    dense = np.where(rng.random(words) < 0.1, rng.integers(-900, 900, words), 0).astype(np.int16)
+    good = pkg.sparse_compact(lay, dense.view(np.uint8))
+    book = pkg.VlcCodebook.from_arrays(np.arange(40, dtype=np.uint32) | 0x100, np.full(40, 9, np.uint8), np.minimum(np.arange(40), 7).clip(1).astype(np.uint32),
+                                       np.arange(64, dtype=np.uint32), np.full(64, 7, np.uint8))
+    outcomes = {"ok": 0, "error": 0}
+    for trial in range(300):
+        bad = np.zeros(pkg.sparse_max_bytes(lay), np.uint8)        # buffers on the wire have the worst-case size (header)
+        bad[:good.size] = good
+        n = int(rng.integers(1, 6))
+        pos = rng.integers(0, good.size, n) if trial % 3 else rng.integers(0, 32 + 16 * ((words + 8191) // 8192), n)   # often hit header / table
+        bad[pos] = rng.integers(0, 256, n).astype(np.uint8)
+        for call in (lambda: pkg.sparse_expand(lay, bad),
+                     lambda: pkg.sparse_vlc_band(lay, bad, 0, 0, 1, book, 1 << 20),
+                     lambda: pkg.sparse_expand_band(lay, bad, 2, 1, 3),
+                     lambda: pkg.sparse_band_nonzeros(lay, bad, 1, 0, 2)):
+            try:
+                call()
+                outcomes["ok"] += 1
+            except pkg.CfbError:
+                outcomes["error"] += 1
+    assert outcomes["error"] > 50 and outcomes["ok"] > 50           # both kinds of damage occurred
+    # random band streams through the table-driven parser
+    dbook = pkg.VlcDecodebook.from_arrays([0b0, 0b10, 0b110, 0b1110, 0b1111], [1, 2, 3, 4, 4], [1, 0, 0, 1, 2], [1, 3, -3, 40, 0])
+    dec = pkg.VlcDecoder(lay, dbook)
+    for trial in range(200):
+        dec.begin()
+        stream = rng.integers(0, 256, int(rng.integers(1, 400))).astype(np.uint8)
+        try:
+            dec.band(0, 2, 1, stream, int(rng.integers(1, 50)))
+            back = pkg.sparse_expand(lay, dec.end())                # whatever was accepted is a well-formed buffer
+            assert back.size == lay.coded_bytes
+        except pkg.CfbError:
+            pass
+    dec.close()
