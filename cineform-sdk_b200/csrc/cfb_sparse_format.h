@@ -16,7 +16,7 @@ namespace cfb {
 constexpr unsigned kSparseMagic = 0x32534643u;      // 'CFS2'
 constexpr unsigned kSparseHeaderBytes = 32;
 constexpr unsigned kSparseTableEntry = 16;          // {u32 chunk offset, u32 groups, u32 values, u32 escapes}
-constexpr unsigned kSparseBlockWords = 8192;        // int16 words per block (one CTA of 1024 threads x 8 words)
+constexpr unsigned kSparseBlockWords = 8192;        // int16 words per block (one CTA: 256 threads x 4 pieces x 8 words)
 constexpr unsigned kSparseGroupWords = 32;
 constexpr unsigned kSparseBlockGroups = kSparseBlockWords / kSparseGroupWords;      // 256
 constexpr unsigned kSparseL1Bytes = kSparseBlockGroups / 8;                         // 32

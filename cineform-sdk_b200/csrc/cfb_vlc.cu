@@ -24,32 +24,38 @@ using namespace cfb;
 
 namespace {
 
-// the reference's bit buffer, widened: `acc` holds `n` pending bits (n <= 32 between codes).  A word is stored only when
-// a code does not fit any more (n + size > 32), exactly as PutBits does, so the state left behind is the reference's.
+// the reference's bit buffer, widened: the low `n` bits of `acc` are pending (n <= 32 between codes).  A word leaves the
+// buffer only when a code does not fit any more (n + size > 32), exactly as PutBits does, so the state left behind is the
+// reference's.  Whether a word leaves is data dependent and close to a coin flip per code, so put() has no branch on it:
+// the candidate word is stored at `cur` after every code and `cur` advances by 0 or 4.  (Up to 4 bytes behind the
+// returned position are therefore scratch, inside [cur, end).)
 struct Bits {
     uint64_t acc;
     int n;
-    uint8_t *cur, *end;
-    int64_t bytes;
+    uint8_t *cur, *end, *start;
+    int64_t bytes0;
     bool overflow;
     explicit Bits(const cfb_bitwriter &bw) : acc(bw.bits_free >= 32 ? 0 : (bw.buffer & (0xffffffffu >> bw.bits_free))), n(32 - bw.bits_free),
-                                             cur(bw.cur), end(bw.end), bytes(bw.bytes), overflow(false) {}
-    inline void put(uint32_t bits, int size)
+                                             cur(bw.cur), end(bw.end), start(bw.cur), bytes0(bw.bytes), overflow(false) {}
+    // `bits` has no set bit above `size`
+    inline void put_masked(uint32_t bits, int size)
     {
-        acc = (acc << size) | (bits & (0xffffffffu >> (32 - size)));
+        acc = (acc << size) | bits;
         n += size;
-        if (n > 32) {
-            const uint32_t word = (uint32_t)(acc >> (n - 32));
-            if (cur + 4 > end) { overflow = true; n -= 32; return; }
-            const uint32_t be = __builtin_bswap32(word);        // big-endian in the stream (bitstream.c PutLong)
-            memcpy(cur, &be, 4);
-            cur += 4; bytes += 4;
-            n -= 32;
+        if (__builtin_expect(cur + 4 > end, 0)) {
+            if (n > 32) { overflow = true; n -= 32; }
+            return;
         }
+        const uint32_t be = __builtin_bswap32((uint32_t)(acc >> ((n - 32) & 63)));      // big-endian in the stream (bitstream.c PutLong)
+        memcpy(cur, &be, 4);
+        const int full = n > 32;
+        cur += 4 * full;
+        n -= 32 * full;
     }
+    inline void put(uint32_t bits, int size) { put_masked(bits & (0xffffffffu >> (32 - size)), size); }
     void store(cfb_bitwriter *bw) const
     {
-        bw->cur = cur; bw->bytes = bytes;
+        bw->cur = cur; bw->bytes = bytes0 + (cur - start);
         bw->bits_free = 32 - n;
         bw->buffer = n ? (uint32_t)(acc & (0xffffffffull >> (32 - n))) : 0u;
     }
@@ -115,12 +121,13 @@ struct Coder {
     Bits &out;
     const int half;
     const FastPairs &fast;
-    Coder(const cfb_vlc_codebook &book, Bits &o) : b(book), out(o), half(book.value_length >> 1), fast(fast_pairs(book)) {}
+    Coder(const cfb_vlc_codebook &book, Bits &o, const FastPairs &f) : b(book), out(o), half(book.value_length >> 1), fast(f) {}
+    Coder(const cfb_vlc_codebook &book, Bits &o) : Coder(book, o, fast_pairs(book)) {}
     inline void token(uint64_t zeros, int v)
     {
         if (zeros < (uint64_t)kFastRuns && v >= -kFastValues && v <= kFastValues) {
             const uint64_t e = fast.e[zeros][v + kFastValues];
-            if (e) { out.put((uint32_t)e, (int)(e >> 32)); return; }
+            if (e) { out.put_masked((uint32_t)e, (int)(e >> 32)); return; }
         }
         run(zeros);
         value(v);
@@ -170,9 +177,36 @@ cfb_error band_range(const cfb_layout *L, int channel, int level, int band, size
     return CFB_OK;
 }
 
-// Calls f(pos, value) for every non-zero word of the flat range [w0, w1) in raster order.  w0 is a multiple of 32.
+// Positions (word offsets inside the block, ascending) of a chunk's non-zero words -> pos[]; false = the bitmaps do not
+// add up to the table entry's counts.  pos[] has room for a whole block plus one group.
+bool chunk_positions(const SparseChunk &c, uint16_t *pos)
+{
+    const uint64_t *l1w = (const uint64_t *)c.l1;           // chunks are 16-byte aligned
+    unsigned gi = 0, k = 0;
+    for (unsigned q = 0; q < kSparseBlockGroups / 64; q++) {
+        uint64_t bits = l1w[q];
+        while (bits) {
+            const unsigned g = q * 64 + (unsigned)__builtin_ctzll(bits);
+            bits &= bits - 1;
+            if (gi >= c.groups) return false;
+            unsigned m = c.masks[gi++];
+            if (!m) return false;
+            const unsigned wbase = g * kSparseGroupWords;
+            do {
+                pos[k++] = (uint16_t)(wbase + (unsigned)__builtin_ctz(m));
+                m &= m - 1;
+            } while (m);
+        }
+    }
+    return gi == c.groups && k == c.values;
+}
+
+// The non-zero words of the flat range [w0, w1) in raster order, one call per block:
+//   f(base, pos, values, wide, n): word base + pos[i] holds values[i], or the next entry of wide[] if values[i] is -128.
+// Two tight loops per block (bitmaps -> positions here, positions + value bytes -> codes in the caller) instead of one with
+// everything live at once: the single loop kept its counters on the stack and ran at the store-forwarding latency.
 template <class F>
-cfb_error walk(const cfb_layout *L, const void *sparse, size_t w0, size_t w1, F &&f)
+cfb_error walk_blocks(const cfb_layout *L, const void *sparse, size_t w0, size_t w1, F &&f)
 {
     const unsigned nwords = (unsigned)(L->coded_bytes / 2);
     const unsigned *h = (const unsigned *)sparse;
@@ -184,47 +218,37 @@ cfb_error walk(const cfb_layout *L, const void *sparse, size_t w0, size_t w1, F 
         return CFB_ERROR_BADFORMAT;
     }
     const size_t total = h[2];
-    for (size_t b = w0 / kSparseBlockWords; b * kSparseBlockWords < w1; b++) {
+    uint16_t pos[kSparseBlockWords + kSparseGroupWords];
+    for (size_t b = w0 / kSparseBlockWords; b * kSparseBlockWords < w1 && b < nblocks; b++) {
         SparseChunk c;
         if (!sparse_chunk_open(sparse, total, (unsigned)b, &c)) { set_error("sparse block %u out of bounds", (unsigned)b); return CFB_ERROR_BADFORMAT; }
         if (!c.groups) continue;
+        if (!chunk_positions(c, pos)) { set_error("sparse block %u: bitmaps and counts disagree", (unsigned)b); return CFB_ERROR_BADFORMAT; }
         const size_t base = b * kSparseBlockWords;
-        const unsigned g_lo = w0 > base ? (unsigned)((w0 - base) / kSparseGroupWords) : 0u;
-        unsigned gi = 0, vi = 0, ei = 0;
-        if (g_lo) {         // the band starts inside this block: skip the groups, values and escapes before it
-            for (unsigned g = 0; g < g_lo; g++) gi += (c.l1[g >> 3] >> (g & 7)) & 1u;
-            if (gi > c.groups) { set_error("sparse block %u: damaged group bitmap", (unsigned)b); return CFB_ERROR_BADFORMAT; }
-            for (unsigned k = 0; k < gi; k++) vi += (unsigned)__builtin_popcount(c.masks[k]);
-            if (vi > c.values) { set_error("sparse block %u: damaged masks", (unsigned)b); return CFB_ERROR_BADFORMAT; }
-            for (unsigned k = 0; k < vi; k++) ei += (c.bytes[k] == -128);
-        }
-        const uint64_t *l1w = (const uint64_t *)c.l1;       // chunks are 16-byte aligned
-        for (unsigned q = g_lo >> 6; q < 4; q++) {
-            uint64_t bits = l1w[q];
-            if (q == (g_lo >> 6)) bits &= ~0ull << (g_lo & 63);
-            while (bits) {
-                const unsigned g = q * 64 + (unsigned)__builtin_ctzll(bits);
-                bits &= bits - 1;
-                const size_t wbase = base + (size_t)g * kSparseGroupWords;
-                if (wbase >= w1) return CFB_OK;
-                if (gi >= c.groups) { set_error("sparse block %u: more groups than the table says", (unsigned)b); return CFB_ERROR_BADFORMAT; }
-                unsigned m = c.masks[gi++];
-                while (m) {
-                    const size_t pos = wbase + (unsigned)__builtin_ctz(m);
-                    m &= m - 1;
-                    if (vi >= c.values) { set_error("sparse block %u: value overrun", (unsigned)b); return CFB_ERROR_BADFORMAT; }
-                    int v = c.bytes[vi++];
-                    if (v == -128) {
-                        if (ei >= c.escapes) { set_error("sparse block %u: escape overrun", (unsigned)b); return CFB_ERROR_BADFORMAT; }
-                        v = c.wide[ei++];
-                    }
-                    if (pos >= w1) return CFB_OK;
-                    f(pos, v);
-                }
-            }
-        }
+        // the part of the block inside [w0, w1)
+        unsigned i0 = 0, i1 = c.values;
+        if (w0 > base) { const unsigned lo = (unsigned)(w0 - base); while (i0 < i1 && pos[i0] < lo) i0++; }
+        if (w1 < base + kSparseBlockWords) { const unsigned hi = (unsigned)(w1 - base); while (i1 > i0 && pos[i1 - 1] >= hi) i1--; }
+        unsigned ei = 0, ne = 0;
+        for (unsigned k = 0; k < i0; k++) ei += (c.bytes[k] == -128);
+        for (unsigned k = i0; k < i1; k++) ne += (c.bytes[k] == -128);
+        if (ei + ne > c.escapes) { set_error("sparse block %u: escape overrun", (unsigned)b); return CFB_ERROR_BADFORMAT; }
+        if (i1 > i0) f(base, pos + i0, c.bytes + i0, c.wide + ei, i1 - i0);
     }
     return CFB_OK;
+}
+
+// f(pos, value) for every non-zero word of [w0, w1)
+template <class F>
+cfb_error walk(const cfb_layout *L, const void *sparse, size_t w0, size_t w1, F &&f)
+{
+    return walk_blocks(L, sparse, w0, w1, [&](size_t base, const uint16_t *pos, const signed char *vb, const int16_t *wide, unsigned n) {
+        for (unsigned i = 0; i < n; i++) {
+            int v = vb[i];
+            if (__builtin_expect(v == -128, 0)) v = *wide++;
+            f(base + pos[i], v);
+        }
+    });
 }
 
 }  // namespace
@@ -240,13 +264,24 @@ cfb_error cfb_sparse_vlc_band(const cfb_layout *L, const void *sparse, int chann
     if (!book_ok(book)) { set_error("bad code book"); return CFB_ERROR_INVALID_ARGUMENT; }
     if (!writer_ok(bw)) { set_error("bad bit writer"); return CFB_ERROR_INVALID_ARGUMENT; }
     Bits bits(*bw);
-    Coder coder(*book, bits);
+    const FastPairs &fast = fast_pairs(*book);
     size_t next = w0;               // first word not yet accounted for
-    e = walk(L, sparse, w0, w1, [&](size_t pos, int v) {
-        coder.token(pos - next, v);
-        next = pos + 1;
+    e = walk_blocks(L, sparse, w0, w1, [&](size_t base, const uint16_t *pos, const signed char *vb, const int16_t *wide, unsigned n) {
+        Bits local = bits;          // bit buffer and run state in registers for the loop
+        Coder coder(*book, local, fast);
+        size_t nx = next;
+        for (unsigned i = 0; i < n; i++) {
+            int v = vb[i];
+            if (__builtin_expect(v == -128, 0)) v = *wide++;
+            const size_t p = base + pos[i];
+            coder.token(p - nx, v);
+            nx = p + 1;
+        }
+        next = nx;
+        bits = local;
     });
     if (e) return e;
+    Coder coder(*book, bits, fast);
     coder.run(w1 - next);           // pending run, incl. the last row's pitch gap (encoder.c:5671)
     if (bits.overflow) { set_error("bit writer out of space"); return CFB_ERROR_OUTOFMEMORY; }
     bits.store(bw);
