@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libcfhd_b200.so")
 
 PIXEL_YUYV, PIXEL_UYVY, PIXEL_RG48, PIXEL_BYR4, PIXEL_PLANAR16, PIXEL_YU64, PIXEL_V210 = 0, 1, 2, 3, 4, 5, 6
 PIXEL_RG30, PIXEL_AB10, PIXEL_AR10, PIXEL_R210, PIXEL_DPX0 = 7, 8, 9, 10, 11
+PIXEL_B64A = 12     # output only: 16-bit A,R,G,B from an RGB 4:4:4 codec
 RESOLUTION_FULL, RESOLUTION_HALF, RESOLUTION_QUARTER = 1, 2, 3
 MAX_CHANNELS, NUM_LEVELS, NUM_BANDS, MAX_BATCH = 4, 3, 4, 16
 BAND_NAMES = ("LL", "LH", "HL", "HH")

@@ -476,6 +476,7 @@ void cfb_codec_destroy(cfb_codec *cd)
     if (cd->d_gop) cudaFree(cd->d_gop);
     if (cd->d_curve) cudaFree(cd->d_curve);
     if (cd->d_sparse) cudaFree(cd->d_sparse);
+    if (cd->d_out64) cudaFree(cd->d_out64);
     if (cd->d_status) cudaFree(cd->d_status);
     if (cd->h_headers) cudaFreeHost(cd->h_headers);
     delete cd;
@@ -824,6 +825,13 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
         if (frame_pitch < out_w * bpp || (frame_pitch & 15)) { set_error("bad output pitch %d", frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
         for (int c = 0; c < L.num_channels; c++)
             if (L.band[c][0][0].width < 16) { set_error("16-bit packed output needs level-1 bands at least 16 coefficients wide"); return CFB_ERROR_UNSUPPORTED; }
+    } else if (out_format == CFB_PIXEL_B64A) {
+        // 16-bit A,R,G,B of an RGB 4:4:4 sample (decoder.c:26862 -> InvertHorizontalStrip16s.c:13298 ...RGB2B64A)
+        if (!is444 || L.num_channels != 3 || L.precision != 12) { set_error("B64A output needs a three-channel 12-bit 4:4:4 codec"); return CFB_ERROR_BADFORMAT; }
+        if (cd->decode_res != CFB_RESOLUTION_FULL || cd->interlaced) { set_error("B64A output: full-resolution progressive decode only"); return CFB_ERROR_UNSUPPORTED; }
+        if (frame_pitch < out_w * 8 || (frame_pitch & 15)) { set_error("bad output pitch %d", frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
+        for (int c = 0; c < L.num_channels; c++)
+            if (L.band[c][0][0].width < 16) { set_error("B64A output needs level-1 bands at least 16 coefficients wide"); return CFB_ERROR_UNSUPPORTED; }
     } else if (out_format == CFB_PIXEL_PLANAR16) {
         if (frame_pitch < out_w * 2 || (frame_pitch & 15)) { set_error("bad output pitch %d", frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
     } else { set_error("output format %d not implemented", out_format); return CFB_ERROR_UNSUPPORTED; }
@@ -912,7 +920,17 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
         for (int c = 0; c < 3; c++) { p.ch[c].out_off = 0; p.ch[c].out_pitch = frame_pitch; }
         p.shift = L.precision - 8; p.uyvy = (out_format == CFB_PIXEL_UYVY);
         p.th = pick_th((p.ch[0].width + kInvStrip - 1) / kInvStrip, p.ch[0].height, n, ctx->sm_count);
-        if (out_format == CFB_PIXEL_YU64 || out_format == CFB_PIXEL_RG48) {
+        if (out_format == CFB_PIXEL_B64A) {
+            // InvertHorizontalStrip16s.c:13319: the 8-column loop runs up to post_column = width - width % 8 and always leaves the
+            // right border column to the scalar code, which saturates at 65535 instead of the 12-bit maximum
+            p.up_shift = 16 - L.precision;
+            p.hi_simd = ((1 << L.precision) - 1) << p.up_shift;
+            for (int c = 0; c < 3; c++) {
+                const int w = p.ch[c].width;
+                p.tail_col[c] = (w % 8) ? w - w % 8 : w - 1;
+            }
+            CFB_CUDA(launch_inv_444_rg48(p, true, ctx->stream));
+        } else if (out_format == CFB_PIXEL_YU64 || out_format == CFB_PIXEL_RG48) {
             p.up_shift = 16 - L.precision;
             p.hi_simd = ((1 << L.precision) - 1) << p.up_shift;
             for (int c = 0; c < 3; c++) {
@@ -921,7 +939,7 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
                 const int w = p.ch[c].width;
                 p.tail_col[c] = (w - (w % 8) - 16) + 7;
             }
-            if (out_format == CFB_PIXEL_RG48) CFB_CUDA(launch_inv_444_rg48(p, ctx->stream));
+            if (out_format == CFB_PIXEL_RG48) CFB_CUDA(launch_inv_444_rg48(p, false, ctx->stream));
             else CFB_CUDA(launch_inv_422(p, true, ctx->stream));
         } else {
             CFB_CUDA(launch_inv_422(p, false, ctx->stream));
@@ -956,7 +974,7 @@ static cfb_error inv_output_geometry(const cfb_codec *cd, int out_format, int *r
     int out_w = 0, out_h = 0;
     cfb_codec_decoded_size(cd, &out_w, &out_h);
     const int kk = cd->decode_res - 1;          // lowest level that is inverted (0 = all three)
-    const int bpp = (out_format == CFB_PIXEL_YU64) ? 4 : (out_format == CFB_PIXEL_RG48) ? 6 : 2;
+    const int bpp = (out_format == CFB_PIXEL_YU64) ? 4 : (out_format == CFB_PIXEL_RG48) ? 6 : (out_format == CFB_PIXEL_B64A) ? 8 : 2;
     *rowbytes = out_w * bpp; *dpitch = (out_w * bpp + 15) & ~15;
     if ((out_format == CFB_PIXEL_YU64 || out_format == CFB_PIXEL_RG48) && (size_t)*dpitch * out_h > cd->frame_stride) {
         set_error("16-bit packed output does not fit the codec's frame staging"); return CFB_ERROR_UNSUPPORTED;
@@ -968,6 +986,21 @@ static cfb_error inv_output_geometry(const cfb_codec *cd, int out_format, int *r
     } else {
         *rows = out_h;
     }
+    return CFB_OK;
+}
+
+// device frame slot the inverse writes for `out_format` (B64A: its own, wider staging, allocated on first use)
+static cfb_error inv_frame_slot(cfb_codec *cd, int out_format, int dpitch, int rows, int slot, unsigned char **out)
+{
+    if (out_format != CFB_PIXEL_B64A) { *out = (unsigned char *)cfb_codec_device_frame(cd, slot); return CFB_OK; }
+    const size_t stride = ((size_t)dpitch * rows + 255) & ~(size_t)255;
+    if (!cd->d_out64 || cd->out64_stride != stride) {
+        CFB_CUDA(cudaSetDevice(cd->ctx->device));
+        if (cd->d_out64) { CFB_CUDA(stream_wait(cd->ctx)); cudaFree(cd->d_out64); cd->d_out64 = nullptr; }
+        CFB_CUDA(cudaMalloc((void **)&cd->d_out64, stride * cd->max_batch));
+        cd->out64_stride = stride;
+    }
+    *out = cd->d_out64 + stride * slot;
     return CFB_OK;
 }
 
@@ -1012,7 +1045,13 @@ cfb_error stage_inv_compute(cfb_codec *cd, int n, const cfb_quant *quant, int ou
     if (err) return err;
     if (sparse) { err = sparse_expand_device(cd, n); if (err) return err; }
     void *dpy[kMaxBatch], *dfr[kMaxBatch];
-    for (int i = 0; i < n; i++) { dpy[i] = cfb_codec_device_pyramid(cd, i); dfr[i] = cfb_codec_device_frame(cd, i); }
+    for (int i = 0; i < n; i++) {
+        dpy[i] = cfb_codec_device_pyramid(cd, i);
+        unsigned char *slot = nullptr;
+        err = inv_frame_slot(cd, out_format, dpitch, rows, i, &slot);
+        if (err) return err;
+        dfr[i] = slot;
+    }
     return cfb_inverse_device(cd, n, dpy, quant, out_format, dfr, dpitch);
 }
 
@@ -1028,10 +1067,13 @@ cfb_error stage_inv_download(cfb_codec *cd, int n, void *const *h_frames, int fr
     CFB_CUDA(cudaSetDevice(ctx->device));
     for (int i = 0; i < n; i++) {
         if (!h_frames[i]) { set_error("null host buffer %d", i); return CFB_ERROR_INVALID_ARGUMENT; }
+        unsigned char *slot = nullptr;
+        err = inv_frame_slot(cd, out_format, dpitch, rows, i, &slot);
+        if (err) return err;
         if (frame_pitch == rowbytes && dpitch == rowbytes)
-            CFB_CUDA(cudaMemcpyAsync(h_frames[i], cfb_codec_device_frame(cd, i), (size_t)rowbytes * rows, cudaMemcpyDeviceToHost, s));
+            CFB_CUDA(cudaMemcpyAsync(h_frames[i], slot, (size_t)rowbytes * rows, cudaMemcpyDeviceToHost, s));
         else
-            CFB_CUDA(cudaMemcpy2DAsync(h_frames[i], frame_pitch, cfb_codec_device_frame(cd, i), dpitch, rowbytes, rows, cudaMemcpyDeviceToHost, s));
+            CFB_CUDA(cudaMemcpy2DAsync(h_frames[i], frame_pitch, slot, dpitch, rowbytes, rows, cudaMemcpyDeviceToHost, s));
         ctx->d2h_bytes += (uint64_t)rowbytes * rows;
     }
     return CFB_OK;

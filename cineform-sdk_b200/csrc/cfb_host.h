@@ -32,7 +32,7 @@ cudaError_t launch_fwd_byr4(const FwdParams &p, cudaStream_t stream);
 cudaError_t launch_fwd_rgb30(const FwdParams &p, cudaStream_t stream);
 cudaError_t launch_inv_plane(const InvParams &p, int descale, cudaStream_t stream);
 cudaError_t launch_inv_422(const InvParams &p, bool out16, cudaStream_t stream);
-cudaError_t launch_inv_444_rg48(const InvParams &p, cudaStream_t stream);
+cudaError_t launch_inv_444_rg48(const InvParams &p, bool b64a, cudaStream_t stream);
 cudaError_t launch_lowpass_422(const InvParams &p, cudaStream_t stream);
 cudaError_t launch_inv_fields(const InvParams &p, const FieldsAux &a, bool planar, cudaStream_t stream);
 cudaError_t launch_fwd_422_fields(const FwdParams &p, cudaStream_t stream);
@@ -99,5 +99,8 @@ struct cfb_codec {
     unsigned long long *d_status = nullptr; // max_batch * (nblocks + 1): look-back state of the one-pass packer
     unsigned *h_headers = nullptr;          // pinned, 4 u32 per slot
     size_t sparse_stride = 0;
+    // B64A output (8 bytes per pixel) does not fit the frame staging of a 6-byte-per-pixel source: own staging, allocated on first use
+    unsigned char *d_out64 = nullptr;
+    size_t out64_stride = 0;
     unsigned value_guess = 0;               // running estimate of a frame's sparse size in bytes (speculative single-pass D2H)
 };

@@ -517,7 +517,12 @@ __global__ void __launch_bounds__(128, MINB) k_inv_422(const __grid_constant__ I
 // per channel (horizontal stage InvertHorizontalStrip16s.c:16571 ...ToRow16u: max(t >> 1, 0) << (16 - precision), limited
 // as InvParams::hi_simd / tail_col describe), then ConvertPlanarRGB16uToPackedRGB48 (plane 1 -> R, 0 -> G, 2 -> B).
 // One warp reconstructs all three channels of its strip, so every lane owns 8 whole pixels = 48 contiguous bytes.
-template <bool SMALLDQ>
+// B64A = true: 16-bit A,R,G,B words instead (64 contiguous bytes per lane), decoder.c:26862 ->
+// InvertHorizontalStrip16s.c:13298 InvertHorizontalStrip16sRGB2B64A: alpha is the constant 0xfff << 4 (:13385 a_epi16); colour
+// samples are limited to the 12-bit maximum where its SSE2 loop runs (:13387 limiterRGB) and to 65535 in its scalar tail and
+// right border column (InvParams::tail_col, here the same for the three channels); native (little-endian) words as the
+// reference's decoder leaves them.
+template <bool SMALLDQ, bool B64A>
 __global__ void __launch_bounds__(128) k_inv_444_rg48(const __grid_constant__ InvParams p)
 {
     const int lane = threadIdx.x;
@@ -536,28 +541,43 @@ __global__ void __launch_bounds__(128) k_inv_444_rg48(const __grid_constant__ In
     const bool has_border = (strip == 0) || ((strip + 1) * kInvStrip + 4 >= gg.width);
     const unsigned cb = (unsigned)(col0 * 2);
     const unsigned char *in = p.in_base[f];
-    unsigned char *out = p.out_base[f] + gg.out_off + (long long)col0 * 12;        // 2 pixels per band column, 6 bytes per pixel
+    unsigned char *out = p.out_base[f] + gg.out_off + (long long)col0 * (B64A ? 16 : 12);      // 2 pixels per band column, 6 (8) bytes per pixel
     const int us = p.up_shift;
 
     auto emit = [&](int r, const int *ge, const int *go, const int *re, const int *ro, const int *be, const int *bo) {
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {
             const int *G = rr ? go : ge, *R = rr ? ro : re, *B = rr ? bo : be;
-            unsigned short v[24];
+            if constexpr (B64A) {
+                unsigned char *q = out + (long long)(2 * r + rr) * gg.out_pitch;
+                const unsigned alpha = (unsigned)p.hi_simd;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int bc = col0 + (i >> 1);
-                v[3 * i + 0] = (unsigned short)row16u(R[i], us, bc >= p.tail_col[1] ? 65535 : p.hi_simd);
-                v[3 * i + 1] = (unsigned short)row16u(G[i], us, bc >= p.tail_col[0] ? 65535 : p.hi_simd);
-                v[3 * i + 2] = (unsigned short)row16u(B[i], us, bc >= p.tail_col[2] ? 65535 : p.hi_simd);
+                for (int i = 0; i < 8; i += 2) {        // pixels i and i + 1 belong to band column col0 + i / 2
+                    const int hi = (col0 + (i >> 1) >= p.tail_col[0]) ? 65535 : p.hi_simd;
+                    uint4 w;
+                    w.x = alpha | (row16u(R[i], us, hi) << 16);
+                    w.y = row16u(G[i], us, hi) | (row16u(B[i], us, hi) << 16);
+                    w.z = alpha | (row16u(R[i + 1], us, hi) << 16);
+                    w.w = row16u(G[i + 1], us, hi) | (row16u(B[i + 1], us, hi) << 16);
+                    *reinterpret_cast<uint4 *>(q + 8 * i) = w;
+                }
+            } else {
+                unsigned short v[24];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int bc = col0 + (i >> 1);
+                    v[3 * i + 0] = (unsigned short)row16u(R[i], us, bc >= p.tail_col[1] ? 65535 : p.hi_simd);
+                    v[3 * i + 1] = (unsigned short)row16u(G[i], us, bc >= p.tail_col[0] ? 65535 : p.hi_simd);
+                    v[3 * i + 2] = (unsigned short)row16u(B[i], us, bc >= p.tail_col[2] ? 65535 : p.hi_simd);
+                }
+                unsigned w[12];
+#pragma unroll
+                for (int i = 0; i < 12; i++) w[i] = (unsigned)v[2 * i] | ((unsigned)v[2 * i + 1] << 16);
+                unsigned char *q = out + (long long)(2 * r + rr) * gg.out_pitch;
+                *reinterpret_cast<uint4 *>(q) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4 *>(q + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+                *reinterpret_cast<uint4 *>(q + 32) = make_uint4(w[8], w[9], w[10], w[11]);
             }
-            unsigned w[12];
-#pragma unroll
-            for (int i = 0; i < 12; i++) w[i] = (unsigned)v[2 * i] | ((unsigned)v[2 * i + 1] << 16);
-            unsigned char *q = out + (long long)(2 * r + rr) * gg.out_pitch;
-            *reinterpret_cast<uint4 *>(q) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4 *>(q + 16) = make_uint4(w[4], w[5], w[6], w[7]);
-            *reinterpret_cast<uint4 *>(q + 32) = make_uint4(w[8], w[9], w[10], w[11]);
         }
     };
 
@@ -889,13 +909,14 @@ cudaError_t launch_inv_422(const InvParams &p, bool out16, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-cudaError_t launch_inv_444_rg48(const InvParams &p, cudaStream_t stream)
+cudaError_t launch_inv_444_rg48(const InvParams &p, bool b64a, cudaStream_t stream)
 {
     dim3 block(32, 4);
     dim3 grid(ceil_div_i(p.ch[0].width, kInvStrip), ceil_div_i(ceil_div_i(p.ch[0].height, p.th), (int)block.y) + 1, p.nframes);
     bool small = true;
     for (int c = 0; c < 3; c++) for (int b = 1; b < 4; b++) small = small && (p.ch[c].dq[b] >= 0 && p.ch[c].dq[b] <= 255);
-    if (small) k_inv_444_rg48<true><<<grid, block, 0, stream>>>(p); else k_inv_444_rg48<false><<<grid, block, 0, stream>>>(p);
+    if (b64a) { if (small) k_inv_444_rg48<true, true><<<grid, block, 0, stream>>>(p); else k_inv_444_rg48<false, true><<<grid, block, 0, stream>>>(p); }
+    else { if (small) k_inv_444_rg48<true, false><<<grid, block, 0, stream>>>(p); else k_inv_444_rg48<false, false><<<grid, block, 0, stream>>>(p); }
     return cudaGetLastError();
 }
 

@@ -76,7 +76,11 @@ typedef enum cfb_pixel_format {
     CFB_PIXEL_AB10 = 8,     /* same layout (A2B10G10R10)                                                   */
     CFB_PIXEL_AR10 = 9,     /* B bits 0-9, G 10-19, R 20-29 (A2R10G10B10)                                   */
     CFB_PIXEL_R210 = 10,    /* big-endian word: R 20-29, G 10-19, B 0-9 after the byte swap               */
-    CFB_PIXEL_DPX0 = 11     /* big-endian word: R 22-31, G 12-21, B 2-11 after the byte swap              */
+    CFB_PIXEL_DPX0 = 11,    /* big-endian word: R 22-31, G 12-21, B 2-11 after the byte swap              */
+    CFB_PIXEL_B64A = 12     /* OUTPUT only: 16-bit A,R,G,B words of an RGB 4:4:4 sample (DECODED_FORMAT_B64A at the codec level,
+                             * Codec/decoder.c:26862 -> InvertHorizontalStrip16s.c:13298): alpha = 0xfff0, colours limited to
+                             * 0xfff0 in the columns of the reference's SSE2 loop and to 65535 in its scalar tail / right
+                             * border, native word order as the reference's decoder writes them */
 } cfb_pixel_format;
 
 enum { CFB_MAX_CHANNELS = 4, CFB_NUM_LEVELS = 3, CFB_NUM_BANDS = 4 };
@@ -227,7 +231,9 @@ CFB_API cfb_error cfb_forward_host(cfb_codec *codec, int n, const void *const *h
 /* ---- inverse: quantised pyramids -> packed frames -------------------------- */
 /* The coded region holds QUANTISED values (as entropy-decoded with quant 1); dequantisation by
  * quant->divisor is fused into the kernels' loads. out_format: CFB_PIXEL_YUYV/UYVY (8-bit, see
- * DESIGN.md for the rounding rule), CFB_PIXEL_PLANAR16 (int16 planes at codec precision). */
+ * DESIGN.md for the rounding rule), CFB_PIXEL_PLANAR16 (int16 planes at codec precision), and the 16-bit packed
+ * outputs of the reference's final level, all bit-exact (no dither): CFB_PIXEL_YU64 from 4:2:2 codecs, CFB_PIXEL_RG48
+ * and CFB_PIXEL_B64A from RGB 4:4:4 codecs (full resolution, progressive). */
 CFB_API cfb_error cfb_inverse_device(cfb_codec *codec, int n, void *const *d_pyramids, const cfb_quant *quant,
                                      int out_format, void *const *d_frames, int frame_pitch);
 CFB_API cfb_error cfb_inverse_host(cfb_codec *codec, int n, const void *const *h_coded, const cfb_quant *quant,

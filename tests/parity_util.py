@@ -444,6 +444,28 @@ def pack_rg48(planes, precision=12):
     return out
 
 
+def b64a_tail_col(band_width):
+    """First band column produced by the scalar code of Codec/InvertHorizontalStrip16s.c:13298 InvertHorizontalStrip16sRGB2B64A:
+    its 8-column SSE2 loop runs up to post_column = width - width % 8 (:13319) and always leaves the right border column."""
+    return band_width - band_width % 8 if band_width % 8 else band_width - 1
+
+
+def pack_b64a(planes, precision=12):
+    """[G, R, B] int16 planes -> 16-bit A R G B words (height x 4*width uint16) as the reference's decoder writes them for
+    DECODED_FORMAT_B64A (Codec/decoder.c:26862 -> InvertHorizontalStrip16s.c:13298 InvertHorizontalStrip16sRGB2B64A): alpha is
+    0xfff << 4 (:13385); colour samples are limited to the 12-bit maximum where its SSE2 loop runs (:13387 limiterRGB) and to
+    65535 in the scalar tail and at the right border (SATURATE_16U)."""
+    s = 16 - precision
+    top = ((1 << precision) - 1) << s
+    h, w = planes[0].shape
+    hi = np.full(w, top, np.int64)
+    hi[2 * b64a_tail_col(w // 2):] = 65535
+    g, r, b = [np.minimum(np.maximum(p.astype(np.int64), 0) << s, hi[None, :]).astype(np.uint16) for p in planes]
+    out = np.full((h, 4 * w), top, np.uint16)
+    out[:, 1::4], out[:, 2::4], out[:, 3::4] = r, g, b
+    return out
+
+
 def ref_decode_sample_raw(ref_lib, sample, width, height, decoded_format, num_channels, pitch):
     """Codec-level reference decode into an arbitrary DECODED_FORMAT_*; returns (bytes (height x pitch), dequantised bands).
 

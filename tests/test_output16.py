@@ -11,7 +11,7 @@ import oracle_lib as ol
 import parity_util as pu
 
 needs_ref = pytest.mark.skipif(not ol.ref_available(), reason="oracle/_ref not built (reference absent)")
-DECODED_FORMAT_YU64, DECODED_FORMAT_RG48 = 12, 120
+DECODED_FORMAT_YU64, DECODED_FORMAT_RG48, DECODED_FORMAT_B64A = 12, 120, 30
 
 
 @pytest.fixture(scope="module")
@@ -63,6 +63,26 @@ def test_oracle_rg48_matches_reference_decoder(size, kind):
     want = pu.pack_rg48(planes)
     got = out.view(np.uint16).reshape(h, 3 * w)
     assert np.array_equal(got, want), np.argwhere(got != want)[:5].tolist()
+
+
+@needs_ref
+@pytest.mark.parametrize("size", [(640, 96), (328, 48), (256, 64), (200, 48), (1016, 64), (720, 480)])
+@pytest.mark.parametrize("kind", ["qbist", "extreme"])
+def test_oracle_b64a_matches_reference_decoder(size, kind):
+    """B64A from an RGB 4:4:4 sample: the same reconstructed planes as RG48, a constant alpha and one limit for all columns."""
+    w, h = size
+    if kind == "extreme" and w * h > 100000:
+        pytest.skip("0/65535 noise at this size does not fit the probe's sample buffer")
+    ref_lib, orc = ol.load_ref(), ol.oracle()
+    sample, prescale = _sample_444(ref_lib, w, h, kind)
+    out, bands = pu.ref_decode_sample_raw(ref_lib, sample, w, h, DECODED_FORMAT_B64A, 3, w * 8)
+    planes = pu.inverse_pyramid(orc, bands, pu.UNIT_DIVISORS, tuple(prescale))
+    want = pu.pack_b64a(planes)
+    got = out.view(np.uint16).reshape(h, 4 * w)
+    assert np.array_equal(got, want), np.argwhere(got != want)[:5].tolist()
+    if kind == "extreme":       # both saturation rules occur: the SSE2 loop's 12-bit limit and the scalar code's 65535
+        assert (got[:, 1::4] == 0xFFF0).any() and (got[:, 1::4] == 65535).any()
+        assert not (got[:, :8 * pu.b64a_tail_col(w // 2)] == 65535).any()
 
 
 @pytest.mark.gpu
