@@ -59,7 +59,22 @@ inline bool sparse_chunk_open(const void *sparse, size_t total, unsigned block, 
     return true;
 }
 
-// ---- host side: compaction of one block (shared by cfb_sparse_compact*, the sparse writer) ----
+// ---- host side: the one place that lays a chunk out (shared by the compaction below and the sparse writer) ----
+// pieces of one block -> `chunk`; returns its size (0 for an empty block, nothing written)
+inline unsigned sparse_emit_chunk(unsigned char *chunk, const unsigned char *l1, const unsigned *masks, unsigned G,
+                                  const signed char *vb, unsigned V, const int16_t *wide, unsigned E)
+{
+    const unsigned cb = sparse_chunk_bytes(G, V, E);
+    if (!G) return 0;
+    memset(chunk, 0, cb);
+    memcpy(chunk, l1, kSparseL1Bytes);
+    memcpy(chunk + kSparseL1Bytes, masks, 4 * (size_t)G);
+    memcpy(chunk + kSparseL1Bytes + 4 * (size_t)G, vb, V);
+    memcpy(chunk + kSparseL1Bytes + 4 * (size_t)G + ((V + 3) & ~3u), wide, 2 * (size_t)E);
+    return cb;
+}
+
+// ---- host side: compaction of one dense block (cfb_sparse_compact*) ----
 // One block of 8192 words -> its chunk at `chunk`; returns the chunk size and the table entry's counts
 inline unsigned sparse_compact_block(const int16_t *in, unsigned nvalid, unsigned char *chunk, unsigned *G_out, unsigned *V_out, unsigned *E_out)
 {
@@ -86,16 +101,8 @@ inline unsigned sparse_compact_block(const int16_t *in, unsigned nvalid, unsigne
         }
         if (m) { l1[g >> 3] |= (unsigned char)(1u << (g & 7)); masks[G++] = m; }
     }
-    const unsigned cb = sparse_chunk_bytes(G, V, E);
-    if (G) {
-        memset(chunk, 0, cb);
-        memcpy(chunk, l1, kSparseL1Bytes);
-        memcpy(chunk + kSparseL1Bytes, masks, 4 * (size_t)G);
-        memcpy(chunk + kSparseL1Bytes + 4 * (size_t)G, vb, V);
-        memcpy(chunk + kSparseL1Bytes + 4 * (size_t)G + ((V + 3) & ~3u), wide, 2 * (size_t)E);
-    }
     *G_out = G; *V_out = V; *E_out = E;
-    return cb;
+    return sparse_emit_chunk(chunk, l1, masks, G, vb, V, wide, E);
 }
 
 

@@ -350,28 +350,42 @@ struct cfb_sparse_writer {
     size_t pos = 0;                 // next word of the flat coded region
     size_t band_end = 0;            // end of the band being written
     unsigned cur_block = 0;
-    bool dirty = false;             // scratch holds a non-zero word
     bool open = false;
-    alignas(64) int16_t scratch[kSparseBlockWords];
+    // the block being written, as the pieces of its chunk: tokens arrive in raster order, so every piece only grows
+    // (round 2's first version kept a dense 16 KB scratch block and compacted it: a memset and a scan per block)
+    int cur_group = -1;             // group of the mask being built, -1 = none
+    unsigned cur_mask = 0;
+    unsigned G = 0, V = 0, E = 0;
+    unsigned char l1[kSparseL1Bytes];
+    unsigned masks[kSparseBlockGroups];
+    signed char vb[kSparseBlockWords];
+    int16_t wide[kSparseBlockWords];
 };
 
 namespace {
 
-// close every block before `block`: the current one from the scratch, the ones in between are empty
+inline void writer_close_group(cfb_sparse_writer *w)
+{
+    if (w->cur_group < 0) return;
+    w->l1[w->cur_group >> 3] |= (unsigned char)(1u << (w->cur_group & 7));
+    w->masks[w->G++] = w->cur_mask;
+    w->cur_group = -1;
+}
+
+// close every block before `block`: the current one from its pieces, the ones in between are empty
 cfb_error writer_flush_until(cfb_sparse_writer *w, unsigned block)
 {
     unsigned *tab = (unsigned *)(w->out + kSparseHeaderBytes);
     while (w->cur_block < block && w->cur_block < w->nblocks) {
         const unsigned b = w->cur_block;
-        unsigned G = 0, V = 0, E = 0, cb = 0;
-        if (w->dirty) {
+        unsigned cb = 0;
+        writer_close_group(w);
+        if (w->G) {
             if (w->off + kSparseMaxChunk > w->capacity) { set_error("sparse writer: output buffer too small"); return CFB_ERROR_OUTOFMEMORY; }
-            const unsigned nvalid = w->nwords - b * kSparseBlockWords < kSparseBlockWords ? w->nwords - b * kSparseBlockWords : kSparseBlockWords;
-            cb = sparse_compact_block(w->scratch, nvalid, w->out + w->off, &G, &V, &E);
-            memset(w->scratch, 0, sizeof(w->scratch));
-            w->dirty = false;
+            cb = sparse_emit_chunk(w->out + w->off, w->l1, w->masks, w->G, w->vb, w->V, w->wide, w->E);
         }
-        tab[4 * b] = (unsigned)w->off; tab[4 * b + 1] = G; tab[4 * b + 2] = V; tab[4 * b + 3] = E;
+        tab[4 * b] = (unsigned)w->off; tab[4 * b + 1] = w->G; tab[4 * b + 2] = w->V; tab[4 * b + 3] = w->E;
+        if (w->G) { memset(w->l1, 0, sizeof(w->l1)); w->G = w->V = w->E = 0; }
         w->off += cb;
         w->cur_block++;
     }
@@ -380,10 +394,24 @@ cfb_error writer_flush_until(cfb_sparse_writer *w, unsigned block)
 
 inline cfb_error writer_advance(cfb_sparse_writer *w, size_t n)
 {
-    if (w->pos + n > w->band_end) { set_error("sparse writer: tokens run past the end of the band"); return CFB_ERROR_BADFORMAT; }
+    if (__builtin_expect(w->pos + n > w->band_end, 0)) { set_error("sparse writer: tokens run past the end of the band"); return CFB_ERROR_BADFORMAT; }
     w->pos += n;
     const unsigned blk = (unsigned)(w->pos / kSparseBlockWords);
-    return blk > w->cur_block ? writer_flush_until(w, blk) : CFB_OK;
+    return __builtin_expect(blk > w->cur_block, 0) ? writer_flush_until(w, blk) : CFB_OK;
+}
+
+inline cfb_error writer_value(cfb_sparse_writer *w, int value)
+{
+    if (__builtin_expect(w->pos >= w->band_end, 0)) { set_error("sparse writer: tokens run past the end of the band"); return CFB_ERROR_BADFORMAT; }
+    const int v = (int16_t)value;
+    if (v) {
+        const unsigned o = (unsigned)(w->pos % kSparseBlockWords);
+        const int g = (int)(o / kSparseGroupWords);
+        if (g != w->cur_group) { writer_close_group(w); w->cur_group = g; w->cur_mask = 0; }
+        w->cur_mask |= 1u << (o % kSparseGroupWords);
+        if (v < -127 || v > 127) { w->vb[w->V++] = -128; w->wide[w->E++] = (int16_t)v; } else w->vb[w->V++] = (signed char)v;
+    }
+    return writer_advance(w, 1);
 }
 
 }  // namespace
@@ -409,8 +437,9 @@ cfb_error cfb_sparse_writer_begin(cfb_sparse_writer *w, void *sparse, size_t cap
     if (capacity < chunks) { set_error("sparse writer: output buffer too small"); return CFB_ERROR_OUTOFMEMORY; }
     w->out = (unsigned char *)sparse; w->capacity = capacity; w->off = chunks;
     memset(w->out, 0, chunks);
-    memset(w->scratch, 0, sizeof(w->scratch));
-    w->pos = 0; w->band_end = 0; w->cur_block = 0; w->dirty = false; w->open = true;
+    memset(w->l1, 0, sizeof(w->l1));
+    w->G = w->V = w->E = 0; w->cur_group = -1; w->cur_mask = 0;
+    w->pos = 0; w->band_end = 0; w->cur_block = 0; w->open = true;
     return CFB_OK;
 }
 
@@ -429,13 +458,7 @@ cfb_error cfb_sparse_writer_band(cfb_sparse_writer *w, int channel, int level, i
 
 cfb_error cfb_sparse_writer_run(cfb_sparse_writer *w, uint32_t zeros) { return writer_advance(w, zeros); }
 
-cfb_error cfb_sparse_writer_value(cfb_sparse_writer *w, int value)
-{
-    if (w->pos >= w->band_end) { set_error("sparse writer: tokens run past the end of the band"); return CFB_ERROR_BADFORMAT; }
-    const int16_t v = (int16_t)value;
-    if (v) { w->scratch[w->pos % kSparseBlockWords] = v; w->dirty = true; }
-    return writer_advance(w, 1);
-}
+cfb_error cfb_sparse_writer_value(cfb_sparse_writer *w, int value) { return writer_value(w, value); }
 
 cfb_error cfb_sparse_writer_dense_band(cfb_sparse_writer *w, int channel, int level, int band, const int16_t *rows, int pitch_bytes)
 {
@@ -445,7 +468,7 @@ cfb_error cfb_sparse_writer_dense_band(cfb_sparse_writer *w, int channel, int le
     if (!rows || pitch_bytes < 2 * bl.width) { set_error("bad band rows"); return CFB_ERROR_INVALID_ARGUMENT; }
     for (int r = 0; r < bl.height && !e; r++) {
         const int16_t *row = (const int16_t *)((const unsigned char *)rows + (size_t)r * pitch_bytes);
-        for (int x = 0; x < bl.width && !e; x++) e = cfb_sparse_writer_value(w, row[x]);
+        for (int x = 0; x < bl.width && !e; x++) e = writer_value(w, row[x]);
         if (!e) e = writer_advance(w, (size_t)(bl.pitch / 2 - bl.width));
     }
     return e;
@@ -466,10 +489,13 @@ cfb_error cfb_sparse_writer_end(cfb_sparse_writer *w, size_t *bytes)
 
 // ---- table-driven band parser -----------------------------------------------------------------------------------
 struct cfb_vlc_decoder {
-    static constexpr int kPrimaryBits = 11;
+    static constexpr int kPrimaryBits = 12;
     struct Token { uint8_t kind; int32_t arg; };
     struct Node { int32_t child[2]; int32_t token; };          // token >= 0: leaf (index into tokens)
-    struct Fast { uint8_t len; int32_t token; int32_t node; };  // len 0: not resolved inside the primary window -> continue at `node`
+    // One look-up of the next kPrimaryBits bits decodes as many whole code words as fit: zero runs add up, a coefficient ends
+    // the entry, the end-of-band code is only ever an entry of its own.  len 0: no code word ends inside the window ->
+    // continue in the trie at `node` (node < 0: no code word starts with these bits).
+    struct Fast { uint8_t len; uint8_t has_value; uint8_t end; uint32_t zeros; int32_t value; int32_t node; };
     std::vector<Token> tokens;
     std::vector<Node> nodes;
     std::vector<Fast> fast;
@@ -503,10 +529,27 @@ cfb_error cfb_vlc_decoder_create(const cfb_vlc_decodebook *book, cfb_vlc_decoder
     const int P = cfb_vlc_decoder::kPrimaryBits;
     d->fast.resize((size_t)1 << P);
     for (unsigned p = 0; p < (1u << P); p++) {
-        int node = 0, len = 0;
-        while (len < P && node >= 0 && d->nodes[node].token < 0) { node = d->nodes[node].child[(p >> (P - 1 - len)) & 1]; len++; }
-        if (node >= 0 && d->nodes[node].token >= 0) d->fast[p] = {(uint8_t)len, d->nodes[node].token, -1};
-        else d->fast[p] = {0, -1, node};          // node < 0: no code starts with these bits
+        cfb_vlc_decoder::Fast f = {0, 0, 0, 0u, 0, -1};
+        int pos = 0;
+        for (;;) {
+            int node = 0, len = pos;
+            while (len < P && node >= 0 && d->nodes[node].token < 0) { node = d->nodes[node].child[(p >> (P - 1 - len)) & 1]; len++; }
+            if (node < 0 || d->nodes[node].token < 0) {         // no (whole) code word from `pos` inside the window
+                if (pos == 0) f.node = node;
+                break;
+            }
+            const cfb_vlc_decoder::Token &t = d->tokens[d->nodes[node].token];
+            if (t.kind == 2) { if (pos == 0) { f.end = 1; pos = len; } break; }
+            if (t.kind == 1) {
+                if ((uint64_t)f.zeros + (uint32_t)t.arg > 0x7fffffffu) break;
+                f.zeros += (uint32_t)t.arg; pos = len;
+                continue;
+            }
+            f.has_value = 1; f.value = t.arg; pos = len;
+            break;
+        }
+        f.len = (uint8_t)pos;
+        d->fast[p] = f;
     }
     *out = d;
     return CFB_OK;
@@ -524,25 +567,36 @@ cfb_error cfb_vlc_decode_band(const cfb_vlc_decoder *d, cfb_sparse_writer *w, in
     uint64_t acc = 0;           // the next `have` bits of the stream, left-aligned at bit 63
     int have = 0;
     size_t rd = 0, bitpos = 0;  // bytes fetched, bits consumed
-    auto fill = [&]() { while (have <= 56 && rd < stream_bytes) { acc |= (uint64_t)stream[rd++] << (56 - have); have += 8; } };
+    auto fill = [&]() {
+        if (have <= 32 && rd + 4 <= stream_bytes) {         // one big-endian word at a time while the stream lasts
+            uint32_t be;
+            memcpy(&be, stream + rd, 4);
+            acc |= (uint64_t)__builtin_bswap32(be) << (32 - have);
+            have += 32; rd += 4;
+        }
+        while (have <= 56 && rd < stream_bytes && rd + 4 > stream_bytes) { acc |= (uint64_t)stream[rd++] << (56 - have); have += 8; }
+    };
     for (;;) {
         fill();
         if (have <= 0) { set_error("band stream ends without an end-of-band code"); return CFB_ERROR_BADFORMAT; }
         const cfb_vlc_decoder::Fast &f = d->fast[(size_t)(acc >> (64 - P))];
-        int token, len;
-        if (f.len) { token = f.token; len = f.len; }
-        else {
-            int node = f.node;
-            len = P;
-            while (node >= 0 && d->nodes[node].token < 0 && len < 32) { node = d->nodes[node].child[(acc >> (63 - len)) & 1]; len++; }
-            if (node < 0 || d->nodes[node].token < 0) { set_error("band stream: no code word matches at bit %zu", bitpos); return CFB_ERROR_BADFORMAT; }
-            token = d->nodes[node].token;
+        if (__builtin_expect(f.len != 0, 1)) {
+            if (f.len > have) { set_error("band stream truncated inside a code word"); return CFB_ERROR_BADFORMAT; }
+            acc <<= f.len; have -= f.len; bitpos += (size_t)f.len;
+            if (f.end) break;
+            if (f.zeros) { e = writer_advance(w, f.zeros); if (e) return e; }
+            if (f.has_value) { e = writer_value(w, (int)(int16_t)(f.value * quant)); if (e) return e; }
+            continue;
         }
+        // a code word longer than the window: finish it in the trie
+        int node = f.node, len = P;
+        while (node >= 0 && d->nodes[node].token < 0 && len < 32) { node = d->nodes[node].child[(acc >> (63 - len)) & 1]; len++; }
+        if (node < 0 || d->nodes[node].token < 0) { set_error("band stream: no code word matches at bit %zu", bitpos); return CFB_ERROR_BADFORMAT; }
         if (len > have) { set_error("band stream truncated inside a code word"); return CFB_ERROR_BADFORMAT; }
         acc <<= len; have -= len; bitpos += (size_t)len;
-        const cfb_vlc_decoder::Token &t = d->tokens[token];
+        const cfb_vlc_decoder::Token &t = d->tokens[d->nodes[node].token];
         if (t.kind == 2) break;
-        e = (t.kind == 1) ? cfb_sparse_writer_run(w, (uint32_t)t.arg) : cfb_sparse_writer_value(w, (int)(int16_t)(t.arg * quant));
+        e = (t.kind == 1) ? writer_advance(w, (uint32_t)t.arg) : writer_value(w, (int)(int16_t)(t.arg * quant));
         if (e) return e;
     }
     if (consumed) *consumed = (bitpos + 7) / 8;

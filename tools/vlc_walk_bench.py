@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import oracle_lib as ol      # noqa: E402
 import parity_util as pu     # noqa: E402
-from test_vlc import all_bands, ref_encode_band, ref_tables     # noqa: E402
+from test_vlc import all_bands, decode_book, ref_decode_band, ref_encode_band, ref_encode_band_finished, ref_tables     # noqa: E402
 
 
 def main():
@@ -98,6 +98,30 @@ def main():
     print(f"  cfb_sparse_vlc_band    {t_sparse:7.2f} ms per frame ({t_sparse * 1e6 / nz:5.2f} ns per coefficient); walk only {t_count:.2f} ms")
     print(f"  cfb_dense_vlc_band     {t_dense:7.2f} ms")
     print(f"  reference coder        {t_ref:7.2f} ms (EncodeQuantLongRuns band by band through the probe)")
+
+    # decoder side: the band streams (with end-of-band code) parsed straight into the sparse format vs the reference's FSM
+    # decoder writing dense bands
+    streams = [(c, k, b, bl, ref_encode_band_finished(ref, p, bl.width, a.codebook)) for c, k, b, bl, p in views if b != 0]
+    ll = [(c, k, b, bl, p) for c, k, b, bl, p in views if b == 0]
+    dec = pkg.VlcDecoder(lay, decode_book(pkg, ref, a.codebook))
+
+    def run_decode():
+        dec.begin()
+        it = iter(streams)
+        for c in range(lay.num_channels):
+            for item in ll:
+                if item[0] == c:
+                    dec.dense_band(item[0], item[1], item[2], item[4][:, :item[3].width])
+            for _ in range(9):
+                cc, k, b, bl, st = next(it)
+                dec.band(cc, k, b, st, 1)
+        return dec.end().size
+
+    t_dec, nsp = best(run_decode)
+    t_fsm, _ = best(lambda: sum(ref_decode_band(ref, st, bl.width, bl.height, bl.pitch, a.codebook, 1).size for _, _, _, bl, st in streams))
+    print(f"  cfb_vlc_decode_band    {t_dec:7.2f} ms per frame, band streams -> sparse buffer ({nsp} bytes)")
+    print(f"  reference FSM decoder  {t_fsm:7.2f} ms (DecodeBandFSM16sNoGap band by band through the probe, dense bands)")
+    dec.close()
 
 
 if __name__ == "__main__":
