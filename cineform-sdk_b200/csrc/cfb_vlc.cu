@@ -76,7 +76,9 @@ uint64_t book_key(const cfb_vlc_codebook &b)
     uint64_t h = 1469598103934665603ull ^ (uint64_t)b.run_length ^ ((uint64_t)b.value_length << 32);
     auto mix = [&](uint64_t x) { h ^= x; h *= 1099511628211ull; h ^= h >> 31; };
     for (int i = 1; i < kFastRuns && i < b.run_length; i++) mix(((uint64_t)b.run_bits[i] << 24) ^ ((uint64_t)b.run_size[i] << 16) ^ b.run_count[i]);
+    const int half = b.value_length >> 1;
     for (int v = -kFastValues; v <= kFastValues; v++) {
+        if (v <= -half || v >= half) continue;          // a table shorter than the fast range
         const int idx = v < 0 ? b.value_length + v : v;
         mix(((uint64_t)b.value_bits[idx] << 8) ^ b.value_size[idx]);
     }

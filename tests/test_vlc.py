@@ -289,3 +289,57 @@ def test_host_parsers_survive_damaged_input(pkg):
         except pkg.CfbError:
             pass
     dec.close()
+
+
+def _toy_books(pkg):
+    """A small prefix-free code set (value table of 8 entries, i.e. shorter than the coder's fast-pair range)."""
+    run_bits, run_size, run_count = [0, 0b10, 0b110, 0b1110], [0, 2, 3, 4], [0, 1, 2, 3]
+    vcode = {1: "00", -1: "010", 2: "0110", -2: "01110", 3: "011110", -3: "0111110"}
+    vb, vs = np.zeros(8, np.uint32), np.zeros(8, np.uint8)
+    for v, text in vcode.items():
+        vb[v if v >= 0 else 8 + v], vs[v if v >= 0 else 8 + v] = int(text, 2), len(text)
+    vb[0], vs[0] = 0b0111111, 7            # never used by the coder (zeros are runs); keeps the table free of zero-length codes
+    vb[4], vs[4] = 0b0111111, 7
+    enc = pkg.VlcCodebook.from_arrays(np.array(run_bits, np.uint32), np.array(run_size, np.uint8), np.array(run_count, np.uint32), vb, vs)
+    bits = [0b10, 0b110, 0b1110, 0b1111] + [int(t, 2) for t in vcode.values()]
+    size = [2, 3, 4, 4] + [len(t) for t in vcode.values()]
+    kind = [1, 1, 1, 2] + [0] * len(vcode)
+    arg = [1, 2, 3, 0] + list(vcode.keys())
+    return enc, pkg.VlcDecodebook.from_arrays(bits, size, kind, arg)
+
+
+def test_toy_code_set_round_trip_through_coder_and_parser(pkg):
+    """Property test without the reference: any prefix-free code set, coder -> band stream -> parser -> the same sparse
+    buffer.  The value table has 8 entries (shorter than the pre-joined pair range: regression for an out-of-bounds read
+    found with AddressSanitizer), runs are longer than the longest run code, values beyond the table are clamped."""
+    lay = pkg.layout_for(pkg.FrameDesc(256, 64, pkg.PIXEL_YUYV))
+    enc, dec_book = _toy_books(pkg)
+    rng = np.random.default_rng(11)
+    coded = np.zeros(lay.coded_bytes, np.uint8)
+    for c, k, b in all_bands(lay):
+        view = pkg.band_view(lay, coded, c, k, b)
+        nz = rng.random(view.shape) < (0.3 if k == 2 else 0.02)
+        view[nz] = rng.choice(np.array([-3, -2, -1, 1, 2, 3], np.int16), int(nz.sum()))
+    sparse = pkg.sparse_compact(lay, coded)
+    dec = pkg.VlcDecoder(lay, dec_book)
+    dec.begin()
+    for c, k, b in all_bands(lay):
+        bl = lay.band[c][k][b]
+        words, pending, free = pkg.sparse_vlc_band(lay, sparse, c, k, b, enc, 8 * bl.pitch * bl.height + 64, 0)
+        padded = coded[bl.offset: bl.offset + bl.pitch * bl.height].view(np.int16).reshape(bl.height, bl.pitch // 2)
+        dense = pkg.dense_vlc_band(padded, bl.pitch, bl.width, enc, 8 * bl.pitch * bl.height + 64, 0)
+        assert np.array_equal(dense[0], words) and dense[1:] == (pending, free)
+        # finish the stream the way the host coder does: pending bits, end-of-band code, zero padding to a word
+        text = "".join(format(int(x), "08b") for x in words) + (format(pending, "b").zfill(32 - free)[-(32 - free):] if free < 32 else "") + "1111"
+        text += "0" * (-len(text) % 32)
+        stream = np.array([int(text[i:i + 8], 2) for i in range(0, len(text), 8)], np.uint8)
+        dec.band(c, k, b, stream, 1)
+    out = dec.end()
+    assert np.array_equal(out, sparse)
+    # a value outside the table is clamped to the largest code (vlc.c:188): 100 decodes as 3
+    one = np.zeros(lay.coded_bytes, np.uint8)
+    pkg.band_view(lay, one, 0, 2, 1)[0, 0] = 100
+    words, pending, free = pkg.sparse_vlc_band(lay, pkg.sparse_compact(lay, one), 0, 2, 1, enc, 4096, 0)
+    head = ("".join(format(int(x), "08b") for x in words) + format(pending, "b").zfill(32 - free))[:6]
+    assert head == "011110"
+    dec.close()
