@@ -825,6 +825,13 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
         if (frame_pitch < out_w * bpp || (frame_pitch & 15)) { set_error("bad output pitch %d", frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
         for (int c = 0; c < L.num_channels; c++)
             if (L.band[c][0][0].width < 16) { set_error("16-bit packed output needs level-1 bands at least 16 coefficients wide"); return CFB_ERROR_UNSUPPORTED; }
+    } else if (out_format >= CFB_PIXEL_RG30 && out_format <= CFB_PIXEL_DPX0) {
+        // 10-bit packed RGB of an RGB 4:4:4 sample (decoder.c:26893 -> InvertHorizontalStrip16s.c:14812 ...RGB2RG30)
+        if (!is444 || L.num_channels != 3 || L.precision != 12) { set_error("10-bit RGB output needs a three-channel 12-bit 4:4:4 codec"); return CFB_ERROR_BADFORMAT; }
+        if (cd->decode_res != CFB_RESOLUTION_FULL || cd->interlaced) { set_error("10-bit RGB output: full-resolution progressive decode only"); return CFB_ERROR_UNSUPPORTED; }
+        if (frame_pitch < out_w * 4 || (frame_pitch & 15)) { set_error("bad output pitch %d", frame_pitch); return CFB_ERROR_INVALID_ARGUMENT; }
+        for (int c = 0; c < L.num_channels; c++)
+            if (L.band[c][0][0].width < 16) { set_error("10-bit RGB output needs level-1 bands at least 16 coefficients wide"); return CFB_ERROR_UNSUPPORTED; }
     } else if (out_format == CFB_PIXEL_B64A) {
         // 16-bit A,R,G,B of an RGB 4:4:4 sample (decoder.c:26862 -> InvertHorizontalStrip16s.c:13298 ...RGB2B64A)
         if (!is444 || L.num_channels != 3 || L.precision != 12) { set_error("B64A output needs a three-channel 12-bit 4:4:4 codec"); return CFB_ERROR_BADFORMAT; }
@@ -920,7 +927,14 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
         for (int c = 0; c < 3; c++) { p.ch[c].out_off = 0; p.ch[c].out_pitch = frame_pitch; }
         p.shift = L.precision - 8; p.uyvy = (out_format == CFB_PIXEL_UYVY);
         p.th = pick_th((p.ch[0].width + kInvStrip - 1) / kInvStrip, p.ch[0].height, n, ctx->sm_count);
-        if (out_format == CFB_PIXEL_B64A) {
+        if (out_format >= CFB_PIXEL_RG30 && out_format <= CFB_PIXEL_DPX0) {
+            // component positions and byte order as on the encode side (spatial.c:2118-2268 / InvertHorizontalStrip16s.c:15562-15613)
+            static const int pos_rgb[5][3] = {{0, 10, 20}, {0, 10, 20}, {20, 10, 0}, {20, 10, 0}, {22, 12, 2}};   // R, G, B of RG30 AB10 AR10 R210 DPX0
+            for (int c = 0; c < 3; c++) p.tail_col[c] = pos_rgb[out_format - CFB_PIXEL_RG30][c];
+            p.uyvy = (out_format == CFB_PIXEL_R210 || out_format == CFB_PIXEL_DPX0);
+            p.up_shift = 0; p.hi_simd = (1 << L.precision) - 1;
+            CFB_CUDA(launch_inv_444_rg48(p, 2, ctx->stream));
+        } else if (out_format == CFB_PIXEL_B64A) {
             // InvertHorizontalStrip16s.c:13319: the 8-column loop runs up to post_column = width - width % 8 and always leaves the
             // right border column to the scalar code, which saturates at 65535 instead of the 12-bit maximum
             p.up_shift = 16 - L.precision;
@@ -929,7 +943,7 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
                 const int w = p.ch[c].width;
                 p.tail_col[c] = (w % 8) ? w - w % 8 : w - 1;
             }
-            CFB_CUDA(launch_inv_444_rg48(p, true, ctx->stream));
+            CFB_CUDA(launch_inv_444_rg48(p, 1, ctx->stream));
         } else if (out_format == CFB_PIXEL_YU64 || out_format == CFB_PIXEL_RG48) {
             p.up_shift = 16 - L.precision;
             p.hi_simd = ((1 << L.precision) - 1) << p.up_shift;
@@ -939,7 +953,7 @@ cfb_error cfb_inverse_device(cfb_codec *cd, int n, void *const *d_pyramids, cons
                 const int w = p.ch[c].width;
                 p.tail_col[c] = (w - (w % 8) - 16) + 7;
             }
-            if (out_format == CFB_PIXEL_RG48) CFB_CUDA(launch_inv_444_rg48(p, false, ctx->stream));
+            if (out_format == CFB_PIXEL_RG48) CFB_CUDA(launch_inv_444_rg48(p, 0, ctx->stream));
             else CFB_CUDA(launch_inv_422(p, true, ctx->stream));
         } else {
             CFB_CUDA(launch_inv_422(p, false, ctx->stream));
@@ -974,10 +988,11 @@ static cfb_error inv_output_geometry(const cfb_codec *cd, int out_format, int *r
     int out_w = 0, out_h = 0;
     cfb_codec_decoded_size(cd, &out_w, &out_h);
     const int kk = cd->decode_res - 1;          // lowest level that is inverted (0 = all three)
-    const int bpp = (out_format == CFB_PIXEL_YU64) ? 4 : (out_format == CFB_PIXEL_RG48) ? 6 : (out_format == CFB_PIXEL_B64A) ? 8 : 2;
+    const bool rgb30 = (out_format >= CFB_PIXEL_RG30 && out_format <= CFB_PIXEL_DPX0);
+    const int bpp = (out_format == CFB_PIXEL_YU64 || rgb30) ? 4 : (out_format == CFB_PIXEL_RG48) ? 6 : (out_format == CFB_PIXEL_B64A) ? 8 : 2;
     *rowbytes = out_w * bpp; *dpitch = (out_w * bpp + 15) & ~15;
-    if ((out_format == CFB_PIXEL_YU64 || out_format == CFB_PIXEL_RG48) && (size_t)*dpitch * out_h > cd->frame_stride) {
-        set_error("16-bit packed output does not fit the codec's frame staging"); return CFB_ERROR_UNSUPPORTED;
+    if ((out_format == CFB_PIXEL_YU64 || out_format == CFB_PIXEL_RG48 || rgb30) && (size_t)*dpitch * out_h > cd->frame_stride) {
+        set_error("packed output does not fit the codec's frame staging"); return CFB_ERROR_UNSUPPORTED;
     }
     if (out_format == CFB_PIXEL_PLANAR16) {
         *rows = 0;

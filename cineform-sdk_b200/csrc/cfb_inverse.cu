@@ -522,7 +522,11 @@ __global__ void __launch_bounds__(128, MINB) k_inv_422(const __grid_constant__ I
 // samples are limited to the 12-bit maximum where its SSE2 loop runs (:13387 limiterRGB) and to 65535 in its scalar tail and
 // right border column (InvParams::tail_col, here the same for the three channels); native (little-endian) words as the
 // reference's decoder leaves them.
-template <bool SMALLDQ, bool B64A>
+// OUT = 2: one 32-bit word per pixel with 10-bit components (RG30 / AB10 / AR10 / R210 / DPX0; decoder.c:26893 ->
+// InvertHorizontalStrip16s.c:14812 InvertHorizontalStrip16sRGB2RG30): the 12-bit sample limited to [0, 4095] in every column
+// (:14892 limiterRGB; the scalar code clamps alike), >> 2 (:15552), components at bit positions tail_col[0..2] = R, G, B,
+// the word byte-swapped when p.uyvy is set (R210, DPX0; :15577-15613).  32 contiguous bytes per lane.
+template <bool SMALLDQ, int OUT>
 __global__ void __launch_bounds__(128) k_inv_444_rg48(const __grid_constant__ InvParams p)
 {
     const int lane = threadIdx.x;
@@ -541,14 +545,26 @@ __global__ void __launch_bounds__(128) k_inv_444_rg48(const __grid_constant__ In
     const bool has_border = (strip == 0) || ((strip + 1) * kInvStrip + 4 >= gg.width);
     const unsigned cb = (unsigned)(col0 * 2);
     const unsigned char *in = p.in_base[f];
-    unsigned char *out = p.out_base[f] + gg.out_off + (long long)col0 * (B64A ? 16 : 12);      // 2 pixels per band column, 6 (8) bytes per pixel
+    constexpr bool B64A = (OUT == 1);
+    unsigned char *out = p.out_base[f] + gg.out_off + (long long)col0 * (OUT == 2 ? 8 : B64A ? 16 : 12);      // 2 pixels per band column, 6 (8, 4) bytes per pixel
     const int us = p.up_shift;
 
     auto emit = [&](int r, const int *ge, const int *go, const int *re, const int *ro, const int *be, const int *bo) {
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {
             const int *G = rr ? go : ge, *R = rr ? ro : re, *B = rr ? bo : be;
-            if constexpr (B64A) {
+            if constexpr (OUT == 2) {
+                unsigned char *q = out + (long long)(2 * r + rr) * gg.out_pitch;
+                unsigned w[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const unsigned word = ((row16u(R[i], 0, 4095) >> 2) << p.tail_col[0]) | ((row16u(G[i], 0, 4095) >> 2) << p.tail_col[1]) |
+                                          ((row16u(B[i], 0, 4095) >> 2) << p.tail_col[2]);
+                    w[i] = p.uyvy ? __byte_perm(word, 0, 0x0123) : word;
+                }
+                *reinterpret_cast<uint4 *>(q) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4 *>(q + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+            } else if constexpr (B64A) {
                 unsigned char *q = out + (long long)(2 * r + rr) * gg.out_pitch;
                 const unsigned alpha = (unsigned)p.hi_simd;
 #pragma unroll
@@ -909,14 +925,16 @@ cudaError_t launch_inv_422(const InvParams &p, bool out16, cudaStream_t stream)
     return cudaGetLastError();
 }
 
-cudaError_t launch_inv_444_rg48(const InvParams &p, bool b64a, cudaStream_t stream)
+// out: 0 RG48, 1 B64A, 2 10-bit packed RGB
+cudaError_t launch_inv_444_rg48(const InvParams &p, int out, cudaStream_t stream)
 {
     dim3 block(32, 4);
     dim3 grid(ceil_div_i(p.ch[0].width, kInvStrip), ceil_div_i(ceil_div_i(p.ch[0].height, p.th), (int)block.y) + 1, p.nframes);
     bool small = true;
     for (int c = 0; c < 3; c++) for (int b = 1; b < 4; b++) small = small && (p.ch[c].dq[b] >= 0 && p.ch[c].dq[b] <= 255);
-    if (b64a) { if (small) k_inv_444_rg48<true, true><<<grid, block, 0, stream>>>(p); else k_inv_444_rg48<false, true><<<grid, block, 0, stream>>>(p); }
-    else { if (small) k_inv_444_rg48<true, false><<<grid, block, 0, stream>>>(p); else k_inv_444_rg48<false, false><<<grid, block, 0, stream>>>(p); }
+    if (out == 2) { if (small) k_inv_444_rg48<true, 2><<<grid, block, 0, stream>>>(p); else k_inv_444_rg48<false, 2><<<grid, block, 0, stream>>>(p); }
+    else if (out == 1) { if (small) k_inv_444_rg48<true, 1><<<grid, block, 0, stream>>>(p); else k_inv_444_rg48<false, 1><<<grid, block, 0, stream>>>(p); }
+    else { if (small) k_inv_444_rg48<true, 0><<<grid, block, 0, stream>>>(p); else k_inv_444_rg48<false, 0><<<grid, block, 0, stream>>>(p); }
     return cudaGetLastError();
 }
 

@@ -232,8 +232,12 @@ CFB_API cfb_error cfb_forward_host(cfb_codec *codec, int n, const void *const *h
 /* The coded region holds QUANTISED values (as entropy-decoded with quant 1); dequantisation by
  * quant->divisor is fused into the kernels' loads. out_format: CFB_PIXEL_YUYV/UYVY (8-bit, see
  * DESIGN.md for the rounding rule), CFB_PIXEL_PLANAR16 (int16 planes at codec precision), and the 16-bit packed
- * outputs of the reference's final level, all bit-exact (no dither): CFB_PIXEL_YU64 from 4:2:2 codecs, CFB_PIXEL_RG48
- * and CFB_PIXEL_B64A from RGB 4:4:4 codecs (full resolution, progressive). */
+ * outputs of the reference's final level, all bit-exact (no dither): CFB_PIXEL_YU64 from 4:2:2 codecs, CFB_PIXEL_RG48,
+ * CFB_PIXEL_B64A and the 10-bit words CFB_PIXEL_RG30 / AB10 / AR10 / R210 / DPX0 (Codec/decoder.c:26893 ->
+ * InvertHorizontalStrip16s.c:14812: the 12-bit sample limited to [0, 4095], >> 2) from RGB 4:4:4 codecs (full resolution,
+ * progressive).  The reference's LOWPASS BAND DECODE adds a per-output-format constant to LL3 (decoder.c:12270-12316: 6 for
+ * the 10-bit RGB outputs, 8 for 8-bit RGB, 0 for RG48 / B64A ...): that belongs to the host's band decode, the caller
+ * passes the bands as its decoder holds them. */
 CFB_API cfb_error cfb_inverse_device(cfb_codec *codec, int n, void *const *d_pyramids, const cfb_quant *quant,
                                      int out_format, void *const *d_frames, int frame_pitch);
 CFB_API cfb_error cfb_inverse_host(cfb_codec *codec, int n, const void *const *h_coded, const cfb_quant *quant,

@@ -466,6 +466,18 @@ def pack_b64a(planes, precision=12):
     return out
 
 
+def pack_rgb30_output(name, planes, precision=12):
+    """[G, R, B] int16 planes -> the reference decoder's 10-bit packed RGB words (height x width uint32) for
+    DECODED_FORMAT_RG30 / R210 / DPX0 / AR10 / AB10 (Codec/decoder.c:26893 -> InvertHorizontalStrip16s.c:14812
+    InvertHorizontalStrip16sRGB2RG30): every sample limited to [0, 2^precision - 1] (:14892 limiterRGB; its scalar code
+    clamps alike), >> 2 (:15552), packed as on the encode side.  NOTE the reference's lowpass decode adds a format-dependent
+    offset to LL3 (decoder.c:12270-12316: 6 for these formats, 0 for RG48 / B64A), so its bands differ between output
+    formats; that offset is applied by the host's band decode, upstream of the transform."""
+    top = (1 << precision) - 1
+    g, r, b = [(np.clip(p.astype(np.int64), 0, top) >> (precision - 10)).astype(np.uint32) for p in planes]
+    return pack_rgb30(name, r, g, b)
+
+
 def ref_decode_sample_raw(ref_lib, sample, width, height, decoded_format, num_channels, pitch):
     """Codec-level reference decode into an arbitrary DECODED_FORMAT_*; returns (bytes (height x pitch), dequantised bands).
 

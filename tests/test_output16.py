@@ -85,6 +85,34 @@ def test_oracle_b64a_matches_reference_decoder(size, kind):
         assert not (got[:, :8 * pu.b64a_tail_col(w // 2)] == 65535).any()
 
 
+@needs_ref
+@pytest.mark.parametrize("size", [(640, 96), (328, 48), (256, 64), (200, 48), (1016, 64), (720, 480)])
+@pytest.mark.parametrize("kind", ["qbist", "extreme"])
+def test_oracle_rgb30_outputs_match_reference_decoder(size, kind):
+    """The five 10-bit packed RGB outputs of an RGB 4:4:4 sample: truncation of the limited 12-bit sample, one rule for all
+    columns.  The bands are the ones the decoder held for THAT output format (its lowpass decode adds a per-format offset)."""
+    w, h = size
+    if kind == "extreme" and w * h > 100000:
+        pytest.skip("0/65535 noise at this size does not fit the probe's sample buffer")
+    ref_lib, orc = ol.load_ref(), ol.oracle()
+    sample, prescale = _sample_444(ref_lib, w, h, kind)
+    rg48_bands = pu.ref_decode_sample_raw(ref_lib, sample, w, h, DECODED_FORMAT_RG48, 3, w * 6)[1]
+    for name, (fmt, _, _) in pu.RGB30_FORMATS.items():
+        out, bands = pu.ref_decode_sample_raw(ref_lib, sample, w, h, fmt, 3, w * 4)
+        planes = pu.inverse_pyramid(orc, bands, pu.UNIT_DIVISORS, tuple(prescale))
+        want = pu.pack_rgb30_output(name, planes)
+        got = out.view(np.uint32).reshape(h, w)
+        assert np.array_equal(got, want), (name, np.argwhere(got != want)[:5].tolist())
+        # the host-side offset of the lowpass decode: the coded bands are the RG48 decode's except for a constant on LL3
+        # (6 where the reference's threaded lowpass decode applies it, decoder.c:12308; 0 otherwise)
+        for key in bands:
+            delta = bands[key].astype(np.int32) - rg48_bands[key].astype(np.int32)
+            if key[2] != "LL":
+                assert not delta.any(), key
+            elif key[1] == 3:
+                assert delta.min() == delta.max() and int(delta.min()) in (0, 6), (key, int(delta.min()), int(delta.max()))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("size", [(256, 64), (640, 96), (704, 96), (720, 480), (1920, 1080), (3840, 2160)])
 @pytest.mark.parametrize("kind", ["natural", "extreme"])
