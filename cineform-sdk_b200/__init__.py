@@ -292,8 +292,9 @@ class VlcDecoder:
         _check(lib().cfb_sparse_writer_create(C.byref(layout), C.byref(self.w)))
         self.out = None
 
-    def begin(self):
-        self.out = np.zeros(sparse_max_bytes(self.layout), np.uint8)
+    def begin(self, out=None):
+        """out: a caller-owned buffer of sparse_max_bytes(layout) to write into (a frame loop reuses one)."""
+        self.out = np.zeros(sparse_max_bytes(self.layout), np.uint8) if out is None else out
         _check(lib().cfb_sparse_writer_begin(self.w, self.out.ctypes.data, self.out.size))
 
     def dense_band(self, c, k, b, rows):

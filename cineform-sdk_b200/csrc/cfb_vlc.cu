@@ -498,9 +498,15 @@ struct cfb_vlc_decoder {
     // the entry, the end-of-band code is only ever an entry of its own.  len 0: no code word ends inside the window ->
     // continue in the trie at `node` (node < 0: no code word starts with these bits).
     struct Fast { uint8_t len; uint8_t has_value; uint8_t end; uint32_t zeros; int32_t value; int32_t node; };
+    // second level for code words longer than the window: per trie node reached after kPrimaryBits bits, a table over the
+    // next kSecondBits bits (one code word per look-up); what is longer still walks the trie bit by bit
+    static constexpr int kSecondBits = 8;
+    struct Second { uint8_t len; int32_t token; int32_t node; };     // len 0: not resolved -> continue at `node` (< 0: no code)
     std::vector<Token> tokens;
     std::vector<Node> nodes;
     std::vector<Fast> fast;
+    std::vector<int32_t> second_of_node;        // node -> first entry of its table in `second`, -1 = none
+    std::vector<Second> second;
 };
 
 cfb_error cfb_vlc_decoder_create(const cfb_vlc_decodebook *book, cfb_vlc_decoder **out)
@@ -553,6 +559,19 @@ cfb_error cfb_vlc_decoder_create(const cfb_vlc_decodebook *book, cfb_vlc_decoder
         f.len = (uint8_t)pos;
         d->fast[p] = f;
     }
+    const int S = cfb_vlc_decoder::kSecondBits;
+    d->second_of_node.assign(d->nodes.size(), -1);
+    for (unsigned p = 0; p < (1u << P); p++) {
+        const int start = d->fast[p].len ? -1 : d->fast[p].node;
+        if (start < 0 || d->second_of_node[start] >= 0) continue;
+        d->second_of_node[start] = (int32_t)d->second.size();
+        for (unsigned q = 0; q < (1u << S); q++) {
+            int node = start, len = 0;
+            while (len < S && node >= 0 && d->nodes[node].token < 0) { node = d->nodes[node].child[(q >> (S - 1 - len)) & 1]; len++; }
+            if (node >= 0 && d->nodes[node].token >= 0) d->second.push_back({(uint8_t)len, d->nodes[node].token, -1});
+            else d->second.push_back({0, -1, node});
+        }
+    }
     *out = d;
     return CFB_OK;
 }
@@ -590,8 +609,23 @@ cfb_error cfb_vlc_decode_band(const cfb_vlc_decoder *d, cfb_sparse_writer *w, in
             if (f.has_value) { e = writer_value(w, (int)(int16_t)(f.value * quant)); if (e) return e; }
             continue;
         }
-        // a code word longer than the window: finish it in the trie
+        // a code word longer than the window: second-level table, then the trie
         int node = f.node, len = P;
+        if (node >= 0) {
+            const int S = cfb_vlc_decoder::kSecondBits;
+            const cfb_vlc_decoder::Second &s2 = d->second[(size_t)d->second_of_node[node] + (size_t)((acc >> (64 - P - S)) & ((1u << S) - 1))];
+            if (s2.len) { node = -2; len = P + s2.len; }
+            else { node = s2.node; len = P + S; }
+            if (node == -2) {
+                if (len > have) { set_error("band stream truncated inside a code word"); return CFB_ERROR_BADFORMAT; }
+                acc <<= len; have -= len; bitpos += (size_t)len;
+                const cfb_vlc_decoder::Token &t2 = d->tokens[s2.token];
+                if (t2.kind == 2) break;
+                e = (t2.kind == 1) ? writer_advance(w, (uint32_t)t2.arg) : writer_value(w, (int)(int16_t)(t2.arg * quant));
+                if (e) return e;
+                continue;
+            }
+        }
         while (node >= 0 && d->nodes[node].token < 0 && len < 32) { node = d->nodes[node].child[(acc >> (63 - len)) & 1]; len++; }
         if (node < 0 || d->nodes[node].token < 0) { set_error("band stream: no code word matches at bit %zu", bitpos); return CFB_ERROR_BADFORMAT; }
         if (len > have) { set_error("band stream truncated inside a code word"); return CFB_ERROR_BADFORMAT; }

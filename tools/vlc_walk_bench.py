@@ -105,8 +105,10 @@ def main():
     ll = [(c, k, b, bl, p) for c, k, b, bl, p in views if b == 0]
     dec = pkg.VlcDecoder(lay, decode_book(pkg, ref, a.codebook))
 
+    sparse_out = np.zeros(pkg.sparse_max_bytes(lay), np.uint8)          # one buffer for the frame loop, as a decoder would keep
+
     def run_decode():
-        dec.begin()
+        dec.begin(sparse_out)
         it = iter(streams)
         for c in range(lay.num_channels):
             for item in ll:
