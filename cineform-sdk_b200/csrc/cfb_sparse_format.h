@@ -4,6 +4,9 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <string.h>
+#if defined(__SSE2__) && !defined(__CUDA_ARCH__)
+#include <emmintrin.h>
+#endif
 
 #ifdef __CUDACC__
 #define CFB_HD __host__ __device__ __forceinline__
@@ -86,13 +89,31 @@ inline unsigned sparse_compact_block(const int16_t *in, unsigned nvalid, unsigne
     for (unsigned g = 0; g * kSparseGroupWords < nvalid; g++) {
         const int16_t *grp = in + (size_t)g * kSparseGroupWords;
         const unsigned n = nvalid - g * kSparseGroupWords < kSparseGroupWords ? nvalid - g * kSparseGroupWords : kSparseGroupWords;
+        unsigned m = 0;
+#if defined(__SSE2__) && !defined(__CUDA_ARCH__)
+        if (n == kSparseGroupWords) {           // most groups are empty: the non-zero mask of 32 words from four 16-byte compares
+            const __m128i zero = _mm_setzero_si128();
+            const __m128i a = _mm_loadu_si128((const __m128i *)grp), b = _mm_loadu_si128((const __m128i *)(grp + 8));
+            const __m128i c = _mm_loadu_si128((const __m128i *)(grp + 16)), d = _mm_loadu_si128((const __m128i *)(grp + 24));
+            const unsigned z0 = (unsigned)_mm_movemask_epi8(_mm_packs_epi16(_mm_cmpeq_epi16(a, zero), _mm_cmpeq_epi16(b, zero)));
+            const unsigned z1 = (unsigned)_mm_movemask_epi8(_mm_packs_epi16(_mm_cmpeq_epi16(c, zero), _mm_cmpeq_epi16(d, zero)));
+            m = ~(z0 | (z1 << 16));
+            if (!m) continue;
+            for (unsigned left = m; left; left &= left - 1) {
+                const int v = grp[__builtin_ctz(left)];
+                if (v < -127 || v > 127) { vb[V++] = -128; wide[E++] = (int16_t)v; } else vb[V++] = (signed char)v;
+            }
+            l1[g >> 3] |= (unsigned char)(1u << (g & 7)); masks[G++] = m;
+            continue;
+        }
+#else
         if (n == kSparseGroupWords) {           // most groups are empty: eight 64-bit tests
             uint64_t any = 0, q[8];
             memcpy(q, grp, sizeof(q));
             for (int k = 0; k < 8; k++) any |= q[k];
             if (!any) continue;
         }
-        unsigned m = 0;
+#endif
         for (unsigned k = 0; k < n; k++) {
             const int v = grp[k];
             if (!v) continue;
