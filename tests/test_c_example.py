@@ -27,6 +27,18 @@ def test_c_example_fails_loudly_without_gpu():
     assert "no CPU fallback" in p.stderr and "failed: 100" in p.stderr
 
 
+@pytest.mark.parametrize("size", [("704", "96"), ("1920", "1080")])
+def test_c_entropy_handover_round_trip(size):
+    """examples/entropy_handover.c: sparse buffer -> band streams (cfb_sparse_vlc_band) -> sparse buffer (cfb_vlc_decode_band +
+    sparse writer) from plain C with a caller-supplied code set; host only, so it runs here."""
+    exe = os.path.join(os.path.dirname(_exe()), "entropy_handover")
+    p = subprocess.run([exe, *size], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr[-1000:]
+    r = json.loads(p.stdout.strip().splitlines()[-1])
+    assert r["sparse_round_trip_identical"] == 1 and r["dense_round_trip_identical"] == 1
+    assert 0 < r["sparse_bytes"] < r["coded_bytes"] // 4 and r["nonzero_coefficients"] > 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("args", [("1920", "1080", "0"), ("720", "480", "1"), ("3840", "2160", "0")])
 def test_c_example_roundtrip(args):
