@@ -1,7 +1,6 @@
 """10-bit packed RGB outputs (RG30 / AB10 / AR10 / R210 / DPX0) of the final inverse level for RGB 4:4:4 codecs on the GPU
 (SURVEY 8f rank 2).  The rule (parity_util.pack_rgb30_output) is pinned to the reference's decoder in test_output16.py.
-These kernels were written after round 2's GPU budget was spent: the file sorts last so that `pytest -x` reaches every
-other parity test first."""
+(First GPU run: profiles/r02_gpu_outputs_sdk.txt.)"""
 import importlib
 
 import numpy as np
