@@ -11,6 +11,10 @@ TMP=$(mktemp -d)
 cp "$LIB" "$TMP/real.so"
 trap 'cp "$TMP/real.so" "$LIB"; rm -rf "$TMP"' EXIT
 cp "$TMP/libsan.so" "$LIB"
-ASAN_OPTIONS=detect_leaks=0 UBSAN_OPTIONS=print_stacktrace=1 \
-LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" \
+export ASAN_OPTIONS=detect_leaks=0 UBSAN_OPTIONS=print_stacktrace=1
+export LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)"
+if [ "$1" = "--fuzz" ]; then
+    python tools/fuzz_host.py "${2:-300}"        # random code sets / band streams / damaged sparse buffers
+else
     python -m pytest tests -q -m "not gpu" -x -s -p no:cacheprovider --deselect tests/test_c_example.py --ignore tests/test_launch_geometry.py
+fi
